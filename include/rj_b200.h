@@ -1,0 +1,254 @@
+/*
+ * rj_b200.h -- C-ABI of the B200-native radix hash-join engine.
+ *
+ * This is the drop-in boundary for the hot path of cliarie/radix-join:
+ *   Contest::build_context / destroy_context / execute   (reference include/plan.h:337-344,
+ *   implemented by the reference in src/execute.cpp:316-330).
+ * Those three symbols are C++-mangled and traffic in C++ containers, so a foreign-function binding
+ * cannot name them directly.  The entry points below carry the same information as plain pointers
+ * and sizes; `radix-join_b200/csrc/contest_execute.cpp` is the 100-line adapter that turns a
+ * `const Plan&` into an `rj_plan_t` and an `rj_result` back into a `ColumnarTable`.
+ *
+ * Conventions
+ *   - every function that can fail returns int: 0 = ok, non-zero = error; the message is kept in the
+ *     context (`rj_last_error`).  The C++ adapter rethrows it as std::runtime_error, which is the
+ *     reference's error contract (src/execute.cpp:280, tests/read_sql.cpp:1329-1332).
+ *   - no torch / C++ types in any signature; device pointers are `void*` / `uint64_t` addresses in the
+ *     CUDA primary context of the device the context was created on; streams are `void*`
+ *     (a `cudaStream_t`; NULL = the context's own stream).
+ *   - there is NO CPU fallback: if no sm_100 device is present every entry point fails.
+ */
+#ifndef RJ_B200_H
+#define RJ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RJ_PAGE_SIZE 8192u /* reference include/plan.h:54 */
+
+/* reference include/attribute.h:8-13 (same numeric values as `enum class DataType`) */
+enum rj_data_type { RJ_INT32 = 0, RJ_INT64 = 1, RJ_FP64 = 2, RJ_VARCHAR = 3 };
+
+/* ------------------------------------------------------------------------------------------------
+ * Flattened plan -- mirrors Plan / PlanNode / ScanNode / JoinNode / ColumnarTable / Column
+ * (reference include/plan.h:32-52, 60-62, 102-116).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Column (plan.h:60-62): a typed list of 8 KB pages.  Give either `pages` (n_pages pointers to
+ * individually allocated pages, as the reference's `std::vector<Page*>`) or `contiguous`
+ * (n_pages * 8192 bytes back to back); `pages` wins if both are set. */
+typedef struct rj_column_t {
+    int32_t            type;       /* rj_data_type */
+    uint32_t           reserved;
+    uint64_t           n_pages;
+    const void* const* pages;
+    const void*        contiguous;
+} rj_column_t;
+
+/* ColumnarTable (plan.h:102-105) */
+typedef struct rj_table_t {
+    uint64_t           num_rows;
+    uint32_t           n_columns;
+    uint32_t           reserved;
+    const rj_column_t* columns;
+} rj_table_t;
+
+/* one element of PlanNode::output_attrs (plan.h:46): (source column index, declared type) */
+typedef struct rj_attr_t {
+    uint64_t index;
+    int32_t  type;
+    uint32_t reserved;
+} rj_attr_t;
+
+/* PlanNode (plan.h:44-52) with its ScanNode (:32-34) or JoinNode (:36-42) payload inlined */
+typedef struct rj_node_t {
+    int32_t          is_join;       /* 0 = ScanNode, 1 = JoinNode */
+    int32_t          build_left;    /* JoinNode::build_left */
+    uint64_t         base_table_id; /* ScanNode::base_table_id (index into inputs) */
+    uint64_t         left, right;   /* JoinNode child node indices */
+    uint64_t         left_attr, right_attr; /* index into the child's output_attrs */
+    uint32_t         n_output_attrs;
+    uint32_t         reserved;
+    const rj_attr_t* output_attrs;
+} rj_node_t;
+
+/* Plan (plan.h:112-116) */
+typedef struct rj_plan_t {
+    uint32_t          n_nodes;
+    uint32_t          n_inputs;
+    const rj_node_t*  nodes;
+    const rj_table_t* inputs;
+    uint64_t          root;
+} rj_plan_t;
+
+typedef struct rj_ctx    rj_ctx;    /* the opaque `void* context` of Contest::build_context      */
+typedef struct rj_inputs rj_inputs; /* base tables resident in HBM (uploaded pages)               */
+typedef struct rj_result rj_result; /* result ColumnarTable: pages resident in HBM until fetched  */
+
+/* ------------------------------------------------------------------------------------------------
+ * Context  -- replaces Contest::build_context / destroy_context (src/execute.cpp:326-330)
+ * ---------------------------------------------------------------------------------------------- */
+int         rj_ctx_create(int device, rj_ctx** out);
+void        rj_ctx_destroy(rj_ctx* ctx);
+const char* rj_last_error(const rj_ctx* ctx); /* ctx may be NULL: error of the last failed rj_ctx_create */
+int         rj_ctx_device(const rj_ctx* ctx);
+int         rj_ctx_sm_count(const rj_ctx* ctx);
+/* host threads used to gather/scatter individually allocated pages through pinned staging */
+int         rj_ctx_set_host_threads(rj_ctx* ctx, int n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole path -- replaces Contest::execute (src/execute.cpp:316-324)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Host pages in -> result.  H2D upload, decode, joins, gather+encode all happen inside. */
+int rj_execute(rj_ctx* ctx, const rj_plan_t* plan, rj_result** out);
+
+/* Same, split so a benchmark can keep the inputs resident in HBM:
+ * rj_inputs_upload copies every column of every table once (plan->inputs of the later call is
+ * ignored); rj_execute_resident runs decode -> joins -> encode on device only. */
+int  rj_inputs_upload(rj_ctx* ctx, const rj_table_t* tables, uint32_t n_tables, rj_inputs** out);
+/* adopt pages that already are in device memory (e.g. produced by rj_gen_* or an exchange):
+ * `contiguous` of every column is then a DEVICE address; nothing is copied or owned. */
+int  rj_inputs_adopt_device(rj_ctx* ctx, const rj_table_t* tables, uint32_t n_tables, rj_inputs** out);
+void rj_inputs_free(rj_ctx* ctx, rj_inputs* in);
+int  rj_execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in, rj_result** out);
+
+/* Result inspection -- the fields of the returned ColumnarTable (plan.h:102-105) */
+uint64_t rj_result_num_rows(const rj_result* r);
+uint32_t rj_result_num_columns(const rj_result* r);
+int32_t  rj_result_column_type(const rj_result* r, uint32_t col);
+uint64_t rj_result_column_pages(const rj_result* r, uint32_t col);
+/* device address of the column's pages (n_pages * 8192 bytes, contiguous) */
+uint64_t rj_result_column_device_ptr(const rj_result* r, uint32_t col);
+/* D2H: copy the pages of one column into caller-owned host pages.  `dst_pages` = n_pages pointers
+ * (the adapter passes freshly `new Page`d pages, plan.h:64-68,95-99) or `dst_contiguous`. */
+int  rj_result_fetch(rj_ctx* ctx, const rj_result* r, uint32_t col, void* const* dst_pages,
+                     void* dst_contiguous);
+void rj_result_free(rj_ctx* ctx, rj_result* r);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-stage entry points (device pointers in, device pointers out).  The whole-path functions above
+ * are composed of exactly these; tests, the bench and the multi-GPU driver call them directly.
+ * All of them are asynchronous on `stream` unless they return a count.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* -- page ingest: replaces Table::from_columnar (src/build_table.cpp:312-436) ------------------- */
+
+/* Per-page row counts and their exclusive prefix: page_row_start[n_pages+1] (uint64, device).
+ * A VARCHAR 0xffff page counts one row, a 0xfffe page none (build_table.cpp:384-405).
+ * totals[0] = rows, totals[1] = non-null values (device uint64[2], may be NULL). */
+int rj_page_row_offsets(rj_ctx* ctx, const void* d_pages, uint64_t n_pages, int32_t type,
+                        uint64_t* d_page_row_start, uint64_t* d_totals, void* stream);
+
+/* INT32 / INT64 / FP64 pages -> dense values[rows] (4 or 8 bytes each, NULL rows = 0) and a
+ * validity bitmap (uint32 words, bit i of word i/32, LSB first; must be zeroed by the caller;
+ * pass NULL when the column is known to hold no NULLs). */
+int rj_decode_fixed(rj_ctx* ctx, const void* d_pages, uint64_t n_pages, int32_t type,
+                    const uint64_t* d_page_row_start, void* d_values, uint32_t* d_valid,
+                    void* stream);
+
+/* VARCHAR pages -> string descriptors desc[rows] (uint64: bits 0-39 byte address of the first char
+ * relative to d_pages, bits 40-62 length, bit 63 = long string spread over a 0xffff/0xfffe page
+ * chain) and the validity bitmap.  Characters stay in the page buffer (late materialisation). */
+int rj_decode_varchar(rj_ctx* ctx, const void* d_pages, uint64_t n_pages,
+                      const uint64_t* d_page_row_start, uint64_t* d_desc, uint32_t* d_valid,
+                      void* stream);
+
+/* -- radix partitioning: replaces the histogram/prefix/scatter of src/execute.cpp:124-184 -------- */
+
+/* Histogram of hash(key) over `bits` radix bits starting at bit `shift` of the 32-bit hash.
+ * keys: uint32 (key_bytes=4) or uint64 (key_bytes=8); valid may be NULL; NULL keys are not counted
+ * (execute.cpp:61-83: NULL keys never match).  d_hist: uint32[1<<bits], zeroed by the caller. */
+int rj_radix_histogram(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, uint64_t n,
+                       int32_t key_bytes, int32_t shift, int32_t bits, uint32_t* d_hist,
+                       void* stream);
+
+/* Scatter (key, row index) into partition order.  d_idx_in may be NULL (= identity row ids).
+ * d_cursor: uint32[1<<bits] holding each partition's start offset (exclusive prefix of the
+ * histogram); it is advanced by the kernel.  Output order inside a partition is unspecified. */
+int rj_radix_scatter(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid,
+                     const uint32_t* d_idx_in, uint64_t n, int32_t key_bytes, int32_t shift,
+                     int32_t bits, uint32_t* d_cursor, void* d_keys_out, uint32_t* d_idx_out,
+                     void* stream);
+
+/* -- join: replaces hash_join_omp steps 2-6 (src/execute.cpp:61-261) ---------------------------- */
+
+/* Inner equi-join of two key columns.  Emits (build row, probe row) pairs in unspecified order.
+ * Returns the number of matches in *n_matches (synchronises).  If it exceeds `capacity` the output
+ * arrays are incomplete and the call must be repeated with larger arrays (the count is exact). */
+int rj_join_keys(rj_ctx* ctx, const void* d_build_keys, const uint32_t* d_build_valid,
+                 uint64_t n_build, const void* d_probe_keys, const uint32_t* d_probe_valid,
+                 uint64_t n_probe, int32_t key_bytes, uint64_t capacity, uint32_t* d_out_build,
+                 uint32_t* d_out_probe, uint64_t* n_matches, void* stream);
+
+/* -- late materialisation ---------------------------------------------------------------------- */
+
+/* out[i] = src[idx[i]] for 4- or 8-byte elements; validity bits gathered alongside when
+ * d_src_valid != NULL (d_out_valid: (n+31)/32 words, fully written). */
+int rj_gather(rj_ctx* ctx, const void* d_src, const uint32_t* d_src_valid, const uint32_t* d_idx,
+              uint64_t n, int32_t elem_bytes, void* d_out, uint32_t* d_out_valid, void* stream);
+
+/* -- page output: replaces Table::to_columnar (src/build_table.cpp:456-681) --------------------- */
+
+/* rows-per-page used by rj_encode_fixed for a type (1984 for INT32, 1007 for INT64/FP64) */
+uint32_t rj_fixed_rows_per_page(int32_t type);
+
+/* Gather `n` rows of a fixed-width column through d_idx (NULL = identity) and write them as pages:
+ * d_pages_out must hold ceil(n / rows_per_page) * 8192 bytes. */
+int rj_encode_fixed(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid,
+                    const uint32_t* d_idx, uint64_t n, int32_t type, void* d_pages_out,
+                    void* stream);
+
+/* VARCHAR output is a two-step call because the page count depends on the data:
+ * plan computes the page layout and returns the page count; write fills the pages. */
+typedef struct rj_varchar_layout rj_varchar_layout;
+int  rj_encode_varchar_plan(rj_ctx* ctx, const void* d_src_pages, const uint64_t* d_desc,
+                            const uint32_t* d_valid, const uint32_t* d_idx, uint64_t n,
+                            rj_varchar_layout** layout, uint64_t* n_pages_out, void* stream);
+int  rj_encode_varchar_write(rj_ctx* ctx, rj_varchar_layout* layout, void* d_pages_out,
+                             void* stream);
+void rj_encode_varchar_free(rj_ctx* ctx, rj_varchar_layout* layout);
+
+/* -- synthetic inputs on device (harness side: the role of ColumnInserter, plan.h:151-228) ------- */
+
+/* Fill INT32/INT64/FP64 pages from dense device arrays, 1984/1007 rows per page (no greedy
+ * packing).  d_valid may be NULL.  Returns the page count via *n_pages_out when d_pages_out is
+ * NULL (size query). */
+int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n,
+                       int32_t type, void* d_pages_out, uint64_t* n_pages_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Profiling: per-kernel-class CUDA-event timings accumulated by the whole-path functions.
+ * ---------------------------------------------------------------------------------------------- */
+enum rj_stage {
+    RJ_ST_H2D = 0,       /* host page gather + H2D copies                  */
+    RJ_ST_ROW_OFFSETS,   /* page header scan                               */
+    RJ_ST_DECODE,        /* page decode kernels                            */
+    RJ_ST_HISTOGRAM,     /* radix histogram                                */
+    RJ_ST_SCATTER,       /* radix scatter (all passes)                     */
+    RJ_ST_JOIN,          /* shared-memory build + probe                    */
+    RJ_ST_GATHER,        /* row-id / key gathers                           */
+    RJ_ST_ENCODE,        /* gather + page encode                           */
+    RJ_ST_D2H,           /* D2H copies + host page scatter                 */
+    RJ_ST_COUNT
+};
+typedef struct rj_stage_stat_t {
+    double   ms;        /* summed device time                      */
+    uint64_t launches;  /* kernel launches (or copies) in the sum  */
+    uint64_t bytes;     /* algorithmic bytes (SURVEY 8d accounting)*/
+} rj_stage_stat_t;
+int         rj_profile_enable(rj_ctx* ctx, int on);
+int         rj_profile_reset(rj_ctx* ctx);
+int         rj_profile_read(rj_ctx* ctx, rj_stage_stat_t* stats /* [RJ_ST_COUNT] */);
+const char* rj_stage_name(int stage);
+
+const char* rj_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RJ_B200_H */

@@ -1,0 +1,143 @@
+"""ctypes binding of include/rj_b200.h -- the C-ABI of the CUDA engine.
+
+This is the Python twin of the cgo/JNI-style stub shown in INTEGRATION.md: struct layouts and
+prototypes only, no logic.  `load_library()` fails loudly when librj_b200.so has not been built;
+there is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+PAGE_SIZE = 8192  # reference include/plan.h:54
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librj_b200.so")
+
+
+class rj_column_t(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("reserved", C.c_uint32),
+        ("n_pages", C.c_uint64),
+        ("pages", C.POINTER(C.c_void_p)),
+        ("contiguous", C.c_void_p),
+    ]
+
+
+class rj_table_t(C.Structure):
+    _fields_ = [
+        ("num_rows", C.c_uint64),
+        ("n_columns", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("columns", C.POINTER(rj_column_t)),
+    ]
+
+
+class rj_attr_t(C.Structure):
+    _fields_ = [("index", C.c_uint64), ("type", C.c_int32), ("reserved", C.c_uint32)]
+
+
+class rj_node_t(C.Structure):
+    _fields_ = [
+        ("is_join", C.c_int32),
+        ("build_left", C.c_int32),
+        ("base_table_id", C.c_uint64),
+        ("left", C.c_uint64),
+        ("right", C.c_uint64),
+        ("left_attr", C.c_uint64),
+        ("right_attr", C.c_uint64),
+        ("n_output_attrs", C.c_uint32),
+        ("reserved", C.c_uint32),
+        ("output_attrs", C.POINTER(rj_attr_t)),
+    ]
+
+
+class rj_plan_t(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_uint32),
+        ("n_inputs", C.c_uint32),
+        ("nodes", C.POINTER(rj_node_t)),
+        ("inputs", C.POINTER(rj_table_t)),
+        ("root", C.c_uint64),
+    ]
+
+
+class rj_stage_stat_t(C.Structure):
+    _fields_ = [("ms", C.c_double), ("launches", C.c_uint64), ("bytes", C.c_uint64)]
+
+
+RJ_ST_COUNT = 9
+STAGE_NAMES = ["h2d", "row_offsets", "decode", "histogram", "scatter", "join", "gather", "encode", "d2h"]
+
+_vp = C.c_void_p
+_u64 = C.c_uint64
+_u32 = C.c_uint32
+_i32 = C.c_int32
+_pvp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); every symbol include/rj_b200.h declares
+PROTOTYPES = {
+    "rj_ctx_create": (C.c_int, [C.c_int, _pvp]),
+    "rj_ctx_destroy": (None, [_vp]),
+    "rj_last_error": (C.c_char_p, [_vp]),
+    "rj_ctx_device": (C.c_int, [_vp]),
+    "rj_ctx_sm_count": (C.c_int, [_vp]),
+    "rj_ctx_set_host_threads": (C.c_int, [_vp, C.c_int]),
+    "rj_execute": (C.c_int, [_vp, C.POINTER(rj_plan_t), _pvp]),
+    "rj_inputs_upload": (C.c_int, [_vp, C.POINTER(rj_table_t), _u32, _pvp]),
+    "rj_inputs_adopt_device": (C.c_int, [_vp, C.POINTER(rj_table_t), _u32, _pvp]),
+    "rj_inputs_free": (None, [_vp, _vp]),
+    "rj_execute_resident": (C.c_int, [_vp, C.POINTER(rj_plan_t), _vp, _pvp]),
+    "rj_result_num_rows": (_u64, [_vp]),
+    "rj_result_num_columns": (_u32, [_vp]),
+    "rj_result_column_type": (_i32, [_vp, _u32]),
+    "rj_result_column_pages": (_u64, [_vp, _u32]),
+    "rj_result_column_device_ptr": (_u64, [_vp, _u32]),
+    "rj_result_fetch": (C.c_int, [_vp, _vp, _u32, _pvp, _vp]),
+    "rj_result_free": (None, [_vp, _vp]),
+    "rj_page_row_offsets": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _vp]),
+    "rj_decode_fixed": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp, _vp, _vp]),
+    "rj_decode_varchar": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp]),
+    "rj_radix_histogram": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp, _vp]),
+    "rj_radix_scatter": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rj_join_keys": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _i32, _u64, _vp, _vp,
+                               C.POINTER(_u64), _vp]),
+    "rj_gather": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),
+    "rj_fixed_rows_per_page": (_u32, [_i32]),
+    "rj_encode_fixed": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _vp]),
+    "rj_encode_varchar_plan": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u64, _pvp, C.POINTER(_u64), _vp]),
+    "rj_encode_varchar_write": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "rj_encode_varchar_free": (None, [_vp, _vp]),
+    "rj_gen_fixed_pages": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, C.POINTER(_u64), _vp]),
+    "rj_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "rj_profile_reset": (C.c_int, [_vp]),
+    "rj_profile_read": (C.c_int, [_vp, C.POINTER(rj_stage_stat_t)]),
+    "rj_stage_name": (C.c_char_p, [C.c_int]),
+    "rj_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+class EngineMissing(RuntimeError):
+    """librj_b200.so is not built: the product has no other code path."""
+
+
+def load_library(path=None):
+    """dlopen librj_b200.so and bind every prototype.  Raises EngineMissing if it is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EngineMissing(
+            f"{p} not found: build the CUDA engine first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "There is no CPU fallback."
+        )
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib

@@ -1,0 +1,172 @@
+"""`build_context / destroy_context / execute` -- the reference's operator interface
+(include/plan.h:337-344, src/execute.cpp:316-330) on top of the CUDA engine's C-ABI.
+
+`execute(plan, ctx)` takes host pages and returns a ColumnarTable of host pages, exactly like the
+reference; the split API (`upload` + `execute_resident`) keeps the base tables resident in HBM for
+the device-only measurement of bench.py.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import PAGE_SIZE
+from .plan import Column, ColumnarTable, DataType, FlatPlan, Plan
+
+
+class EngineError(RuntimeError):
+    """The engine's error contract: the reference throws std::runtime_error (src/execute.cpp:280)."""
+
+
+class Context:
+    """The opaque `void* context` of Contest::build_context()."""
+
+    def __init__(self, device=0):
+        self.lib = _cabi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.rj_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self.lib.rj_last_error(None)
+            raise EngineError(msg.decode() if msg else f"rj_ctx_create failed ({rc})")
+        self.handle = h
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self.lib.rj_last_error(self.handle)
+            raise EngineError(msg.decode() if msg else f"engine error {rc}")
+
+    def close(self):
+        if self.handle:
+            self.lib.rj_ctx_destroy(self.handle)
+            self.handle = None
+
+    @property
+    def sm_count(self):
+        return self.lib.rj_ctx_sm_count(self.handle)
+
+    # ---- profiling -------------------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self.check(self.lib.rj_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_reset(self):
+        self.check(self.lib.rj_profile_reset(self.handle))
+
+    def profile_read(self):
+        stats = (_cabi.rj_stage_stat_t * _cabi.RJ_ST_COUNT)()
+        self.check(self.lib.rj_profile_read(self.handle, stats))
+        return {
+            _cabi.STAGE_NAMES[i]: {"ms": stats[i].ms, "launches": int(stats[i].launches),
+                                   "bytes": int(stats[i].bytes)}
+            for i in range(_cabi.RJ_ST_COUNT)
+        }
+
+
+class Result:
+    """Result pages resident in HBM until fetched."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    @property
+    def num_rows(self):
+        return int(self.ctx.lib.rj_result_num_rows(self.handle))
+
+    @property
+    def num_columns(self):
+        return int(self.ctx.lib.rj_result_num_columns(self.handle))
+
+    def column_type(self, c):
+        return DataType(self.ctx.lib.rj_result_column_type(self.handle, c))
+
+    def column_pages(self, c):
+        return int(self.ctx.lib.rj_result_column_pages(self.handle, c))
+
+    def column_device_ptr(self, c):
+        return int(self.ctx.lib.rj_result_column_device_ptr(self.handle, c))
+
+    def total_pages(self):
+        return sum(self.column_pages(c) for c in range(self.num_columns))
+
+    def fetch_column(self, c, out=None):
+        n = self.column_pages(c)
+        if out is None:
+            out = np.empty((n, PAGE_SIZE), dtype=np.uint8)
+        if n:
+            self.ctx.check(self.ctx.lib.rj_result_fetch(self.ctx.handle, self.handle, c, None,
+                                                        out.ctypes.data))
+        return out
+
+    def to_columnar(self) -> ColumnarTable:
+        t = ColumnarTable(num_rows=self.num_rows)
+        for c in range(self.num_columns):
+            t.columns.append(Column(self.column_type(c), self.fetch_column(c)))
+        return t
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.rj_result_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+class ResidentInputs:
+    def __init__(self, ctx: Context, handle, keep=None):
+        self.ctx = ctx
+        self.handle = handle
+        self._keep = keep
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.rj_inputs_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+def build_context(device=0) -> Context:
+    """Contest::build_context (src/execute.cpp:326-328)"""
+    return Context(device)
+
+
+def destroy_context(ctx: Context):
+    """Contest::destroy_context (src/execute.cpp:330)"""
+    if ctx is not None:
+        ctx.close()
+
+
+def execute_to_device(plan: Plan, ctx: Context) -> Result:
+    """Host pages in, result pages left in HBM."""
+    flat = FlatPlan(plan)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.rj_execute(ctx.handle, flat.pointer(), C.byref(h)))
+    return Result(ctx, h)
+
+
+def execute(plan: Plan, ctx: Context) -> ColumnarTable:
+    """Contest::execute (src/execute.cpp:316-324): host pages in, an owning ColumnarTable out."""
+    res = execute_to_device(plan, ctx)
+    try:
+        return res.to_columnar()
+    finally:
+        res.free()
+
+
+def upload(plan: Plan, ctx: Context) -> ResidentInputs:
+    """Copy every input column's pages into HBM once (bench: inputs resident before the timer)."""
+    flat = FlatPlan(plan)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.rj_inputs_upload(ctx.handle, flat.tables, flat.n_tables, C.byref(h)))
+    return ResidentInputs(ctx, h)
+
+
+def adopt_device(plan: Plan, device_pages, ctx: Context, keep=None) -> ResidentInputs:
+    """Use pages that already live in device memory: device_pages[table][column] = (address, n_pages)."""
+    flat = FlatPlan(plan, device_pages=device_pages)
+    h = C.c_void_p()
+    ctx.check(ctx.lib.rj_inputs_adopt_device(ctx.handle, flat.tables, flat.n_tables, C.byref(h)))
+    return ResidentInputs(ctx, h, keep=keep)
+
+
+def execute_resident(plan: Plan, inputs: ResidentInputs, ctx: Context) -> Result:
+    flat = FlatPlan(plan, device_pages=[[(0, 0) for _ in t.columns] for t in plan.inputs])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.rj_execute_resident(ctx.handle, flat.pointer(), inputs.handle, C.byref(h)))
+    return Result(ctx, h)
