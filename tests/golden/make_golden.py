@@ -54,8 +54,8 @@ def gap_cases():
     tr = H.table_from_python([I], [(1,), (2,), (3,), (3,), (4,)])
     cases["long_strings"] = H.single_join_plan(tl, tr, [I, V], [I], 0, 0, True)
     # many NULLs, more than one page per column, duplicate output attrs
-    tl, _ = H.random_table(rng, [I, L], 6000, key_cols=(0,), key_range=500, null_frac=0.6)
-    tr, _ = H.random_table(rng, [I, F], 9000, key_cols=(0,), key_range=500, null_frac=0.6)
+    tl, _ = H.random_table(rng, [I, L], 2500, key_cols=(0,), key_range=1500, null_frac=0.6)
+    tr, _ = H.random_table(rng, [I, F], 3000, key_cols=(0,), key_range=1500, null_frac=0.6)
     cases["multi_page_nulls_dup_attrs"] = H.single_join_plan(tl, tr, [I, L], [I, F], 0, 0, True,
                                                              out_cols=[1, 3, 1, 0])
     return cases
