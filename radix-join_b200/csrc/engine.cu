@@ -1,0 +1,1102 @@
+// Host side of the engine: context, stream-ordered memory, page upload/download through pinned
+// staging, the plan-tree driver with late materialisation, and the C-ABI of include/rj_b200.h.
+//
+// Plan driver (replaces execute_impl / execute_scan / execute_hash_join / hash_join_omp of the
+// reference, src/execute.cpp:43-314) -- the reference materialises every intermediate as
+// vector<vector<variant>> rows; here an intermediate is a set of ROW-ID LISTS, one per base-table scan
+// below the node, kept in HBM.  Join keys of an intermediate are gathered through its row ids, only the
+// root's output_attrs are ever materialised, straight into result pages.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <set>
+#include <thread>
+
+#include "rj_internal.h"
+
+using namespace rj;
+
+// ================================================================================================
+// context
+// ================================================================================================
+struct PendingTiming {
+    int         stage;
+    cudaEvent_t a, b;
+};
+
+struct rj_ctx {
+    int          device    = 0;
+    int          sm_count  = 0;
+    cudaStream_t stream    = nullptr;
+    std::string  err;
+    int          host_threads = 8;
+    bool         profiling = false;
+    rj_stage_stat_t            stats[RJ_ST_COUNT] = {};
+    std::vector<PendingTiming> pending;
+    std::vector<cudaEvent_t>   free_events;
+    // pinned staging ring for H2D / D2H of individually allocated pages
+    static constexpr size_t kStageBytes = size_t(64) << 20;
+    uint8_t*     pinned[2]    = {nullptr, nullptr};
+    cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
+};
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+struct EngineError: std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ---- stream-ordered device memory --------------------------------------------------------------
+struct DevMem {
+    void*        p = nullptr;
+    size_t       bytes = 0;
+    cudaStream_t stream = nullptr;
+    DevMem(size_t n, cudaStream_t s): bytes(n), stream(s) {
+        RJ_CUDA(cudaMallocAsync(&p, n ? n : 16, s));
+    }
+    ~DevMem() {
+        if (p) cudaFreeAsync(p, stream);
+    }
+    DevMem(const DevMem&) = delete;
+    DevMem& operator=(const DevMem&) = delete;
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+using Buf = std::shared_ptr<DevMem>;
+
+Buf dev_alloc(size_t bytes, cudaStream_t s) { return std::make_shared<DevMem>(bytes, s); }
+
+Buf dev_alloc_zero(size_t bytes, cudaStream_t s) {
+    Buf b = dev_alloc(bytes, s);
+    RJ_CUDA(cudaMemsetAsync(b->p, 0, bytes ? bytes : 16, s));
+    return b;
+}
+
+// ---- profiling ---------------------------------------------------------------------------------
+struct StageScope {
+    rj_ctx*      ctx;
+    int          stage;
+    cudaStream_t stream;
+    cudaEvent_t  a = nullptr, b = nullptr;
+    StageScope(rj_ctx* c, int st, cudaStream_t s, uint64_t launches, uint64_t bytes): ctx(c), stage(st), stream(s) {
+        if (!ctx->profiling) return;
+        ctx->stats[stage].launches += launches;
+        ctx->stats[stage].bytes += bytes;
+        a = take();
+        b = take();
+        cudaEventRecord(a, stream);
+    }
+    ~StageScope() {
+        if (!a) return;
+        cudaEventRecord(b, stream);
+        ctx->pending.push_back({stage, a, b});
+    }
+    cudaEvent_t take() {
+        if (!ctx->free_events.empty()) {
+            cudaEvent_t e = ctx->free_events.back();
+            ctx->free_events.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+void profile_collect(rj_ctx* ctx) {
+    for (auto& t: ctx->pending) {
+        cudaEventSynchronize(t.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) ctx->stats[t.stage].ms += ms;
+        ctx->free_events.push_back(t.a);
+        ctx->free_events.push_back(t.b);
+    }
+    ctx->pending.clear();
+}
+
+// ---- host helpers ------------------------------------------------------------------------------
+template <class F>
+void parallel_for(int n_threads, uint64_t n, F fn) {
+    // static split of [0, n) over up to n_threads host threads; fn(begin, end, thread)
+    if (n == 0) return;
+    uint64_t per = 512; // do not spawn a thread for less than this many items
+    int t = static_cast<int>(std::min<uint64_t>(n_threads, (n + per - 1) / per));
+    if (t <= 1) {
+        fn(uint64_t(0), n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int i = 0; i < t; ++i) {
+        uint64_t b = n * i / t, e = n * (i + 1) / t;
+        th.emplace_back([=] { fn(b, e, i); });
+    }
+    for (auto& x: th) x.join();
+}
+
+size_t type_width(int t) { return t == RJ_INT32 ? 4 : 8; }
+
+const uint8_t* host_page(const rj_column_t& c, uint64_t i) {
+    if (c.pages) return static_cast<const uint8_t*>(c.pages[i]);
+    return static_cast<const uint8_t*>(c.contiguous) + i * RJ_PAGE_SIZE;
+}
+
+// rows / non-NULL values a page contributes (reference src/build_table.cpp:326,383-407)
+inline void page_counts(const uint8_t* pg, int type, uint64_t* rows, uint64_t* vals) {
+    uint16_t n_r, n_v;
+    std::memcpy(&n_r, pg, 2);
+    std::memcpy(&n_v, pg + 2, 2);
+    if (type == RJ_VARCHAR && n_r >= 0xfffe) {
+        *rows += n_r == 0xffff ? 1 : 0;
+        *vals += n_r == 0xffff ? 1 : 0;
+    } else {
+        *rows += n_r;
+        *vals += n_v;
+    }
+}
+
+} // namespace
+
+// ================================================================================================
+// resident inputs / results
+// ================================================================================================
+struct ColumnDev {
+    int            type = 0;
+    uint64_t       n_pages = 0;
+    uint64_t       page_rows = 0; // rows held by the pages
+    uint64_t       non_null = 0;
+    const uint8_t* pages = nullptr;
+    Buf            owned;
+};
+
+struct TableDev {
+    uint64_t               num_rows = 0;
+    std::vector<ColumnDev> cols;
+};
+
+struct rj_inputs {
+    std::vector<TableDev> tables;
+};
+
+struct ResultColumn {
+    int      type = 0;
+    uint64_t n_pages = 0;
+    Buf      pages;
+};
+
+struct rj_result {
+    uint64_t                  num_rows = 0;
+    std::vector<ResultColumn> cols;
+};
+
+namespace {
+
+void ensure_pinned(rj_ctx* ctx) {
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->pinned[i]) {
+            RJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->pinned[i]), rj_ctx::kStageBytes));
+            RJ_CUDA(cudaEventCreateWithFlags(&ctx->pinned_ev[i], cudaEventDisableTiming));
+        }
+    }
+}
+
+// H2D of one column: pages are gathered into a pinned ring by host threads while the previous chunk
+// is in flight.  Returns per-column totals computed from the page headers on the way.
+void upload_column(rj_ctx* ctx, const rj_column_t& c, ColumnDev* out) {
+    out->type = c.type;
+    out->n_pages = c.n_pages;
+    out->owned = dev_alloc(c.n_pages * size_t(RJ_PAGE_SIZE), ctx->stream);
+    out->pages = out->owned->as<uint8_t>();
+    if (c.n_pages == 0) return;
+    if (!c.pages && !c.contiguous) throw EngineError("column has pages but no page pointers");
+    ensure_pinned(ctx);
+    const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
+    std::vector<uint64_t> rows(ctx->host_threads, 0), vals(ctx->host_threads, 0);
+    int slot = 0;
+    for (uint64_t p0 = 0; p0 < c.n_pages; p0 += chunk_pages, slot ^= 1) {
+        const uint64_t cnt = std::min<uint64_t>(chunk_pages, c.n_pages - p0);
+        RJ_CUDA(cudaEventSynchronize(ctx->pinned_ev[slot])); // the copy that last used this slot is done
+        uint8_t* stage = ctx->pinned[slot];
+        parallel_for(ctx->host_threads, cnt, [&](uint64_t b, uint64_t e, int t) {
+            uint64_t r = 0, v = 0;
+            for (uint64_t i = b; i < e; ++i) {
+                const uint8_t* pg = host_page(c, p0 + i);
+                std::memcpy(stage + i * RJ_PAGE_SIZE, pg, RJ_PAGE_SIZE);
+                page_counts(pg, c.type, &r, &v);
+            }
+            rows[t] += r;
+            vals[t] += v;
+        });
+        RJ_CUDA(cudaMemcpyAsync(out->owned->as<uint8_t>() + p0 * RJ_PAGE_SIZE, stage, cnt * RJ_PAGE_SIZE,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        RJ_CUDA(cudaEventRecord(ctx->pinned_ev[slot], ctx->stream));
+    }
+    for (int t = 0; t < ctx->host_threads; ++t) {
+        out->page_rows += rows[t];
+        out->non_null += vals[t];
+    }
+}
+
+void check_column_rows(const TableDev& t, const ColumnDev& c) {
+    // the reference throws "row_idx" when a page holds a value beyond num_rows (build_table.cpp:334-336)
+    if (c.page_rows > t.num_rows) throw EngineError("row_idx");
+}
+
+std::unique_ptr<rj_inputs> upload_tables(rj_ctx* ctx, const rj_table_t* tables, uint32_t n, const std::set<std::pair<uint32_t, uint32_t>>* wanted) {
+    auto in = std::make_unique<rj_inputs>();
+    in->tables.resize(n);
+    uint64_t bytes = 0, copies = 0;
+    for (uint32_t t = 0; t < n; ++t)
+        for (uint32_t c = 0; c < tables[t].n_columns; ++c)
+            if (!wanted || wanted->count({t, c})) {
+                bytes += tables[t].columns[c].n_pages * RJ_PAGE_SIZE;
+                ++copies;
+            }
+    StageScope scope(ctx, RJ_ST_H2D, ctx->stream, copies, bytes);
+    for (uint32_t t = 0; t < n; ++t) {
+        TableDev& td = in->tables[t];
+        td.num_rows = tables[t].num_rows;
+        td.cols.resize(tables[t].n_columns);
+        for (uint32_t c = 0; c < tables[t].n_columns; ++c) {
+            td.cols[c].type = tables[t].columns[c].type;
+            if (wanted && !wanted->count({t, c})) continue; // never referenced by the plan
+            upload_column(ctx, tables[t].columns[c], &td.cols[c]);
+            check_column_rows(td, td.cols[c]);
+        }
+    }
+    return in;
+}
+
+// ================================================================================================
+// execution state
+// ================================================================================================
+struct DecodedCol {
+    int             type = 0;
+    uint64_t        rows = 0;
+    Buf             values; // INT32: u32[rows]; INT64/FP64: u64[rows]; VARCHAR: desc u64[rows]
+    Buf             valid;  // null when the column holds no NULL
+    const uint8_t*  pages = nullptr;
+    Buf             str_hash; // VARCHAR join keys: 64-bit hash per row (lazily)
+    const uint32_t* valid_ptr() const { return valid ? valid->as<uint32_t>() : nullptr; }
+};
+
+struct Attr {
+    int      leaf;  // scan node index
+    uint32_t table;
+    uint32_t col;
+};
+
+struct Rel {
+    uint64_t           rows = 0;
+    std::map<int, Buf> rid; // leaf -> row ids into that scan's base table; null Buf = identity
+};
+
+struct Exec {
+    rj_ctx*          ctx;
+    const rj_plan_t* plan;
+    const rj_inputs* in;
+    cudaStream_t     s;
+    std::map<std::pair<uint32_t, uint32_t>, DecodedCol> decoded;
+
+    Exec(rj_ctx* c, const rj_plan_t* p, const rj_inputs* i): ctx(c), plan(p), in(i), s(c->stream) {}
+
+    const rj_node_t& node(uint64_t i) const {
+        if (i >= plan->n_nodes) throw EngineError("plan node index out of range");
+        return plan->nodes[i];
+    }
+
+    // where does output attribute `a` of node `n` come from?
+    Attr resolve(uint64_t n, uint64_t a) const {
+        const rj_node_t& nd = node(n);
+        if (a >= nd.n_output_attrs) throw EngineError("attribute index out of range");
+        const uint64_t src = nd.output_attrs[a].index;
+        if (!nd.is_join) {
+            if (nd.base_table_id >= in->tables.size()) throw EngineError("base table out of range");
+            if (src >= in->tables[nd.base_table_id].cols.size()) throw EngineError("scan attribute out of range");
+            return {static_cast<int>(n), static_cast<uint32_t>(nd.base_table_id), static_cast<uint32_t>(src)};
+        }
+        const uint64_t left_w = node(nd.left).n_output_attrs; // src/execute.cpp:57,238-241
+        return src < left_w ? resolve(nd.left, src) : resolve(nd.right, src - left_w);
+    }
+
+    const DecodedCol& column(uint32_t t, uint32_t c);
+    const DecodedCol& string_hash(uint32_t t, uint32_t c);
+    Rel  run(uint64_t n);
+    Rel  join(uint64_t n, const Rel& L, const Rel& R);
+    void join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void* pk, const uint32_t* pv, uint64_t np,
+                   int key_bytes, Buf* out_b, Buf* out_p, uint64_t* n_out);
+    Buf  gather_u32(const Buf& src, const Buf& idx, uint64_t n);
+    std::unique_ptr<rj_result> root(uint64_t n, const Rel& r);
+    ResultColumn encode_varchar(const DecodedCol& col, const uint32_t* idx, uint64_t n);
+};
+
+// ---- page ingest -----------------------------------------------------------------------------------
+void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_pages, int type, uint64_t rows,
+                  bool need_valid, DecodedCol* out) {
+    out->type = type;
+    out->rows = rows;
+    out->pages = pages;
+    const size_t w = type == RJ_INT32 ? 4 : 8;
+    out->values = dev_alloc(rows * w, s);
+    if (need_valid) out->valid = dev_alloc_zero(((rows + 31) / 32 + 1) * 4, s);
+    if (n_pages == 0) return;
+    Buf row_cnt = dev_alloc(n_pages * 4, s);
+    Buf row_start = dev_alloc((n_pages + 1) * 8, s);
+    Buf tmp = dev_alloc(scan_tmp_bytes(n_pages), s);
+    {
+        StageScope sc(ctx, RJ_ST_ROW_OFFSETS, s, 4, n_pages * 4);
+        launch_page_rows(pages, n_pages, type, row_cnt->as<uint32_t>(), nullptr, s);
+        launch_exclusive_scan_u32_u64(row_cnt->as<uint32_t>(), row_start->as<uint64_t>(), n_pages, tmp->p, s);
+    }
+    {
+        // 8192 * pages read + rows * w + rows / 8 written
+        StageScope sc(ctx, RJ_ST_DECODE, s, 1, n_pages * uint64_t(RJ_PAGE_SIZE) + rows * w + rows / 8);
+        if (need_valid && rows * w) {
+            // rows the pages do not cover stay NULL; covered NULL rows must read as 0
+            RJ_CUDA(cudaMemsetAsync(out->values->p, 0, rows * w, s));
+        }
+        if (type == RJ_VARCHAR) {
+            launch_decode_varchar(pages, n_pages, row_start->as<uint64_t>(), out->values->as<uint64_t>(),
+                                  need_valid ? out->valid->as<uint32_t>() : nullptr, ctx->sm_count, s);
+        } else {
+            launch_decode_fixed(pages, n_pages, type, row_start->as<uint64_t>(), out->values->p,
+                                need_valid ? out->valid->as<uint32_t>() : nullptr, ctx->sm_count, s);
+        }
+    }
+}
+
+const DecodedCol& Exec::column(uint32_t t, uint32_t c) {
+    auto key = std::make_pair(t, c);
+    auto it = decoded.find(key);
+    if (it != decoded.end()) return it->second;
+    const TableDev&  td = in->tables[t];
+    const ColumnDev& cd = td.cols[c];
+    if (cd.n_pages && !cd.pages) throw EngineError("column was not uploaded");
+    DecodedCol d;
+    const bool need_valid = cd.non_null != td.num_rows;
+    decode_pages(ctx, s, cd.pages, cd.n_pages, cd.type, td.num_rows, need_valid, &d);
+    return decoded.emplace(key, std::move(d)).first->second;
+}
+
+const DecodedCol& Exec::string_hash(uint32_t t, uint32_t c) {
+    DecodedCol& d = const_cast<DecodedCol&>(column(t, c));
+    if (!d.str_hash) {
+        d.str_hash = dev_alloc(d.rows * 8, s);
+        StageScope sc(ctx, RJ_ST_GATHER, s, 1, d.rows * 16);
+        launch_varchar_hash(d.pages, d.values->as<uint64_t>(), d.valid_ptr(), d.rows, d.str_hash->as<uint64_t>(),
+                            ctx->sm_count, s);
+    }
+    return d;
+}
+
+Buf Exec::gather_u32(const Buf& src, const Buf& idx, uint64_t n) {
+    Buf out = dev_alloc(n * 4, s);
+    StageScope sc(ctx, RJ_ST_GATHER, s, 1, n * 12);
+    launch_gather(src->p, nullptr, idx->as<uint32_t>(), n, 4, out->p, nullptr, ctx->sm_count, s);
+    return out;
+}
+
+// ---- the join pipeline: histogram -> plan -> scatter (1 or 2 passes) -> shared-memory build+probe ------
+int choose_total_bits(uint64_t n_build) {
+    if (n_build <= kJoinBuildCap) return 0; // small build side: one table, no partitioning
+    int b = 0;
+    while ((n_build >> b) > kJoinTargetFill && b < kMaxTotalBits) ++b;
+    return b;
+}
+
+void Exec::join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void* pk, const uint32_t* pv, uint64_t np,
+                     int key_bytes, Buf* out_b, Buf* out_p, uint64_t* n_out) {
+    if (nb >= 0xffffffffull || np >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
+    const int      bits  = choose_total_bits(nb);
+    const int      bits1 = bits > kMaxPassBits ? (bits + 1) / 2 : 0; // two passes above 8 bits
+    const int      bits2 = bits - bits1;
+    const uint32_t nparts = 1u << bits;
+    Buf plan_mem = dev_alloc(partition_plan_words(bits, bits1) * 4, s);
+    PartitionPlanDev pl;
+    partition_plan_carve(plan_mem->as<uint32_t>(), bits, bits1, &pl);
+
+    JoinLaunch jl{};
+    Buf keys_b, idx_b, keys_p, idx_p; // partitioned relations
+    const uint64_t n_in = nb + np;
+    if (bits == 0) {
+        launch_partition_plan(nullptr, nullptr, static_cast<uint32_t>(nb), static_cast<uint32_t>(np), 0, 0, key_bytes, pl, s);
+        jl.bkeys = bk; jl.bidx = nullptr; jl.bvalid = bv;
+        jl.pkeys = pk; jl.pidx = nullptr; jl.pvalid = pv;
+    } else {
+        Buf hist = dev_alloc_zero(size_t(2) * nparts * 4, s);
+        uint32_t* hist_b = hist->as<uint32_t>();
+        uint32_t* hist_p = hist_b + nparts;
+        {
+            StageScope sc(ctx, RJ_ST_HISTOGRAM, s, 2, n_in * key_bytes);
+            launch_radix_histogram(bk, bv, nb, key_bytes, 0, bits, hist_b, ctx->sm_count, s);
+            launch_radix_histogram(pk, pv, np, key_bytes, 0, bits, hist_p, ctx->sm_count, s);
+        }
+        launch_partition_plan(hist_b, hist_p, 0, 0, bits, bits1, key_bytes, pl, s);
+        keys_b = dev_alloc(nb * key_bytes, s);
+        idx_b  = dev_alloc(nb * 4, s);
+        keys_p = dev_alloc(np * key_bytes, s);
+        idx_p  = dev_alloc(np * 4, s);
+        // SURVEY 8d numerator: one-pass scatter = N*w_k read + N*(w_k+4) written, whatever the pass count
+        StageScope sc(ctx, RJ_ST_SCATTER, s, bits1 ? 4 : 2, n_in * (2 * key_bytes + 4));
+        if (bits1 == 0) {
+            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, 0, bits, pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), ctx->sm_count, s);
+            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, 0, bits, pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), ctx->sm_count, s);
+        } else {
+            Buf tk_b = dev_alloc(nb * key_bytes, s), ti_b = dev_alloc(nb * 4, s);
+            Buf tk_p = dev_alloc(np * key_bytes, s), ti_p = dev_alloc(np * 4, s);
+            // pass 1: the high `bits1` of the partition id; pass 2: the low `bits2` inside each region
+            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, bits2, bits1, pl.cur1_b, tk_b->p, ti_b->as<uint32_t>(), ctx->sm_count, s);
+            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, bits2, bits1, pl.cur1_p, tk_p->p, ti_p->as<uint32_t>(), ctx->sm_count, s);
+            launch_radix_scatter_regions(tk_b->p, ti_b->as<uint32_t>(), pl.reg_b, pl.tile_b, 1u << bits1, nb, key_bytes, 0, bits2,
+                                         pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), ctx->sm_count, s);
+            launch_radix_scatter_regions(tk_p->p, ti_p->as<uint32_t>(), pl.reg_p, pl.tile_p, 1u << bits1, np, key_bytes, 0, bits2,
+                                         pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), ctx->sm_count, s);
+        }
+        jl.bkeys = keys_b->p; jl.bidx = idx_b->as<uint32_t>(); jl.bvalid = nullptr;
+        jl.pkeys = keys_p->p; jl.pidx = idx_p->as<uint32_t>(); jl.pvalid = nullptr;
+    }
+    jl.off_b = pl.off_b; jl.off_p = pl.off_p; jl.unit_start = pl.unit_start;
+    jl.nparts = nparts; jl.part_bits = bits; jl.key_bytes = key_bytes;
+
+    Buf counter = dev_alloc(8, s);
+    jl.out_count = counter->as<unsigned long long>();
+    // Output cardinality is unknown (non-unique keys on both sides are legal).  Run with room for
+    // max(|build|, |probe|) pairs -- enough for every key/foreign-key join -- and let the kernel keep
+    // counting when that overflows; the exact count then sizes a second run.
+    uint64_t capacity = std::max(nb, np);
+    uint64_t matches = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        *out_b = dev_alloc(capacity * 4, s);
+        *out_p = dev_alloc(capacity * 4, s);
+        jl.out_b = (*out_b)->as<uint32_t>();
+        jl.out_p = (*out_p)->as<uint32_t>();
+        jl.capacity = capacity;
+        RJ_CUDA(cudaMemsetAsync(counter->p, 0, 8, s));
+        {
+            // N*(w_k+4) read + M*8 written (M is added once known)
+            StageScope sc(ctx, RJ_ST_JOIN, s, 1, n_in * (key_bytes + 4));
+            launch_join(jl, ctx->sm_count, s);
+        }
+        RJ_CUDA(cudaMemcpyAsync(&matches, counter->p, 8, cudaMemcpyDeviceToHost, s));
+        RJ_CUDA(cudaStreamSynchronize(s));
+        if (matches <= capacity) break;
+        if (attempt == 1) throw EngineError("join output overflowed twice");
+        capacity = matches;
+    }
+    if (ctx->profiling) ctx->stats[RJ_ST_JOIN].bytes += matches * 8;
+    if (matches >= 0xffffffffull) throw EngineError("join result exceeds 2^32-1 rows");
+    *n_out = matches;
+}
+
+struct SideKeys {
+    const void*     keys = nullptr;
+    const uint32_t* valid = nullptr;
+    Buf             hold_k, hold_v;
+    int             key_bytes = 4;
+};
+
+Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
+    const rj_node_t& nd = node(n);
+    Rel out;
+    // key type = the BUILD side's declared attribute type (src/execute.cpp:271-273)
+    const rj_node_t& bnode = node(nd.build_left ? nd.left : nd.right);
+    const uint64_t   battr = nd.build_left ? nd.left_attr : nd.right_attr;
+    if (battr >= bnode.n_output_attrs) throw EngineError("join attribute out of range");
+    const int key_type = bnode.output_attrs[battr].type;
+    if (key_type < RJ_INT32 || key_type > RJ_VARCHAR) throw EngineError("Unsupported join type"); // :280
+    const Attr la = resolve(nd.left, nd.left_attr), ra = resolve(nd.right, nd.right_attr);
+    if (L.rows == 0 || R.rows == 0) return out; // :50
+    // a cell is a valid key only if it physically holds the key type (:61-83)
+    if (in->tables[la.table].cols[la.col].type != key_type || in->tables[ra.table].cols[ra.col].type != key_type) return out;
+    if (key_type == RJ_FP64) {
+        // HashUtil<double>::hash recurses forever in the reference (:28-31); there is no behaviour to match
+        throw EngineError("Unsupported join type: FP64 join key (the reference does not terminate on it)");
+    }
+
+    auto side_keys = [&](const Rel& rel, const Attr& a) {
+        SideKeys k;
+        const DecodedCol& col = key_type == RJ_VARCHAR ? string_hash(a.table, a.col) : column(a.table, a.col);
+        const void* base = key_type == RJ_VARCHAR ? col.str_hash->p : col.values->p;
+        k.key_bytes = key_type == RJ_INT32 ? 4 : 8;
+        auto it = rel.rid.find(a.leaf);
+        if (it == rel.rid.end()) throw EngineError("internal: join key leaf not tracked");
+        if (!it->second) { // scan: the decoded column is the key column
+            k.keys = base;
+            k.valid = col.valid_ptr();
+            return k;
+        }
+        k.hold_k = dev_alloc(rel.rows * k.key_bytes, s);
+        if (col.valid) k.hold_v = dev_alloc(((rel.rows + 31) / 32) * 4, s);
+        StageScope sc(ctx, RJ_ST_GATHER, s, 1, rel.rows * (4 + 2 * k.key_bytes));
+        launch_gather(base, col.valid_ptr(), it->second->as<uint32_t>(), rel.rows, k.key_bytes, k.hold_k->p,
+                      k.hold_v ? k.hold_v->as<uint32_t>() : nullptr, ctx->sm_count, s);
+        k.keys = k.hold_k->p;
+        k.valid = k.hold_v ? k.hold_v->as<uint32_t>() : nullptr;
+        return k;
+    };
+    SideKeys lk = side_keys(L, la), rk = side_keys(R, ra);
+
+    // The hash table goes on the SMALLER side whatever build_left says: the result is the same
+    // multiset of (left row, right row) pairs, and a small table side means fewer partitions.
+    const bool table_left = L.rows <= R.rows;
+    Buf t_idx, p_idx;
+    uint64_t m = 0;
+    if (table_left) {
+        join_keys(lk.keys, lk.valid, L.rows, rk.keys, rk.valid, R.rows, lk.key_bytes, &t_idx, &p_idx, &m);
+    } else {
+        join_keys(rk.keys, rk.valid, R.rows, lk.keys, lk.valid, L.rows, lk.key_bytes, &t_idx, &p_idx, &m);
+    }
+    Buf l_idx = table_left ? t_idx : p_idx, r_idx = table_left ? p_idx : t_idx;
+
+    if (key_type == RJ_VARCHAR && m > 0) {
+        // the join ran on 64-bit string hashes: keep only pairs whose strings are byte-equal
+        const DecodedCol& lc = column(la.table, la.col);
+        const DecodedCol& rc = column(ra.table, ra.col);
+        Buf lrow = L.rid.at(la.leaf) ? gather_u32(L.rid.at(la.leaf), l_idx, m) : l_idx;
+        Buf rrow = R.rid.at(ra.leaf) ? gather_u32(R.rid.at(ra.leaf), r_idx, m) : r_idx;
+        Buf keep = dev_alloc(m * 4, s), pos = dev_alloc((m + 1) * 8, s), tmp = dev_alloc(scan_tmp_bytes(m), s);
+        StageScope sc(ctx, RJ_ST_GATHER, s, 5, m * 32);
+        launch_varchar_pairs_equal(lc.pages, lc.values->as<uint64_t>(), lrow->as<uint32_t>(), rc.pages,
+                                   rc.values->as<uint64_t>(), rrow->as<uint32_t>(), m, keep->as<uint32_t>(), ctx->sm_count, s);
+        launch_exclusive_scan_u32_u64(keep->as<uint32_t>(), pos->as<uint64_t>(), m, tmp->p, s);
+        uint64_t kept = 0;
+        RJ_CUDA(cudaMemcpyAsync(&kept, pos->as<uint64_t>() + m, 8, cudaMemcpyDeviceToHost, s));
+        RJ_CUDA(cudaStreamSynchronize(s));
+        Buf nl = dev_alloc(kept * 4, s), nr = dev_alloc(kept * 4, s);
+        launch_compact_pairs(l_idx->as<uint32_t>(), r_idx->as<uint32_t>(), keep->as<uint32_t>(), pos->as<uint64_t>(), m,
+                             nl->as<uint32_t>(), nr->as<uint32_t>(), s);
+        l_idx = nl;
+        r_idx = nr;
+        m = kept;
+    }
+    out.rows = m;
+    if (m == 0) return out;
+    // row-id lists of every scan the parents can still see through this node's output_attrs
+    std::set<int> needed;
+    for (uint32_t a = 0; a < nd.n_output_attrs; ++a) needed.insert(resolve(n, a).leaf);
+    for (int leaf: needed) {
+        auto li = L.rid.find(leaf);
+        if (li != L.rid.end()) {
+            out.rid[leaf] = li->second ? gather_u32(li->second, l_idx, m) : l_idx;
+            continue;
+        }
+        auto ri = R.rid.find(leaf);
+        if (ri == R.rid.end()) throw EngineError("internal: output leaf not below this join");
+        out.rid[leaf] = ri->second ? gather_u32(ri->second, r_idx, m) : r_idx;
+    }
+    return out;
+}
+
+Rel Exec::run(uint64_t n) {
+    const rj_node_t& nd = node(n);
+    if (!nd.is_join) {
+        if (nd.base_table_id >= in->tables.size()) throw EngineError("base table out of range");
+        Rel r;
+        r.rows = in->tables[nd.base_table_id].num_rows;
+        r.rid[static_cast<int>(n)] = nullptr; // identity
+        return r;
+    }
+    if (nd.left >= plan->n_nodes || nd.right >= plan->n_nodes) throw EngineError("join child out of range");
+    Rel L = run(nd.left);  // depth first, left then right (src/execute.cpp:48-49)
+    Rel R = run(nd.right);
+    return join(n, L, R);
+}
+
+// ---- page output -----------------------------------------------------------------------------------
+ResultColumn Exec::encode_varchar(const DecodedCol& col, const uint32_t* idx, uint64_t n) {
+    ResultColumn rc;
+    rc.type = RJ_VARCHAR;
+    VarcharLayoutDev L;
+    L.n = n;
+    L.src_pages = col.pages;
+    L.desc = col.values->as<uint64_t>();
+    L.valid = col.valid_ptr();
+    L.idx = idx;
+    Buf weights = dev_alloc(n * 8, s), wscan = dev_alloc(n * 8, s), marks = dev_alloc(n * 8, s), bscan = dev_alloc(n * 8, s);
+    Buf heads = dev_alloc(n * 4, s), page_of = dev_alloc((n + 1) * 8, s), scalars = dev_alloc_zero(32, s);
+    Buf tmp = dev_alloc(scan_tmp_bytes(n), s);
+    L.weight_scan = wscan->as<uint64_t>();
+    L.base_scan = bscan->as<uint64_t>();
+    L.head_pages = heads->as<uint32_t>();
+    L.page_of = page_of->as<uint64_t>();
+    L.scalars = scalars->as<uint64_t>();
+    uint64_t n_pages = 0;
+    {
+        StageScope sc(ctx, RJ_ST_ENCODE, s, 13, n * 48);
+        launch_varchar_weights(L, weights->as<uint64_t>(), ctx->sm_count, s);
+        launch_inclusive_sum_u64(weights->as<uint64_t>(), L.weight_scan, n, tmp->p, s);
+        launch_varchar_marks(L, marks->as<uint64_t>(), ctx->sm_count, s);
+        launch_inclusive_max_u64(marks->as<uint64_t>(), L.base_scan, n, tmp->p, s);
+        launch_varchar_heads(L, weights->as<uint64_t>(), ctx->sm_count, s);
+        launch_exclusive_scan_u32_u64(L.head_pages, L.page_of, n, tmp->p, s);
+        RJ_CUDA(cudaMemcpyAsync(&n_pages, L.page_of + n, 8, cudaMemcpyDeviceToHost, s));
+    }
+    RJ_CUDA(cudaStreamSynchronize(s));
+    L.n_pages = n_pages;
+    Buf page_row = dev_alloc(n_pages * 4, s);
+    L.page_row = page_row->as<uint32_t>();
+    rc.n_pages = n_pages;
+    rc.pages = dev_alloc(n_pages * size_t(RJ_PAGE_SIZE), s);
+    {
+        StageScope sc(ctx, RJ_ST_ENCODE, s, 2, n_pages * uint64_t(RJ_PAGE_SIZE) * 2);
+        launch_varchar_page_rows(L, ctx->sm_count, s);
+        launch_varchar_write(L, rc.pages->as<uint8_t>(), ctx->sm_count, s);
+    }
+    return rc;
+}
+
+std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
+    const rj_node_t& nd = node(n);
+    auto res = std::make_unique<rj_result>();
+    res->num_rows = r.rows;
+    res->cols.resize(nd.n_output_attrs);
+    for (uint32_t a = 0; a < nd.n_output_attrs; ++a) {
+        ResultColumn& rc = res->cols[a];
+        rc.type = nd.output_attrs[a].type;
+        if (rc.type < RJ_INT32 || rc.type > RJ_VARCHAR) throw EngineError("unknown output attribute type");
+        if (r.rows == 0) {
+            resolve(n, a); // still validate the plan
+            continue;      // typed, page-less column (tests/unit_tests.cpp:24-27)
+        }
+        const Attr at = resolve(n, a);
+        if (in->tables[at.table].cols[at.col].type != rc.type) {
+            // the reference silently drops mistyped cells (build_table.cpp:484-501) or throws for
+            // VARCHAR (:667-669); a plan like that is malformed, refuse it
+            throw EngineError(rc.type == RJ_VARCHAR ? "not string or null" : "output attribute type does not match the column");
+        }
+        const DecodedCol& col = column(at.table, at.col);
+        auto it = r.rid.find(at.leaf);
+        if (it == r.rid.end()) throw EngineError("internal: root leaf not tracked");
+        const uint32_t* idx = it->second ? it->second->as<uint32_t>() : nullptr;
+        if (rc.type == RJ_VARCHAR) {
+            rc = encode_varchar(col, idx, r.rows);
+            continue;
+        }
+        const uint32_t rpp = rj_fixed_rows_per_page(rc.type);
+        rc.n_pages = (r.rows + rpp - 1) / rpp;
+        rc.pages = dev_alloc(rc.n_pages * size_t(RJ_PAGE_SIZE), s);
+        const size_t w = type_width(rc.type);
+        // M*4 + M*w read + 8192 * pages written
+        StageScope sc(ctx, RJ_ST_ENCODE, s, 1, r.rows * (4 + w) + rc.n_pages * uint64_t(RJ_PAGE_SIZE));
+        launch_encode_fixed(col.values->p, col.valid_ptr(), idx, r.rows, rc.type, rc.pages->p, ctx->sm_count, s);
+    }
+    return res;
+}
+
+std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in) {
+    if (plan->root >= plan->n_nodes) throw EngineError("plan root out of range");
+    Exec ex(ctx, plan, in);
+    Rel  r = ex.run(plan->root);
+    auto res = ex.root(plan->root, r);
+    RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return res;
+}
+
+// columns the plan can reach (join keys + root outputs); only those are uploaded and decoded
+void collect_wanted(const rj_plan_t* plan, std::set<std::pair<uint32_t, uint32_t>>* wanted) {
+    struct Walker {
+        const rj_plan_t* plan;
+        std::pair<uint32_t, uint32_t> resolve(uint64_t n, uint64_t a) const {
+            if (n >= plan->n_nodes) throw EngineError("plan node index out of range");
+            const rj_node_t& nd = plan->nodes[n];
+            if (a >= nd.n_output_attrs) throw EngineError("attribute index out of range");
+            const uint64_t src = nd.output_attrs[a].index;
+            if (!nd.is_join) return {static_cast<uint32_t>(nd.base_table_id), static_cast<uint32_t>(src)};
+            if (nd.left >= plan->n_nodes || nd.right >= plan->n_nodes) throw EngineError("join child out of range");
+            const uint64_t left_w = plan->nodes[nd.left].n_output_attrs;
+            return src < left_w ? resolve(nd.left, src) : resolve(nd.right, src - left_w);
+        }
+        void walk(uint64_t n, std::set<std::pair<uint32_t, uint32_t>>* w) const {
+            if (n >= plan->n_nodes) throw EngineError("plan node index out of range");
+            const rj_node_t& nd = plan->nodes[n];
+            if (!nd.is_join) return;
+            w->insert(resolve(nd.left, nd.left_attr));
+            w->insert(resolve(nd.right, nd.right_attr));
+            walk(nd.left, w);
+            walk(nd.right, w);
+        }
+    } wk{plan};
+    if (plan->root >= plan->n_nodes) throw EngineError("plan root out of range");
+    wk.walk(plan->root, wanted);
+    const rj_node_t& root = plan->nodes[plan->root];
+    for (uint32_t a = 0; a < root.n_output_attrs; ++a) wanted->insert(wk.resolve(plan->root, a));
+    for (auto& tc: *wanted) {
+        if (tc.first >= plan->n_inputs) throw EngineError("base table out of range");
+        if (tc.second >= plan->inputs[tc.first].n_columns) throw EngineError("scan attribute out of range");
+    }
+}
+
+template <class F>
+int guarded(rj_ctx* ctx, F f) {
+    if (!ctx) return 1;
+    try {
+        cudaSetDevice(ctx->device);
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        cudaGetLastError(); // clear a sticky launch error so the next call reports its own
+        return 1;
+    }
+}
+
+cudaStream_t pick_stream(rj_ctx* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
+
+} // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+const char* rj_version(void) { return "radix-join_b200 0.1 (sm_100a)"; }
+
+int rj_ctx_create(int device, rj_ctx** out) {
+    try {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+            throw EngineError("no CUDA device: the B200 engine has no CPU fallback");
+        }
+        if (device < 0 || device >= n) throw EngineError("device index out of range");
+        RJ_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        RJ_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) {
+            throw EngineError(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                              "; this engine is built for sm_100a only");
+        }
+        auto ctx = std::make_unique<rj_ctx>();
+        ctx->device = device;
+        ctx->sm_count = prop.multiProcessorCount;
+        RJ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        // keep freed blocks in the pool: no cudaMalloc inside execute() after warm-up
+        cudaMemPool_t pool;
+        RJ_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t threshold = UINT64_MAX;
+        RJ_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        unsigned hc = std::thread::hardware_concurrency();
+        ctx->host_threads = hc ? static_cast<int>(std::min(hc, 32u)) : 8;
+        *out = ctx.release();
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return 1;
+    }
+}
+
+void rj_ctx_destroy(rj_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    profile_collect(ctx);
+    for (auto e: ctx->free_events) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (ctx->pinned_ev[i]) cudaEventDestroy(ctx->pinned_ev[i]);
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rj_last_error(const rj_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int rj_ctx_device(const rj_ctx* ctx) { return ctx->device; }
+int rj_ctx_sm_count(const rj_ctx* ctx) { return ctx->sm_count; }
+int rj_ctx_set_host_threads(rj_ctx* ctx, int n) {
+    if (!ctx || n < 1) return 1;
+    ctx->host_threads = std::min(n, 256);
+    return 0;
+}
+
+int rj_inputs_upload(rj_ctx* ctx, const rj_table_t* tables, uint32_t n_tables, rj_inputs** out) {
+    return guarded(ctx, [&] {
+        auto in = upload_tables(ctx, tables, n_tables, nullptr);
+        RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+        *out = in.release();
+    });
+}
+
+int rj_inputs_adopt_device(rj_ctx* ctx, const rj_table_t* tables, uint32_t n_tables, rj_inputs** out) {
+    return guarded(ctx, [&] {
+        auto in = std::make_unique<rj_inputs>();
+        in->tables.resize(n_tables);
+        std::vector<Buf> totals;
+        for (uint32_t t = 0; t < n_tables; ++t) {
+            TableDev& td = in->tables[t];
+            td.num_rows = tables[t].num_rows;
+            td.cols.resize(tables[t].n_columns);
+            for (uint32_t c = 0; c < tables[t].n_columns; ++c) {
+                const rj_column_t& col = tables[t].columns[c];
+                ColumnDev& cd = td.cols[c];
+                cd.type = col.type;
+                cd.n_pages = col.n_pages;
+                cd.pages = static_cast<const uint8_t*>(col.contiguous);
+                if (col.n_pages && !cd.pages) throw EngineError("adopted column needs a contiguous device address");
+                Buf tot = dev_alloc_zero(16, ctx->stream);
+                Buf rows = dev_alloc(col.n_pages * 4, ctx->stream);
+                launch_page_rows(cd.pages, cd.n_pages, cd.type, rows->as<uint32_t>(), tot->as<uint64_t>(), ctx->stream);
+                uint64_t h[2] = {0, 0};
+                RJ_CUDA(cudaMemcpyAsync(h, tot->p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+                RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+                cd.page_rows = h[0];
+                cd.non_null = h[1];
+                check_column_rows(td, cd);
+            }
+        }
+        *out = in.release();
+    });
+}
+
+void rj_inputs_free(rj_ctx* ctx, rj_inputs* in) {
+    if (ctx) cudaSetDevice(ctx->device);
+    delete in;
+}
+
+int rj_execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in, rj_result** out) {
+    return guarded(ctx, [&] {
+        if (!plan || !in) throw EngineError("null plan or inputs");
+        *out = execute_resident(ctx, plan, in).release();
+    });
+}
+
+int rj_execute(rj_ctx* ctx, const rj_plan_t* plan, rj_result** out) {
+    return guarded(ctx, [&] {
+        if (!plan) throw EngineError("null plan");
+        std::set<std::pair<uint32_t, uint32_t>> wanted;
+        collect_wanted(plan, &wanted);
+        auto in = upload_tables(ctx, plan->inputs, plan->n_inputs, &wanted);
+        *out = execute_resident(ctx, plan, in.get()).release();
+    });
+}
+
+uint64_t rj_result_num_rows(const rj_result* r) { return r->num_rows; }
+uint32_t rj_result_num_columns(const rj_result* r) { return static_cast<uint32_t>(r->cols.size()); }
+int32_t  rj_result_column_type(const rj_result* r, uint32_t c) { return r->cols[c].type; }
+uint64_t rj_result_column_pages(const rj_result* r, uint32_t c) { return r->cols[c].n_pages; }
+uint64_t rj_result_column_device_ptr(const rj_result* r, uint32_t c) {
+    return r->cols[c].pages ? reinterpret_cast<uint64_t>(r->cols[c].pages->p) : 0;
+}
+
+int rj_result_fetch(rj_ctx* ctx, const rj_result* r, uint32_t col, void* const* dst_pages, void* dst_contiguous) {
+    return guarded(ctx, [&] {
+        if (col >= r->cols.size()) throw EngineError("result column out of range");
+        const ResultColumn& rc = r->cols[col];
+        if (rc.n_pages == 0) return;
+        if (!dst_pages && !dst_contiguous) throw EngineError("no destination pages");
+        ensure_pinned(ctx);
+        StageScope scope(ctx, RJ_ST_D2H, ctx->stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
+        const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
+        // two-slot ring: the D2H copy of chunk k+1 overlaps the host scatter of chunk k
+        auto issue = [&](uint64_t p0, int slot) {
+            const uint64_t cnt = std::min<uint64_t>(chunk_pages, rc.n_pages - p0);
+            RJ_CUDA(cudaMemcpyAsync(ctx->pinned[slot], rc.pages->as<uint8_t>() + p0 * RJ_PAGE_SIZE, cnt * RJ_PAGE_SIZE,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+            RJ_CUDA(cudaEventRecord(ctx->pinned_ev[slot], ctx->stream));
+        };
+        issue(0, 0);
+        int slot = 0;
+        for (uint64_t p0 = 0; p0 < rc.n_pages; p0 += chunk_pages, slot ^= 1) {
+            const uint64_t cnt = std::min<uint64_t>(chunk_pages, rc.n_pages - p0);
+            if (p0 + chunk_pages < rc.n_pages) issue(p0 + chunk_pages, slot ^ 1);
+            RJ_CUDA(cudaEventSynchronize(ctx->pinned_ev[slot]));
+            const uint8_t* stage = ctx->pinned[slot];
+            parallel_for(ctx->host_threads, cnt, [&](uint64_t b, uint64_t e, int) {
+                for (uint64_t i = b; i < e; ++i) {
+                    void* dst = dst_pages ? dst_pages[p0 + i] : static_cast<uint8_t*>(dst_contiguous) + (p0 + i) * RJ_PAGE_SIZE;
+                    std::memcpy(dst, stage + i * RJ_PAGE_SIZE, RJ_PAGE_SIZE);
+                }
+            });
+        }
+        // the upload path waits on these events before reusing a slot; they are complete here
+    });
+}
+
+void rj_result_free(rj_ctx* ctx, rj_result* r) {
+    if (ctx) cudaSetDevice(ctx->device);
+    delete r;
+}
+
+// ---- per-stage entry points ------------------------------------------------------------------------
+int rj_page_row_offsets(rj_ctx* ctx, const void* d_pages, uint64_t n_pages, int32_t type, uint64_t* d_page_row_start,
+                        uint64_t* d_totals, void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t s = pick_stream(ctx, stream);
+        Buf rows = dev_alloc(n_pages * 4, s), tmp = dev_alloc(scan_tmp_bytes(n_pages), s);
+        if (d_totals) RJ_CUDA(cudaMemsetAsync(d_totals, 0, 16, s));
+        launch_page_rows(d_pages, n_pages, type, rows->as<uint32_t>(), d_totals, s);
+        launch_exclusive_scan_u32_u64(rows->as<uint32_t>(), d_page_row_start, n_pages, tmp->p, s);
+    });
+}
+
+int rj_decode_fixed(rj_ctx* ctx, const void* d_pages, uint64_t n_pages, int32_t type, const uint64_t* d_page_row_start,
+                    void* d_values, uint32_t* d_valid, void* stream) {
+    return guarded(ctx, [&] {
+        if (type == RJ_VARCHAR) throw EngineError("rj_decode_fixed: VARCHAR column");
+        launch_decode_fixed(d_pages, n_pages, type, d_page_row_start, d_values, d_valid, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+int rj_decode_varchar(rj_ctx* ctx, const void* d_pages, uint64_t n_pages, const uint64_t* d_page_row_start,
+                      uint64_t* d_desc, uint32_t* d_valid, void* stream) {
+    return guarded(ctx, [&] {
+        launch_decode_varchar(d_pages, n_pages, d_page_row_start, d_desc, d_valid, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+int rj_radix_histogram(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, uint64_t n, int32_t key_bytes,
+                       int32_t shift, int32_t bits, uint32_t* d_hist, void* stream) {
+    return guarded(ctx, [&] {
+        if ((key_bytes != 4 && key_bytes != 8) || bits < 0 || bits > kMaxTotalBits) throw EngineError("rj_radix_histogram: bad arguments");
+        launch_radix_histogram(d_keys, d_valid, n, key_bytes, shift, bits, d_hist, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+int rj_radix_scatter(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, const uint32_t* d_idx_in, uint64_t n,
+                     int32_t key_bytes, int32_t shift, int32_t bits, uint32_t* d_cursor, void* d_keys_out,
+                     uint32_t* d_idx_out, void* stream) {
+    return guarded(ctx, [&] {
+        if ((key_bytes != 4 && key_bytes != 8) || bits < 0 || bits > 9) throw EngineError("rj_radix_scatter: bits must be in [0, 9]");
+        if (n >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
+        launch_radix_scatter(d_keys, d_valid, d_idx_in, n, key_bytes, shift, bits, d_cursor, d_keys_out, d_idx_out,
+                             ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+int rj_join_keys(rj_ctx* ctx, const void* d_build_keys, const uint32_t* d_build_valid, uint64_t n_build,
+                 const void* d_probe_keys, const uint32_t* d_probe_valid, uint64_t n_probe, int32_t key_bytes,
+                 uint64_t capacity, uint32_t* d_out_build, uint32_t* d_out_probe, uint64_t* n_matches, void* stream) {
+    return guarded(ctx, [&] {
+        if (key_bytes != 4 && key_bytes != 8) throw EngineError("rj_join_keys: key_bytes must be 4 or 8");
+        // runs on the context stream; order it after the caller's stream
+        cudaStream_t cs = pick_stream(ctx, stream);
+        if (cs != ctx->stream) RJ_CUDA(cudaStreamSynchronize(cs));
+        Exec ex(ctx, nullptr, nullptr);
+        Buf ob, op;
+        uint64_t m = 0;
+        if (n_build == 0 || n_probe == 0) {
+            *n_matches = 0;
+            return;
+        }
+        ex.join_keys(d_build_keys, d_build_valid, n_build, d_probe_keys, d_probe_valid, n_probe, key_bytes, &ob, &op, &m);
+        *n_matches = m;
+        if (m <= capacity && m > 0) {
+            RJ_CUDA(cudaMemcpyAsync(d_out_build, ob->p, m * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            RJ_CUDA(cudaMemcpyAsync(d_out_probe, op->p, m * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int rj_gather(rj_ctx* ctx, const void* d_src, const uint32_t* d_src_valid, const uint32_t* d_idx, uint64_t n,
+              int32_t elem_bytes, void* d_out, uint32_t* d_out_valid, void* stream) {
+    return guarded(ctx, [&] {
+        if (elem_bytes != 4 && elem_bytes != 8) throw EngineError("rj_gather: elem_bytes must be 4 or 8");
+        launch_gather(d_src, d_src_valid, d_idx, n, elem_bytes, d_out, d_out_valid, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+uint32_t rj_fixed_rows_per_page(int32_t type) { return type == RJ_INT32 ? 1984u : 1007u; }
+
+int rj_encode_fixed(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, const uint32_t* d_idx, uint64_t n,
+                    int32_t type, void* d_pages_out, void* stream) {
+    return guarded(ctx, [&] {
+        if (type == RJ_VARCHAR) throw EngineError("rj_encode_fixed: VARCHAR column");
+        launch_encode_fixed(d_values, d_valid, d_idx, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+struct rj_varchar_layout {
+    VarcharLayoutDev L;
+    std::vector<Buf> hold;
+};
+
+int rj_encode_varchar_plan(rj_ctx* ctx, const void* d_src_pages, const uint64_t* d_desc, const uint32_t* d_valid,
+                           const uint32_t* d_idx, uint64_t n, rj_varchar_layout** layout, uint64_t* n_pages_out, void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t s = pick_stream(ctx, stream);
+        auto lay = std::make_unique<rj_varchar_layout>();
+        VarcharLayoutDev& L = lay->L;
+        L.n = n;
+        L.src_pages = static_cast<const uint8_t*>(d_src_pages);
+        L.desc = d_desc;
+        L.valid = d_valid;
+        L.idx = d_idx;
+        Buf weights = dev_alloc(n * 8, s), wscan = dev_alloc(n * 8, s), marks = dev_alloc(n * 8, s), bscan = dev_alloc(n * 8, s);
+        Buf heads = dev_alloc(n * 4, s), page_of = dev_alloc((n + 1) * 8, s), scalars = dev_alloc_zero(32, s);
+        Buf tmp = dev_alloc(scan_tmp_bytes(n), s);
+        L.weight_scan = wscan->as<uint64_t>();
+        L.base_scan = bscan->as<uint64_t>();
+        L.head_pages = heads->as<uint32_t>();
+        L.page_of = page_of->as<uint64_t>();
+        L.scalars = scalars->as<uint64_t>();
+        launch_varchar_weights(L, weights->as<uint64_t>(), ctx->sm_count, s);
+        launch_inclusive_sum_u64(weights->as<uint64_t>(), L.weight_scan, n, tmp->p, s);
+        launch_varchar_marks(L, marks->as<uint64_t>(), ctx->sm_count, s);
+        launch_inclusive_max_u64(marks->as<uint64_t>(), L.base_scan, n, tmp->p, s);
+        launch_varchar_heads(L, weights->as<uint64_t>(), ctx->sm_count, s);
+        launch_exclusive_scan_u32_u64(L.head_pages, L.page_of, n, tmp->p, s);
+        uint64_t n_pages = 0;
+        RJ_CUDA(cudaMemcpyAsync(&n_pages, L.page_of + n, 8, cudaMemcpyDeviceToHost, s));
+        RJ_CUDA(cudaStreamSynchronize(s));
+        L.n_pages = n_pages;
+        Buf page_row = dev_alloc(n_pages * 4, s);
+        L.page_row = page_row->as<uint32_t>();
+        launch_varchar_page_rows(L, ctx->sm_count, s);
+        lay->hold = {wscan, bscan, heads, page_of, scalars, page_row};
+        *n_pages_out = n_pages;
+        *layout = lay.release();
+    });
+}
+
+int rj_encode_varchar_write(rj_ctx* ctx, rj_varchar_layout* layout, void* d_pages_out, void* stream) {
+    return guarded(ctx, [&] {
+        launch_varchar_write(layout->L, static_cast<uint8_t*>(d_pages_out), ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+void rj_encode_varchar_free(rj_ctx* ctx, rj_varchar_layout* layout) {
+    if (ctx) cudaSetDevice(ctx->device);
+    delete layout;
+}
+
+int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n, int32_t type,
+                       void* d_pages_out, uint64_t* n_pages_out, void* stream) {
+    return guarded(ctx, [&] {
+        if (type == RJ_VARCHAR) throw EngineError("rj_gen_fixed_pages: VARCHAR column");
+        const uint32_t rpp = rj_fixed_rows_per_page(type);
+        if (n_pages_out) *n_pages_out = (n + rpp - 1) / rpp;
+        if (d_pages_out) launch_encode_fixed(d_values, d_valid, nullptr, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+// ---- profiling -------------------------------------------------------------------------------------
+int rj_profile_enable(rj_ctx* ctx, int on) {
+    if (!ctx) return 1;
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int rj_profile_reset(rj_ctx* ctx) {
+    if (!ctx) return 1;
+    profile_collect(ctx);
+    std::memset(ctx->stats, 0, sizeof ctx->stats);
+    return 0;
+}
+
+int rj_profile_read(rj_ctx* ctx, rj_stage_stat_t* stats) {
+    if (!ctx || !stats) return 1;
+    cudaSetDevice(ctx->device);
+    profile_collect(ctx);
+    std::memcpy(stats, ctx->stats, sizeof ctx->stats);
+    return 0;
+}
+
+const char* rj_stage_name(int stage) {
+    static const char* names[RJ_ST_COUNT] = {"h2d", "row_offsets", "decode", "histogram", "scatter",
+                                             "join", "gather", "encode", "d2h"};
+    return stage >= 0 && stage < RJ_ST_COUNT ? names[stage] : "?";
+}
+
+} // extern "C"

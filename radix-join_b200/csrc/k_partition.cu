@@ -1,0 +1,414 @@
+// Radix partitioning -- the GPU replacement of the reference's serial histogram / prefix / scatter
+// (src/execute.cpp:85-92 bucket count, :124-132 histogram, :169-184 prefix sum + scatter of row ids).
+//
+// Differences by design (none observable in results):
+//   * the fan-out is sized for SHARED MEMORY, not a 1 MiB CPU L2: partitions target <= 4096 build
+//     tuples so that the build side of one partition fits an 8192-slot table in one CTA's smem;
+//   * (key, row id) pairs are scattered, not bare row ids, so build/probe never gather keys again;
+//   * up to 16 radix bits in at most two passes of <= 8 bits; ONE histogram kernel over all bits
+//     yields every offset of both passes;
+//   * NULL keys are dropped here (execute.cpp:61-83: a NULL key never matches).
+//
+// Scatter kernel: a CTA takes a tile of 8192 tuples, ranks every tuple inside its partition with a
+// shared-memory atomic (warp-aggregated through __match_any_sync when a warp is dominated by one
+// partition -- skewed keys), stages the tile in shared memory IN PARTITION ORDER (software
+// write-combining), reserves each partition's run with one global atomic, and streams the runs out
+// with coalesced stores: consecutive threads write consecutive addresses inside a run.
+#include "rj_common.cuh"
+#include "rj_internal.h"
+
+namespace rj {
+namespace {
+
+constexpr int kHistThreads    = 512;
+constexpr int kScatterThreads = 512;
+template <typename K>
+struct ScatterCfg {
+    // tuples per thread: 16 x 4-byte keys or 8 x 8-byte keys keep the kernel under 64 registers
+    static constexpr int      kItems = sizeof(K) == 4 ? 16 : 8;
+    static constexpr uint32_t kTile  = kItems * kScatterThreads;
+};
+constexpr int kPlanThreads    = 1024;
+
+template <typename K>
+__global__ void __launch_bounds__(kHistThreads)
+    radix_hist_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid, uint64_t n, int shift,
+                      int bits, uint32_t* __restrict__ hist) {
+    extern __shared__ uint32_t s_hist[];
+    const uint32_t nb = 1u << bits, mask = nb - 1;
+    for (uint32_t b = threadIdx.x; b < nb; b += kHistThreads) s_hist[b] = 0;
+    __syncthreads();
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kHistThreads;
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * kHistThreads + threadIdx.x;
+    // 4 independent loads in flight per thread
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        K k0 = keys[i], k1 = keys[i + stride], k2 = keys[i + 2 * stride], k3 = keys[i + 3 * stride];
+        bool v0 = true, v1 = true, v2 = true, v3 = true;
+        if (valid) {
+            v0 = test_bit(valid, i);
+            v1 = test_bit(valid, i + stride);
+            v2 = test_bit(valid, i + 2 * stride);
+            v3 = test_bit(valid, i + 3 * stride);
+        }
+        if (v0) atomicAdd(&s_hist[(hash_key(k0) >> shift) & mask], 1u);
+        if (v1) atomicAdd(&s_hist[(hash_key(k1) >> shift) & mask], 1u);
+        if (v2) atomicAdd(&s_hist[(hash_key(k2) >> shift) & mask], 1u);
+        if (v3) atomicAdd(&s_hist[(hash_key(k3) >> shift) & mask], 1u);
+    }
+    for (; i < n; i += stride) {
+        if (!valid || test_bit(valid, i)) atomicAdd(&s_hist[(hash_key(keys[i]) >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nb; b += kHistThreads) {
+        uint32_t c = s_hist[b];
+        if (c) atomicAdd(&hist[b], c);
+    }
+}
+
+// ---- single-block planner ---------------------------------------------------------------------------
+// exclusive scan of f(i) for i in [0, n) into out[0..n] (out[n] = total); whole block cooperates
+template <class F>
+__device__ void block_exclusive_scan(uint32_t n, uint32_t* out, F f) {
+    __shared__ uint32_t warp_sums[kPlanThreads / 32];
+    __shared__ uint32_t s_carry;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += kPlanThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? f(i) : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        uint32_t prefix = 0, total = 0;
+        for (uint32_t w = 0; w < kPlanThreads / 32; ++w) {
+            uint32_t s = warp_sums[w];
+            if (w < warp) prefix += s;
+            total += s;
+        }
+        const uint32_t carry = s_carry;
+        if (i < n) out[i] = carry + prefix + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPlanThreads)
+    partition_plan_kernel(const uint32_t* __restrict__ hist_b, const uint32_t* __restrict__ hist_p, uint32_t flat_b,
+                          uint32_t flat_p, int total_bits, int pass1_bits, uint32_t tile, PartitionPlanDev plan) {
+    const uint32_t nparts = 1u << total_bits;
+    // final offsets (partition-major layout of the fully partitioned relations)
+    if (total_bits == 0) {
+        if (threadIdx.x == 0) {
+            plan.off_b[0] = 0;
+            plan.off_b[1] = flat_b;
+            plan.off_p[0] = 0;
+            plan.off_p[1] = flat_p;
+        }
+        __syncthreads();
+    } else {
+        block_exclusive_scan(nparts, plan.off_b, [&](uint32_t i) { return hist_b[i]; });
+        block_exclusive_scan(nparts, plan.off_p, [&](uint32_t i) { return hist_p[i]; });
+        for (uint32_t i = threadIdx.x; i < nparts; i += kPlanThreads) {
+            plan.cur_b[i] = plan.off_b[i];
+            plan.cur_p[i] = plan.off_p[i];
+        }
+    }
+    if (pass1_bits > 0) {
+        // pass-1 regions = groups of 2^(total-pass1) consecutive final partitions
+        const uint32_t nreg = 1u << pass1_bits;
+        const int      b2   = total_bits - pass1_bits;
+        for (uint32_t r = threadIdx.x; r <= nreg; r += kPlanThreads) {
+            plan.reg_b[r] = plan.off_b[r << b2];
+            plan.reg_p[r] = plan.off_p[r << b2];
+            if (r < nreg) {
+                plan.cur1_b[r] = plan.off_b[r << b2];
+                plan.cur1_p[r] = plan.off_p[r << b2];
+            }
+        }
+        __syncthreads();
+        block_exclusive_scan(nreg, plan.tile_b, [&](uint32_t r) {
+            return (plan.reg_b[r + 1] - plan.reg_b[r] + tile - 1) / tile;
+        });
+        block_exclusive_scan(nreg, plan.tile_p, [&](uint32_t r) {
+            return (plan.reg_p[r + 1] - plan.reg_p[r] + tile - 1) / tile;
+        });
+    }
+    // join work units: (build chunk) x (probe chunk) per partition; none if either side is empty
+    block_exclusive_scan(nparts, plan.unit_start, [&](uint32_t i) {
+        const uint32_t nb = plan.off_b[i + 1] - plan.off_b[i];
+        const uint32_t np = plan.off_p[i + 1] - plan.off_p[i];
+        if (nb == 0 || np == 0) return 0u;
+        return ((nb + kJoinBuildCap - 1) / kJoinBuildCap) * ((np + kJoinProbeChunk - 1) / kJoinProbeChunk);
+    });
+}
+
+// ---- scatter ----------------------------------------------------------------------------------------
+template <typename K, bool kRegions>
+__global__ void __launch_bounds__(kScatterThreads, 2)
+    radix_scatter_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
+                         const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
+                         const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
+                         uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+    constexpr int      kScatterItems = ScatterCfg<K>::kItems;
+    constexpr uint32_t kTile         = ScatterCfg<K>::kTile;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    K*        s_keys  = reinterpret_cast<K*>(smem_raw);
+    uint32_t* s_idx   = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kTile);
+    uint32_t* s_count = s_idx + kTile;            // [nb]  tuples of this tile per partition
+    uint32_t* s_start = s_count + (1u << bits);   // [nb]  exclusive prefix inside the tile
+    uint32_t* s_gbase = s_start + (1u << bits);   // [nb]  global run start minus s_start
+    __shared__ uint32_t s_warp_sums[kScatterThreads / 32];
+    __shared__ uint32_t s_total;
+
+    const uint32_t nb = 1u << bits, mask = nb - 1;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = lanemask_lt();
+
+    uint64_t n_tiles;
+    if (kRegions) {
+        n_tiles = tile_start[n_regions];
+    } else {
+        n_tiles = (n + kTile - 1) / kTile;
+    }
+    for (uint32_t b = threadIdx.x; b < nb; b += kScatterThreads) s_count[b] = 0;
+    __syncthreads();
+
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint64_t lo, hi;
+        uint32_t cursor_base = 0;
+        if (kRegions) {
+            // region of this tile: last r with tile_start[r] <= t
+            uint32_t a = 0, b = n_regions;
+            while (b - a > 1) {
+                uint32_t m = (a + b) >> 1;
+                if (tile_start[m] <= t) a = m; else b = m;
+            }
+            lo = static_cast<uint64_t>(region_start[a]) + (t - tile_start[a]) * kTile;
+            hi = region_start[a + 1];
+            if (hi > lo + kTile) hi = lo + kTile;
+            cursor_base = a << bits;
+        } else {
+            lo = t * kTile;
+            hi = lo + kTile < n ? lo + kTile : n;
+        }
+
+        // 1) load + rank inside the partition
+        K        key[kScatterItems];
+        uint32_t pr[kScatterItems]; // partition << 16 | rank (rank < 8192, partition < 512)
+#pragma unroll
+        for (int k = 0; k < kScatterItems; ++k) {
+            const uint64_t i = lo + static_cast<uint64_t>(k) * kScatterThreads + threadIdx.x;
+            bool ok = i < hi;
+            key[k] = ok ? keys[i] : K(0);
+            if (ok && valid != nullptr) ok = test_bit(valid, i);
+            pr[k]  = ok ? ((hash_key(key[k]) >> shift) & mask) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < kScatterItems; ++k) {
+            const uint32_t part = pr[k];
+            const bool     ok   = part != 0xffffffffu;
+            // skew detector: how many lanes share the partition of their neighbour?
+            const uint32_t nbr  = __shfl_xor_sync(RJ_FULL_MASK, part, 1);
+            const uint32_t same = __ballot_sync(RJ_FULL_MASK, ok && nbr == part);
+            uint32_t rank = 0;
+            if (__popc(same) >= 4) {
+                // warp dominated by few partitions: one shared-memory atomic per distinct partition
+                const uint32_t peers  = __match_any_sync(RJ_FULL_MASK, part);
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (ok && lane == leader) base = atomicAdd(&s_count[part], static_cast<uint32_t>(__popc(peers)));
+                base = __shfl_sync(RJ_FULL_MASK, base, leader);
+                rank = base + __popc(peers & lt);
+            } else if (ok) {
+                rank = atomicAdd(&s_count[part], 1u);
+            }
+            pr[k] = ok ? ((part << 16) | rank) : 0xffffffffu;
+        }
+        __syncthreads();
+
+        // 2) exclusive scan of the per-partition counts (nb <= kScatterThreads), reserve global runs
+        {
+            const uint32_t c = threadIdx.x < nb ? s_count[threadIdx.x] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) s_warp_sums[warp] = inc;
+            __syncthreads();
+            uint32_t prefix = 0;
+            for (uint32_t w = 0; w < warp; ++w) prefix += s_warp_sums[w];
+            const uint32_t start = prefix + inc - c;
+            if (threadIdx.x < nb) {
+                s_start[threadIdx.x] = start;
+                uint32_t g = 0;
+                if (c) g = atomicAdd(&cursor[cursor_base + threadIdx.x], c);
+                s_gbase[threadIdx.x] = g - start;
+                s_count[threadIdx.x] = 0; // ready for the next tile
+            }
+            if (threadIdx.x == kScatterThreads - 1) s_total = prefix + inc;
+        }
+        __syncthreads();
+
+        // 3) stage the tile in partition order
+#pragma unroll
+        for (int k = 0; k < kScatterItems; ++k) {
+            if (pr[k] != 0xffffffffu) {
+                const uint64_t i   = lo + static_cast<uint64_t>(k) * kScatterThreads + threadIdx.x;
+                const uint32_t pos = s_start[pr[k] >> 16] + (pr[k] & 0xffffu);
+                s_keys[pos] = key[k];
+                s_idx[pos]  = idx_in != nullptr ? idx_in[i] : static_cast<uint32_t>(i);
+            }
+        }
+        __syncthreads();
+
+        // 4) stream the runs out: thread -> staged position, neighbours write neighbouring addresses
+        const uint32_t total = s_total;
+        for (uint32_t pos = threadIdx.x; pos < total; pos += kScatterThreads) {
+            const K        k    = s_keys[pos];
+            const uint32_t part = (hash_key(k) >> shift) & mask;
+            const uint32_t dst  = s_gbase[part] + pos;
+            keys_out[dst] = k;
+            idx_out[dst]  = s_idx[pos];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename K>
+size_t scatter_smem_bytes(int bits) {
+    return (sizeof(K) + 4) * ScatterCfg<K>::kTile + 3 * sizeof(uint32_t) * (1u << bits);
+}
+
+template <typename K, bool kRegions>
+void scatter_set_attr(size_t smem) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<K, kRegions>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+        configured = smem;
+    }
+}
+
+} // namespace
+
+size_t partition_plan_words(int total_bits, int pass1_bits) {
+    const size_t nparts = size_t(1) << total_bits;
+    const size_t nreg   = pass1_bits > 0 ? (size_t(1) << pass1_bits) : 0;
+    return 2 * (nparts + 1) + 2 * nparts + (nparts + 1) + (nreg ? 2 * (nreg + 1) + 2 * nreg + 2 * (nreg + 1) : 0) + 16;
+}
+
+void partition_plan_carve(uint32_t* base, int total_bits, int pass1_bits, PartitionPlanDev* plan) {
+    const size_t nparts = size_t(1) << total_bits;
+    const size_t nreg   = pass1_bits > 0 ? (size_t(1) << pass1_bits) : 0;
+    uint32_t* p = base;
+    plan->off_b = p; p += nparts + 1;
+    plan->off_p = p; p += nparts + 1;
+    plan->cur_b = p; p += nparts;
+    plan->cur_p = p; p += nparts;
+    plan->unit_start = p; p += nparts + 1;
+    if (nreg) {
+        plan->reg_b = p; p += nreg + 1;
+        plan->reg_p = p; p += nreg + 1;
+        plan->cur1_b = p; p += nreg;
+        plan->cur1_p = p; p += nreg;
+        plan->tile_b = p; p += nreg + 1;
+        plan->tile_p = p; p += nreg + 1;
+    } else {
+        plan->reg_b = plan->reg_p = plan->cur1_b = plan->cur1_p = plan->tile_b = plan->tile_p = nullptr;
+    }
+}
+
+void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift, int bits,
+                            uint32_t* hist, int sm_count, cudaStream_t s) {
+    if (n == 0) return;
+    const size_t smem = sizeof(uint32_t) << bits;
+    uint64_t want = (n + kHistThreads * 8 - 1) / (kHistThreads * 8);
+    unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 4 ? want : static_cast<uint64_t>(sm_count) * 4);
+    if (blocks == 0) blocks = 1;
+    if (key_bytes == 4) {
+        static size_t configured = 0;
+        if (smem > configured) {
+            RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        radix_hist_kernel<uint32_t><<<blocks, kHistThreads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, n, shift, bits, hist);
+    } else {
+        static size_t configured = 0;
+        if (smem > configured) {
+            RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        radix_hist_kernel<uint64_t><<<blocks, kHistThreads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, n, shift, bits, hist);
+    }
+    RJ_LAUNCH_CHECK();
+}
+
+void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint32_t flat_b, uint32_t flat_p,
+                           int total_bits, int pass1_bits, int key_bytes, const PartitionPlanDev& plan,
+                           cudaStream_t s) {
+    partition_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist_b, hist_p, flat_b, flat_p, total_bits, pass1_bits,
+                                                     scatter_tile(key_bytes), plan);
+    RJ_LAUNCH_CHECK();
+}
+
+void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_t* idx_in, uint64_t n, int key_bytes,
+                          int shift, int bits, uint32_t* cursor, void* keys_out, uint32_t* idx_out, int sm_count,
+                          cudaStream_t s) {
+    if (n == 0) return;
+    const uint32_t tile = scatter_tile(key_bytes);
+    uint64_t n_tiles = (n + tile - 1) / tile;
+    unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 2 ? n_tiles : static_cast<uint64_t>(sm_count) * 2);
+    if (key_bytes == 4) {
+        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
+        scatter_set_attr<uint32_t, false>(smem);
+        radix_scatter_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint32_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
+            static_cast<uint32_t*>(keys_out), idx_out);
+    } else {
+        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
+        scatter_set_attr<uint64_t, false>(smem);
+        radix_scatter_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint64_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
+            static_cast<uint64_t*>(keys_out), idx_out);
+    }
+    RJ_LAUNCH_CHECK();
+}
+
+void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,
+                                  const uint32_t* tile_start, uint32_t n_regions, uint64_t n_upper, int key_bytes,
+                                  int shift, int bits, uint32_t* cursor, void* keys_out, uint32_t* idx_out,
+                                  int sm_count, cudaStream_t s) {
+    if (n_upper == 0) return;
+    // the exact tile count lives on the device (tile_start[n_regions]); size the persistent grid from
+    // its upper bound so no host synchronisation is needed
+    const uint32_t tile = scatter_tile(key_bytes);
+    uint64_t tiles_upper = (n_upper + tile - 1) / tile + n_regions;
+    unsigned blocks = static_cast<unsigned>(tiles_upper < static_cast<uint64_t>(sm_count) * 2 ? tiles_upper : static_cast<uint64_t>(sm_count) * 2);
+    if (key_bytes == 4) {
+        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
+        scatter_set_attr<uint32_t, true>(smem);
+        radix_scatter_kernel<uint32_t, true><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint32_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
+            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out);
+    } else {
+        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
+        scatter_set_attr<uint64_t, true>(smem);
+        radix_scatter_kernel<uint64_t, true><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint64_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
+            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out);
+    }
+    RJ_LAUNCH_CHECK();
+}
+
+} // namespace rj

@@ -1,0 +1,150 @@
+// Shared device-side helpers of the sm_100a join engine: hashing, warp utilities, and thin wrappers
+// around the Blackwell/Hopper async-copy PTX (1-D TMA bulk copies + mbarrier) used to stage 8 KB
+// pages and write-combined partition runs through shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RJ_PAGE 8192u
+#define RJ_FULL_MASK 0xffffffffu
+
+// string descriptor produced by the VARCHAR decoder (see include/rj_b200.h: rj_decode_varchar)
+#define RJ_DESC_ADDR_MASK 0xFFFFFFFFFFull
+#define RJ_DESC_LEN_SHIFT 40
+#define RJ_DESC_LEN_MASK  0x7FFFFFull
+#define RJ_DESC_LONG      (1ull << 63)
+
+namespace rj {
+
+// ---- hashing --------------------------------------------------------------------------------------
+// The reference hashes with MurmurHash3's 64-bit finaliser (src/execute.cpp:21-27).  The hash is not
+// observable in results, so the engine uses the 32-bit finaliser (2 IMADs instead of 64-bit
+// multiplies): radix bits are taken from the low end, the in-partition slot from the bits above.
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+
+__host__ __device__ __forceinline__ uint32_t hash_key(uint32_t k) { return fmix32(k); }
+
+__host__ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
+    return fmix32(static_cast<uint32_t>(k) ^ fmix32(static_cast<uint32_t>(k >> 32) ^ 0x9e3779b9u));
+}
+
+// ---- warp helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() {
+    uint32_t l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ bitmap, uint64_t i) {
+    return (bitmap[i >> 5] >> (i & 31)) & 1u;
+}
+
+// ---- shared-memory address / mbarrier / TMA bulk copies --------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void fence_mbar_init() {
+    // make the initialised barrier visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// 1-D TMA bulk load global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 1-D TMA bulk store shared -> global (bulk async-group completion).
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    // wait until all but the N most recent bulk groups have finished READING their shared source
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// generic-proxy writes to shared memory must be fenced before the async proxy (TMA) reads them
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// streaming loads/stores that do not pollute L1
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ uint4 ld_stream_u128(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ uint16_t ld_u16_unaligned(const uint8_t* p) {
+    return static_cast<uint16_t>(p[0]) | static_cast<uint16_t>(p[1]) << 8;
+}
+
+} // namespace rj

@@ -1,0 +1,150 @@
+// Host-side internal interface of the engine: the context, the launch wrappers of every kernel
+// file, and small RAII helpers.  Nothing here is exported; the C-ABI lives in engine.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rj_b200.h"
+
+namespace rj {
+
+struct CudaError: std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define RJ_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t rj_e_ = (expr);                                                                \
+        if (rj_e_ != cudaSuccess) {                                                                \
+            throw ::rj::CudaError(std::string(#expr) + ": " + cudaGetErrorString(rj_e_) + " (" +   \
+                                  __FILE__ + ":" + std::to_string(__LINE__) + ")");                \
+        }                                                                                          \
+    } while (0)
+
+#define RJ_LAUNCH_CHECK() RJ_CUDA(cudaGetLastError())
+
+// ---- join geometry (shared by the partition planner and the join kernel) ---------------------------
+constexpr uint32_t kJoinSlots      = 8192;  // shared-memory hash table slots per CTA
+constexpr uint32_t kJoinBuildCap   = 6144;  // build tuples per table (75 % fill); larger partitions are chunked
+constexpr uint32_t kJoinTargetFill = 4096;  // partition fan-out aims at <= this many build tuples on average
+constexpr uint32_t kJoinProbeChunk = 16384; // probe tuples per work unit
+// tuples per scatter tile: 512 threads x 16 (4-byte keys) or x 8 (8-byte keys)
+constexpr uint32_t scatter_tile(int key_bytes) { return key_bytes == 4 ? 8192u : 4096u; }
+constexpr int      kMaxPassBits    = 8;     // radix bits per scatter pass
+constexpr int      kMaxTotalBits   = 16;
+
+// Device-resident partition plan, filled by launch_partition_plan (single small kernel, no host sync)
+struct PartitionPlanDev {
+    uint32_t* off_b;        // [nparts+1] final build offsets (exclusive prefix of the histogram)
+    uint32_t* off_p;        // [nparts+1]
+    uint32_t* cur_b;        // [nparts]   pass-2 (or single-pass) cursors, advanced by the scatter
+    uint32_t* cur_p;        // [nparts]
+    uint32_t* reg_b;        // [nreg+1]   pass-1 region starts (two-pass only)
+    uint32_t* reg_p;        // [nreg+1]
+    uint32_t* cur1_b;       // [nreg]     pass-1 cursors
+    uint32_t* cur1_p;       // [nreg]
+    uint32_t* tile_b;       // [nreg+1]   exclusive prefix of pass-2 tiles per region
+    uint32_t* tile_p;       // [nreg+1]
+    uint32_t* unit_start;   // [nparts+1] exclusive prefix of join work units per partition
+};
+
+size_t partition_plan_words(int total_bits, int pass1_bits);
+void   partition_plan_carve(uint32_t* base, int total_bits, int pass1_bits, PartitionPlanDev* plan);
+
+// ---- k_scan.cu ------------------------------------------------------------------------------------
+size_t scan_tmp_bytes(uint64_t n);
+// out[i] = sum_{k<i} in[k], out[n] = total
+void launch_exclusive_scan_u32_u64(const uint32_t* in, uint64_t* out, uint64_t n, void* tmp, cudaStream_t s);
+// inclusive scans over uint64 (sum or max)
+void launch_inclusive_sum_u64(const uint64_t* in, uint64_t* out, uint64_t n, void* tmp, cudaStream_t s);
+void launch_inclusive_max_u64(const uint64_t* in, uint64_t* out, uint64_t n, void* tmp, cudaStream_t s);
+
+// ---- k_decode.cu ----------------------------------------------------------------------------------
+void launch_page_rows(const void* pages, uint64_t n_pages, int type, uint32_t* rows, uint64_t* totals,
+                      cudaStream_t s);
+void launch_decode_fixed(const void* pages, uint64_t n_pages, int type, const uint64_t* row_start,
+                         void* values, uint32_t* valid, int sm_count, cudaStream_t s);
+void launch_decode_varchar(const void* pages, uint64_t n_pages, const uint64_t* row_start, uint64_t* desc,
+                           uint32_t* valid, int sm_count, cudaStream_t s);
+
+// ---- k_partition.cu -------------------------------------------------------------------------------
+void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift,
+                            int bits, uint32_t* hist, int sm_count, cudaStream_t s);
+void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint32_t flat_b, uint32_t flat_p,
+                           int total_bits, int pass1_bits, int key_bytes, const PartitionPlanDev& plan,
+                           cudaStream_t s);
+// flat scatter over [0, n): cursor index = radix digit
+void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_t* idx_in, uint64_t n,
+                          int key_bytes, int shift, int bits, uint32_t* cursor, void* keys_out,
+                          uint32_t* idx_out, int sm_count, cudaStream_t s);
+// segmented scatter (pass 2): region r covers [region_start[r], region_start[r+1]) of the input,
+// tiles are enumerated through tile_start, cursor index = (r << bits) | digit
+void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,
+                                  const uint32_t* tile_start, uint32_t n_regions, uint64_t n_upper,
+                                  int key_bytes, int shift, int bits, uint32_t* cursor, void* keys_out,
+                                  uint32_t* idx_out, int sm_count, cudaStream_t s);
+
+// ---- k_join.cu ------------------------------------------------------------------------------------
+struct JoinLaunch {
+    const void*     bkeys;
+    const uint32_t* bidx;   // NULL = identity
+    const uint32_t* bvalid; // NULL = all valid
+    const void*     pkeys;
+    const uint32_t* pidx;
+    const uint32_t* pvalid;
+    const uint32_t* off_b;  // [nparts+1]
+    const uint32_t* off_p;
+    const uint32_t* unit_start; // [nparts+1]
+    uint32_t        nparts;
+    int             part_bits;  // hash bits consumed by the partitioning
+    int             key_bytes;
+    uint32_t*       out_b;
+    uint32_t*       out_p;
+    uint64_t        capacity;
+    unsigned long long* out_count; // device counter (zeroed by the caller)
+};
+void launch_join(const JoinLaunch& a, int sm_count, cudaStream_t s);
+
+// ---- k_gather_encode.cu ---------------------------------------------------------------------------
+void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* idx, uint64_t n,
+                   int elem_bytes, void* out, uint32_t* out_valid, int sm_count, cudaStream_t s);
+void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32_t* idx, uint64_t n,
+                         int type, void* pages_out, int sm_count, cudaStream_t s);
+void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
+
+// ---- k_varchar.cu ---------------------------------------------------------------------------------
+struct VarcharLayoutDev {
+    uint64_t  n = 0;          // output rows
+    const uint8_t*  src_pages = nullptr;
+    const uint64_t* desc = nullptr;
+    const uint32_t* valid = nullptr;
+    const uint32_t* idx = nullptr;
+    uint64_t* weight_scan = nullptr; // [n] inclusive prefix of row weights (bits)
+    uint64_t* base_scan = nullptr;   // [n] weight prefix at the last segment breaker
+    uint32_t* head_pages = nullptr;  // [n] pages started by row j (0 = not a page head)
+    uint64_t* page_of = nullptr;     // [n+1] exclusive prefix of head_pages
+    uint32_t* page_row = nullptr;    // [n_pages] first row of each page
+    uint64_t* scalars = nullptr;     // [4] device: max normal weight, ...
+    uint64_t  n_pages = 0;
+};
+// per-row 64-bit hash of a VARCHAR column (join keys); NULL rows hash to 0
+void launch_varchar_hash(const uint8_t* pages, const uint64_t* desc, const uint32_t* valid, uint64_t n,
+                         uint64_t* out_hash, int sm_count, cudaStream_t s);
+// keep[i] = 1 iff the strings of pair i are byte-equal
+void launch_varchar_pairs_equal(const uint8_t* pages_a, const uint64_t* desc_a, const uint32_t* idx_a,
+                                const uint8_t* pages_b, const uint64_t* desc_b, const uint32_t* idx_b,
+                                uint64_t n, uint32_t* keep, int sm_count, cudaStream_t s);
+void launch_compact_pairs(const uint32_t* a, const uint32_t* b, const uint32_t* keep, const uint64_t* pos,
+                          uint64_t n, uint32_t* out_a, uint32_t* out_b, cudaStream_t s);
+void launch_varchar_weights(const VarcharLayoutDev& L, uint64_t* weights, int sm_count, cudaStream_t s);
+void launch_varchar_marks(const VarcharLayoutDev& L, uint64_t* marks, int sm_count, cudaStream_t s);
+void launch_varchar_heads(const VarcharLayoutDev& L, const uint64_t* weights, int sm_count, cudaStream_t s);
+void launch_varchar_page_rows(const VarcharLayoutDev& L, int sm_count, cudaStream_t s);
+void launch_varchar_write(const VarcharLayoutDev& L, uint8_t* pages_out, int sm_count, cudaStream_t s);
+
+} // namespace rj

@@ -174,3 +174,28 @@ def single_join_plan(t_left, t_right, left_types, right_types, left_key, right_k
     plan.new_input(t_right)
     plan.root = 2
     return plan
+
+
+# --------------------------------------------------------------------------------------------------
+# numpy mirror of the engine's radix hash (radix-join_b200/csrc/rj_common.cuh: hash_key) -- used by
+# the stage tests to predict which radix digit a key falls into
+# --------------------------------------------------------------------------------------------------
+def _fmix32(h):
+    h = h.astype(np.uint32).copy()
+    with np.errstate(over="ignore"):
+        h ^= h >> np.uint32(16)
+        h *= np.uint32(0x85EBCA6B)
+        h ^= h >> np.uint32(13)
+        h *= np.uint32(0xC2B2AE35)
+        h ^= h >> np.uint32(16)
+    return h
+
+
+def hash_keys(keys):
+    keys = np.asarray(keys)
+    if keys.dtype.itemsize == 4:
+        return _fmix32(keys.view(np.uint32))
+    k = keys.view(np.uint64)
+    lo = (k & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    hi = (k >> np.uint64(32)).astype(np.uint32)
+    return _fmix32(lo ^ _fmix32(hi ^ np.uint32(0x9E3779B9)))

@@ -1,0 +1,405 @@
+"""GPU tests (-m gpu): the CUDA path, called through the C-ABI, against the oracle.
+
+Bit-exact multiset equality of result rows (INT32/INT64/FP64 by bit pattern, VARCHAR by bytes, NULL
+distinct from every value) -- the check of the reference harness (tests/read_sql.cpp:1159-1222).
+"""
+import base64
+import ctypes as C
+import json
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import FP64, INT32, INT64, VARCHAR, orc, rj
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rj.build_context(0)
+    yield c
+    rj.destroy_context(c)
+
+
+def oracle_impl():
+    return "ref" if orc.available("ref") else "port"
+
+
+def check_plan(plan, ctx, impl=None, expect_rows=None):
+    got = rj.execute(plan, ctx)
+    want = orc.execute(plan, impl=impl or oracle_impl())
+    assert got.num_rows == want.num_rows
+    assert [int(c.type) for c in got.columns] == [int(c.type) for c in want.columns]
+    if expect_rows is not None:
+        assert got.num_rows == expect_rows
+    assert orc.result_equal(got, want)
+    return got
+
+
+# ---- golden vectors ----------------------------------------------------------------------------------
+def load_fixture():
+    with open(os.path.join(H.ROOT, "tests", "golden", "unit_cases.json")) as f:
+        return json.load(f)
+
+
+def plan_from_fixture(d):
+    plan = rj.Plan()
+    for t in d["inputs"]:
+        cols = []
+        for c in t["columns"]:
+            raw = zlib.decompress(base64.b64decode(c["pages"]))
+            cols.append(rj.Column(c["type"], np.frombuffer(raw, dtype=np.uint8).reshape(-1, 8192).copy()))
+        plan.new_input(rj.ColumnarTable(num_rows=t["num_rows"], columns=cols))
+    for n in d["nodes"]:
+        out = [(i, t) for i, t in n["out"]]
+        if "join" in n:
+            bl, l, r, la, ra = n["join"]
+            plan.new_join_node(bl, l, r, la, ra, out)
+        else:
+            plan.new_scan_node(n["scan"], out)
+    plan.root = d["root"]
+    return plan
+
+
+FIXTURE_NAMES = ["empty_join", "one_line_join", "simple_join", "empty_result", "multiple_same_keys",
+                 "null_keys", "multiple_columns", "build_on_right", "int64_key_fp64_varchar_payload",
+                 "varchar_key", "long_strings", "multi_page_nulls_dup_attrs"]
+
+
+@pytest.mark.parametrize("name", FIXTURE_NAMES)
+def test_golden_fixture(ctx, name):
+    """committed fixtures: inputs + the rows the UNMODIFIED reference produced for them"""
+    case = load_fixture()[name]
+    got = rj.execute(plan_from_fixture(case["plan"]), ctx)
+    assert got.num_rows == case["num_rows"]
+    assert [int(c.type) for c in got.columns] == case["types"]
+    if case["num_rows"] == 0:
+        assert all(c.n_pages == 0 for c in got.columns)  # typed, page-less (unit_tests.cpp:24-27)
+    want = []
+    for r in case["rows"]:
+        row = []
+        for v, t in zip(r, case["types"]):
+            if v is None:
+                row.append(None)
+            elif t == VARCHAR:
+                row.append(v.encode())
+            elif t == FP64:
+                row.append(float.fromhex(v) if isinstance(v, str) else float(v))
+            else:
+                row.append(v)
+        want.append(tuple(row))
+    got_rows = H.rows_of(got)
+    assert len(got_rows) == len(want)
+    # compare FP64 by bit pattern (-0.0 != 0.0 here)
+    canon = lambda rows: sorted(repr(tuple(np.float64(v).tobytes().hex() if isinstance(v, float) else v
+                                           for v in r)) for r in rows)
+    assert canon(got_rows) == canon(want)
+
+
+def test_reference_unit_tests_on_the_engine():
+    """the reference's tests/unit_tests.cpp, compiled UNMODIFIED and linked against
+    Contest::execute of this repo (radix-join_b200/csrc/contest_execute.cpp)"""
+    exe = os.path.join(H.ROOT, "oracle", "_ref", "unit_tests_b200")
+    if not os.path.exists(exe):
+        pytest.skip("unit_tests_b200 not built (needs the reference headers at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 failures / 8 cases" in out.stdout
+
+
+# ---- random plans vs the oracle ------------------------------------------------------------------------
+@pytest.mark.parametrize("key_type", [INT32, INT64, VARCHAR])
+@pytest.mark.parametrize("build_left", [True, False])
+def test_single_join_all_types(ctx, key_type, build_left):
+    rng = np.random.default_rng(100 + key_type)
+    lt = [key_type, INT64, VARCHAR]
+    rt = [FP64, key_type, INT32]
+    tl, _ = H.random_table(rng, lt, 1500, key_cols=(0,), key_range=600)
+    tr, _ = H.random_table(rng, rt, 6000, key_cols=(1,), key_range=600, long_frac=0.002)
+    plan = H.single_join_plan(tl, tr, lt, rt, 0, 1, build_left, out_cols=[5, 0, 2, 1, 3, 3, 4])
+    check_plan(plan, ctx)
+
+
+def test_multi_join_tree(ctx):
+    import test_oracle
+    plan = test_oracle._three_way_plan(np.random.default_rng(3))
+    got = check_plan(plan, ctx)
+    assert got.num_rows > 0
+
+
+def test_scan_as_root_and_empty_side(ctx):
+    t = H.table_from_python([INT32, VARCHAR], [(1, "a"), (None, ""), (3, None)])
+    plan = rj.Plan()
+    plan.new_input(t)
+    plan.root = plan.new_scan_node(0, [(1, VARCHAR), (0, INT32), (1, VARCHAR)])
+    check_plan(plan, ctx, expect_rows=3)
+    plan = H.single_join_plan(t, H.empty_table([INT32]), [INT32, VARCHAR], [INT32], 0, 0, True)
+    got = check_plan(plan, ctx, expect_rows=0)
+    assert all(c.n_pages == 0 for c in got.columns)
+
+
+def test_key_type_mismatch_matches_nothing(ctx):
+    t = H.table_from_python([INT32], [(1,), (2,)])
+    plan = rj.Plan()
+    plan.new_input(t)
+    plan.new_input(t)
+    plan.new_scan_node(0, [(0, INT64)])
+    plan.new_scan_node(1, [(0, INT32)])
+    plan.root = plan.new_join_node(True, 0, 1, 0, 0, [(1, INT32)])
+    check_plan(plan, ctx, expect_rows=0)
+
+
+def test_errors_surface_as_engine_errors(ctx):
+    t = H.table_from_python([INT32], [(1,)])
+    plan = rj.Plan()
+    plan.new_input(t)
+    plan.new_scan_node(0, [(0, INT32)])
+    plan.root = 7  # out of range
+    with pytest.raises(rj.EngineError):
+        rj.execute(plan, ctx)
+    # FP64 join key: the reference never terminates on it (src/execute.cpp:28-31); the engine refuses
+    tf = H.table_from_python([FP64], [(1.0,)])
+    plan = H.single_join_plan(tf, tf, [FP64], [FP64], 0, 0, True)
+    with pytest.raises(rj.EngineError):
+        rj.execute(plan, ctx)
+    # and the context is still usable afterwards
+    check_plan(H.single_join_plan(t, t, [INT32], [INT32], 0, 0, True), ctx, expect_rows=1)
+
+
+def test_duplicates_on_both_sides_overflow_the_first_guess(ctx):
+    """M >> max(|build|, |probe|): the speculative output buffer overflows and the exact count sizes
+    the second run ('unknown, possibly exploding output cardinality')"""
+    rng = np.random.default_rng(9)
+    a = H.table_from_cells([orc.Cells.from_values(INT32, rng.integers(0, 20, 3000).astype(np.int32))])
+    b = H.table_from_cells([orc.Cells.from_values(INT32, rng.integers(0, 20, 4000).astype(np.int32))])
+    got = check_plan(H.single_join_plan(a, b, [INT32], [INT32], 0, 0, True), ctx, impl="port")
+    assert got.num_rows > 400_000
+
+
+def test_one_heavy_build_key_uses_the_overflow_path(ctx):
+    """one key repeated 20000 times on the build side: its partition exceeds a shared-memory table
+    and is processed as several build chunks"""
+    rng = np.random.default_rng(10)
+    bk = np.concatenate([np.full(20000, 7, np.int32), rng.permutation(30000).astype(np.int32) + 100])
+    pk = np.concatenate([np.full(5, 7, np.int32), rng.integers(100, 30100, 50000).astype(np.int32)])
+    a = H.table_from_cells([orc.Cells.from_values(INT32, bk)])
+    b = H.table_from_cells([orc.Cells.from_values(INT32, pk)])
+    check_plan(H.single_join_plan(a, b, [INT32], [INT32], 0, 0, True), ctx, impl="port",
+               expect_rows=5 * 20000 + 50000)
+
+
+@pytest.mark.parametrize("n_build,n_probe", [(200_000, 1_000_000),     # one scatter pass (6 bits)
+                                             (3_000_000, 4_000_000)])  # two passes (10 bits)
+def test_partitioned_join_with_payloads(ctx, n_build, n_probe):
+    rng = np.random.default_rng(n_build)
+    bk = rng.permutation(n_build).astype(np.int32)
+    ba = orc.Cells(INT64, (rng.random(n_build) > 0.01).astype(np.uint8),
+                   values=rng.integers(-2**62, 2**62, n_build))
+    pk = orc.Cells(INT32, (rng.random(n_probe) > 0.02).astype(np.uint8),
+                   values=rng.integers(0, int(n_build * 1.1), n_probe).astype(np.int32))
+    pb = H.random_cells(rng, FP64, n_probe, null_frac=0.01)
+    tl = H.table_from_cells([orc.Cells.from_values(INT32, bk), ba])
+    tr = H.table_from_cells([pk, pb])
+    plan = H.single_join_plan(tl, tr, [INT32, INT64], [INT32, FP64], 0, 0, True, out_cols=[0, 1, 3])
+    check_plan(plan, ctx, impl="port")
+
+
+def test_config1_shape_1m_x_10m(ctx):
+    """BASELINE config 1: single INT32 equi-join, 1 M build x 10 M probe, unique FK keys"""
+    rng = np.random.default_rng(42)
+    n_b, n_p = 1_000_000, 10_000_000
+    tb = H.table_from_cells([orc.Cells.from_values(INT32, rng.permutation(n_b).astype(np.int32))])
+    tp = H.table_from_cells([orc.Cells.from_values(INT32, rng.integers(0, n_b, n_p).astype(np.int32))])
+    assert tb.columns[0].n_pages == 505 and tp.columns[0].n_pages == 5041
+    plan = H.single_join_plan(tb, tp, [INT32], [INT32], 0, 0, True)
+    got = rj.execute(plan, ctx)
+    assert got.num_rows == n_p
+    # size-independent property: both output columns equal the probe keys as a multiset
+    cells = orc.decode_table(got)
+    assert np.array_equal(cells[0].values, cells[1].values)
+    assert np.array_equal(np.sort(cells[0].values), np.sort(orc.decode(tp.columns[0], n_p).values))
+    # and the full oracle comparison on this size (the port finishes in seconds)
+    assert orc.result_equal(got, orc.execute(plan, impl="port"))
+
+
+def test_zipf_skew(ctx):
+    rng = np.random.default_rng(44)
+    n_b, n_p = 500_000, 3_000_000
+    perm = rng.permutation(n_b).astype(np.int32)
+    ranks = np.minimum(rng.zipf(1.3, n_p) - 1, n_b - 1)
+    tb = H.table_from_cells([orc.Cells.from_values(INT32, perm)])
+    tp = H.table_from_cells([orc.Cells.from_values(INT32, perm[ranks])])
+    check_plan(H.single_join_plan(tb, tp, [INT32], [INT32], 0, 0, False), ctx, impl="port", expect_rows=n_p)
+
+
+# ---- per-stage entry points ----------------------------------------------------------------------------
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def unpack_valid(words, n):
+    bits = np.unpackbits(words.view(np.uint8), bitorder="little")
+    return bits[:n]
+
+
+@pytest.mark.parametrize("type,n,null_frac", [(INT32, 100_000, 0.0), (INT32, 100_000, 0.3), (INT64, 50_000, 0.5),
+                                              (FP64, 50_000, 0.05), (INT32, 200_000, 1.0), (INT64, 140_000, 0.999)])
+def test_stage_decode_fixed(ctx, type, n, null_frac):
+    """rj_page_row_offsets + rj_decode_fixed vs the oracle's from_columnar, incl. all-NULL pages of
+    65504 / 65472 rows (SURVEY section 7 'pages with up to 65 504 rows')"""
+    rng = np.random.default_rng(1)
+    cells = H.random_cells(rng, type, n, null_frac)
+    col = orc.encode([cells], impl=H.encoder_impl()).columns[0]
+    lib, h = ctx.lib, ctx.handle
+    d_pages = dev(col.pages)
+    d_start = torch.zeros(col.n_pages + 1, dtype=torch.int64, device="cuda")
+    d_tot = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ctx.check(lib.rj_page_row_offsets(h, d_pages.data_ptr(), col.n_pages, type, d_start.data_ptr(), d_tot.data_ptr(), None))
+    w = 4 if type == INT32 else 8
+    d_vals = torch.zeros(n * w, dtype=torch.uint8, device="cuda")
+    d_valid = torch.zeros((n + 31) // 32 + 1, dtype=torch.int32, device="cuda")
+    ctx.check(lib.rj_decode_fixed(h, d_pages.data_ptr(), col.n_pages, type, d_start.data_ptr(), d_vals.data_ptr(),
+                                  d_valid.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert d_tot.cpu().tolist() == [n, int(cells.valid.sum())]
+    assert int(d_start.cpu()[-1]) == n
+    valid = unpack_valid(d_valid.cpu().numpy(), n)
+    assert np.array_equal(valid, cells.valid)
+    vals = d_vals.cpu().numpy().view(np.uint32 if w == 4 else np.uint64)
+    got = vals.astype(np.uint64)
+    got[valid == 0] = 0
+    assert np.array_equal(got, cells.bits())
+
+
+@pytest.mark.parametrize("n,null_frac,long_frac,max_len", [(20_000, 0.1, 0.0, 60), (3_000, 0.2, 0.02, 300),
+                                                           (70_000, 1.0, 0.0, 10), (5_000, 0.0, 0.0, 0),
+                                                           (2_000, 0.1, 0.0, 3000)])
+def test_stage_varchar_roundtrip(ctx, n, null_frac, long_frac, max_len):
+    """rj_decode_varchar -> rj_encode_varchar_plan/write (through a shuffled row-id list) -> oracle decode"""
+    rng = np.random.default_rng(2)
+    cells = H.random_cells(rng, VARCHAR, n, null_frac, max_len=max_len, long_frac=long_frac)
+    col = orc.encode([cells], impl=H.encoder_impl()).columns[0]
+    lib, h = ctx.lib, ctx.handle
+    d_pages = dev(col.pages)
+    d_start = torch.zeros(col.n_pages + 1, dtype=torch.int64, device="cuda")
+    ctx.check(lib.rj_page_row_offsets(h, d_pages.data_ptr(), col.n_pages, VARCHAR, d_start.data_ptr(), None, None))
+    d_desc = torch.zeros(n, dtype=torch.int64, device="cuda")
+    d_valid = torch.zeros((n + 31) // 32 + 1, dtype=torch.int32, device="cuda")
+    ctx.check(lib.rj_decode_varchar(h, d_pages.data_ptr(), col.n_pages, d_start.data_ptr(), d_desc.data_ptr(),
+                                    d_valid.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(unpack_valid(d_valid.cpu().numpy(), n), cells.valid)
+    desc = d_desc.cpu().numpy().view(np.uint64)
+    lens = ((desc >> np.uint64(40)) & np.uint64(0x7FFFFF)).astype(np.int64)
+    want_lens = (cells.str_off[1:] - cells.str_off[:-1]).astype(np.int64)
+    assert np.array_equal(lens[cells.valid == 1], want_lens[cells.valid == 1])
+    # re-encode through a permutation with repeats
+    m = n + n // 3
+    idx = rng.integers(0, n, m).astype(np.uint32)
+    d_idx = dev(idx)
+    layout, n_pages = C.c_void_p(), C.c_uint64()
+    ctx.check(lib.rj_encode_varchar_plan(h, d_pages.data_ptr(), d_desc.data_ptr(), d_valid.data_ptr(), d_idx.data_ptr(), m,
+                                         C.byref(layout), C.byref(n_pages), None))
+    out = torch.zeros(max(n_pages.value, 1) * 8192, dtype=torch.uint8, device="cuda")
+    ctx.check(lib.rj_encode_varchar_write(h, layout, out.data_ptr(), None))
+    torch.cuda.synchronize()
+    lib.rj_encode_varchar_free(h, layout)
+    pages = out.cpu().numpy()[: n_pages.value * 8192].reshape(-1, 8192)
+    back = orc.decode(rj.Column(VARCHAR, pages), m, impl=H.encoder_impl())
+    want = cells.to_python()
+    assert back.to_python() == [want[i] for i in idx]
+    # page budget: the parallel layout may under-fill pages, but not by much for short strings
+    if max_len and max_len <= 300 and long_frac == 0 and null_frac < 1:
+        greedy = orc.encode([orc.Cells.from_strings([want[i] for i in idx])], impl=H.encoder_impl()).columns[0].n_pages
+        assert n_pages.value <= greedy * 1.15 + 2
+
+
+@pytest.mark.parametrize("key_bytes", [4, 8])
+def test_stage_histogram_scatter(ctx, key_bytes):
+    """rj_radix_histogram / rj_radix_scatter: counts match numpy; the scatter is a permutation that
+    groups tuples by radix digit and drops NULL keys"""
+    hash_keys = H.hash_keys
+    rng = np.random.default_rng(3)
+    n, bits, shift = 300_000, 7, 3
+    keys = (rng.integers(0, 50_000, n).astype(np.uint32) if key_bytes == 4
+            else rng.integers(0, 2**63, n).astype(np.uint64))
+    validb = (rng.random(n) > 0.1)
+    words = np.packbits(validb, bitorder="little")
+    words = np.concatenate([words, np.zeros((-len(words)) % 4 + 4, np.uint8)]).view(np.uint32)
+    lib, h = ctx.lib, ctx.handle
+    d_keys, d_valid = dev(keys), dev(words.view(np.int32))
+    d_hist = torch.zeros(1 << bits, dtype=torch.int32, device="cuda")
+    ctx.check(lib.rj_radix_histogram(h, d_keys.data_ptr(), d_valid.data_ptr(), n, key_bytes, shift, bits, d_hist.data_ptr(), None))
+    digit = (hash_keys(keys) >> np.uint32(shift)) & np.uint32((1 << bits) - 1)
+    want_hist = np.bincount(digit[validb], minlength=1 << bits)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_hist.cpu().numpy(), want_hist)
+    start = np.concatenate([[0], np.cumsum(want_hist)]).astype(np.uint32)
+    d_cur = dev(start[:-1].view(np.int32).copy())
+    d_ko = torch.zeros(n * key_bytes, dtype=torch.uint8, device="cuda")
+    d_io = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ctx.check(lib.rj_radix_scatter(h, d_keys.data_ptr(), d_valid.data_ptr(), None, n, key_bytes, shift, bits,
+                                   d_cur.data_ptr(), d_ko.data_ptr(), d_io.data_ptr(), None))
+    torch.cuda.synchronize()
+    n_valid = int(validb.sum())
+    ko = d_ko.cpu().numpy().view(keys.dtype)[:n_valid]
+    io = d_io.cpu().numpy().view(np.uint32)[:n_valid]
+    assert np.array_equal(np.sort(io), np.nonzero(validb)[0].astype(np.uint32))  # a permutation of the valid rows
+    assert np.array_equal(keys[io], ko)                                          # key travels with its row id
+    dig_out = (hash_keys(ko) >> np.uint32(shift)) & np.uint32((1 << bits) - 1)
+    assert np.all(np.diff(dig_out.astype(np.int64)) >= 0)                        # grouped by digit
+    assert np.array_equal(d_cur.cpu().numpy().view(np.uint32), start[1:])        # cursors advanced to the ends
+
+
+def test_stage_join_keys_and_gather(ctx):
+    rng = np.random.default_rng(4)
+    nb, np_ = 40_000, 150_000
+    bk = rng.integers(0, 30_000, nb).astype(np.uint32)
+    pk = rng.integers(0, 60_000, np_).astype(np.uint32)
+    lib, h = ctx.lib, ctx.handle
+    d_bk, d_pk = dev(bk), dev(pk)
+    cap = 1 << 20
+    d_ob = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    d_op = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    m = C.c_uint64()
+    ctx.check(lib.rj_join_keys(h, d_bk.data_ptr(), None, nb, d_pk.data_ptr(), None, np_, 4, cap, d_ob.data_ptr(),
+                               d_op.data_ptr(), C.byref(m), None))
+    cnt = np.bincount(bk, minlength=60_000)
+    assert m.value == int(cnt[pk].sum())
+    ob = d_ob.cpu().numpy().view(np.uint32)[: m.value]
+    op = d_op.cpu().numpy().view(np.uint32)[: m.value]
+    assert np.array_equal(bk[ob], pk[op])
+    pairs = np.unique(ob.astype(np.uint64) << np.uint64(32) | op.astype(np.uint64))
+    assert len(pairs) == m.value  # no pair twice
+    # gather
+    d_out = torch.zeros(m.value, dtype=torch.int32, device="cuda")
+    ctx.check(lib.rj_gather(h, d_bk.data_ptr(), None, d_ob.data_ptr(), m.value, 4, d_out.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), bk[ob])
+
+
+def test_resident_inputs_and_profile(ctx):
+    """upload once, execute twice from HBM; per-stage timers are populated"""
+    rng = np.random.default_rng(6)
+    tl, _ = H.random_table(rng, [INT32, INT64], 300_000, key_cols=(0,), key_range=10**6, null_frac=0.0, key_null_frac=0.0)
+    tr, _ = H.random_table(rng, [INT32, FP64], 900_000, key_cols=(0,), key_range=10**6, null_frac=0.0, key_null_frac=0.0)
+    plan = H.single_join_plan(tl, tr, [INT32, INT64], [INT32, FP64], 0, 0, True, out_cols=[0, 1, 3])
+    inputs = rj.upload(plan, ctx)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    want = orc.execute(plan, impl="port")
+    for _ in range(2):
+        res = rj.execute_resident(plan, inputs, ctx)
+        assert orc.result_equal(res.to_columnar(), want)
+        res.free()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    inputs.free()
+    for st in ("decode", "histogram", "scatter", "join", "encode"):
+        assert prof[st]["ms"] > 0 and prof[st]["launches"] > 0 and prof[st]["bytes"] > 0, (st, prof)
