@@ -97,6 +97,10 @@ void        rj_ctx_destroy(rj_ctx* ctx);
 const char* rj_last_error(const rj_ctx* ctx); /* ctx may be NULL: error of the last failed rj_ctx_create */
 int         rj_ctx_device(const rj_ctx* ctx);
 int         rj_ctx_sm_count(const rj_ctx* ctx);
+/* the cudaStream_t every whole-path call of this context runs on (for timing with CUDA events) */
+void*       rj_ctx_stream(const rj_ctx* ctx);
+/* number of kernels this library has launched in the process so far (all contexts) */
+uint64_t    rj_kernel_launch_count(void);
 /* host threads used to gather/scatter individually allocated pages through pinned staging */
 int         rj_ctx_set_host_threads(rj_ctx* ctx, int n);
 

@@ -81,6 +81,8 @@ PROTOTYPES = {
     "rj_last_error": (C.c_char_p, [_vp]),
     "rj_ctx_device": (C.c_int, [_vp]),
     "rj_ctx_sm_count": (C.c_int, [_vp]),
+    "rj_ctx_stream": (_vp, [_vp]),
+    "rj_kernel_launch_count": (_u64, []),
     "rj_ctx_set_host_threads": (C.c_int, [_vp, C.c_int]),
     "rj_execute": (C.c_int, [_vp, C.POINTER(rj_plan_t), _pvp]),
     "rj_inputs_upload": (C.c_int, [_vp, C.POINTER(rj_table_t), _u32, _pvp]),

@@ -9,14 +9,21 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
 #include <thread>
 
 #include "rj_internal.h"
 
 using namespace rj;
+
+namespace rj {
+std::atomic<uint64_t> g_kernel_launches{0};
+}
 
 // ================================================================================================
 // context
@@ -50,16 +57,86 @@ struct EngineError: std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
-// ---- stream-ordered device memory --------------------------------------------------------------
+// ---- device memory: a caching block allocator ------------------------------------------------------
+// execute() allocates ~35 buffers (tens of GB at config 2).  cudaMallocAsync cost 4-290 ms per call
+// sequence on B200 (pool growth / remapping), more than all kernels together, so freed blocks are kept
+// in a per-device cache keyed by size and handed out again: after the first execute() of a given plan
+// shape no driver allocation happens.  All engine work is ordered on the context stream, so a block
+// may be reused as soon as it is released; releases from a foreign stream synchronise that stream.
+// host-side cost of the allocator, printed per execute() when RJ_TRACE is set
+uint64_t g_alloc_ns = 0, g_free_ns = 0, g_alloc_bytes = 0, g_alloc_calls = 0, g_alloc_misses = 0;
+
+struct BlockCache {
+    std::mutex                   mu;
+    std::multimap<size_t, void*> free_blocks;
+    size_t                       cached_bytes = 0;
+
+    static size_t round(size_t n) {
+        if (n < 512) return 512;
+        if (n < (size_t(1) << 20)) return (n + 511) & ~size_t(511);
+        return (n + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+    }
+    void* take(size_t n, size_t* got) {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = free_blocks.lower_bound(n);
+        if (it != free_blocks.end() && it->first <= n + n / 8 + 4096) {
+            void* p = it->second;
+            *got = it->first;
+            cached_bytes -= it->first;
+            free_blocks.erase(it);
+            return p;
+        }
+        return nullptr;
+    }
+    void give(void* p, size_t n) {
+        std::lock_guard<std::mutex> lk(mu);
+        free_blocks.emplace(n, p);
+        cached_bytes += n;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto& kv: free_blocks) cudaFree(kv.second);
+        free_blocks.clear();
+        cached_bytes = 0;
+    }
+};
+BlockCache g_cache[64];
+std::atomic<int> g_live_contexts[64];
+
 struct DevMem {
     void*        p = nullptr;
-    size_t       bytes = 0;
+    size_t       bytes = 0;    // requested
+    size_t       block = 0;    // size of the underlying block
     cudaStream_t stream = nullptr;
-    DevMem(size_t n, cudaStream_t s): bytes(n), stream(s) {
-        RJ_CUDA(cudaMallocAsync(&p, n ? n : 16, s));
+    cudaStream_t home = nullptr; // the context stream: releases from it need no synchronisation
+    int          device = 0;
+    DevMem(size_t n, cudaStream_t s, cudaStream_t ctx_stream, int dev): bytes(n), stream(s), home(ctx_stream), device(dev) {
+        auto t0 = std::chrono::steady_clock::now();
+        const size_t want = BlockCache::round(n);
+        p = g_cache[device].take(want, &block);
+        if (!p) {
+            ++g_alloc_misses;
+            block = want;
+            cudaError_t e = cudaMalloc(&p, block);
+            if (e == cudaErrorMemoryAllocation) {
+                cudaGetLastError();
+                cudaDeviceSynchronize();
+                g_cache[device].trim(); // give the cached blocks back and retry once
+                e = cudaMalloc(&p, block);
+            }
+            if (e != cudaSuccess) {
+                p = nullptr;
+                throw CudaError(std::string("cudaMalloc(") + std::to_string(block) + "): " + cudaGetErrorString(e));
+            }
+        }
+        g_alloc_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        g_alloc_bytes += n;
+        ++g_alloc_calls;
     }
     ~DevMem() {
-        if (p) cudaFreeAsync(p, stream);
+        if (!p) return;
+        if (stream != home) cudaStreamSynchronize(stream);
+        g_cache[device].give(p, block);
     }
     DevMem(const DevMem&) = delete;
     DevMem& operator=(const DevMem&) = delete;
@@ -68,7 +145,10 @@ struct DevMem {
 };
 using Buf = std::shared_ptr<DevMem>;
 
-Buf dev_alloc(size_t bytes, cudaStream_t s) { return std::make_shared<DevMem>(bytes, s); }
+thread_local cudaStream_t t_home_stream = nullptr; // set by guarded() for the duration of an API call
+thread_local int          t_device = 0;
+
+Buf dev_alloc(size_t bytes, cudaStream_t s) { return std::make_shared<DevMem>(bytes, s, t_home_stream, t_device); }
 
 Buf dev_alloc_zero(size_t bytes, cudaStream_t s) {
     Buf b = dev_alloc(bytes, s);
@@ -212,6 +292,20 @@ void upload_column(rj_ctx* ctx, const rj_column_t& c, ColumnDev* out) {
     out->pages = out->owned->as<uint8_t>();
     if (c.n_pages == 0) return;
     if (!c.pages && !c.contiguous) throw EngineError("column has pages but no page pointers");
+    if (!c.pages) {
+        // contiguous host buffer: one DMA straight from the caller's memory (full PCIe rate when it is
+        // pinned); the page headers are scanned on the host meanwhile for the row / non-NULL totals
+        RJ_CUDA(cudaMemcpyAsync(out->owned->p, c.contiguous, c.n_pages * size_t(RJ_PAGE_SIZE), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<uint64_t> rows(ctx->host_threads, 0), vals(ctx->host_threads, 0);
+        parallel_for(ctx->host_threads, c.n_pages, [&](uint64_t b, uint64_t e, int t) {
+            for (uint64_t i = b; i < e; ++i) page_counts(host_page(c, i), c.type, &rows[t], &vals[t]);
+        });
+        for (int t = 0; t < ctx->host_threads; ++t) {
+            out->page_rows += rows[t];
+            out->non_null += vals[t];
+        }
+        return;
+    }
     ensure_pinned(ctx);
     const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
     std::vector<uint64_t> rows(ctx->host_threads, 0), vals(ctx->host_threads, 0);
@@ -688,10 +782,24 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
 
 std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in) {
     if (plan->root >= plan->n_nodes) throw EngineError("plan root out of range");
-    Exec ex(ctx, plan, in);
-    Rel  r = ex.run(plan->root);
-    auto res = ex.root(plan->root, r);
-    RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+    static const bool trace = getenv("RJ_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    g_alloc_ns = g_free_ns = g_alloc_bytes = g_alloc_calls = g_alloc_misses = 0;
+    std::unique_ptr<rj_result> res;
+    double t_run = 0, t_root = 0;
+    {
+        Exec ex(ctx, plan, in);
+        Rel  r = ex.run(plan->root);
+        t_run = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        res = ex.root(plan->root, r);
+        RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+        t_root = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (trace) {
+        double t_all = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[rj] execute: joins %.2f ms, +root/sync %.2f ms, +teardown %.2f ms | alloc %llu calls (%llu misses) %.1f MB %.2f ms\n",
+                t_run, t_root, t_all, (unsigned long long)g_alloc_calls, (unsigned long long)g_alloc_misses, g_alloc_bytes / 1e6, g_alloc_ns / 1e6);
+    }
     return res;
 }
 
@@ -734,6 +842,8 @@ int guarded(rj_ctx* ctx, F f) {
     if (!ctx) return 1;
     try {
         cudaSetDevice(ctx->device);
+        t_home_stream = ctx->stream;
+        t_device = ctx->device;
         f();
         return 0;
     } catch (const std::exception& e) {
@@ -772,11 +882,18 @@ int rj_ctx_create(int device, rj_ctx** out) {
         ctx->device = device;
         ctx->sm_count = prop.multiProcessorCount;
         RJ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        // keep freed blocks in the pool: no cudaMalloc inside execute() after warm-up
-        cudaMemPool_t pool;
-        RJ_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t threshold = UINT64_MAX;
-        RJ_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        if (device >= 64) throw EngineError("device index out of range");
+        g_live_contexts[device].fetch_add(1);
+        // Row-id gathers (late materialisation) read 4-8 useful bytes per random access.  ncu showed
+        // ~117 B of DRAM traffic per gathered row with the default L2 fetch granularity (a whole 128 B
+        // line per miss); 32 B sectors are what a random gather needs.  Coalesced kernels request every
+        // sector anyway, so the hint costs them nothing.
+        {
+            size_t gran = 32;
+            if (const char* e = getenv("RJ_L2_FETCH")) gran = static_cast<size_t>(atoi(e));
+            if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+            cudaGetLastError();
+        }
         unsigned hc = std::thread::hardware_concurrency();
         ctx->host_threads = hc ? static_cast<int>(std::min(hc, 32u)) : 8;
         *out = ctx.release();
@@ -798,11 +915,14 @@ void rj_ctx_destroy(rj_ctx* ctx) {
         if (ctx->pinned_ev[i]) cudaEventDestroy(ctx->pinned_ev[i]);
     }
     cudaStreamDestroy(ctx->stream);
+    if (g_live_contexts[ctx->device].fetch_sub(1) == 1) g_cache[ctx->device].trim(); // last context: release HBM
     delete ctx;
 }
 
 const char* rj_last_error(const rj_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 int rj_ctx_device(const rj_ctx* ctx) { return ctx->device; }
+void* rj_ctx_stream(const rj_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+uint64_t rj_kernel_launch_count(void) { return g_kernel_launches.load(); }
 int rj_ctx_sm_count(const rj_ctx* ctx) { return ctx->sm_count; }
 int rj_ctx_set_host_threads(rj_ctx* ctx, int n) {
     if (!ctx || n < 1) return 1;
@@ -885,8 +1005,14 @@ int rj_result_fetch(rj_ctx* ctx, const rj_result* r, uint32_t col, void* const* 
         const ResultColumn& rc = r->cols[col];
         if (rc.n_pages == 0) return;
         if (!dst_pages && !dst_contiguous) throw EngineError("no destination pages");
-        ensure_pinned(ctx);
         StageScope scope(ctx, RJ_ST_D2H, ctx->stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
+        if (!dst_pages) {
+            // contiguous destination: one DMA into the caller's buffer
+            RJ_CUDA(cudaMemcpyAsync(dst_contiguous, rc.pages->p, rc.n_pages * size_t(RJ_PAGE_SIZE), cudaMemcpyDeviceToHost, ctx->stream));
+            RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+            return;
+        }
+        ensure_pinned(ctx);
         const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
         // two-slot ring: the D2H copy of chunk k+1 overlaps the host scatter of chunk k
         auto issue = [&](uint64_t p0, int slot) {

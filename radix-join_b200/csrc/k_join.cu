@@ -7,10 +7,14 @@
 //           (keys[] + row ids[], the row id doubles as the occupancy flag).  Duplicate keys simply take
 //           separate slots; the probe walks the cluster until an empty slot and emits every equal key,
 //           which yields the reference's "one row per duplicate" semantics (tests/unit_tests.cpp:125-161).
-//   probe : the probe chunk is streamed from global memory (coalesced, software-prefetched), every
-//           thread looks its key up in the table and stages (build row, probe row) pairs in a
-//           shared-memory buffer through warp-aggregated slot reservation; full buffers are flushed
-//           with one global atomic per flush and coalesced stores.
+//           All global loads of the chunk are issued before the first insert (12 per thread in flight).
+//   probe : the probe chunk is streamed in super-batches of 8 tuples per thread (4096 per CTA): the 16
+//           loads of the NEXT super-batch are in flight while the current one is probed, so the kernel is
+//           bound by bandwidth, not by load latency.  Matches are staged as (build row, probe row) pairs
+//           in shared memory through warp-aggregated slot reservation; the buffer is flushed once per
+//           super-batch with ONE global atomic and coalesced stores (one block barrier per 4096 probes).
+//           A thread that finds the staging buffer full remembers where it stopped and resumes after the
+//           flush, so any number of duplicates per probe tuple is handled.
 // Partitions whose build side exceeds one table are processed as several build chunks against the
 // same probe tuples (the union of the chunk joins is the join) -- the overflow path.
 // The slot hash uses the hash bits ABOVE the ones consumed by partitioning, so tuples of one
@@ -24,6 +28,12 @@ namespace {
 constexpr int      kJoinThreads = 512;
 constexpr uint32_t kOutCap      = 4096;        // staged pairs per CTA
 constexpr uint32_t kEmpty       = 0xffffffffu; // row ids are < 2^32 - 1
+constexpr int      kBuildItems  = kJoinBuildCap / kJoinThreads; // 12
+
+template <typename K>
+struct JoinCfg {
+    static constexpr int kProbeItems = sizeof(K) == 4 ? 8 : 4; // tuples per thread per super-batch
+};
 
 struct JoinArgs {
     const void*     bkeys;
@@ -45,6 +55,8 @@ struct JoinArgs {
 
 template <typename K>
 __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
+    constexpr int      kItems = JoinCfg<K>::kProbeItems;
+    constexpr uint32_t kBatch = kItems * kJoinThreads;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     K*        s_keys  = reinterpret_cast<K*>(smem_raw);
     uint32_t* s_rows  = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kJoinSlots);
@@ -60,6 +72,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
     const uint32_t lt   = lanemask_lt();
     const uint32_t n_units = a.unit_start[a.nparts];
     const bool     do_write = a.out_b != nullptr;
+    const int      part_bits = a.part_bits;
 
     if (threadIdx.x == 0) s_out_n = 0;
 
@@ -81,68 +94,117 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
         const uint32_t ps = p_lo + pc * kJoinProbeChunk;
         const uint32_t pe = (p_hi - ps > kJoinProbeChunk) ? ps + kJoinProbeChunk : p_hi;
 
-        // ---- build -----------------------------------------------------------------------------------
-        __syncthreads(); // previous unit is done with the table
-        for (uint32_t s = threadIdx.x; s < kJoinSlots; s += kJoinThreads) s_rows[s] = kEmpty;
-        __syncthreads();
-        for (uint32_t i = bs + threadIdx.x; i < be; i += kJoinThreads) {
-            if (a.bvalid != nullptr && !test_bit(a.bvalid, i)) continue;
-            const K        key = bkeys[i];
-            const uint32_t row = a.bidx != nullptr ? a.bidx[i] : i;
-            uint32_t slot = (hash_key(key) >> a.part_bits) & kSlotMask;
-            while (atomicCAS(&s_rows[slot], kEmpty, row) != kEmpty) slot = (slot + 1) & kSlotMask;
-            s_keys[slot] = key;
+        // first probe super-batch: issue its loads before anything else so they overlap the build
+        K        nkey[kItems];
+        uint32_t nrow[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const uint32_t i = ps + k * kJoinThreads + threadIdx.x;
+            nkey[k] = K(0);
+            nrow[k] = kEmpty; // kEmpty = no tuple / NULL key
+            if (i < pe && (a.pvalid == nullptr || test_bit(a.pvalid, i))) {
+                nkey[k] = pkeys[i];
+                nrow[k] = a.pidx != nullptr ? a.pidx[i] : i;
+            }
         }
-        __syncthreads();
+
+        // ---- build -----------------------------------------------------------------------------------
+        {
+            K        bkey[kBuildItems];
+            uint32_t brow[kBuildItems];
+#pragma unroll
+            for (int k = 0; k < kBuildItems; ++k) {
+                const uint32_t i = bs + k * kJoinThreads + threadIdx.x;
+                bkey[k] = K(0);
+                brow[k] = kEmpty;
+                if (i < be && (a.bvalid == nullptr || test_bit(a.bvalid, i))) {
+                    bkey[k] = bkeys[i];
+                    brow[k] = a.bidx != nullptr ? a.bidx[i] : i;
+                }
+            }
+            __syncthreads(); // previous unit is done with the table
+            for (uint32_t s = threadIdx.x; s < kJoinSlots; s += kJoinThreads) s_rows[s] = kEmpty;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kBuildItems; ++k) {
+                if (brow[k] != kEmpty) {
+                    uint32_t slot = (hash_key(bkey[k]) >> part_bits) & kSlotMask;
+                    while (atomicCAS(&s_rows[slot], kEmpty, brow[k]) != kEmpty) slot = (slot + 1) & kSlotMask;
+                    s_keys[slot] = bkey[k];
+                }
+                __syncwarp(); // keep the warp converged from one insert to the next
+            }
+            __syncthreads();
+        }
 
         // ---- probe -----------------------------------------------------------------------------------
-        // software prefetch: the tuple of the next batch is loaded before the current one is probed
-        uint32_t i_next = ps + threadIdx.x;
-        K        key_next = K(0);
-        uint32_t row_next = 0;
-        bool     ok_next  = false;
-        if (i_next < pe) {
-            ok_next = a.pvalid == nullptr || test_bit(a.pvalid, i_next);
-            key_next = pkeys[i_next];
-            row_next = a.pidx != nullptr ? a.pidx[i_next] : i_next;
-        }
-        for (uint32_t base = ps; base < pe; base += kJoinThreads) {
-            const K        key = key_next;
-            const uint32_t row = row_next;
-            bool           pending = ok_next;
-            i_next = base + kJoinThreads + threadIdx.x;
-            ok_next = false;
-            if (i_next < pe) {
-                ok_next = a.pvalid == nullptr || test_bit(a.pvalid, i_next);
-                key_next = pkeys[i_next];
-                row_next = a.pidx != nullptr ? a.pidx[i_next] : i_next;
+        for (uint32_t base = ps; base < pe; base += kBatch) {
+            K        key[kItems];
+            uint32_t row[kItems];
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                key[k] = nkey[k];
+                row[k] = nrow[k];
             }
-            uint32_t slot = (hash_key(key) >> a.part_bits) & kSlotMask;
-            for (;;) {
-                // walk the cluster; suspend when the staging buffer is full
-                while (pending) {
-                    const uint32_t brow = s_rows[slot];
-                    if (brow == kEmpty) {
-                        pending = false;
-                        break;
-                    }
-                    if (s_keys[slot] == key) {
-                        // warp-aggregated reservation among the lanes that found a match right now
-                        const uint32_t active = __activemask();
-                        const uint32_t leader = __ffs(active) - 1;
-                        uint32_t       pos = 0;
-                        if (lane == leader) pos = atomicAdd(&s_out_n, static_cast<uint32_t>(__popc(active)));
-                        pos = __shfl_sync(active, pos, leader) + __popc(active & lt);
-                        if (pos >= kOutCap) break; // retry this slot after the flush
-                        s_out_b[pos] = brow;
-                        s_out_p[pos] = row;
-                    }
-                    slot = (slot + 1) & kSlotMask;
+            // loads of the next super-batch
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                const uint32_t i = base + kBatch + k * kJoinThreads + threadIdx.x;
+                nkey[k] = K(0);
+                nrow[k] = kEmpty;
+                if (i < pe && (a.pvalid == nullptr || test_bit(a.pvalid, i))) {
+                    nkey[k] = pkeys[i];
+                    nrow[k] = a.pidx != nullptr ? a.pidx[i] : i;
                 }
-                const int any_pending = __syncthreads_or(pending ? 1 : 0);
+            }
+            int      item = 0;           // first item of this thread that is not finished
+            uint32_t slot = 0xffffffffu; // its current slot (0xffffffff = start at the home slot)
+            for (;;) {
+                bool stalled = false;
+                // Items are walked in LOCKSTEP by the warp: the loop is fully unrolled (static register
+                // indices) and every item ends in __syncwarp(), so lanes whose cluster walk is short wait
+                // for the others instead of running ahead into the next item -- without it the warp
+                // splits into 32 independent instruction streams (measured: 3 active threads / instr).
+#pragma unroll
+                for (int k = 0; k < kItems; ++k) {
+                    if (k >= item && !stalled && row[k] != kEmpty) {
+                        const K mykey = key[k];
+                        if (slot == 0xffffffffu) slot = (hash_key(mykey) >> part_bits) & kSlotMask;
+                        for (;;) {
+                            const uint32_t brow = s_rows[slot];
+                            if (brow == kEmpty) break;
+                            if (s_keys[slot] == mykey) {
+                                // warp-aggregated reservation among the lanes that found a match right now
+                                const uint32_t active = __activemask();
+                                const uint32_t leader = __ffs(active) - 1;
+                                uint32_t       pos = 0;
+                                if (lane == leader) pos = atomicAdd(&s_out_n, static_cast<uint32_t>(__popc(active)));
+                                pos = __shfl_sync(active, pos, leader) + __popc(active & lt);
+                                if (pos >= kOutCap) {
+                                    stalled = true; // staging buffer full: resume at this slot after the flush
+                                    break;
+                                }
+                                s_out_b[pos] = brow;
+                                s_out_p[pos] = row[k];
+                            }
+                            slot = (slot + 1) & kSlotMask;
+                        }
+                        if (stalled) {
+                            item = k;
+                        } else {
+                            item = k + 1;
+                            slot = 0xffffffffu;
+                        }
+                    } else if (k >= item && !stalled) {
+                        item = k + 1; // no tuple / NULL key
+                    }
+                    __syncwarp();
+                }
+                const int any_stalled = __syncthreads_or(stalled ? 1 : 0);
                 const uint32_t staged = s_out_n < kOutCap ? s_out_n : kOutCap;
-                const bool last_batch = base + kJoinThreads >= pe;
-                if (any_pending || last_batch || staged + kJoinThreads > kOutCap) {
+                const bool last_batch = base + kBatch >= pe;
+                // the next super-batch can add up to kBatch pairs without stalling only if there is room
+                if (any_stalled || last_batch || staged + kBatch > kOutCap) {
                     // ---- flush: one global atomic, coalesced stores ---------------------------------
                     if (threadIdx.x == 0) s_flush_base = atomicAdd(a.out_count, static_cast<unsigned long long>(staged));
                     __syncthreads();
@@ -157,7 +219,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                     if (threadIdx.x == 0) s_out_n = 0;
                     __syncthreads();
                 }
-                if (!any_pending) break;
+                if (!any_stalled) break;
             }
         }
     }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -26,7 +27,13 @@ struct CudaError: std::runtime_error {
         }                                                                                          \
     } while (0)
 
-#define RJ_LAUNCH_CHECK() RJ_CUDA(cudaGetLastError())
+// every kernel launch of the engine goes through this macro; the counter backs rj_kernel_launch_count()
+extern std::atomic<uint64_t> g_kernel_launches;
+#define RJ_LAUNCH_CHECK()                                  \
+    do {                                                   \
+        ::rj::g_kernel_launches.fetch_add(1, std::memory_order_relaxed); \
+        RJ_CUDA(cudaGetLastError());                       \
+    } while (0)
 
 // ---- join geometry (shared by the partition planner and the join kernel) ---------------------------
 constexpr uint32_t kJoinSlots      = 8192;  // shared-memory hash table slots per CTA

@@ -44,6 +44,14 @@ class Context:
     def sm_count(self):
         return self.lib.rj_ctx_sm_count(self.handle)
 
+    @property
+    def stream(self):
+        """the cudaStream_t (as an int) all whole-path calls run on"""
+        return int(self.lib.rj_ctx_stream(self.handle) or 0)
+
+    def kernel_launches(self):
+        return int(self.lib.rj_kernel_launch_count())
+
     # ---- profiling -------------------------------------------------------------------------------
     def profile_enable(self, on=True):
         self.check(self.lib.rj_profile_enable(self.handle, 1 if on else 0))
