@@ -884,16 +884,6 @@ int rj_ctx_create(int device, rj_ctx** out) {
         RJ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         if (device >= 64) throw EngineError("device index out of range");
         g_live_contexts[device].fetch_add(1);
-        // Row-id gathers (late materialisation) read 4-8 useful bytes per random access.  ncu showed
-        // ~117 B of DRAM traffic per gathered row with the default L2 fetch granularity (a whole 128 B
-        // line per miss); 32 B sectors are what a random gather needs.  Coalesced kernels request every
-        // sector anyway, so the hint costs them nothing.
-        {
-            size_t gran = 32;
-            if (const char* e = getenv("RJ_L2_FETCH")) gran = static_cast<size_t>(atoi(e));
-            if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-            cudaGetLastError();
-        }
         unsigned hc = std::thread::hardware_concurrency();
         ctx->host_threads = hc ? static_cast<int>(std::min(hc, 32u)) : 8;
         *out = ctx.release();

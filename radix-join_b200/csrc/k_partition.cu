@@ -31,15 +31,15 @@ struct ScatterCfg {
 constexpr int kPlanThreads    = 1024;
 
 template <typename K>
-__global__ void __launch_bounds__(kHistThreads)
+__global__ void __launch_bounds__(1024)
     radix_hist_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid, uint64_t n, int shift,
                       int bits, uint32_t* __restrict__ hist) {
     extern __shared__ uint32_t s_hist[];
     const uint32_t nb = 1u << bits, mask = nb - 1;
-    for (uint32_t b = threadIdx.x; b < nb; b += kHistThreads) s_hist[b] = 0;
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) s_hist[b] = 0;
     __syncthreads();
-    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kHistThreads;
-    uint64_t i = static_cast<uint64_t>(blockIdx.x) * kHistThreads + threadIdx.x;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     // 4 independent loads in flight per thread
     for (; i + 3 * stride < n; i += 4 * stride) {
         K k0 = keys[i], k1 = keys[i + stride], k2 = keys[i + 2 * stride], k3 = keys[i + 3 * stride];
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kHistThreads)
         if (!valid || test_bit(valid, i)) atomicAdd(&s_hist[(hash_key(keys[i]) >> shift) & mask], 1u);
     }
     __syncthreads();
-    for (uint32_t b = threadIdx.x; b < nb; b += kHistThreads) {
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
         uint32_t c = s_hist[b];
         if (c) atomicAdd(&hist[b], c);
     }
@@ -333,8 +333,11 @@ void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n,
                             uint32_t* hist, int sm_count, cudaStream_t s) {
     if (n == 0) return;
     const size_t smem = sizeof(uint32_t) << bits;
-    uint64_t want = (n + kHistThreads * 8 - 1) / (kHistThreads * 8);
-    unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 4 ? want : static_cast<uint64_t>(sm_count) * 4);
+    // a 2^15-bin histogram is 128 KB of shared memory: one CTA per SM, so give it 1024 threads
+    const unsigned threads = smem > 48 * 1024 ? 1024 : kHistThreads;
+    const unsigned per_sm  = smem > 96 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+    uint64_t want = (n + threads * 8 - 1) / (threads * 8);
+    unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * per_sm ? want : static_cast<uint64_t>(sm_count) * per_sm);
     if (blocks == 0) blocks = 1;
     if (key_bytes == 4) {
         static size_t configured = 0;
@@ -342,14 +345,14 @@ void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n,
             RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        radix_hist_kernel<uint32_t><<<blocks, kHistThreads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, n, shift, bits, hist);
+        radix_hist_kernel<uint32_t><<<blocks, threads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, n, shift, bits, hist);
     } else {
         static size_t configured = 0;
         if (smem > configured) {
             RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        radix_hist_kernel<uint64_t><<<blocks, kHistThreads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, n, shift, bits, hist);
+        radix_hist_kernel<uint64_t><<<blocks, threads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, n, shift, bits, hist);
     }
     RJ_LAUNCH_CHECK();
 }

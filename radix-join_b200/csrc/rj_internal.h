@@ -38,7 +38,7 @@ extern std::atomic<uint64_t> g_kernel_launches;
 // ---- join geometry (shared by the partition planner and the join kernel) ---------------------------
 constexpr uint32_t kJoinSlots      = 8192;  // shared-memory hash table slots per CTA
 constexpr uint32_t kJoinBuildCap   = 6144;  // build tuples per table (75 % fill); larger partitions are chunked
-constexpr uint32_t kJoinTargetFill = 4096;  // partition fan-out aims at <= this many build tuples on average
+constexpr uint32_t kJoinTargetFill = 2048;  // partition fan-out aims at <= this many build tuples on average (25 % fill)
 constexpr uint32_t kJoinProbeChunk = 16384; // probe tuples per work unit
 // tuples per scatter tile: 512 threads x 16 (4-byte keys) or x 8 (8-byte keys)
 constexpr uint32_t scatter_tile(int key_bytes) { return key_bytes == 4 ? 8192u : 4096u; }
