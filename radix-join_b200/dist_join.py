@@ -1,0 +1,216 @@
+"""Multi-GPU single join: shard -> radix exchange -> local join.
+
+One process per GPU (torch.distributed: NCCL on GPUs, gloo in the CPU tests).  Every rank holds a
+contiguous 1/G slice of the rows of both relations.  Ownership of a tuple is decided by the TOP
+log2(G) bits of the same 32-bit radix hash the single-GPU engine partitions on (the local partitioner
+uses the LOW bits, so the two never interfere):
+
+    1. decode the local pages                         (rj_page_row_offsets, rj_decode_fixed)
+    2. histogram + scatter of (key, row) by owner     (rj_radix_histogram / rj_radix_scatter, shift = 32 - g)
+       and gather of the payload columns in that order (rj_gather)      -- NULL keys are dropped here
+    3. exchange: G x G count matrix, then all-to-all-v of keys / payloads / validity over NVLink
+    4. local join of what was received                (rj_join_keys: partition -> build/probe in smem)
+    5. gather + page encode of the output columns     (rj_encode_fixed)
+
+The payloads travel with the tuples (early materialisation across the exchange), so step 5 only
+touches local memory.  The result of the job is the concatenation of the ranks' page lists: a
+ColumnarTable is just per-column page lists (reference include/plan.h:60-62,102-105).
+
+`ops` abstracts the device work: `CudaOps` binds the engine's C-ABI stage entry points; the CPU tests
+inject a numpy stand-in (tests/test_dist_gloo.py) to exercise the sharding / exchange logic with gloo.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+INT32, INT64, FP64 = 0, 1, 2
+
+
+def log2_exact(n):
+    g = n.bit_length() - 1
+    if n < 1 or (1 << g) != n:
+        raise ValueError("world size must be a power of two (ownership = top hash bits)")
+    return g
+
+
+class CudaOps:
+    """Stage entry points of librj_b200.so on torch CUDA tensors (device memory plumbing only)."""
+
+    def __init__(self, ctx):
+        self.ctx, self.lib, self.h = ctx, ctx.lib, ctx.handle
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def sync(self):
+        torch.cuda.synchronize()
+
+    def empty(self, n, dtype):
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]
+
+    def zeros(self, n, dtype):
+        return torch.zeros(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def decode_fixed(self, pages_ptr, n_pages, type_, n_rows, want_valid):
+        """-> (values tensor, validity bitmap words or None)"""
+        self.sync()  # inputs may come from torch / NCCL streams
+        start = self.empty(n_pages + 1, torch.int64)
+        self.ctx.check(self.lib.rj_page_row_offsets(self.h, pages_ptr, n_pages, type_, self._p(start), None, None))
+        values = self.empty(n_rows, torch.int32 if type_ == INT32 else torch.int64)
+        valid = self.zeros((n_rows + 31) // 32 + 1, torch.int32) if want_valid else None
+        self.ctx.check(self.lib.rj_decode_fixed(self.h, pages_ptr, n_pages, type_, self._p(start), self._p(values),
+                                                self._p(valid), None))
+        self.sync()
+        return values, valid
+
+    def owner_partition(self, keys, valid, g):
+        """group (key, row) by owner rank = top g hash bits -> (keys_out, rows_out, counts[G] on host)"""
+        self.sync()  # inputs may come from torch / NCCL streams
+        n, G = keys.numel(), 1 << g
+        hist = self.zeros(G, torch.int32)
+        if g == 0:
+            raise ValueError("owner_partition needs world > 1")
+        self.ctx.check(self.lib.rj_radix_histogram(self.h, self._p(keys), self._p(valid), n, 4, 32 - g, g, self._p(hist), None))
+        self.sync()
+        counts = hist.cpu().to(torch.int64)
+        cursor = (torch.cumsum(counts, 0) - counts).to(torch.int32).to(self.device)
+        total = int(counts.sum())
+        keys_out, rows_out = self.empty(n, torch.int32), self.empty(n, torch.int32)
+        self.ctx.check(self.lib.rj_radix_scatter(self.h, self._p(keys), self._p(valid), None, n, 4, 32 - g, g,
+                                                 self._p(cursor), self._p(keys_out), self._p(rows_out), None))
+        self.sync()
+        return keys_out[:total], rows_out[:total], counts
+
+    def gather(self, values, valid, rows):
+        """values[rows], valid bits -> (gathered values, uint8 validity per row or None)"""
+        self.sync()  # inputs may come from torch / NCCL streams
+        n = rows.numel()
+        out = self.empty(n, values.dtype)
+        out_valid = self.zeros((n + 31) // 32 + 1, torch.int32) if valid is not None else None
+        self.ctx.check(self.lib.rj_gather(self.h, self._p(values), self._p(valid), self._p(rows), n,
+                                          values.element_size(), self._p(out), self._p(out_valid), None))
+        self.sync()
+        if out_valid is None:
+            return out, None
+        return out, unpack_bits(out_valid, n)
+
+    def join_keys(self, build_keys, probe_keys):
+        self.sync()  # inputs may come from torch / NCCL streams
+        nb, np_ = build_keys.numel(), probe_keys.numel()
+        cap = max(nb, np_, 1)
+        m = C.c_uint64()
+        for _ in range(2):
+            ob, op = self.empty(cap, torch.int32), self.empty(cap, torch.int32)
+            self.ctx.check(self.lib.rj_join_keys(self.h, self._p(build_keys), None, nb, self._p(probe_keys), None, np_, 4,
+                                                 cap, self._p(ob), self._p(op), C.byref(m), None))
+            if m.value <= cap:
+                break
+            cap = m.value
+        return ob[:m.value], op[:m.value]
+
+    def encode_fixed(self, values, valid_bytes, rows, type_):
+        """-> device tensor of pages (uint8, n_pages * 8192)"""
+        n = rows.numel()
+        rpp = self.lib.rj_fixed_rows_per_page(type_)
+        n_pages = (n + rpp - 1) // rpp
+        pages = self.empty(n_pages * 8192, torch.uint8)
+        valid = pack_bits(valid_bytes) if valid_bytes is not None else None
+        self.sync()
+        self.ctx.check(self.lib.rj_encode_fixed(self.h, self._p(values), self._p(valid), self._p(rows), n, type_,
+                                                self._p(pages), None))
+        self.sync()
+        return pages, n_pages
+
+
+def unpack_bits(words, n):
+    """uint32 bitmap words (int32 tensor) -> uint8[n]"""
+    shifts = torch.arange(32, device=words.device, dtype=torch.int32)
+    bits = (words.view(-1, 1) >> shifts) & 1
+    return bits.to(torch.uint8).view(-1)[:n].contiguous()
+
+
+def pack_bits(valid_bytes):
+    """uint8[n] -> uint32 bitmap words (int32 tensor, one spare word)"""
+    n = valid_bytes.numel()
+    pad = (-n) % 32
+    v = valid_bytes
+    if pad:
+        v = torch.cat([v, torch.zeros(pad, dtype=v.dtype, device=v.device)])
+    w = (v.view(-1, 32).to(torch.int64) << torch.arange(32, device=v.device, dtype=torch.int64)).sum(dim=1)
+    w = torch.where(w >= (1 << 31), w - (1 << 32), w).to(torch.int32)
+    return torch.cat([w, torch.zeros(1, dtype=torch.int32, device=v.device)])
+
+
+def all_to_all_v(tensor, send_counts, recv_counts, group=None):
+    """variable-size all-to-all of a 1-D tensor grouped by destination rank"""
+    out = torch.empty(int(sum(recv_counts)), dtype=tensor.dtype, device=tensor.device)
+    dist.all_to_all_single(out, tensor.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
+                           input_split_sizes=[int(c) for c in send_counts], group=group)
+    return out
+
+
+def exchange_counts(counts, group=None):
+    """counts[d] = tuples this rank sends to rank d  ->  recv[s] = tuples rank s sends to this rank"""
+    world = dist.get_world_size(group)
+    device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    send = counts.to(torch.int64).to(device)
+    recv = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.cpu()
+
+
+class Relation:
+    """one rank's slice of a relation: a key column and payload columns, as device pages"""
+
+    def __init__(self, n_rows, key, payloads):
+        # key / payloads: (pages_ptr, n_pages, type, has_nulls)
+        self.n_rows, self.key, self.payloads = n_rows, key, payloads
+
+
+def shuffle_relation(ops, rel, g, group=None):
+    """steps 1-3 for one relation: returns (keys, [payload values], [payload validity bytes or None])
+    of the tuples this rank OWNS, plus the bytes it sent"""
+    kp, kn, kt, knull = rel.key
+    keys, kvalid = ops.decode_fixed(kp, kn, kt, rel.n_rows, knull)
+    keys_o, rows_o, counts = ops.owner_partition(keys, kvalid, g)
+    recv = exchange_counts(counts, group)
+    sent_bytes = 0
+    out_keys = all_to_all_v(keys_o, counts, recv, group)
+    sent_bytes += keys_o.numel() * 4
+    vals, valids = [], []
+    for (pp, pn, pt, pnull) in rel.payloads:
+        v, vv = ops.decode_fixed(pp, pn, pt, rel.n_rows, pnull)
+        gv, gvalid = ops.gather(v, vv, rows_o)
+        vals.append(all_to_all_v(gv, counts, recv, group))
+        sent_bytes += gv.numel() * gv.element_size()
+        if gvalid is not None:
+            valids.append(all_to_all_v(gvalid, counts, recv, group))
+            sent_bytes += gvalid.numel()
+        else:
+            valids.append(None)
+    return out_keys, vals, valids, sent_bytes
+
+
+def distributed_join(ops, build, probe, out_cols, group=None):
+    """Inner equi-join of two sharded relations.  out_cols: list of ("b"|"p", "key"|payload index, type).
+    Returns (n_rows, [(pages tensor, n_pages, type)], stats) for THIS rank's share of the result."""
+    world = dist.get_world_size(group)
+    g = log2_exact(world)
+    bk, bvals, bvalids, sent_b = shuffle_relation(ops, build, g, group)
+    pk, pvals, pvalids, sent_p = shuffle_relation(ops, probe, g, group)
+    ob, op = ops.join_keys(bk, pk)
+    cols = []
+    for side, which, type_ in out_cols:
+        rows = ob if side == "b" else op
+        if which == "key":
+            values, valid = (bk if side == "b" else pk), None
+        else:
+            values = (bvals if side == "b" else pvals)[which]
+            valid = (bvalids if side == "b" else pvalids)[which]
+        pages, n_pages = ops.encode_fixed(values, valid, rows, type_)
+        cols.append((pages, n_pages, type_))
+    stats = {"sent_bytes": sent_b + sent_p, "owned_build": int(bk.numel()), "owned_probe": int(pk.numel())}
+    return int(ob.numel()), cols, stats

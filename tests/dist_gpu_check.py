@@ -1,0 +1,61 @@
+"""Multi-GPU parity check, run under torchrun on a GPU box (not collected by pytest):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py
+Every rank joins its shard of a scaled config 2 through radix_join_b200.dist_join (CUDA ops + NCCL);
+rank 0 appends the ranks' result pages and compares the multiset of rows with the single-GPU engine
+AND the CPU oracle on the unsharded tables."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import radix_join_b200 as rj  # noqa: E402
+from radix_join_b200 import dist_bench, dist_join as dj, synthetic as syn  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_b, n_p = 1 << 19, 1 << 22
+    ctx = rj.build_context(local)
+    dt = syn.make_c2_device(ctx, n_b, n_p, rank=rank, world=world)
+    build, probe = dist_bench._relations(dt)
+    rows, cols, stats = dj.distributed_join(dj.CudaOps(ctx), build, probe, dist_bench.OUT_COLS)
+    outdir = os.environ.get("RJ_CHECK_DIR", "/tmp/rj_dist_check")
+    os.makedirs(outdir, exist_ok=True)
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c[0].cpu().numpy() for i, c in enumerate(cols)})
+    dist.barrier()
+    ok = True
+    if rank == 0:
+        from oracle import pyoracle as orc
+        parts = [np.load(os.path.join(outdir, f"rank{r}.npz")) for r in range(world)]
+        total = int(sum(p["rows"] for p in parts))
+        types = [0, 1, 2]
+        got = rj.ColumnarTable(num_rows=total, columns=[
+            rj.Column(t, np.concatenate([p[f"c{i}"].reshape(-1, 8192) for p in parts])) for i, t in enumerate(types)])
+        full = syn.make_c2_device(ctx, n_b, n_p)
+        inputs = rj.adopt_device(full.plan, full.device_pages, ctx, keep=full.keep)
+        res = rj.execute_resident(full.plan, inputs, ctx)
+        single = res.to_columnar()
+        res.free()
+        host_plan, _keep = syn.to_host_plan(full, pinned=False)
+        want = orc.execute(host_plan, impl="port")
+        ok = total == n_p == single.num_rows == want.num_rows
+        ok = ok and orc.result_equal(got, single) and orc.result_equal(single, want)
+        print(f"dist parity ({world} GPUs): rows {total}, sent/rank {stats['sent_bytes']} B ->", "OK" if ok else "MISMATCH", flush=True)
+        inputs.free()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    rj.destroy_context(ctx)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()
