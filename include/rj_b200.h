@@ -196,6 +196,11 @@ int rj_join_keys(rj_ctx* ctx, const void* d_build_keys, const uint32_t* d_build_
 int rj_gather(rj_ctx* ctx, const void* d_src, const uint32_t* d_src_valid, const uint32_t* d_idx,
               uint64_t n, int32_t elem_bytes, void* d_out, uint32_t* d_out_valid, void* stream);
 
+/* validity bitmap (bit i of word i/32) <-> one byte per row: the byte form is what travels through
+ * an all-to-all-v, whose segments are not word aligned.  d_bits of rj_bytes_to_bitmap: (n+31)/32 words. */
+int rj_bitmap_to_bytes(rj_ctx* ctx, const uint32_t* d_bits, uint64_t n, uint8_t* d_bytes, void* stream);
+int rj_bytes_to_bitmap(rj_ctx* ctx, const uint8_t* d_bytes, uint64_t n, uint32_t* d_bits, void* stream);
+
 /* -- page output: replaces Table::to_columnar (src/build_table.cpp:456-681) --------------------- */
 
 /* rows-per-page used by rj_encode_fixed for a type (1984 for INT32, 1007 for INT64/FP64) */

@@ -104,6 +104,8 @@ PROTOTYPES = {
     "rj_join_keys": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _i32, _u64, _vp, _vp,
                                C.POINTER(_u64), _vp]),
     "rj_gather": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),
+    "rj_bitmap_to_bytes": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
+    "rj_bytes_to_bitmap": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "rj_fixed_rows_per_page": (_u32, [_i32]),
     "rj_encode_fixed": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _vp]),
     "rj_encode_varchar_plan": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _u64, _pvp, C.POINTER(_u64), _vp]),

@@ -1113,6 +1113,14 @@ int rj_gather(rj_ctx* ctx, const void* d_src, const uint32_t* d_src_valid, const
     });
 }
 
+int rj_bitmap_to_bytes(rj_ctx* ctx, const uint32_t* d_bits, uint64_t n, uint8_t* d_bytes, void* stream) {
+    return guarded(ctx, [&] { launch_bitmap_to_bytes(d_bits, n, d_bytes, ctx->sm_count, pick_stream(ctx, stream)); });
+}
+
+int rj_bytes_to_bitmap(rj_ctx* ctx, const uint8_t* d_bytes, uint64_t n, uint32_t* d_bits, void* stream) {
+    return guarded(ctx, [&] { launch_bytes_to_bitmap(d_bytes, n, d_bits, ctx->sm_count, pick_stream(ctx, stream)); });
+}
+
 uint32_t rj_fixed_rows_per_page(int32_t type) { return type == RJ_INT32 ? 1984u : 1007u; }
 
 int rj_encode_fixed(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, const uint32_t* d_idx, uint64_t n,

@@ -110,6 +110,24 @@ __global__ void __launch_bounds__(kEncWarps * 32)
     if (lane == 0) tma_store_wait_all<0>();
 }
 
+__global__ void __launch_bounds__(256) bitmap_to_bytes_kernel(const uint32_t* __restrict__ bits, uint64_t n, uint8_t* __restrict__ out) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = test_bit(bits, i) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) bytes_to_bitmap_kernel(const uint8_t* __restrict__ bytes, uint64_t n, uint32_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t gw = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+    const uint64_t n_groups = (n + 31) >> 5;
+    for (uint64_t g = gw; g < n_groups; g += nw) {
+        const uint64_t i = (g << 5) + lane;
+        const uint32_t word = __ballot_sync(RJ_FULL_MASK, i < n && bytes[i] != 0);
+        if (lane == 0) out[g] = word;
+    }
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint64_t n) {
     uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -157,6 +175,22 @@ void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32
         encode_fixed_kernel<uint64_t><<<blocks, kEncWarps * 32, smem, s>>>(
             static_cast<const uint64_t*>(values), valid, idx, n, static_cast<uint8_t*>(pages_out));
     }
+    RJ_LAUNCH_CHECK();
+}
+
+void launch_bitmap_to_bytes(const uint32_t* bits, uint64_t n, uint8_t* out, int sm_count, cudaStream_t s) {
+    if (n == 0) return;
+    uint64_t want = (n + 255) / 256;
+    unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 16 ? want : static_cast<uint64_t>(sm_count) * 16);
+    bitmap_to_bytes_kernel<<<blocks, 256, 0, s>>>(bits, n, out);
+    RJ_LAUNCH_CHECK();
+}
+
+void launch_bytes_to_bitmap(const uint8_t* bytes, uint64_t n, uint32_t* out, int sm_count, cudaStream_t s) {
+    if (n == 0) return;
+    uint64_t want = (n + 255) / 256;
+    unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 16 ? want : static_cast<uint64_t>(sm_count) * 16);
+    bytes_to_bitmap_kernel<<<blocks, 256, 0, s>>>(bytes, n, out);
     RJ_LAUNCH_CHECK();
 }
 

@@ -123,6 +123,8 @@ void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* i
 void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32_t* idx, uint64_t n,
                          int type, void* pages_out, int sm_count, cudaStream_t s);
 void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
+void launch_bitmap_to_bytes(const uint32_t* bits, uint64_t n, uint8_t* out, int sm_count, cudaStream_t s);
+void launch_bytes_to_bitmap(const uint8_t* bytes, uint64_t n, uint32_t* out, int sm_count, cudaStream_t s);
 
 // ---- k_varchar.cu ---------------------------------------------------------------------------------
 struct VarcharLayoutDev {

@@ -20,6 +20,8 @@ ColumnarTable is just per-column page lists (reference include/plan.h:60-62,102-
 inject a numpy stand-in (tests/test_dist_gloo.py) to exercise the sharding / exchange logic with gloo.
 """
 import ctypes as C
+import os
+import time
 
 import torch
 import torch.distributed as dist
@@ -35,14 +37,20 @@ def log2_exact(n):
 
 
 class CudaOps:
-    """Stage entry points of librj_b200.so on torch CUDA tensors (device memory plumbing only)."""
+    """Stage entry points of librj_b200.so on torch CUDA tensors (device memory plumbing only).
+    Every kernel is launched on torch's CURRENT stream, so it is ordered with torch's own ops and with
+    NCCL (which synchronises with the current stream); the host only waits where it needs a count."""
 
     def __init__(self, ctx):
         self.ctx, self.lib, self.h = ctx, ctx.lib, ctx.handle
         self.device = torch.device("cuda", torch.cuda.current_device())
 
+    @property
+    def stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
     def sync(self):
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
 
     def empty(self, n, dtype):
         return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)[:int(n)]
@@ -56,56 +64,51 @@ class CudaOps:
 
     def decode_fixed(self, pages_ptr, n_pages, type_, n_rows, want_valid):
         """-> (values tensor, validity bitmap words or None)"""
-        self.sync()  # inputs may come from torch / NCCL streams
         start = self.empty(n_pages + 1, torch.int64)
-        self.ctx.check(self.lib.rj_page_row_offsets(self.h, pages_ptr, n_pages, type_, self._p(start), None, None))
+        self.ctx.check(self.lib.rj_page_row_offsets(self.h, pages_ptr, n_pages, type_, self._p(start), None, self.stream))
         values = self.empty(n_rows, torch.int32 if type_ == INT32 else torch.int64)
         valid = self.zeros((n_rows + 31) // 32 + 1, torch.int32) if want_valid else None
         self.ctx.check(self.lib.rj_decode_fixed(self.h, pages_ptr, n_pages, type_, self._p(start), self._p(values),
-                                                self._p(valid), None))
-        self.sync()
+                                                self._p(valid), self.stream))
         return values, valid
 
     def owner_partition(self, keys, valid, g):
         """group (key, row) by owner rank = top g hash bits -> (keys_out, rows_out, counts[G] on host)"""
-        self.sync()  # inputs may come from torch / NCCL streams
         n, G = keys.numel(), 1 << g
-        hist = self.zeros(G, torch.int32)
         if g == 0:
             raise ValueError("owner_partition needs world > 1")
-        self.ctx.check(self.lib.rj_radix_histogram(self.h, self._p(keys), self._p(valid), n, 4, 32 - g, g, self._p(hist), None))
-        self.sync()
-        counts = hist.cpu().to(torch.int64)
+        hist = self.zeros(G, torch.int32)
+        self.ctx.check(self.lib.rj_radix_histogram(self.h, self._p(keys), self._p(valid), n, 4, 32 - g, g, self._p(hist), self.stream))
+        counts = hist.cpu().to(torch.int64)  # the one host round trip: the exchange needs the split sizes
         cursor = (torch.cumsum(counts, 0) - counts).to(torch.int32).to(self.device)
         total = int(counts.sum())
         keys_out, rows_out = self.empty(n, torch.int32), self.empty(n, torch.int32)
         self.ctx.check(self.lib.rj_radix_scatter(self.h, self._p(keys), self._p(valid), None, n, 4, 32 - g, g,
-                                                 self._p(cursor), self._p(keys_out), self._p(rows_out), None))
-        self.sync()
+                                                 self._p(cursor), self._p(keys_out), self._p(rows_out), self.stream))
         return keys_out[:total], rows_out[:total], counts
 
     def gather(self, values, valid, rows):
         """values[rows], valid bits -> (gathered values, uint8 validity per row or None)"""
-        self.sync()  # inputs may come from torch / NCCL streams
         n = rows.numel()
         out = self.empty(n, values.dtype)
-        out_valid = self.zeros((n + 31) // 32 + 1, torch.int32) if valid is not None else None
+        out_valid = self.empty((n + 31) // 32 + 1, torch.int32) if valid is not None else None
         self.ctx.check(self.lib.rj_gather(self.h, self._p(values), self._p(valid), self._p(rows), n,
-                                          values.element_size(), self._p(out), self._p(out_valid), None))
-        self.sync()
+                                          values.element_size(), self._p(out), self._p(out_valid), self.stream))
         if out_valid is None:
             return out, None
-        return out, unpack_bits(out_valid, n)
+        as_bytes = self.empty(n, torch.uint8)  # all-to-all-v segments are not word aligned: ship bytes
+        self.ctx.check(self.lib.rj_bitmap_to_bytes(self.h, self._p(out_valid), n, self._p(as_bytes), self.stream))
+        return out, as_bytes
 
     def join_keys(self, build_keys, probe_keys):
-        self.sync()  # inputs may come from torch / NCCL streams
         nb, np_ = build_keys.numel(), probe_keys.numel()
         cap = max(nb, np_, 1)
         m = C.c_uint64()
         for _ in range(2):
             ob, op = self.empty(cap, torch.int32), self.empty(cap, torch.int32)
+            # rj_join_keys orders itself after `stream` and returns once the pairs are written
             self.ctx.check(self.lib.rj_join_keys(self.h, self._p(build_keys), None, nb, self._p(probe_keys), None, np_, 4,
-                                                 cap, self._p(ob), self._p(op), C.byref(m), None))
+                                                 cap, self._p(ob), self._p(op), C.byref(m), self.stream))
             if m.value <= cap:
                 break
             cap = m.value
@@ -117,11 +120,12 @@ class CudaOps:
         rpp = self.lib.rj_fixed_rows_per_page(type_)
         n_pages = (n + rpp - 1) // rpp
         pages = self.empty(n_pages * 8192, torch.uint8)
-        valid = pack_bits(valid_bytes) if valid_bytes is not None else None
-        self.sync()
+        valid = None
+        if valid_bytes is not None:
+            valid = self.empty((valid_bytes.numel() + 31) // 32 + 1, torch.int32)
+            self.ctx.check(self.lib.rj_bytes_to_bitmap(self.h, self._p(valid_bytes), valid_bytes.numel(), self._p(valid), self.stream))
         self.ctx.check(self.lib.rj_encode_fixed(self.h, self._p(values), self._p(valid), self._p(rows), n, type_,
-                                                self._p(pages), None))
-        self.sync()
+                                                self._p(pages), self.stream))
         return pages, n_pages
 
 
@@ -199,9 +203,20 @@ def distributed_join(ops, build, probe, out_cols, group=None):
     Returns (n_rows, [(pages tensor, n_pages, type)], stats) for THIS rank's share of the result."""
     world = dist.get_world_size(group)
     g = log2_exact(world)
+    trace = os.environ.get("RJ_DIST_TRACE") and hasattr(ops, "sync")
+    t = [time.perf_counter()]
+
+    def mark():
+        if trace:
+            ops.sync()
+            t.append(time.perf_counter())
+
     bk, bvals, bvalids, sent_b = shuffle_relation(ops, build, g, group)
+    mark()
     pk, pvals, pvalids, sent_p = shuffle_relation(ops, probe, g, group)
+    mark()
     ob, op = ops.join_keys(bk, pk)
+    mark()
     cols = []
     for side, which, type_ in out_cols:
         rows = ob if side == "b" else op
@@ -212,5 +227,11 @@ def distributed_join(ops, build, probe, out_cols, group=None):
             valid = (bvalids if side == "b" else pvalids)[which]
         pages, n_pages = ops.encode_fixed(values, valid, rows, type_)
         cols.append((pages, n_pages, type_))
+    mark()
     stats = {"sent_bytes": sent_b + sent_p, "owned_build": int(bk.numel()), "owned_probe": int(pk.numel())}
+    if trace:
+        names = ["shuffle_build", "shuffle_probe", "join", "encode"]
+        stats["phase_ms"] = {n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t[:-1], t[1:])}
+        if dist.get_rank(group) == 0:
+            print("[rj dist]", stats["phase_ms"], flush=True)
     return int(ob.numel()), cols, stats

@@ -84,6 +84,12 @@ def _pack_valid_torch(valid_bool):
     return torch.cat([words, torch.zeros(1, dtype=torch.int32, device=v.device)])
 
 
+def _not_null_torch(rows, salt, null_frac):
+    """bool[n]: row is not NULL -- a function of the global row number only"""
+    h = splitmix64_torch(rows * 2 + salt)
+    return ((h >> 11) & 0xFFFFF) >= int(null_frac * (1 << 20))
+
+
 def _finite_double_bits_torch(bits):
     import torch
     exp_all_ones = ((bits >> 52) & 0x7FF) == 0x7FF
@@ -142,9 +148,8 @@ def make_c2_device(ctx, n_build, n_probe, rank=0, world=1, theta=0.75, null_frac
     # ---- R(k, a) ----
     rk = perm[b_lo:b_hi].contiguous()
     ra = splitmix64_torch(rk.to(torch.int64))
-    gv = torch.Generator(device=device)
-    gv.manual_seed(1043 + rank)
-    ra_valid = _pack_valid_torch(torch.rand(b_hi - b_lo, generator=gv, device=device) >= null_frac)
+    # NULLs are a hash of the GLOBAL row number, so every sharding sees the same table
+    ra_valid = _pack_valid_torch(_not_null_torch(torch.arange(b_lo, b_hi, device=device, dtype=torch.int64), 1043, null_frac))
     # ---- S(k, b) ---- generated in chunks keyed by the GLOBAL chunk index so every sharding sees the same table
     zipf = Zipf(n_build, theta)
     chunk = 1 << 24
@@ -159,9 +164,8 @@ def make_c2_device(ctx, n_build, n_probe, rank=0, world=1, theta=0.75, null_frac
         del u, keys
     rows = torch.arange(p_lo, p_hi, device=device, dtype=torch.int64)
     sb = _finite_double_bits_torch(splitmix64_torch(rows))
+    sb_valid = _pack_valid_torch(_not_null_torch(rows, 2044, null_frac))
     del rows
-    gv.manual_seed(2044 + rank)
-    sb_valid = _pack_valid_torch(torch.rand(p_hi - p_lo, generator=gv, device=device) >= null_frac)
     del perm
     tables = []
     for cols in (((rk, None, DataType.INT32), (ra, ra_valid, DataType.INT64)),
