@@ -38,16 +38,19 @@ def log2_exact(n):
 
 class CudaOps:
     """Stage entry points of librj_b200.so on torch CUDA tensors (device memory plumbing only).
-    Every kernel is launched on torch's CURRENT stream, so it is ordered with torch's own ops and with
-    NCCL (which synchronises with the current stream); the host only waits where it needs a count."""
+    Engine kernels, torch ops and NCCL (which synchronises with the current stream) all run on ONE
+    stream, the engine context's; the host only waits where it needs a count."""
 
     def __init__(self, ctx):
         self.ctx, self.lib, self.h = ctx, ctx.lib, ctx.handle
         self.device = torch.device("cuda", torch.cuda.current_device())
+        # one stream for everything: the engine context's stream becomes torch's current stream
+        # (the legacy default stream has handle 0, which the C-ABI reads as "the context stream")
+        torch.cuda.synchronize()
+        self.torch_stream = torch.cuda.ExternalStream(ctx.stream)
+        torch.cuda.set_stream(self.torch_stream)
 
-    @property
-    def stream(self):
-        return torch.cuda.current_stream().cuda_stream
+    stream = None  # C-ABI: NULL = the context stream = torch's current stream (set above)
 
     def sync(self):
         torch.cuda.current_stream().synchronize()
