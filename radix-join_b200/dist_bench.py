@@ -122,5 +122,6 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
-    destroy_context(ctx)
+    ops.close()
     dist.destroy_process_group()
+    destroy_context(ctx)

@@ -52,6 +52,11 @@ class CudaOps:
 
     stream = None  # C-ABI: NULL = the context stream = torch's current stream (set above)
 
+    def close(self):
+        """give torch its default stream back (call before the engine context is destroyed)"""
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.default_stream())
+
     def sync(self):
         torch.cuda.current_stream().synchronize()
 

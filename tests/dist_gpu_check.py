@@ -25,7 +25,8 @@ def main():
     ctx = rj.build_context(local)
     dt = syn.make_c2_device(ctx, n_b, n_p, rank=rank, world=world)
     build, probe = dist_bench._relations(dt)
-    rows, cols, stats = dj.distributed_join(dj.CudaOps(ctx), build, probe, dist_bench.OUT_COLS)
+    ops = dj.CudaOps(ctx)
+    rows, cols, stats = dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS)
     outdir = os.environ.get("RJ_CHECK_DIR", "/tmp/rj_dist_check")
     os.makedirs(outdir, exist_ok=True)
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c[0].cpu().numpy() for i, c in enumerate(cols)})
@@ -52,9 +53,11 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
-    rj.destroy_context(ctx)
+    ok = bool(int(flag))
+    ops.close()
     dist.destroy_process_group()
-    sys.exit(0 if int(flag) else 1)
+    rj.destroy_context(ctx)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
