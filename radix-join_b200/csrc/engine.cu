@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <set>
@@ -383,9 +384,48 @@ struct Attr {
     uint32_t col;
 };
 
+// Row ids of a scan reached through a partitioned join side: rid[i] = rows_of_pos[pos[i]], where
+// `pos` indexes the side's position order (the pass-1 / single-pass scatter output).  Kept lazy: the
+// root encodes carried columns straight from position order and may never need the row ids.
+struct PosSpace {
+    Buf pos;         // [rows]
+    Buf rows_of_pos; // [side rows]
+};
+
+// A column that travelled through the scatter: values_of_pos[pos[i]] is row i's value.
+struct CarriedCol {
+    Buf         hold;              // owner of values_of_pos when it is a scatter output
+    const void* values_of_pos = nullptr;
+    Buf         pos;
+    bool        never_null = false; // a matched join key is never NULL
+};
+
 struct Rel {
-    uint64_t           rows = 0;
-    std::map<int, Buf> rid; // leaf -> row ids into that scan's base table; null Buf = identity
+    uint64_t                rows = 0;
+    mutable std::map<int, Buf> rid;  // leaf -> row ids into that scan's base table; null Buf = identity
+    std::map<int, PosSpace>    lazy; // leaf -> row ids not materialised yet
+    std::map<std::pair<int, uint32_t>, CarriedCol> carried; // (leaf, column) -> values in position order
+    bool has_leaf(int leaf) const { return rid.count(leaf) || lazy.count(leaf); }
+};
+
+// one side of a join as the kernels see it
+struct CarryCol {
+    uint32_t    col = 0;
+    const void* src = nullptr; // decoded values by row
+    int         width = 0;
+    Buf         out;           // values by position (filled by the scatter)
+};
+
+struct JoinSide {
+    const void*     keys = nullptr;
+    const uint32_t* valid = nullptr;
+    uint64_t        n = 0;
+    std::vector<CarryCol> carry; // columns to move with the tuples (only honoured when partitioned)
+    // results
+    bool partitioned = false;
+    Buf  pos;          // [M] position (= row when not partitioned)
+    Buf  rows_of_pos;  // [n]
+    Buf  keys_of_pos;  // [n]
 };
 
 struct Exec {
@@ -420,9 +460,10 @@ struct Exec {
     const DecodedCol& string_hash(uint32_t t, uint32_t c);
     Rel  run(uint64_t n);
     Rel  join(uint64_t n, const Rel& L, const Rel& R);
-    void join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void* pk, const uint32_t* pv, uint64_t np,
-                   int key_bytes, Buf* out_b, Buf* out_p, uint64_t* n_out);
+    void join_keys(JoinSide& b, JoinSide& p, int key_bytes, uint64_t* n_out);
     Buf  gather_u32(const Buf& src, const Buf& idx, uint64_t n);
+    Buf  side_rows(const JoinSide& sd, uint64_t m);
+    Buf  rid_of(const Rel& r, int leaf);
     std::unique_ptr<rj_result> root(uint64_t n, const Rel& r);
     ResultColumn encode_varchar(const DecodedCol& col, const uint32_t* idx, uint64_t n);
 };
@@ -501,8 +542,9 @@ int choose_total_bits(uint64_t n_build) {
     return b;
 }
 
-void Exec::join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void* pk, const uint32_t* pv, uint64_t np,
-                     int key_bytes, Buf* out_b, Buf* out_p, uint64_t* n_out) {
+void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
+    const void* bk = B.keys; const uint32_t* bv = B.valid; const uint64_t nb = B.n;
+    const void* pk = P.keys; const uint32_t* pv = P.valid; const uint64_t np = P.n;
     if (nb >= 0xffffffffull || np >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
     const int      bits  = choose_total_bits(nb);
     const int      bits1 = bits > kMaxPassBits ? (bits + 1) / 2 : 0; // two passes above 8 bits
@@ -513,7 +555,7 @@ void Exec::join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void
     partition_plan_carve(plan_mem->as<uint32_t>(), bits, bits1, &pl);
 
     JoinLaunch jl{};
-    Buf keys_b, idx_b, keys_p, idx_p; // partitioned relations
+    Buf keys_b, idx_b, keys_p, idx_p; // fully partitioned relations
     const uint64_t n_in = nb + np;
     if (bits == 0) {
         launch_partition_plan(nullptr, nullptr, static_cast<uint32_t>(nb), static_cast<uint32_t>(np), 0, 0, key_bytes, pl, s);
@@ -533,24 +575,51 @@ void Exec::join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void
         idx_b  = dev_alloc(nb * 4, s);
         keys_p = dev_alloc(np * key_bytes, s);
         idx_p  = dev_alloc(np * 4, s);
+        auto payload_of = [&](JoinSide& sd) {
+            ScatterPayload pay;
+            for (auto& c: sd.carry) {
+                if (pay.n == ScatterPayload::kMax) break;
+                c.out = dev_alloc(sd.n * c.width, s);
+                pay.src[pay.n] = c.src;
+                pay.dst[pay.n] = c.out->p;
+                pay.width[pay.n] = c.width;
+                ++pay.n;
+            }
+            return pay;
+        };
+        const ScatterPayload pay_b = payload_of(B), pay_p = payload_of(P);
+        uint64_t carried_bytes = 0;
+        for (auto& c: B.carry) if (c.out) carried_bytes += 2 * nb * c.width;
+        for (auto& c: P.carry) if (c.out) carried_bytes += 2 * np * c.width;
         // SURVEY 8d numerator: one-pass scatter = N*w_k read + N*(w_k+4) written, whatever the pass count
-        StageScope sc(ctx, RJ_ST_SCATTER, s, bits1 ? 4 : 2, n_in * (2 * key_bytes + 4));
+        StageScope sc(ctx, RJ_ST_SCATTER, s, bits1 ? 4 : 2, n_in * (2 * key_bytes + 4) + carried_bytes);
+        B.partitioned = P.partitioned = true;
         if (bits1 == 0) {
-            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, 0, bits, pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), ctx->sm_count, s);
-            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, 0, bits, pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), ctx->sm_count, s);
+            // single pass: position order = final partition order
+            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, 0, bits, pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), pay_b, ctx->sm_count, s);
+            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, 0, bits, pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), pay_p, ctx->sm_count, s);
+            jl.bkeys = keys_b->p; jl.bidx = nullptr; jl.bvalid = nullptr; // emit positions
+            jl.pkeys = keys_p->p; jl.pidx = nullptr; jl.pvalid = nullptr;
+            B.rows_of_pos = idx_b; B.keys_of_pos = keys_b;
+            P.rows_of_pos = idx_p; P.keys_of_pos = keys_p;
         } else {
+            // pass 1 (high bits1 of the partition id) defines the position order: row ids, keys and the
+            // carried payloads are written once, in regions of |side| / 2^bits1 tuples.  Pass 2 (low
+            // bits2 inside each region) only moves (key, POSITION in the pass-1 arrays), so everything a
+            // match refers to later lies inside one L2-sized region.
             Buf tk_b = dev_alloc(nb * key_bytes, s), ti_b = dev_alloc(nb * 4, s);
             Buf tk_p = dev_alloc(np * key_bytes, s), ti_p = dev_alloc(np * 4, s);
-            // pass 1: the high `bits1` of the partition id; pass 2: the low `bits2` inside each region
-            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, bits2, bits1, pl.cur1_b, tk_b->p, ti_b->as<uint32_t>(), ctx->sm_count, s);
-            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, bits2, bits1, pl.cur1_p, tk_p->p, ti_p->as<uint32_t>(), ctx->sm_count, s);
-            launch_radix_scatter_regions(tk_b->p, ti_b->as<uint32_t>(), pl.reg_b, pl.tile_b, 1u << bits1, nb, key_bytes, 0, bits2,
+            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, bits2, bits1, pl.cur1_b, tk_b->p, ti_b->as<uint32_t>(), pay_b, ctx->sm_count, s);
+            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, bits2, bits1, pl.cur1_p, tk_p->p, ti_p->as<uint32_t>(), pay_p, ctx->sm_count, s);
+            launch_radix_scatter_regions(tk_b->p, nullptr, pl.reg_b, pl.tile_b, 1u << bits1, nb, key_bytes, 0, bits2,
                                          pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), ctx->sm_count, s);
-            launch_radix_scatter_regions(tk_p->p, ti_p->as<uint32_t>(), pl.reg_p, pl.tile_p, 1u << bits1, np, key_bytes, 0, bits2,
+            launch_radix_scatter_regions(tk_p->p, nullptr, pl.reg_p, pl.tile_p, 1u << bits1, np, key_bytes, 0, bits2,
                                          pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), ctx->sm_count, s);
+            jl.bkeys = keys_b->p; jl.bidx = idx_b->as<uint32_t>(); jl.bvalid = nullptr; // idx = pass-1 position
+            jl.pkeys = keys_p->p; jl.pidx = idx_p->as<uint32_t>(); jl.pvalid = nullptr;
+            B.rows_of_pos = ti_b; B.keys_of_pos = tk_b;
+            P.rows_of_pos = ti_p; P.keys_of_pos = tk_p;
         }
-        jl.bkeys = keys_b->p; jl.bidx = idx_b->as<uint32_t>(); jl.bvalid = nullptr;
-        jl.pkeys = keys_p->p; jl.pidx = idx_p->as<uint32_t>(); jl.pvalid = nullptr;
     }
     jl.off_b = pl.off_b; jl.off_p = pl.off_p; jl.unit_start = pl.unit_start;
     jl.nparts = nparts; jl.part_bits = bits; jl.key_bytes = key_bytes;
@@ -563,10 +632,10 @@ void Exec::join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void
     uint64_t capacity = std::max(nb, np);
     uint64_t matches = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        *out_b = dev_alloc(capacity * 4, s);
-        *out_p = dev_alloc(capacity * 4, s);
-        jl.out_b = (*out_b)->as<uint32_t>();
-        jl.out_p = (*out_p)->as<uint32_t>();
+        B.pos = dev_alloc(capacity * 4, s);
+        P.pos = dev_alloc(capacity * 4, s);
+        jl.out_b = B.pos->as<uint32_t>();
+        jl.out_p = P.pos->as<uint32_t>();
         jl.capacity = capacity;
         RJ_CUDA(cudaMemsetAsync(counter->p, 0, 8, s));
         {
@@ -583,6 +652,21 @@ void Exec::join_keys(const void* bk, const uint32_t* bv, uint64_t nb, const void
     if (ctx->profiling) ctx->stats[RJ_ST_JOIN].bytes += matches * 8;
     if (matches >= 0xffffffffull) throw EngineError("join result exceeds 2^32-1 rows");
     *n_out = matches;
+}
+
+// row index (into the side's input relation) of every match
+Buf Exec::side_rows(const JoinSide& sd, uint64_t m) {
+    return sd.partitioned ? gather_u32(sd.rows_of_pos, sd.pos, m) : sd.pos;
+}
+
+Buf Exec::rid_of(const Rel& r, int leaf) {
+    auto it = r.rid.find(leaf);
+    if (it != r.rid.end()) return it->second;
+    auto lz = r.lazy.find(leaf);
+    if (lz == r.lazy.end()) throw EngineError("internal: leaf not tracked");
+    Buf rows = gather_u32(lz->second.rows_of_pos, lz->second.pos, r.rows);
+    r.rid[leaf] = rows;
+    return rows;
 }
 
 struct SideKeys {
@@ -615,9 +699,9 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
         const DecodedCol& col = key_type == RJ_VARCHAR ? string_hash(a.table, a.col) : column(a.table, a.col);
         const void* base = key_type == RJ_VARCHAR ? col.str_hash->p : col.values->p;
         k.key_bytes = key_type == RJ_INT32 ? 4 : 8;
-        auto it = rel.rid.find(a.leaf);
-        if (it == rel.rid.end()) throw EngineError("internal: join key leaf not tracked");
-        if (!it->second) { // scan: the decoded column is the key column
+        if (!rel.has_leaf(a.leaf)) throw EngineError("internal: join key leaf not tracked");
+        Buf rid = rid_of(rel, a.leaf);
+        if (!rid) { // scan: the decoded column is the key column
             k.keys = base;
             k.valid = col.valid_ptr();
             return k;
@@ -625,7 +709,7 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
         k.hold_k = dev_alloc(rel.rows * k.key_bytes, s);
         if (col.valid) k.hold_v = dev_alloc(((rel.rows + 31) / 32) * 4, s);
         StageScope sc(ctx, RJ_ST_GATHER, s, 1, rel.rows * (4 + 2 * k.key_bytes));
-        launch_gather(base, col.valid_ptr(), it->second->as<uint32_t>(), rel.rows, k.key_bytes, k.hold_k->p,
+        launch_gather(base, col.valid_ptr(), rid->as<uint32_t>(), rel.rows, k.key_bytes, k.hold_k->p,
                       k.hold_v ? k.hold_v->as<uint32_t>() : nullptr, ctx->sm_count, s);
         k.keys = k.hold_k->p;
         k.valid = k.hold_v ? k.hold_v->as<uint32_t>() : nullptr;
@@ -633,24 +717,58 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
     };
     SideKeys lk = side_keys(L, la), rk = side_keys(R, ra);
 
+    JoinSide ls, rs;
+    ls.keys = lk.keys; ls.valid = lk.valid; ls.n = L.rows;
+    rs.keys = rk.keys; rs.valid = rk.valid; rs.n = R.rows;
+    // At the ROOT join, fixed-width output columns of a child that is a plain scan travel through the
+    // scatter with the tuples ("carried"): the root then encodes them from position order, where a
+    // match's neighbours are its partition's tuples, instead of gathering 8 bytes per 128-byte DRAM
+    // line from the whole table through row ids.
+    const bool is_root = n == plan->root;
+    auto pure_scan = [&](const Rel& rel, const Attr& a) {
+        auto it = rel.rid.find(a.leaf);
+        return rel.rid.size() == 1 && rel.lazy.empty() && it != rel.rid.end() && !it->second;
+    };
+    auto plan_carry = [&](const Rel& rel, const Attr& key_attr, JoinSide& sd) {
+        if (!is_root || key_type == RJ_VARCHAR || !pure_scan(rel, key_attr)) return;
+        std::set<uint32_t> seen;
+        for (uint32_t a = 0; a < nd.n_output_attrs; ++a) {
+            const Attr at = resolve(n, a);
+            if (at.leaf != key_attr.leaf || at.col == key_attr.col || seen.count(at.col)) continue;
+            const int t = in->tables[at.table].cols[at.col].type;
+            if (t == RJ_VARCHAR || t != nd.output_attrs[a].type) continue;
+            seen.insert(at.col);
+            CarryCol c;
+            c.col = at.col;
+            c.src = column(at.table, at.col).values->p;
+            c.width = t == RJ_INT32 ? 4 : 8;
+            sd.carry.push_back(c);
+        }
+    };
+    plan_carry(L, la, ls);
+    plan_carry(R, ra, rs);
+
     // The hash table goes on the SMALLER side whatever build_left says: the result is the same
     // multiset of (left row, right row) pairs, and a small table side means fewer partitions.
     const bool table_left = L.rows <= R.rows;
-    Buf t_idx, p_idx;
     uint64_t m = 0;
     if (table_left) {
-        join_keys(lk.keys, lk.valid, L.rows, rk.keys, rk.valid, R.rows, lk.key_bytes, &t_idx, &p_idx, &m);
+        join_keys(ls, rs, lk.key_bytes, &m);
     } else {
-        join_keys(rk.keys, rk.valid, R.rows, lk.keys, lk.valid, L.rows, lk.key_bytes, &t_idx, &p_idx, &m);
+        join_keys(rs, ls, lk.key_bytes, &m);
     }
-    Buf l_idx = table_left ? t_idx : p_idx, r_idx = table_left ? p_idx : t_idx;
+
+    Buf l_rows, r_rows; // row index into L / R of every match (materialised only when needed)
+    auto rows_l = [&]() { if (!l_rows) l_rows = side_rows(ls, m); return l_rows; };
+    auto rows_r = [&]() { if (!r_rows) r_rows = side_rows(rs, m); return r_rows; };
 
     if (key_type == RJ_VARCHAR && m > 0) {
         // the join ran on 64-bit string hashes: keep only pairs whose strings are byte-equal
         const DecodedCol& lc = column(la.table, la.col);
         const DecodedCol& rc = column(ra.table, ra.col);
-        Buf lrow = L.rid.at(la.leaf) ? gather_u32(L.rid.at(la.leaf), l_idx, m) : l_idx;
-        Buf rrow = R.rid.at(ra.leaf) ? gather_u32(R.rid.at(ra.leaf), r_idx, m) : r_idx;
+        Buf l_idx = rows_l(), r_idx = rows_r();
+        Buf lrow = rid_of(L, la.leaf) ? gather_u32(rid_of(L, la.leaf), l_idx, m) : l_idx;
+        Buf rrow = rid_of(R, ra.leaf) ? gather_u32(rid_of(R, ra.leaf), r_idx, m) : r_idx;
         Buf keep = dev_alloc(m * 4, s), pos = dev_alloc((m + 1) * 8, s), tmp = dev_alloc(scan_tmp_bytes(m), s);
         StageScope sc(ctx, RJ_ST_GATHER, s, 5, m * 32);
         launch_varchar_pairs_equal(lc.pages, lc.values->as<uint64_t>(), lrow->as<uint32_t>(), rc.pages,
@@ -662,8 +780,14 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
         Buf nl = dev_alloc(kept * 4, s), nr = dev_alloc(kept * 4, s);
         launch_compact_pairs(l_idx->as<uint32_t>(), r_idx->as<uint32_t>(), keep->as<uint32_t>(), pos->as<uint64_t>(), m,
                              nl->as<uint32_t>(), nr->as<uint32_t>(), s);
-        l_idx = nl;
-        r_idx = nr;
+        // from here on the sides are plain row lists again
+        l_rows = nl;
+        r_rows = nr;
+        ls.partitioned = rs.partitioned = false;
+        ls.pos = nl;
+        rs.pos = nr;
+        ls.carry.clear();
+        rs.carry.clear();
         m = kept;
     }
     out.rows = m;
@@ -671,15 +795,43 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
     // row-id lists of every scan the parents can still see through this node's output_attrs
     std::set<int> needed;
     for (uint32_t a = 0; a < nd.n_output_attrs; ++a) needed.insert(resolve(n, a).leaf);
-    for (int leaf: needed) {
-        auto li = L.rid.find(leaf);
-        if (li != L.rid.end()) {
-            out.rid[leaf] = li->second ? gather_u32(li->second, l_idx, m) : l_idx;
-            continue;
+    auto attach = [&](int leaf, const Rel& child, JoinSide& sd, const Attr& key_attr, const std::function<Buf()>& rows) {
+        auto ci = child.rid.find(leaf);
+        const bool identity = ci != child.rid.end() && !ci->second && child.rid.size() == 1 && child.lazy.empty();
+        if (identity) {
+            // the child is a scan of this leaf: its row index IS the row id
+            if (sd.partitioned) {
+                out.lazy[leaf] = PosSpace{sd.pos, sd.rows_of_pos};
+                // the join key and the carried columns are available in position order
+                CarriedCol kc;
+                kc.hold = sd.keys_of_pos;
+                kc.values_of_pos = sd.keys_of_pos->p;
+                kc.pos = sd.pos;
+                kc.never_null = true;
+                if (key_type != RJ_VARCHAR && leaf == key_attr.leaf) out.carried[{leaf, key_attr.col}] = kc;
+                for (auto& c: sd.carry) {
+                    if (!c.out) continue;
+                    CarriedCol cc;
+                    cc.hold = c.out;
+                    cc.values_of_pos = c.out->p;
+                    cc.pos = sd.pos;
+                    out.carried[{leaf, c.col}] = cc;
+                }
+            } else {
+                out.rid[leaf] = sd.pos;
+            }
+            return;
         }
-        auto ri = R.rid.find(leaf);
-        if (ri == R.rid.end()) throw EngineError("internal: output leaf not below this join");
-        out.rid[leaf] = ri->second ? gather_u32(ri->second, r_idx, m) : r_idx;
+        out.rid[leaf] = gather_u32(rid_of(child, leaf), rows(), m);
+    };
+    for (int leaf: needed) {
+        if (L.has_leaf(leaf)) {
+            attach(leaf, L, ls, la, rows_l);
+        } else if (R.has_leaf(leaf)) {
+            attach(leaf, R, rs, ra, rows_r);
+        } else {
+            throw EngineError("internal: output leaf not below this join");
+        }
     }
     return out;
 }
@@ -762,20 +914,38 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
             throw EngineError(rc.type == RJ_VARCHAR ? "not string or null" : "output attribute type does not match the column");
         }
         const DecodedCol& col = column(at.table, at.col);
-        auto it = r.rid.find(at.leaf);
-        if (it == r.rid.end()) throw EngineError("internal: root leaf not tracked");
-        const uint32_t* idx = it->second ? it->second->as<uint32_t>() : nullptr;
+        if (!r.has_leaf(at.leaf)) throw EngineError("internal: root leaf not tracked");
         if (rc.type == RJ_VARCHAR) {
-            rc = encode_varchar(col, idx, r.rows);
+            Buf rid = rid_of(r, at.leaf);
+            rc = encode_varchar(col, rid ? rid->as<uint32_t>() : nullptr, r.rows);
             continue;
         }
         const uint32_t rpp = rj_fixed_rows_per_page(rc.type);
         rc.n_pages = (r.rows + rpp - 1) / rpp;
         rc.pages = dev_alloc(rc.n_pages * size_t(RJ_PAGE_SIZE), s);
         const size_t w = type_width(rc.type);
+        const void*     values = col.values->p;
+        const uint32_t* idx = nullptr;
+        const uint32_t* vidx = nullptr;
+        Buf             hold_rid;
+        auto carried = r.carried.find({at.leaf, at.col});
+        if (carried != r.carried.end()) {
+            // values in position order; validity (if the column has NULLs) still lives at the row id
+            values = carried->second.values_of_pos;
+            idx = carried->second.pos->as<uint32_t>();
+            vidx = idx;
+            if (col.valid && !carried->second.never_null) {
+                hold_rid = rid_of(r, at.leaf);
+                vidx = hold_rid ? hold_rid->as<uint32_t>() : nullptr;
+            }
+        } else {
+            hold_rid = rid_of(r, at.leaf);
+            idx = vidx = hold_rid ? hold_rid->as<uint32_t>() : nullptr;
+        }
         // M*4 + M*w read + 8192 * pages written
         StageScope sc(ctx, RJ_ST_ENCODE, s, 1, r.rows * (4 + w) + rc.n_pages * uint64_t(RJ_PAGE_SIZE));
-        launch_encode_fixed(col.values->p, col.valid_ptr(), idx, r.rows, rc.type, rc.pages->p, ctx->sm_count, s);
+        const bool all_valid = carried != r.carried.end() && carried->second.never_null;
+        launch_encode_fixed(values, all_valid ? nullptr : col.valid_ptr(), idx, vidx, r.rows, rc.type, rc.pages->p, ctx->sm_count, s);
     }
     return res;
 }
@@ -1076,7 +1246,7 @@ int rj_radix_scatter(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, c
         if ((key_bytes != 4 && key_bytes != 8) || bits < 0 || bits > 9) throw EngineError("rj_radix_scatter: bits must be in [0, 9]");
         if (n >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
         launch_radix_scatter(d_keys, d_valid, d_idx_in, n, key_bytes, shift, bits, d_cursor, d_keys_out, d_idx_out,
-                             ctx->sm_count, pick_stream(ctx, stream));
+                             ScatterPayload{}, ctx->sm_count, pick_stream(ctx, stream));
     });
 }
 
@@ -1089,14 +1259,17 @@ int rj_join_keys(rj_ctx* ctx, const void* d_build_keys, const uint32_t* d_build_
         cudaStream_t cs = pick_stream(ctx, stream);
         if (cs != ctx->stream) RJ_CUDA(cudaStreamSynchronize(cs));
         Exec ex(ctx, nullptr, nullptr);
-        Buf ob, op;
         uint64_t m = 0;
         if (n_build == 0 || n_probe == 0) {
             *n_matches = 0;
             return;
         }
-        ex.join_keys(d_build_keys, d_build_valid, n_build, d_probe_keys, d_probe_valid, n_probe, key_bytes, &ob, &op, &m);
+        JoinSide bs, ps;
+        bs.keys = d_build_keys; bs.valid = d_build_valid; bs.n = n_build;
+        ps.keys = d_probe_keys; ps.valid = d_probe_valid; ps.n = n_probe;
+        ex.join_keys(bs, ps, key_bytes, &m);
         *n_matches = m;
+        Buf ob = ex.side_rows(bs, m), op = ex.side_rows(ps, m);
         if (m <= capacity && m > 0) {
             RJ_CUDA(cudaMemcpyAsync(d_out_build, ob->p, m * 4, cudaMemcpyDeviceToDevice, ctx->stream));
             RJ_CUDA(cudaMemcpyAsync(d_out_probe, op->p, m * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1127,7 +1300,7 @@ int rj_encode_fixed(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, 
                     int32_t type, void* d_pages_out, void* stream) {
     return guarded(ctx, [&] {
         if (type == RJ_VARCHAR) throw EngineError("rj_encode_fixed: VARCHAR column");
-        launch_encode_fixed(d_values, d_valid, d_idx, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
+        launch_encode_fixed(d_values, d_valid, d_idx, d_idx, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
     });
 }
 
@@ -1191,7 +1364,7 @@ int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_vali
         if (type == RJ_VARCHAR) throw EngineError("rj_gen_fixed_pages: VARCHAR column");
         const uint32_t rpp = rj_fixed_rows_per_page(type);
         if (n_pages_out) *n_pages_out = (n + rpp - 1) / rpp;
-        if (d_pages_out) launch_encode_fixed(d_values, d_valid, nullptr, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
+        if (d_pages_out) launch_encode_fixed(d_values, d_valid, nullptr, nullptr, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
     });
 }
 

@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
     radix_scatter_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
                          const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
                          const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
-                         uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+                         uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
+                         ScatterPayload pay) {
     constexpr int      kScatterItems = ScatterCfg<K>::kItems;
     constexpr uint32_t kTile         = ScatterCfg<K>::kTile;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -278,8 +279,17 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
             const K        k    = s_keys[pos];
             const uint32_t part = (hash_key(k) >> shift) & mask;
             const uint32_t dst  = s_gbase[part] + pos;
+            const uint32_t row  = s_idx[pos];
             keys_out[dst] = k;
-            idx_out[dst]  = s_idx[pos];
+            idx_out[dst]  = row;
+            // payload columns ride along: the reads stay inside this tile's row window
+            for (int c = 0; c < pay.n; ++c) {
+                if (pay.width[c] == 8) {
+                    static_cast<uint64_t*>(pay.dst[c])[dst] = static_cast<const uint64_t*>(pay.src[c])[row];
+                } else {
+                    static_cast<uint32_t*>(pay.dst[c])[dst] = static_cast<const uint32_t*>(pay.src[c])[row];
+                }
+            }
         }
         __syncthreads();
     }
@@ -366,8 +376,8 @@ void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint3
 }
 
 void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_t* idx_in, uint64_t n, int key_bytes,
-                          int shift, int bits, uint32_t* cursor, void* keys_out, uint32_t* idx_out, int sm_count,
-                          cudaStream_t s) {
+                          int shift, int bits, uint32_t* cursor, void* keys_out, uint32_t* idx_out,
+                          const ScatterPayload& payload, int sm_count, cudaStream_t s) {
     if (n == 0) return;
     const uint32_t tile = scatter_tile(key_bytes);
     uint64_t n_tiles = (n + tile - 1) / tile;
@@ -377,13 +387,13 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
         scatter_set_attr<uint32_t, false>(smem);
         radix_scatter_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<uint32_t*>(keys_out), idx_out);
+            static_cast<uint32_t*>(keys_out), idx_out, payload);
     } else {
         const size_t smem = scatter_smem_bytes<uint64_t>(bits);
         scatter_set_attr<uint64_t, false>(smem);
         radix_scatter_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<uint64_t*>(keys_out), idx_out);
+            static_cast<uint64_t*>(keys_out), idx_out, payload);
     }
     RJ_LAUNCH_CHECK();
 }
@@ -403,13 +413,13 @@ void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, cons
         scatter_set_attr<uint32_t, true>(smem);
         radix_scatter_kernel<uint32_t, true><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out);
+            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{});
     } else {
         const size_t smem = scatter_smem_bytes<uint64_t>(bits);
         scatter_set_attr<uint64_t, true>(smem);
         radix_scatter_kernel<uint64_t, true><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out);
+            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{});
     }
     RJ_LAUNCH_CHECK();
 }

@@ -85,10 +85,20 @@ void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n,
 void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint32_t flat_b, uint32_t flat_p,
                            int total_bits, int pass1_bits, int key_bytes, const PartitionPlanDev& plan,
                            cudaStream_t s);
+// Payload columns that travel with the tuples of a flat scatter: dst[c][pos] = src[c][row of the tuple].
+// The source is read inside the tile's own row window (sequential DRAM traffic), so a later gather
+// through positions of the scattered order stays inside one partition / region instead of the table.
+struct ScatterPayload {
+    static constexpr int kMax = 4;
+    int         n = 0;
+    const void* src[kMax] = {nullptr, nullptr, nullptr, nullptr};
+    void*       dst[kMax] = {nullptr, nullptr, nullptr, nullptr};
+    int         width[kMax] = {0, 0, 0, 0}; // 4 or 8 bytes
+};
 // flat scatter over [0, n): cursor index = radix digit
 void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_t* idx_in, uint64_t n,
                           int key_bytes, int shift, int bits, uint32_t* cursor, void* keys_out,
-                          uint32_t* idx_out, int sm_count, cudaStream_t s);
+                          uint32_t* idx_out, const ScatterPayload& payload, int sm_count, cudaStream_t s);
 // segmented scatter (pass 2): region r covers [region_start[r], region_start[r+1]) of the input,
 // tiles are enumerated through tile_start, cursor index = (r << bits) | digit
 void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,
@@ -120,8 +130,10 @@ void launch_join(const JoinLaunch& a, int sm_count, cudaStream_t s);
 // ---- k_gather_encode.cu ---------------------------------------------------------------------------
 void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* idx, uint64_t n,
                    int elem_bytes, void* out, uint32_t* out_valid, int sm_count, cudaStream_t s);
-void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32_t* idx, uint64_t n,
-                         int type, void* pages_out, int sm_count, cudaStream_t s);
+// values are read through idx, validity bits through vidx (both NULL = identity; vidx == idx is the
+// plain row-id case, vidx != idx when the values were carried into a partitioned order)
+void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32_t* idx, const uint32_t* vidx,
+                         uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s);
 void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
 void launch_bitmap_to_bytes(const uint32_t* bits, uint64_t n, uint8_t* out, int sm_count, cudaStream_t s);
 void launch_bytes_to_bitmap(const uint8_t* bytes, uint64_t n, uint32_t* out, int sm_count, cudaStream_t s);
