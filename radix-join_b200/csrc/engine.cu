@@ -396,6 +396,7 @@ struct PosSpace {
 struct CarriedCol {
     Buf         hold;              // owner of values_of_pos when it is a scatter output
     const void* values_of_pos = nullptr;
+    Buf         valid_hold;        // one validity byte per position (carried with the values), or null
     Buf         pos;
     bool        never_null = false; // a matched join key is never NULL
 };
@@ -414,6 +415,8 @@ struct CarryCol {
     const void* src = nullptr; // decoded values by row
     int         width = 0;
     Buf         out;           // values by position (filled by the scatter)
+    const uint32_t* valid_src = nullptr; // validity bitmap by row (null: no NULLs)
+    Buf         valid_out;     // validity bytes by position
 };
 
 struct JoinSide {
@@ -578,19 +581,26 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
         auto payload_of = [&](JoinSide& sd) {
             ScatterPayload pay;
             for (auto& c: sd.carry) {
-                if (pay.n == ScatterPayload::kMax) break;
+                if (pay.n + (c.valid_src ? 2 : 1) > ScatterPayload::kMax) break;
                 c.out = dev_alloc(sd.n * c.width, s);
                 pay.src[pay.n] = c.src;
                 pay.dst[pay.n] = c.out->p;
                 pay.width[pay.n] = c.width;
                 ++pay.n;
+                if (c.valid_src) {
+                    c.valid_out = dev_alloc(sd.n, s);
+                    pay.src[pay.n] = c.valid_src;
+                    pay.dst[pay.n] = c.valid_out->p;
+                    pay.width[pay.n] = 1;
+                    ++pay.n;
+                }
             }
             return pay;
         };
         const ScatterPayload pay_b = payload_of(B), pay_p = payload_of(P);
         uint64_t carried_bytes = 0;
-        for (auto& c: B.carry) if (c.out) carried_bytes += 2 * nb * c.width;
-        for (auto& c: P.carry) if (c.out) carried_bytes += 2 * np * c.width;
+        for (auto& c: B.carry) if (c.out) carried_bytes += 2 * nb * (c.width + (c.valid_out ? 1 : 0));
+        for (auto& c: P.carry) if (c.out) carried_bytes += 2 * np * (c.width + (c.valid_out ? 1 : 0));
         // SURVEY 8d numerator: one-pass scatter = N*w_k read + N*(w_k+4) written, whatever the pass count
         StageScope sc(ctx, RJ_ST_SCATTER, s, bits1 ? 4 : 2, n_in * (2 * key_bytes + 4) + carried_bytes);
         B.partitioned = P.partitioned = true;
@@ -740,7 +750,9 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
             seen.insert(at.col);
             CarryCol c;
             c.col = at.col;
-            c.src = column(at.table, at.col).values->p;
+            const DecodedCol& dc = column(at.table, at.col);
+            c.src = dc.values->p;
+            c.valid_src = dc.valid_ptr();
             c.width = t == RJ_INT32 ? 4 : 8;
             sd.carry.push_back(c);
         }
@@ -814,6 +826,7 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
                     CarriedCol cc;
                     cc.hold = c.out;
                     cc.values_of_pos = c.out->p;
+                    cc.valid_hold = c.valid_out;
                     cc.pos = sd.pos;
                     out.carried[{leaf, c.col}] = cc;
                 }
@@ -927,6 +940,7 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
         const void*     values = col.values->p;
         const uint32_t* idx = nullptr;
         const uint32_t* vidx = nullptr;
+        const uint8_t*  valid_bytes = nullptr;
         Buf             hold_rid;
         auto carried = r.carried.find({at.leaf, at.col});
         if (carried != r.carried.end()) {
@@ -934,7 +948,9 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
             values = carried->second.values_of_pos;
             idx = carried->second.pos->as<uint32_t>();
             vidx = idx;
-            if (col.valid && !carried->second.never_null) {
+            if (carried->second.valid_hold) {
+                valid_bytes = carried->second.valid_hold->as<uint8_t>();
+            } else if (col.valid && !carried->second.never_null) {
                 hold_rid = rid_of(r, at.leaf);
                 vidx = hold_rid ? hold_rid->as<uint32_t>() : nullptr;
             }
@@ -945,7 +961,7 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
         // M*4 + M*w read + 8192 * pages written
         StageScope sc(ctx, RJ_ST_ENCODE, s, 1, r.rows * (4 + w) + rc.n_pages * uint64_t(RJ_PAGE_SIZE));
         const bool all_valid = carried != r.carried.end() && carried->second.never_null;
-        launch_encode_fixed(values, all_valid ? nullptr : col.valid_ptr(), idx, vidx, r.rows, rc.type, rc.pages->p, ctx->sm_count, s);
+        launch_encode_fixed(values, all_valid ? nullptr : col.valid_ptr(), valid_bytes, idx, vidx, r.rows, rc.type, rc.pages->p, ctx->sm_count, s);
     }
     return res;
 }
@@ -1300,7 +1316,7 @@ int rj_encode_fixed(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, 
                     int32_t type, void* d_pages_out, void* stream) {
     return guarded(ctx, [&] {
         if (type == RJ_VARCHAR) throw EngineError("rj_encode_fixed: VARCHAR column");
-        launch_encode_fixed(d_values, d_valid, d_idx, d_idx, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
+        launch_encode_fixed(d_values, d_valid, nullptr, d_idx, d_idx, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
     });
 }
 
@@ -1364,7 +1380,7 @@ int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_vali
         if (type == RJ_VARCHAR) throw EngineError("rj_gen_fixed_pages: VARCHAR column");
         const uint32_t rpp = rj_fixed_rows_per_page(type);
         if (n_pages_out) *n_pages_out = (n + rpp - 1) / rpp;
-        if (d_pages_out) launch_encode_fixed(d_values, d_valid, nullptr, nullptr, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
+        if (d_pages_out) launch_encode_fixed(d_values, d_valid, nullptr, nullptr, nullptr, n, type, d_pages_out, ctx->sm_count, pick_stream(ctx, stream));
     });
 }
 

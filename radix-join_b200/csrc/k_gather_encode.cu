@@ -47,8 +47,8 @@ __host__ __device__ constexpr uint32_t rows_per_page(int width) { return width =
 template <typename T>
 __global__ void __launch_bounds__(kEncWarps * 32)
     encode_fixed_kernel(const T* __restrict__ values, const uint32_t* __restrict__ valid,
-                        const uint32_t* __restrict__ idx, const uint32_t* __restrict__ vidx, uint64_t n,
-                        uint8_t* __restrict__ pages_out) {
+                        const uint8_t* __restrict__ valid_bytes, const uint32_t* __restrict__ idx,
+                        const uint32_t* __restrict__ vidx, uint64_t n, uint8_t* __restrict__ pages_out) {
     constexpr uint32_t kRows  = rows_per_page(sizeof(T));
     constexpr uint32_t kBegin = sizeof(T) == 4 ? 4 : 8;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -89,7 +89,12 @@ __global__ void __launch_bounds__(kEncWarps * 32)
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                ok[u] = in[u] && (valid == nullptr || test_bit(valid, vr[u]));
+                ok[u] = in[u];
+                if (valid_bytes != nullptr) {
+                    ok[u] = in[u] && valid_bytes[r[u]] != 0;
+                } else if (valid != nullptr) {
+                    ok[u] = in[u] && test_bit(valid, vr[u]);
+                }
                 v[u]  = ok[u] ? values[r[u]] : T(0);
             }
 #pragma unroll
@@ -153,8 +158,8 @@ void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* i
     RJ_LAUNCH_CHECK();
 }
 
-void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32_t* idx, const uint32_t* vidx, uint64_t n,
-                         int type, void* pages_out, int sm_count, cudaStream_t s) {
+void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_t* valid_bytes, const uint32_t* idx,
+                         const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s) {
     if (n == 0) return;
     const size_t smem = kEncWarps * kEncBufs * RJ_PAGE;
     const uint32_t rows = type == RJ_INT32 ? rows_per_page(4) : rows_per_page(8);
@@ -168,7 +173,7 @@ void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32
             configured = true;
         }
         encode_fixed_kernel<uint32_t><<<blocks, kEncWarps * 32, smem, s>>>(
-            static_cast<const uint32_t*>(values), valid, idx, vidx, n, static_cast<uint8_t*>(pages_out));
+            static_cast<const uint32_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out));
     } else {
         static bool configured = false;
         if (!configured) {
@@ -176,7 +181,7 @@ void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32
             configured = true;
         }
         encode_fixed_kernel<uint64_t><<<blocks, kEncWarps * 32, smem, s>>>(
-            static_cast<const uint64_t*>(values), valid, idx, vidx, n, static_cast<uint8_t*>(pages_out));
+            static_cast<const uint64_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out));
     }
     RJ_LAUNCH_CHECK();
 }

@@ -34,7 +34,10 @@ constexpr uint32_t kOutCap      = 4096;        // staged pairs per CTA
 constexpr uint32_t kEmpty       = 0xffffffffu; // row ids are < 2^32 - 1
 constexpr int      kBuildItems  = kJoinBuildCap / kJoinThreads; // 12
 constexpr uint32_t kSlotMask    = kJoinSlots - 1;
-constexpr uint32_t kUnitBatch   = 4;           // consecutive work units a CTA takes per binary search
+// Units are dealt out round-robin ONE at a time: the units in flight at any instant are ~2 x #SM
+// consecutive ones, i.e. about one pass-1 region, so everything the matches of that moment refer to
+// (row ids, keys, carried payloads in position order) is an L2-sized window.
+constexpr uint32_t kUnitBatch   = 1;
 
 struct JoinArgs {
     const void*     bkeys;

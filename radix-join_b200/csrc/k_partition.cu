@@ -286,6 +286,9 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
             for (int c = 0; c < pay.n; ++c) {
                 if (pay.width[c] == 8) {
                     static_cast<uint64_t*>(pay.dst[c])[dst] = static_cast<const uint64_t*>(pay.src[c])[row];
+                } else if (pay.width[c] == 1) {
+                    // a validity bitmap travels as one byte per tuple
+                    static_cast<uint8_t*>(pay.dst[c])[dst] = test_bit(static_cast<const uint32_t*>(pay.src[c]), row) ? 1 : 0;
                 } else {
                     static_cast<uint32_t*>(pay.dst[c])[dst] = static_cast<const uint32_t*>(pay.src[c])[row];
                 }

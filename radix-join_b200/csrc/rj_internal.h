@@ -89,11 +89,11 @@ void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint3
 // The source is read inside the tile's own row window (sequential DRAM traffic), so a later gather
 // through positions of the scattered order stays inside one partition / region instead of the table.
 struct ScatterPayload {
-    static constexpr int kMax = 4;
+    static constexpr int kMax = 6;
     int         n = 0;
-    const void* src[kMax] = {nullptr, nullptr, nullptr, nullptr};
-    void*       dst[kMax] = {nullptr, nullptr, nullptr, nullptr};
-    int         width[kMax] = {0, 0, 0, 0}; // 4 or 8 bytes
+    const void* src[kMax] = {};
+    void*       dst[kMax] = {};
+    int         width[kMax] = {}; // 4 or 8 bytes; 1 = src is a validity BITMAP, dst one byte per tuple
 };
 // flat scatter over [0, n): cursor index = radix digit
 void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_t* idx_in, uint64_t n,
@@ -131,9 +131,10 @@ void launch_join(const JoinLaunch& a, int sm_count, cudaStream_t s);
 void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* idx, uint64_t n,
                    int elem_bytes, void* out, uint32_t* out_valid, int sm_count, cudaStream_t s);
 // values are read through idx, validity bits through vidx (both NULL = identity; vidx == idx is the
-// plain row-id case, vidx != idx when the values were carried into a partitioned order)
-void launch_encode_fixed(const void* values, const uint32_t* valid, const uint32_t* idx, const uint32_t* vidx,
-                         uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s);
+// plain row-id case, vidx != idx when the values were carried into a partitioned order);
+// valid_bytes (one byte per value, read through idx) replaces the bitmap when it was carried too
+void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_t* valid_bytes, const uint32_t* idx,
+                         const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s);
 void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
 void launch_bitmap_to_bytes(const uint32_t* bits, uint64_t n, uint8_t* out, int sm_count, cudaStream_t s);
 void launch_bytes_to_bitmap(const uint8_t* bytes, uint64_t n, uint32_t* out, int sm_count, cudaStream_t s);
