@@ -631,7 +631,7 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
             P.rows_of_pos = ti_p; P.keys_of_pos = tk_p;
         }
     }
-    jl.off_b = pl.off_b; jl.off_p = pl.off_p; jl.unit_start = pl.unit_start;
+    jl.off_b = pl.off_b; jl.off_p = pl.off_p; jl.unit_start = pl.unit_start; jl.unit_cursor = pl.unit_cursor;
     jl.nparts = nparts; jl.part_bits = bits; jl.key_bytes = key_bytes;
 
     Buf counter = dev_alloc(8, s);
@@ -648,6 +648,7 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
         jl.out_p = P.pos->as<uint32_t>();
         jl.capacity = capacity;
         RJ_CUDA(cudaMemsetAsync(counter->p, 0, 8, s));
+        RJ_CUDA(cudaMemsetAsync(pl.unit_cursor, 0, 4, s));
         {
             // N*(w_k+4) read + M*8 written (M is added once known)
             StageScope sc(ctx, RJ_ST_JOIN, s, 1, n_in * (key_bytes + 4));
@@ -660,6 +661,24 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
         capacity = matches;
     }
     if (ctx->profiling) ctx->stats[RJ_ST_JOIN].bytes += matches * 8;
+    if (getenv("RJ_DEBUG_POS") && matches > (1u << 22)) {
+        // development aid: how far apart are the positions referenced by consecutive output rows?
+        const size_t cnt = 1u << 21;
+        std::vector<uint32_t> hp(cnt), hb(cnt);
+        for (uint64_t off: {uint64_t(0), matches / 2}) {
+            RJ_CUDA(cudaMemcpy(hp.data(), P.pos->as<uint32_t>() + off, cnt * 4, cudaMemcpyDeviceToHost));
+            RJ_CUDA(cudaMemcpy(hb.data(), B.pos->as<uint32_t>() + off, cnt * 4, cudaMemcpyDeviceToHost));
+            for (size_t w: {size_t(4096), size_t(1) << 16, cnt}) {
+                uint32_t pmin = ~0u, pmax = 0, bmin = ~0u, bmax = 0;
+                for (size_t i = 0; i < w; ++i) {
+                    pmin = std::min(pmin, hp[i]); pmax = std::max(pmax, hp[i]);
+                    bmin = std::min(bmin, hb[i]); bmax = std::max(bmax, hb[i]);
+                }
+                fprintf(stderr, "[rj pos] off=%llu window=%zu probe span=%u (of %llu) build span=%u (of %llu)\n",
+                        (unsigned long long)off, w, pmax - pmin, (unsigned long long)np, bmax - bmin, (unsigned long long)nb);
+            }
+        }
+    }
     if (matches >= 0xffffffffull) throw EngineError("join result exceeds 2^32-1 rows");
     *n_out = matches;
 }

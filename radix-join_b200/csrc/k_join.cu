@@ -34,10 +34,11 @@ constexpr uint32_t kOutCap      = 4096;        // staged pairs per CTA
 constexpr uint32_t kEmpty       = 0xffffffffu; // row ids are < 2^32 - 1
 constexpr int      kBuildItems  = kJoinBuildCap / kJoinThreads; // 12
 constexpr uint32_t kSlotMask    = kJoinSlots - 1;
-// Units are dealt out round-robin ONE at a time: the units in flight at any instant are ~2 x #SM
-// consecutive ones, i.e. about one pass-1 region, so everything the matches of that moment refer to
-// (row ids, keys, carried payloads in position order) is an L2-sized window.
-constexpr uint32_t kUnitBatch   = 1;
+// Units are handed out IN ORDER through a global cursor (one atomic per unit): the units in flight at
+// any instant are the ~2 x #SM most recently started ones, i.e. about one pass-1 region, so everything
+// the matches of that moment refer to (row ids, keys, carried payloads in position order) is an
+// L2-sized window.  A static round-robin lets CTAs drift apart under skew: measured, 4096 consecutive
+// output rows then span 20 regions and every gathered value costs a DRAM line.
 
 struct JoinArgs {
     const void*     bkeys;
@@ -49,6 +50,7 @@ struct JoinArgs {
     const uint32_t* off_b;
     const uint32_t* off_p;
     const uint32_t* unit_start;
+    uint32_t*       unit_cursor;
     uint32_t        nparts;
     int             part_bits;
     uint32_t*       out_b;
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
     uint32_t* s_out_p = s_out_b + kOutCap;
     __shared__ uint32_t           s_out_n;
     __shared__ int                s_dups;
+    __shared__ uint32_t           s_unit;
     __shared__ unsigned long long s_flush_base;
 
     const K* __restrict__ bkeys = static_cast<const K*>(a.bkeys);
@@ -145,18 +148,20 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
 
     if (threadIdx.x == 0) s_out_n = 0;
 
-    // CTAs take batches of kUnitBatch consecutive units: one binary search per batch, then the unit
-    // cursor just walks forward through (partition, chunk) space
-    for (uint32_t u0 = blockIdx.x * kUnitBatch; u0 < n_units; u0 += gridDim.x * kUnitBatch) {
-        uint32_t lo = 0, hi = a.nparts;
-        while (hi - lo > 1) {
-            uint32_t m = (lo + hi) >> 1;
-            if (a.unit_start[m] <= u0) lo = m; else hi = m;
-        }
-        uint32_t part = lo;
-        const uint32_t u1 = u0 + kUnitBatch < n_units ? u0 + kUnitBatch : n_units;
-        for (uint32_t u = u0; u < u1; ++u) {
-            while (a.unit_start[part + 1] <= u) ++part; // skips partitions without units
+    for (;;) {
+        // ---- next work unit, in global order ---------------------------------------------------------
+        __syncthreads();
+        if (threadIdx.x == 0) s_unit = atomicAdd(a.unit_cursor, 1u);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= n_units) break;
+        {
+            uint32_t lo = 0, hi = a.nparts;
+            while (hi - lo > 1) {
+                uint32_t m = (lo + hi) >> 1;
+                if (a.unit_start[m] <= u) lo = m; else hi = m;
+            }
+            const uint32_t part = lo;
             const uint32_t local = u - a.unit_start[part];
             const uint32_t b_lo = a.off_b[part], b_hi = a.off_b[part + 1];
             const uint32_t p_lo = a.off_p[part], p_hi = a.off_p[part + 1];
@@ -330,7 +335,7 @@ void run_join(const JoinLaunch& L, int sm_count, cudaStream_t s) {
     JoinArgs a;
     a.bkeys = L.bkeys; a.bidx = L.bidx; a.bvalid = L.bvalid;
     a.pkeys = L.pkeys; a.pidx = L.pidx; a.pvalid = L.pvalid;
-    a.off_b = L.off_b; a.off_p = L.off_p; a.unit_start = L.unit_start;
+    a.off_b = L.off_b; a.off_p = L.off_p; a.unit_start = L.unit_start; a.unit_cursor = L.unit_cursor;
     a.nparts = L.nparts; a.part_bits = L.part_bits;
     a.out_b = L.out_b; a.out_p = L.out_p; a.capacity = L.capacity; a.out_count = L.out_count;
     // persistent grid: 2 CTAs per SM pull batches of work units in a strided order

@@ -330,6 +330,7 @@ void partition_plan_carve(uint32_t* base, int total_bits, int pass1_bits, Partit
     plan->cur_b = p; p += nparts;
     plan->cur_p = p; p += nparts;
     plan->unit_start = p; p += nparts + 1;
+    plan->unit_cursor = p; p += 1;
     if (nreg) {
         plan->reg_b = p; p += nreg + 1;
         plan->reg_p = p; p += nreg + 1;

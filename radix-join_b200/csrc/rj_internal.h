@@ -58,6 +58,7 @@ struct PartitionPlanDev {
     uint32_t* tile_b;       // [nreg+1]   exclusive prefix of pass-2 tiles per region
     uint32_t* tile_p;       // [nreg+1]
     uint32_t* unit_start;   // [nparts+1] exclusive prefix of join work units per partition
+    uint32_t* unit_cursor;  // [1]        dynamic work distribution of the join kernel
 };
 
 size_t partition_plan_words(int total_bits, int pass1_bits);
@@ -117,6 +118,7 @@ struct JoinLaunch {
     const uint32_t* off_b;  // [nparts+1]
     const uint32_t* off_p;
     const uint32_t* unit_start; // [nparts+1]
+    uint32_t*       unit_cursor; // device word, zeroed before every launch: next unit to hand out
     uint32_t        nparts;
     int             part_bits;  // hash bits consumed by the partitioning
     int             key_bytes;
