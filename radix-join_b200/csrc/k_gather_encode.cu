@@ -6,9 +6,9 @@
 //                   (:488,:495); only the decoded multiset is observable (tests/read_sql.cpp:1206-1221),
 //                   and under-filling a page is always legal, so every page takes a FIXED number of rows
 //                   (1984 x 4 B or 1007 x 8 B: 4|8 + rows*width + ceil(rows/8) <= 8192) and pages become
-//                   independent: one warp gathers the rows of a page through the row-id list, compacts the
-//                   non-NULL values with ballot/popcount, assembles header + values + bitmap in shared
-//                   memory and writes the page with ONE 8 KB TMA bulk store (cp.async.bulk, double
+//                   independent: one CTA gathers the rows of a page through the row-id list, compacts the
+//                   non-NULL values with a block-wide prefix sum, assembles header + values + bitmap in
+//                   shared memory and writes the page with ONE 8 KB TMA bulk store (cp.async.bulk, double
 //                   buffered so the next page is assembled while the previous one drains).
 #include "rj_common.cuh"
 #include "rj_internal.h"
@@ -16,8 +16,8 @@
 namespace rj {
 namespace {
 
-constexpr int kEncWarps = 4;
-constexpr int kEncBufs  = 2;
+constexpr int kEncThreads = 256;
+constexpr int kEncBufs    = 2;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -44,78 +44,99 @@ __global__ void __launch_bounds__(256)
 
 __host__ __device__ constexpr uint32_t rows_per_page(int width) { return width == 4 ? 1984u : 1007u; }
 
+// One CTA of 256 threads per output page.  Thread t owns the kPer consecutive rows
+// [t*kPer, (t+1)*kPer) of the page (8 rows of a 4-byte column = exactly one bitmap byte, 4 rows of an
+// 8-byte column = one nibble), so ALL row-id loads of the page are issued at once, then all value /
+// validity gathers: 1000-2000 independent gathers in flight per CTA and up to 8 CTAs per SM, instead
+// of 128 per warp with 12 warps per SM in the first (warp-per-page) version, which ncu showed to be
+// latency bound (18 % active warps, 12 % issue slots, DRAM at 19 %).
 template <typename T>
-__global__ void __launch_bounds__(kEncWarps * 32)
+__global__ void __launch_bounds__(kEncThreads)
     encode_fixed_kernel(const T* __restrict__ values, const uint32_t* __restrict__ valid,
                         const uint8_t* __restrict__ valid_bytes, const uint32_t* __restrict__ idx,
                         const uint32_t* __restrict__ vidx, uint64_t n, uint8_t* __restrict__ pages_out) {
     constexpr uint32_t kRows  = rows_per_page(sizeof(T));
     constexpr uint32_t kBegin = sizeof(T) == 4 ? 4 : 8;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt = lanemask_lt();
-    uint8_t* mybuf = smem + warp * kEncBufs * RJ_PAGE;
+    constexpr int      kPer   = (kRows + kEncThreads - 1) / kEncThreads; // 8 or 4
+    __shared__ __align__(128) uint8_t bufs[kEncBufs][RJ_PAGE];
+    __shared__ uint32_t warp_sums[kEncThreads / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t n_pages = (n + kRows - 1) / kRows;
-    const uint64_t gw = static_cast<uint64_t>(blockIdx.x) * kEncWarps + warp;
-    const uint64_t nw = static_cast<uint64_t>(gridDim.x) * kEncWarps;
     uint32_t it = 0;
-    for (uint64_t p = gw; p < n_pages; p += nw, ++it) {
-        uint8_t* buf = mybuf + (it & 1) * RJ_PAGE;
+    for (uint64_t p = blockIdx.x; p < n_pages; p += gridDim.x, ++it) {
+        uint8_t* buf = bufs[it & 1];
         // the bulk store issued from this buffer two pages ago must have finished reading it
-        if (lane == 0) tma_store_wait_read<kEncBufs - 1>();
-        __syncwarp();
-        // zero the page (header, value gap and bitmap tail must be deterministic)
+        if (tid == 0) tma_store_wait_read<kEncBufs - 1>();
+        __syncthreads();
         uint4* b4 = reinterpret_cast<uint4*>(buf);
 #pragma unroll
-        for (int k = 0; k < RJ_PAGE / 16 / 32; ++k) b4[k * 32 + lane] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
+        for (int k = 0; k < RJ_PAGE / 16 / kEncThreads; ++k) b4[k * kEncThreads + tid] = make_uint4(0, 0, 0, 0);
         const uint64_t j0  = p * kRows;
         const uint32_t cnt = (n - j0 < kRows) ? static_cast<uint32_t>(n - j0) : kRows;
-        T*       vals = reinterpret_cast<T*>(buf + kBegin);
-        uint8_t* bm   = buf + RJ_PAGE - ((cnt + 7) >> 3);
-        uint32_t running = 0;
-        // 4 groups of 32 rows per iteration: 4 independent row-id loads, then 4 independent gathers
-        for (uint32_t base = 0; base < cnt; base += 128) {
-            uint32_t r[4], vr[4];
-            bool     in[4], ok[4];
-            T        v[4];
+        const uint32_t i0  = tid * kPer;
+        uint32_t r[kPer], vr[kPer];
+        bool     ok[kPer];
+        T        v[kPer];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t i = base + u * 32 + lane;
-                in[u] = i < cnt;
-                r[u]  = in[u] ? (idx != nullptr ? idx[j0 + i] : static_cast<uint32_t>(j0 + i)) : 0u;
-                vr[u] = r[u];
-                if (valid != nullptr && vidx != idx && in[u]) vr[u] = vidx != nullptr ? vidx[j0 + i] : static_cast<uint32_t>(j0 + i);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                ok[u] = in[u];
-                if (valid_bytes != nullptr) {
-                    ok[u] = in[u] && valid_bytes[r[u]] != 0;
-                } else if (valid != nullptr) {
-                    ok[u] = in[u] && test_bit(valid, vr[u]);
-                }
-                v[u]  = ok[u] ? values[r[u]] : T(0);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t word = __ballot_sync(RJ_FULL_MASK, ok[u]);
-                if (ok[u]) vals[running + __popc(word & lt)] = v[u];
-                running += __popc(word);
-                const uint32_t byte0 = (base + u * 32) >> 3; // first bitmap byte of this group
-                if (lane < 4 && base + u * 32 + lane * 8 < cnt) bm[byte0 + lane] = static_cast<uint8_t>(word >> (8 * lane));
-            }
+        for (int k = 0; k < kPer; ++k) {
+            const bool in = i0 + k < cnt;
+            r[k]  = in ? (idx != nullptr ? idx[j0 + i0 + k] : static_cast<uint32_t>(j0 + i0 + k)) : 0u;
+            vr[k] = r[k];
+            if (valid != nullptr && valid_bytes == nullptr && vidx != idx && in)
+                vr[k] = vidx != nullptr ? vidx[j0 + i0 + k] : static_cast<uint32_t>(j0 + i0 + k);
         }
-        if (lane == 0) *reinterpret_cast<uint32_t*>(buf) = cnt | (running << 16); // n_r @0, n_v @2
-        // generic-proxy writes -> async proxy: fence by every writer, then one lane issues the store
+        uint32_t mine = 0, bits = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            ok[k] = i0 + k < cnt;
+            if (valid_bytes != nullptr) {
+                ok[k] = ok[k] && valid_bytes[r[k]] != 0;
+            } else if (valid != nullptr) {
+                ok[k] = ok[k] && test_bit(valid, vr[k]);
+            }
+            v[k] = ok[k] ? values[r[k]] : T(0);
+            mine += ok[k] ? 1u : 0u;
+            bits |= (ok[k] ? 1u : 0u) << k;
+        }
+        // exclusive scan of the per-thread non-NULL counts across the CTA
+        uint32_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads(); // also: the zero fill above is complete
+        uint32_t base = inc - mine, total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kEncThreads / 32; ++w) {
+            const uint32_t sw = warp_sums[w];
+            if (w < warp) base += sw;
+            total += sw;
+        }
+        T* vals = reinterpret_cast<T*>(buf + kBegin);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            if (ok[k]) vals[base++] = v[k];
+        }
+        uint8_t* bm = buf + RJ_PAGE - ((cnt + 7) >> 3);
+        if (kPer == 8) {
+            if (i0 < cnt) bm[tid] = static_cast<uint8_t>(bits);
+        } else {
+            // two threads share a bitmap byte
+            const uint32_t hi = __shfl_down_sync(RJ_FULL_MASK, bits, 1);
+            if ((tid & 1) == 0 && i0 < cnt) bm[tid >> 1] = static_cast<uint8_t>(bits | (hi << 4));
+        }
+        if (tid == 0) *reinterpret_cast<uint32_t*>(buf) = cnt | (total << 16); // n_r @0, n_v @2
+        // generic-proxy writes -> async proxy: fence by every writer, then one thread issues the store
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
+        __syncthreads();
+        if (tid == 0) {
             tma_store_1d(pages_out + p * RJ_PAGE, buf, RJ_PAGE);
             tma_store_commit();
         }
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    if (tid == 0) tma_store_wait_all<0>();
 }
 
 __global__ void __launch_bounds__(256) bitmap_to_bytes_kernel(const uint32_t* __restrict__ bits, uint64_t n, uint8_t* __restrict__ out) {
@@ -161,26 +182,16 @@ void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* i
 void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_t* valid_bytes, const uint32_t* idx,
                          const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s) {
     if (n == 0) return;
-    const size_t smem = kEncWarps * kEncBufs * RJ_PAGE;
     const uint32_t rows = type == RJ_INT32 ? rows_per_page(4) : rows_per_page(8);
-    uint64_t n_pages = (n + rows - 1) / rows;
-    uint64_t want = (n_pages + kEncWarps - 1) / kEncWarps;
-    unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 3 ? want : static_cast<uint64_t>(sm_count) * 3);
+    const uint64_t n_pages = (n + rows - 1) / rows;
+    // persistent CTAs, 8 per SM (16 KB of static shared memory each)
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
+    const unsigned blocks = static_cast<unsigned>(n_pages < cap ? n_pages : cap);
     if (type == RJ_INT32) {
-        static bool configured = false;
-        if (!configured) {
-            RJ_CUDA(cudaFuncSetAttribute(encode_fixed_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        encode_fixed_kernel<uint32_t><<<blocks, kEncWarps * 32, smem, s>>>(
+        encode_fixed_kernel<uint32_t><<<blocks, kEncThreads, 0, s>>>(
             static_cast<const uint32_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out));
     } else {
-        static bool configured = false;
-        if (!configured) {
-            RJ_CUDA(cudaFuncSetAttribute(encode_fixed_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        encode_fixed_kernel<uint64_t><<<blocks, kEncWarps * 32, smem, s>>>(
+        encode_fixed_kernel<uint64_t><<<blocks, kEncThreads, 0, s>>>(
             static_cast<const uint64_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out));
     }
     RJ_LAUNCH_CHECK();
