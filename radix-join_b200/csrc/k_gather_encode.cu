@@ -17,7 +17,6 @@ namespace rj {
 namespace {
 
 constexpr int kEncThreads = 256;
-constexpr int kEncBufs    = 2;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -58,16 +57,14 @@ __global__ void __launch_bounds__(kEncThreads)
     constexpr uint32_t kRows  = rows_per_page(sizeof(T));
     constexpr uint32_t kBegin = sizeof(T) == 4 ? 4 : 8;
     constexpr int      kPer   = (kRows + kEncThreads - 1) / kEncThreads; // 8 or 4
-    __shared__ __align__(128) uint8_t bufs[kEncBufs][RJ_PAGE];
+    __shared__ __align__(128) uint8_t buf[RJ_PAGE];
     __shared__ uint32_t warp_sums[kEncThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t n_pages = (n + kRows - 1) / kRows;
-    uint32_t it = 0;
-    for (uint64_t p = blockIdx.x; p < n_pages; p += gridDim.x, ++it) {
-        uint8_t* buf = bufs[it & 1];
-        // the bulk store issued from this buffer two pages ago must have finished reading it
-        if (tid == 0) tma_store_wait_read<kEncBufs - 1>();
-        __syncthreads();
+    // ONE page per CTA, grid = pages: the hardware hands CTAs out in page order, so the pages in flight
+    // are always a contiguous window of the output (persistent CTAs with a static stride drift apart,
+    // and the gathers of a wide window no longer fit L2 -- measured 86 B of DRAM reads per row).
+    {
+        const uint64_t p = blockIdx.x;
         uint4* b4 = reinterpret_cast<uint4*>(buf);
 #pragma unroll
         for (int k = 0; k < RJ_PAGE / 16 / kEncThreads; ++k) b4[k * kEncThreads + tid] = make_uint4(0, 0, 0, 0);
@@ -136,7 +133,7 @@ __global__ void __launch_bounds__(kEncThreads)
             tma_store_commit();
         }
     }
-    if (tid == 0) tma_store_wait_all<0>();
+    if (tid == 0) tma_store_wait_read<0>(); // the page must be read out of shared memory before the CTA retires
 }
 
 __global__ void __launch_bounds__(256) bitmap_to_bytes_kernel(const uint32_t* __restrict__ bits, uint64_t n, uint8_t* __restrict__ out) {
@@ -184,9 +181,9 @@ void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_
     if (n == 0) return;
     const uint32_t rows = type == RJ_INT32 ? rows_per_page(4) : rows_per_page(8);
     const uint64_t n_pages = (n + rows - 1) / rows;
-    // persistent CTAs, 8 per SM (16 KB of static shared memory each)
-    const uint64_t cap = static_cast<uint64_t>(sm_count) * 8;
-    const unsigned blocks = static_cast<unsigned>(n_pages < cap ? n_pages : cap);
+    (void)sm_count;
+    if (n_pages > 0x7fffffffull) throw CudaError("encode: too many pages for one launch");
+    const unsigned blocks = static_cast<unsigned>(n_pages);
     if (type == RJ_INT32) {
         encode_fixed_kernel<uint32_t><<<blocks, kEncThreads, 0, s>>>(
             static_cast<const uint32_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out));
