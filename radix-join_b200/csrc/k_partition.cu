@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kPlanThreads)
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------
-template <typename K, bool kRegions, bool kPay>
+template <typename K, bool kRegions>
 __global__ void __launch_bounds__(kScatterThreads, 2)
     radix_scatter_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
                          const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
@@ -167,7 +167,6 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
     uint32_t* s_count = s_idx + kTile;            // [nb]  tuples of this tile per partition
     uint32_t* s_start = s_count + (1u << bits);   // [nb]  exclusive prefix inside the tile
     uint32_t* s_gbase = s_start + (1u << bits);   // [nb]  global run start minus s_start
-    uint32_t* s_dst   = s_gbase + (1u << bits);   // [kTile] global position of every staged tuple (kPay only)
     __shared__ uint32_t s_warp_sums[kScatterThreads / 32];
     __shared__ uint32_t s_total;
 
@@ -280,83 +279,37 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
             const K        k    = s_keys[pos];
             const uint32_t part = (hash_key(k) >> shift) & mask;
             const uint32_t dst  = s_gbase[part] + pos;
+            const uint32_t row  = s_idx[pos];
             keys_out[dst] = k;
-            idx_out[dst]  = s_idx[pos];
-            if (kPay) s_dst[pos] = dst;
-        }
-        __syncthreads();
-
-        // 5) payload columns ride along, one at a time through the same staging area: read in ROW order
-        //    (coalesced, sequential DRAM traffic), staged at the tuple's position, written out in runs
-        if (kPay) {
+            idx_out[dst]  = row;
+            // payload columns ride along: the reads stay inside this tile's row window
             for (int c = 0; c < pay.n; ++c) {
-                const int w = pay.width[c];
-#pragma unroll
-                for (int k = 0; k < kScatterItems; ++k) {
-                    if (pr[k] != 0xffffffffu) {
-                        const uint64_t i   = lo + static_cast<uint64_t>(k) * kScatterThreads + threadIdx.x;
-                        const uint64_t row = idx_in != nullptr ? idx_in[i] : i;
-                        const uint32_t pos = s_start[pr[k] >> 16] + (pr[k] & 0xffffu);
-                        if (w == 8) {
-                            reinterpret_cast<uint64_t*>(smem_raw)[pos] = static_cast<const uint64_t*>(pay.src[c])[row];
-                        } else if (w == 4) {
-                            reinterpret_cast<uint32_t*>(smem_raw)[pos] = static_cast<const uint32_t*>(pay.src[c])[row];
-                        } else { // a validity bitmap travels as one byte per tuple
-                            smem_raw[pos] = test_bit(static_cast<const uint32_t*>(pay.src[c]), row) ? 1 : 0;
-                        }
-                    }
+                if (pay.width[c] == 8) {
+                    static_cast<uint64_t*>(pay.dst[c])[dst] = static_cast<const uint64_t*>(pay.src[c])[row];
+                } else if (pay.width[c] == 1) {
+                    // a validity bitmap travels as one byte per tuple
+                    static_cast<uint8_t*>(pay.dst[c])[dst] = test_bit(static_cast<const uint32_t*>(pay.src[c]), row) ? 1 : 0;
+                } else {
+                    static_cast<uint32_t*>(pay.dst[c])[dst] = static_cast<const uint32_t*>(pay.src[c])[row];
                 }
-                __syncthreads();
-                for (uint32_t pos = threadIdx.x; pos < total; pos += kScatterThreads) {
-                    const uint32_t dst = s_dst[pos];
-                    if (w == 8) {
-                        static_cast<uint64_t*>(pay.dst[c])[dst] = reinterpret_cast<const uint64_t*>(smem_raw)[pos];
-                    } else if (w == 4) {
-                        static_cast<uint32_t*>(pay.dst[c])[dst] = reinterpret_cast<const uint32_t*>(smem_raw)[pos];
-                    } else {
-                        static_cast<uint8_t*>(pay.dst[c])[dst] = smem_raw[pos];
-                    }
-                }
-                __syncthreads();
             }
         }
+        __syncthreads();
     }
 }
 
 template <typename K>
-size_t scatter_smem_bytes(int bits, bool with_payload) {
-    // staging must hold an 8-byte payload column per tuple as well as (key, row)
-    size_t stage = (sizeof(K) + 4) * ScatterCfg<K>::kTile;
-    if (with_payload && stage < 8 * size_t(ScatterCfg<K>::kTile)) stage = 8 * size_t(ScatterCfg<K>::kTile);
-    return stage + 3 * sizeof(uint32_t) * (1u << bits) + (with_payload ? sizeof(uint32_t) * ScatterCfg<K>::kTile : 0);
+size_t scatter_smem_bytes(int bits) {
+    return (sizeof(K) + 4) * ScatterCfg<K>::kTile + 3 * sizeof(uint32_t) * (1u << bits);
 }
 
-template <typename K, bool kRegions, bool kPay>
+template <typename K, bool kRegions>
 void scatter_set_attr(size_t smem) {
     static size_t configured = 0;
     if (smem > configured) {
-        RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<K, kRegions, kPay>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<K, kRegions>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
         configured = smem;
-    }
-}
-
-template <typename K>
-void run_flat_scatter(const void* keys, const uint32_t* valid, const uint32_t* idx_in, uint64_t n, int shift, int bits,
-                      uint32_t* cursor, void* keys_out, uint32_t* idx_out, const ScatterPayload& payload, unsigned blocks,
-                      cudaStream_t s) {
-    if (payload.n > 0) {
-        const size_t smem = scatter_smem_bytes<K>(bits, true);
-        scatter_set_attr<K, false, true>(smem);
-        radix_scatter_kernel<K, false, true><<<blocks, kScatterThreads, smem, s>>>(
-            static_cast<const K*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<K*>(keys_out), idx_out, payload);
-    } else {
-        const size_t smem = scatter_smem_bytes<K>(bits, false);
-        scatter_set_attr<K, false, false>(smem);
-        radix_scatter_kernel<K, false, false><<<blocks, kScatterThreads, smem, s>>>(
-            static_cast<const K*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<K*>(keys_out), idx_out, payload);
     }
 }
 
@@ -434,9 +387,17 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
     uint64_t n_tiles = (n + tile - 1) / tile;
     unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 2 ? n_tiles : static_cast<uint64_t>(sm_count) * 2);
     if (key_bytes == 4) {
-        run_flat_scatter<uint32_t>(keys, valid, idx_in, n, shift, bits, cursor, keys_out, idx_out, payload, blocks, s);
+        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
+        scatter_set_attr<uint32_t, false>(smem);
+        radix_scatter_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint32_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
+            static_cast<uint32_t*>(keys_out), idx_out, payload);
     } else {
-        run_flat_scatter<uint64_t>(keys, valid, idx_in, n, shift, bits, cursor, keys_out, idx_out, payload, blocks, s);
+        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
+        scatter_set_attr<uint64_t, false>(smem);
+        radix_scatter_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint64_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
+            static_cast<uint64_t*>(keys_out), idx_out, payload);
     }
     RJ_LAUNCH_CHECK();
 }
@@ -452,15 +413,15 @@ void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, cons
     uint64_t tiles_upper = (n_upper + tile - 1) / tile + n_regions;
     unsigned blocks = static_cast<unsigned>(tiles_upper < static_cast<uint64_t>(sm_count) * 2 ? tiles_upper : static_cast<uint64_t>(sm_count) * 2);
     if (key_bytes == 4) {
-        const size_t smem = scatter_smem_bytes<uint32_t>(bits, false);
-        scatter_set_attr<uint32_t, true, false>(smem);
-        radix_scatter_kernel<uint32_t, true, false><<<blocks, kScatterThreads, smem, s>>>(
+        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
+        scatter_set_attr<uint32_t, true>(smem);
+        radix_scatter_kernel<uint32_t, true><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
             bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{});
     } else {
-        const size_t smem = scatter_smem_bytes<uint64_t>(bits, false);
-        scatter_set_attr<uint64_t, true, false>(smem);
-        radix_scatter_kernel<uint64_t, true, false><<<blocks, kScatterThreads, smem, s>>>(
+        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
+        scatter_set_attr<uint64_t, true>(smem);
+        radix_scatter_kernel<uint64_t, true><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
             bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{});
     }
