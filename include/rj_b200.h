@@ -118,6 +118,22 @@ int  rj_inputs_upload(rj_ctx* ctx, const rj_table_t* tables, uint32_t n_tables, 
 /* adopt pages that already are in device memory (e.g. produced by rj_gen_* or an exchange):
  * `contiguous` of every column is then a DEVICE address; nothing is copied or owned. */
 int  rj_inputs_adopt_device(rj_ctx* ctx, const rj_table_t* tables, uint32_t n_tables, rj_inputs** out);
+/* adopt columns that are already DECODED in device memory (dense values + optional validity bitmap),
+ * e.g. what a rank owns after the multi-GPU exchange: the page decode is skipped for them.
+ * Fixed-width types only; nothing is copied or owned. */
+typedef struct rj_dense_column_t {
+    int32_t         type;     /* RJ_INT32 / RJ_INT64 / RJ_FP64 */
+    uint32_t        reserved;
+    const void*     d_values; /* num_rows elements of 4 or 8 bytes */
+    const uint32_t* d_valid;  /* bitmap words, bit i of word i/32; NULL = no NULLs */
+} rj_dense_column_t;
+typedef struct rj_dense_table_t {
+    uint64_t                 num_rows;
+    uint32_t                 n_columns;
+    uint32_t                 reserved;
+    const rj_dense_column_t* columns;
+} rj_dense_table_t;
+int  rj_inputs_adopt_dense(rj_ctx* ctx, const rj_dense_table_t* tables, uint32_t n_tables, rj_inputs** out);
 void rj_inputs_free(rj_ctx* ctx, rj_inputs* in);
 int  rj_execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in, rj_result** out);
 

@@ -32,6 +32,15 @@ class rj_table_t(C.Structure):
     ]
 
 
+class rj_dense_column_t(C.Structure):
+    _fields_ = [("type", C.c_int32), ("reserved", C.c_uint32), ("d_values", C.c_void_p), ("d_valid", C.c_void_p)]
+
+
+class rj_dense_table_t(C.Structure):
+    _fields_ = [("num_rows", C.c_uint64), ("n_columns", C.c_uint32), ("reserved", C.c_uint32),
+                ("columns", C.POINTER(rj_dense_column_t))]
+
+
 class rj_attr_t(C.Structure):
     _fields_ = [("index", C.c_uint64), ("type", C.c_int32), ("reserved", C.c_uint32)]
 
@@ -87,6 +96,7 @@ PROTOTYPES = {
     "rj_execute": (C.c_int, [_vp, C.POINTER(rj_plan_t), _pvp]),
     "rj_inputs_upload": (C.c_int, [_vp, C.POINTER(rj_table_t), _u32, _pvp]),
     "rj_inputs_adopt_device": (C.c_int, [_vp, C.POINTER(rj_table_t), _u32, _pvp]),
+    "rj_inputs_adopt_dense": (C.c_int, [_vp, C.POINTER(rj_dense_table_t), _u32, _pvp]),
     "rj_inputs_free": (None, [_vp, _vp]),
     "rj_execute_resident": (C.c_int, [_vp, C.POINTER(rj_plan_t), _vp, _pvp]),
     "rj_result_num_rows": (_u64, [_vp]),

@@ -135,10 +135,13 @@ struct DevMem {
         ++g_alloc_calls;
     }
     ~DevMem() {
-        if (!p) return;
+        if (!p || view) return;
         if (stream != home) cudaStreamSynchronize(stream);
         g_cache[device].give(p, block);
     }
+    // non-owning view of caller memory (adopted dense columns)
+    DevMem(void* ptr, size_t n): p(ptr), bytes(n), view(true) {}
+    bool view = false;
     DevMem(const DevMem&) = delete;
     DevMem& operator=(const DevMem&) = delete;
     template <class T>
@@ -251,6 +254,10 @@ struct ColumnDev {
     uint64_t       non_null = 0;
     const uint8_t* pages = nullptr;
     Buf            owned;
+    // already decoded by the caller (rj_inputs_adopt_dense)
+    bool            dense = false;
+    const void*     dense_values = nullptr;
+    const uint32_t* dense_valid = nullptr;
 };
 
 struct TableDev {
@@ -512,6 +519,15 @@ const DecodedCol& Exec::column(uint32_t t, uint32_t c) {
     if (it != decoded.end()) return it->second;
     const TableDev&  td = in->tables[t];
     const ColumnDev& cd = td.cols[c];
+    if (cd.dense) {
+        DecodedCol d;
+        d.type = cd.type;
+        d.rows = td.num_rows;
+        const size_t w = cd.type == RJ_INT32 ? 4 : 8;
+        d.values = std::make_shared<DevMem>(const_cast<void*>(cd.dense_values), td.num_rows * w);
+        if (cd.dense_valid) d.valid = std::make_shared<DevMem>(const_cast<uint32_t*>(cd.dense_valid), ((td.num_rows + 31) / 32) * 4);
+        return decoded.emplace(key, std::move(d)).first->second;
+    }
     if (cd.n_pages && !cd.pages) throw EngineError("column was not uploaded");
     DecodedCol d;
     const bool need_valid = cd.non_null != td.num_rows;
@@ -1158,6 +1174,31 @@ int rj_inputs_adopt_device(rj_ctx* ctx, const rj_table_t* tables, uint32_t n_tab
                 cd.page_rows = h[0];
                 cd.non_null = h[1];
                 check_column_rows(td, cd);
+            }
+        }
+        *out = in.release();
+    });
+}
+
+int rj_inputs_adopt_dense(rj_ctx* ctx, const rj_dense_table_t* tables, uint32_t n_tables, rj_inputs** out) {
+    return guarded(ctx, [&] {
+        auto in = std::make_unique<rj_inputs>();
+        in->tables.resize(n_tables);
+        for (uint32_t t = 0; t < n_tables; ++t) {
+            TableDev& td = in->tables[t];
+            td.num_rows = tables[t].num_rows;
+            td.cols.resize(tables[t].n_columns);
+            for (uint32_t c = 0; c < tables[t].n_columns; ++c) {
+                const rj_dense_column_t& col = tables[t].columns[c];
+                if (col.type != RJ_INT32 && col.type != RJ_INT64 && col.type != RJ_FP64) throw EngineError("dense columns must be fixed-width");
+                if (td.num_rows && !col.d_values) throw EngineError("dense column without values");
+                ColumnDev& cd = td.cols[c];
+                cd.type = col.type;
+                cd.dense = true;
+                cd.dense_values = col.d_values;
+                cd.dense_valid = col.d_valid;
+                cd.page_rows = td.num_rows;
+                cd.non_null = col.d_valid ? 0 : td.num_rows;
             }
         }
         *out = in.release();

@@ -62,7 +62,7 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     value = (n_build + n_probe) / 1e6 / (ms_per_step / 1e3)
     sent = torch.tensor([stats["sent_bytes"]], dtype=torch.int64, device="cuda")
     dist.all_reduce(sent, op=dist.ReduceOp.MAX)
-    out_bytes = sum(n * 8192 for _, n, _ in cols)
+    out_bytes = sum(c.nbytes for c in cols)
 
     # end to end: this rank's input pages start in pinned host memory, its result pages end there
     e2e = None
@@ -76,7 +76,7 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
                 h.copy_(d[: n_pages * 8192])
                 host_in.append(h)
                 dev_in.append(d)
-        host_out = [torch.empty(c[0].numel(), dtype=torch.uint8, pin_memory=True) for c in cols]
+        host_out = [torch.empty(max(c.nbytes, 8192), dtype=torch.uint8, pin_memory=True) for c in cols]
         times = []
         for i in range(1 + max(1, min(args.steps, 3))):
             dist.barrier()
@@ -85,10 +85,8 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
             for h, d in zip(host_in, dev_in):
                 d[: h.numel()].copy_(h, non_blocking=True)
             r, c, _ = step()
-            for (pages, _, _), h in zip(c, host_out):
-                if h.numel() < pages.numel():  # result size can differ slightly between steps? (it does not: fixed rows/page)
-                    h = torch.empty(pages.numel(), dtype=torch.uint8, pin_memory=True)
-                h[: pages.numel()].copy_(pages, non_blocking=True)
+            for col, h in zip(c, host_out):
+                col.copy_to_host(h)  # page counts are fixed by the row count (fixed rows per page)
             torch.cuda.synchronize()
             dt_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
             dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)

@@ -23,10 +23,47 @@ import ctypes as C
 import os
 import time
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _cabi
+from .plan import DataType, FlatPlan, Plan
+
 INT32, INT64, FP64 = 0, 1, 2
+
+
+class ResultPages:
+    """One output column of this rank's share of the result: pages in device memory (a torch tensor, or a
+    column of an engine result that is kept alive here)."""
+
+    def __init__(self, n_pages, type_, tensor=None, result=None, col=None):
+        self.n_pages, self.type, self.tensor, self.result, self.col = int(n_pages), int(type_), tensor, result, col
+
+    @property
+    def nbytes(self):
+        return self.n_pages * 8192
+
+    def copy_to_host(self, host):
+        """host: pinned uint8 torch tensor (or numpy array) of at least nbytes"""
+        if self.n_pages == 0:
+            return
+        if self.tensor is not None:
+            dst = host if isinstance(host, torch.Tensor) else torch.from_numpy(host)
+            dst.view(-1)[: self.nbytes].copy_(self.tensor.view(-1)[: self.nbytes], non_blocking=True)
+            torch.cuda.current_stream().synchronize() if self.tensor.is_cuda else None
+        else:
+            arr = host.numpy() if isinstance(host, torch.Tensor) else host
+            self.result.fetch_column(self.col, out=arr.reshape(-1)[: self.nbytes].reshape(-1, 8192))
+
+    def to_numpy(self):
+        out = np.empty((self.n_pages, 8192), dtype=np.uint8)
+        if self.n_pages:
+            if self.tensor is not None:
+                out[:] = self.tensor.view(-1)[: self.nbytes].cpu().numpy().reshape(-1, 8192)
+            else:
+                self.result.fetch_column(self.col, out=out)
+        return out
 
 
 def log2_exact(n):
@@ -121,6 +158,47 @@ class CudaOps:
                 break
             cap = m.value
         return ob[:m.value], op[:m.value]
+
+    def local_join_encode(self, bk, bvals, bvalids, pk, pvals, pvalids, out_cols):
+        """The local join on what this rank owns, through the engine's whole path: the dense columns are
+        adopted as two already-decoded base tables and joined by a 2 x Scan -> Join plan, so the root
+        join carries the payloads in position order and encodes the result pages itself."""
+        from .engine import ResidentInputs, Result
+        keep, tables = [], (_cabi.rj_dense_table_t * 2)()
+        for t, (keys, vals, valids) in enumerate(((bk, bvals, bvalids), (pk, pvals, pvalids))):
+            cols = (_cabi.rj_dense_column_t * (1 + len(vals)))()
+            cols[0].type, cols[0].d_values, cols[0].d_valid = INT32, self._p(keys), None
+            for i, (v, vb) in enumerate(zip(vals, valids)):
+                bits = None
+                if vb is not None:
+                    bits = self.empty((vb.numel() + 31) // 32 + 1, torch.int32)
+                    self.ctx.check(self.lib.rj_bytes_to_bitmap(self.h, self._p(vb), vb.numel(), self._p(bits), self.stream))
+                    keep.append(bits)
+                cols[1 + i].type = self._types[t][i]
+                cols[1 + i].d_values, cols[1 + i].d_valid = self._p(v), self._p(bits)
+            keep.append(cols)
+            tables[t].num_rows, tables[t].n_columns, tables[t].columns = keys.numel(), 1 + len(vals), cols
+        plan = Plan()
+        widths = [1 + len(bvals), 1 + len(pvals)]
+        for t in range(2):
+            plan.new_scan_node(t, [(0, DataType.INT32)] + [(1 + i, DataType(self._types[t][i])) for i in range(widths[t] - 1)])
+        outs = []
+        for side, which, type_ in out_cols:
+            base = 0 if side == "b" else widths[0]
+            outs.append((base + (0 if which == "key" else 1 + which), DataType(type_)))
+        plan.root = plan.new_join_node(True, 0, 1, 0, 0, outs)
+        hin = C.c_void_p()
+        self.ctx.check(self.lib.rj_inputs_adopt_dense(self.h, tables, 2, C.byref(hin)))
+        inputs = ResidentInputs(self.ctx, hin, keep=keep)
+        flat = FlatPlan(plan)  # nodes only: the inputs live in the rj_inputs object
+        hres = C.c_void_p()
+        self.ctx.check(self.lib.rj_execute_resident(self.h, flat.pointer(), inputs.handle, C.byref(hres)))
+        res = Result(self.ctx, hres)
+        inputs.free()
+        cols = [ResultPages(res.column_pages(c), int(res.column_type(c)), result=res, col=c) for c in range(res.num_columns)]
+        return res.num_rows, cols
+
+    _types = ((INT64,), (FP64,))  # payload types per side; set by distributed_join
 
     def encode_fixed(self, values, valid_bytes, rows, type_):
         """-> device tensor of pages (uint8, n_pages * 8192)"""
@@ -223,23 +301,30 @@ def distributed_join(ops, build, probe, out_cols, group=None):
     mark()
     pk, pvals, pvalids, sent_p = shuffle_relation(ops, probe, g, group)
     mark()
-    ob, op = ops.join_keys(bk, pk)
-    mark()
-    cols = []
-    for side, which, type_ in out_cols:
-        rows = ob if side == "b" else op
-        if which == "key":
-            values, valid = (bk if side == "b" else pk), None
-        else:
-            values = (bvals if side == "b" else pvals)[which]
-            valid = (bvalids if side == "b" else pvalids)[which]
-        pages, n_pages = ops.encode_fixed(values, valid, rows, type_)
-        cols.append((pages, n_pages, type_))
+    if hasattr(ops, "local_join_encode"):
+        # whole-path local join (CUDA engine): partition -> build/probe -> carried payloads -> page encode
+        ops._types = (tuple(p[2] for p in build.payloads), tuple(p[2] for p in probe.payloads))
+        n_rows, cols = ops.local_join_encode(bk, bvals, bvalids, pk, pvals, pvalids, out_cols)
+        mark()
+    else:
+        ob, op = ops.join_keys(bk, pk)
+        mark()
+        cols = []
+        for side, which, type_ in out_cols:
+            rows = ob if side == "b" else op
+            if which == "key":
+                values, valid = (bk if side == "b" else pk), None
+            else:
+                values = (bvals if side == "b" else pvals)[which]
+                valid = (bvalids if side == "b" else pvalids)[which]
+            pages, n_pages = ops.encode_fixed(values, valid, rows, type_)
+            cols.append(ResultPages(n_pages, type_, tensor=pages))
+        n_rows = int(ob.numel())
     mark()
     stats = {"sent_bytes": sent_b + sent_p, "owned_build": int(bk.numel()), "owned_probe": int(pk.numel())}
     if trace:
-        names = ["shuffle_build", "shuffle_probe", "join", "encode"]
+        names = ["shuffle_build", "shuffle_probe", "join(+encode)", "encode"]
         stats["phase_ms"] = {n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t[:-1], t[1:])}
         if dist.get_rank(group) == 0:
             print("[rj dist]", stats["phase_ms"], flush=True)
-    return int(ob.numel()), cols, stats
+    return n_rows, cols, stats

@@ -116,6 +116,12 @@ class Result:
             self.ctx.lib.rj_result_free(self.ctx.handle, self.handle)
             self.handle = None
 
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
 
 class ResidentInputs:
     def __init__(self, ctx: Context, handle, keep=None):

@@ -29,7 +29,7 @@ def main():
     rows, cols, stats = dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS)
     outdir = os.environ.get("RJ_CHECK_DIR", "/tmp/rj_dist_check")
     os.makedirs(outdir, exist_ok=True)
-    np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c[0].cpu().numpy() for i, c in enumerate(cols)})
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
     dist.barrier()
     ok = True
     if rank == 0:

@@ -86,7 +86,7 @@ def worker(rank, world, port, outdir, n_b, n_p):
     out_cols = [("b", "key", INT32), ("b", 0, INT64), ("p", 0, FP64), ("p", "key", INT32)]
     rows, cols, stats = dj.distributed_join(NumpyOps(), rels[0], rels[1], out_cols)
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, sent=stats["sent_bytes"],
-             **{f"c{i}": c[0].numpy() for i, c in enumerate(cols)})
+             **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
     dist.barrier()
     dist.destroy_process_group()
 
