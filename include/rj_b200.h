@@ -195,6 +195,25 @@ int rj_radix_scatter(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid,
                      int32_t bits, uint32_t* d_cursor, void* d_keys_out, uint32_t* d_idx_out,
                      void* stream);
 
+/* Scatter with one output base PER PARTITION (<= 8 partitions) and payload columns that travel with
+ * the tuples.  The bases may be peer-mapped memory of other GPUs: with the partitions being the owner
+ * ranks of a multi-GPU join this one kernel is partition + exchange (its write-combined runs become
+ * coalesced stores over NVLink; no separate collective).  d_cursor[p] = first free slot in partition p's
+ * buffer (advanced by the kernel).  rows_out may be all NULL.  pay_width: 4 / 8 = values, 1 = pay_src is a
+ * validity BITMAP and one byte per tuple is written. */
+typedef struct rj_scatter_multi_t {
+    void*       keys_out[8];
+    uint32_t*   rows_out[8];
+    uint32_t    n_payload; /* <= 6 */
+    uint32_t    reserved;
+    const void* pay_src[6];
+    int32_t     pay_width[6];
+    void*       pay_dst[6][8];
+} rj_scatter_multi_t;
+int rj_radix_scatter_multi(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, uint64_t n, int32_t key_bytes,
+                           int32_t shift, int32_t bits, uint32_t* d_cursor, const rj_scatter_multi_t* out,
+                           void* stream);
+
 /* -- join: replaces hash_join_omp steps 2-6 (src/execute.cpp:61-261) ---------------------------- */
 
 /* Inner equi-join of two key columns.  Emits (build row, probe row) pairs in unspecified order.

@@ -41,6 +41,12 @@ class rj_dense_table_t(C.Structure):
                 ("columns", C.POINTER(rj_dense_column_t))]
 
 
+class rj_scatter_multi_t(C.Structure):
+    _fields_ = [("keys_out", C.c_void_p * 8), ("rows_out", C.c_void_p * 8), ("n_payload", C.c_uint32),
+                ("reserved", C.c_uint32), ("pay_src", C.c_void_p * 6), ("pay_width", C.c_int32 * 6),
+                ("pay_dst", (C.c_void_p * 8) * 6)]
+
+
 class rj_attr_t(C.Structure):
     _fields_ = [("index", C.c_uint64), ("type", C.c_int32), ("reserved", C.c_uint32)]
 
@@ -111,6 +117,7 @@ PROTOTYPES = {
     "rj_decode_varchar": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _vp, _vp]),
     "rj_radix_histogram": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp, _vp]),
     "rj_radix_scatter": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "rj_radix_scatter_multi": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _vp, C.POINTER(rj_scatter_multi_t), _vp]),
     "rj_join_keys": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _i32, _u64, _vp, _vp,
                                C.POINTER(_u64), _vp]),
     "rj_gather": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, _vp, _vp, _vp]),

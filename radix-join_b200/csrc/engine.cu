@@ -1326,6 +1326,16 @@ int rj_radix_scatter(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, c
     });
 }
 
+int rj_radix_scatter_multi(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, uint64_t n, int32_t key_bytes,
+                           int32_t shift, int32_t bits, uint32_t* d_cursor, const rj_scatter_multi_t* out, void* stream) {
+    return guarded(ctx, [&] {
+        if ((key_bytes != 4 && key_bytes != 8) || bits < 0 || bits > 3 || !out) throw EngineError("rj_radix_scatter_multi: at most 8 partitions");
+        if (out->n_payload > 6) throw EngineError("rj_radix_scatter_multi: at most 6 payload columns");
+        if (n >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
+        launch_radix_scatter_multi(d_keys, d_valid, n, key_bytes, shift, bits, d_cursor, *out, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
 int rj_join_keys(rj_ctx* ctx, const void* d_build_keys, const uint32_t* d_build_valid, uint64_t n_build,
                  const void* d_probe_keys, const uint32_t* d_probe_valid, uint64_t n_probe, int32_t key_bytes,
                  uint64_t capacity, uint32_t* d_out_build, uint32_t* d_out_probe, uint64_t* n_matches, void* stream) {

@@ -152,13 +152,14 @@ __global__ void __launch_bounds__(kPlanThreads)
 }
 
 // ---- scatter ----------------------------------------------------------------------------------------
-template <typename K, bool kRegions>
+// kMulti: every partition has its own output bases (`multi`), possibly in another GPU's memory
+template <typename K, bool kRegions, bool kMulti = false>
 __global__ void __launch_bounds__(kScatterThreads, 2)
     radix_scatter_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
                          const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
                          const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
                          uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
-                         ScatterPayload pay) {
+                         ScatterPayload pay, const rj_scatter_multi_t* __restrict__ multi = nullptr) {
     constexpr int      kScatterItems = ScatterCfg<K>::kItems;
     constexpr uint32_t kTile         = ScatterCfg<K>::kTile;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -280,6 +281,22 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
             const uint32_t part = (hash_key(k) >> shift) & mask;
             const uint32_t dst  = s_gbase[part] + pos;
             const uint32_t row  = s_idx[pos];
+            if (kMulti) {
+                // per-partition bases (peer memory when the partitions are owner ranks)
+                static_cast<K*>(multi->keys_out[part])[dst] = k;
+                if (multi->rows_out[part] != nullptr) multi->rows_out[part][dst] = row;
+                for (uint32_t c = 0; c < multi->n_payload; ++c) {
+                    const int w = multi->pay_width[c];
+                    if (w == 8) {
+                        static_cast<uint64_t*>(multi->pay_dst[c][part])[dst] = static_cast<const uint64_t*>(multi->pay_src[c])[row];
+                    } else if (w == 1) {
+                        static_cast<uint8_t*>(multi->pay_dst[c][part])[dst] = test_bit(static_cast<const uint32_t*>(multi->pay_src[c]), row) ? 1 : 0;
+                    } else {
+                        static_cast<uint32_t*>(multi->pay_dst[c][part])[dst] = static_cast<const uint32_t*>(multi->pay_src[c])[row];
+                    }
+                }
+                continue;
+            }
             keys_out[dst] = k;
             idx_out[dst]  = row;
             // payload columns ride along: the reads stay inside this tile's row window
@@ -398,6 +415,40 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
         radix_scatter_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
             static_cast<uint64_t*>(keys_out), idx_out, payload);
+    }
+    RJ_LAUNCH_CHECK();
+}
+
+void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift, int bits,
+                                uint32_t* cursor, const rj_scatter_multi_t& out, int sm_count, cudaStream_t s) {
+    if (n == 0) return;
+    // the descriptor (~600 bytes of pointers) lives in device memory for the duration of the launch
+    static thread_local rj_scatter_multi_t* d_desc = nullptr;
+    if (!d_desc) RJ_CUDA(cudaMalloc(&d_desc, sizeof(rj_scatter_multi_t)));
+    RJ_CUDA(cudaMemcpyAsync(d_desc, &out, sizeof(rj_scatter_multi_t), cudaMemcpyHostToDevice, s));
+    const uint32_t tile = scatter_tile(key_bytes);
+    uint64_t n_tiles = (n + tile - 1) / tile;
+    unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 2 ? n_tiles : static_cast<uint64_t>(sm_count) * 2);
+    if (key_bytes == 4) {
+        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
+        static size_t configured = 0;
+        if (smem > configured) {
+            RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<uint32_t, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        radix_scatter_kernel<uint32_t, false, true><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint32_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift, bits, cursor, nullptr, nullptr,
+            ScatterPayload{}, d_desc);
+    } else {
+        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
+        static size_t configured = 0;
+        if (smem > configured) {
+            RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<uint64_t, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        radix_scatter_kernel<uint64_t, false, true><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint64_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift, bits, cursor, nullptr, nullptr,
+            ScatterPayload{}, d_desc);
     }
     RJ_LAUNCH_CHECK();
 }

@@ -100,6 +100,9 @@ struct ScatterPayload {
 void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_t* idx_in, uint64_t n,
                           int key_bytes, int shift, int bits, uint32_t* cursor, void* keys_out,
                           uint32_t* idx_out, const ScatterPayload& payload, int sm_count, cudaStream_t s);
+// flat scatter with one output base per partition (<= 8) -- see rj_radix_scatter_multi
+void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift, int bits,
+                                uint32_t* cursor, const rj_scatter_multi_t& out, int sm_count, cudaStream_t s);
 // segmented scatter (pass 2): region r covers [region_start[r], region_start[r+1]) of the input,
 // tiles are enumerated through tile_start, cursor index = (r << bits) | digit
 void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,

@@ -132,6 +132,40 @@ class CudaOps:
                                                  self._p(cursor), self._p(keys_out), self._p(rows_out), self.stream))
         return keys_out[:total], rows_out[:total], counts
 
+    def owner_counts(self, keys, valid, g):
+        """tuples per owner rank (host tensor int64[G])"""
+        hist = self.zeros(1 << g, torch.int32)
+        self.ctx.check(self.lib.rj_radix_histogram(self.h, self._p(keys), self._p(valid), keys.numel(), 4, 32 - g, g,
+                                                   self._p(hist), self.stream))
+        return hist.cpu().to(torch.int64)
+
+    def scatter_to_peers(self, keys, valid, payloads, g, offsets, xchg):
+        """Fused partition + exchange: ONE kernel groups the tuples by owner rank and writes the runs
+        (keys, payload values, validity bytes) straight into the owners' receive buffers -- peer-mapped
+        symmetric memory, i.e. coalesced stores over NVLink; no collective moves the data."""
+        desc = _cabi.rj_scatter_multi_t()
+        G = 1 << g
+        for d in range(G):
+            desc.keys_out[d] = xchg.keys.ptrs[d]
+            desc.rows_out[d] = None
+        n_pay = 0
+        for i, (values, vbits) in enumerate(payloads):
+            desc.pay_src[n_pay] = self._p(values)
+            desc.pay_width[n_pay] = values.element_size()
+            for d in range(G):
+                desc.pay_dst[n_pay][d] = xchg.vals[i].ptrs[d]
+            n_pay += 1
+            if vbits is not None:
+                desc.pay_src[n_pay] = self._p(vbits)
+                desc.pay_width[n_pay] = 1
+                for d in range(G):
+                    desc.pay_dst[n_pay][d] = xchg.valids[i].ptrs[d]
+                n_pay += 1
+        desc.n_payload = n_pay
+        cursor = offsets.to(torch.int32).to(self.device)
+        self.ctx.check(self.lib.rj_radix_scatter_multi(self.h, self._p(keys), self._p(valid), keys.numel(), 4, 32 - g, g,
+                                                       self._p(cursor), C.byref(desc), self.stream))
+
     def gather(self, values, valid, rows):
         """values[rows], valid bits -> (gathered values, uint8 validity per row or None)"""
         n = rows.numel()
@@ -252,6 +286,60 @@ def exchange_counts(counts, group=None):
     return recv.cpu()
 
 
+class _SymBuf:
+    def __init__(self, n, dtype, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.tensor = symm.empty(n, dtype=dtype, device=device)
+        self.handle = symm.rendezvous(self.tensor, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+
+class PeerExchange:
+    """Receive buffers of one relation in symmetric memory: every rank can store into every other
+    rank's buffers through NVLink.  Created once, reused by every join."""
+
+    def __init__(self, device, cap_rows, payload_dtypes, payload_nullable, group=None):
+        self.cap = int(cap_rows)
+        self.keys = _SymBuf(self.cap, torch.int32, device, group)
+        self.vals = [_SymBuf(self.cap, dt, device, group) for dt in payload_dtypes]
+        self.valids = [_SymBuf(self.cap, torch.uint8, device, group) if nn else None for nn in payload_nullable]
+
+    def barrier(self):
+        self.keys.handle.barrier()  # device-side barrier on the current stream, all ranks
+
+
+def shuffle_relation_p2p(ops, rel, g, xchg, group=None):
+    """steps 1-3 with the exchange fused into the partition kernel (peer stores instead of NCCL)"""
+    world, me = dist.get_world_size(group), dist.get_rank(group)
+    kp, kn, kt, knull = rel.key
+    keys, kvalid = ops.decode_fixed(kp, kn, kt, rel.n_rows, knull)
+    payloads = [ops.decode_fixed(pp, pn, pt, rel.n_rows, pnull) for (pp, pn, pt, pnull) in rel.payloads]
+    counts = ops.owner_counts(keys, kvalid, g)
+    # G x G count matrix: row s = what rank s sends to each owner
+    mat = torch.empty(world * world, dtype=torch.int64, device=ops.device)
+    dist.all_gather_into_tensor(mat, counts.to(ops.device), group=group)
+    mat = mat.view(world, world).cpu()
+    offsets = mat[:me].sum(dim=0)          # where my run starts in each owner's buffer
+    total = int(mat[:, me].sum())          # what I receive
+    if int(mat.sum(dim=0).max()) > xchg.cap:
+        raise RuntimeError("peer exchange buffers too small for this key distribution")
+    xchg.barrier()                         # every rank is done reading the previous contents
+    ops.scatter_to_peers(keys, kvalid, payloads, g, offsets, xchg)
+    xchg.barrier()                         # every rank's stores have landed
+    sent = int(counts.sum() - counts[me])
+    sent_bytes = sent * 4
+    vals, valids = [], []
+    for i, (v, vbits) in enumerate(payloads):
+        vals.append(xchg.vals[i].tensor[:total])
+        sent_bytes += sent * v.element_size()
+        if vbits is not None:
+            valids.append(xchg.valids[i].tensor[:total])
+            sent_bytes += sent
+        else:
+            valids.append(None)
+    return xchg.keys.tensor[:total], vals, valids, sent_bytes
+
+
 class Relation:
     """one rank's slice of a relation: a key column and payload columns, as device pages"""
 
@@ -263,17 +351,32 @@ class Relation:
 def shuffle_relation(ops, rel, g, group=None):
     """steps 1-3 for one relation: returns (keys, [payload values], [payload validity bytes or None])
     of the tuples this rank OWNS, plus the bytes it sent"""
+    trace = os.environ.get("RJ_DIST_TRACE") and hasattr(ops, "sync")
+    marks = []
+
+    def mark(name):
+        if trace:
+            ops.sync()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     kp, kn, kt, knull = rel.key
     keys, kvalid = ops.decode_fixed(kp, kn, kt, rel.n_rows, knull)
+    mark("decode_key")
     keys_o, rows_o, counts = ops.owner_partition(keys, kvalid, g)
+    mark("owner_partition")
     recv = exchange_counts(counts, group)
+    mark("counts")
     sent_bytes = 0
     out_keys = all_to_all_v(keys_o, counts, recv, group)
+    mark("a2a_keys")
     sent_bytes += keys_o.numel() * 4
     vals, valids = [], []
     for (pp, pn, pt, pnull) in rel.payloads:
         v, vv = ops.decode_fixed(pp, pn, pt, rel.n_rows, pnull)
+        mark("decode_payload")
         gv, gvalid = ops.gather(v, vv, rows_o)
+        mark("gather_payload")
         vals.append(all_to_all_v(gv, counts, recv, group))
         sent_bytes += gv.numel() * gv.element_size()
         if gvalid is not None:
@@ -281,12 +384,17 @@ def shuffle_relation(ops, rel, g, group=None):
             sent_bytes += gvalid.numel()
         else:
             valids.append(None)
+        mark("a2a_payload")
+    if trace and dist.get_rank(group) == 0:
+        print("[rj dist shuffle]", {n: round((t1 - t0) * 1e3, 2) for (n, t1), (_, t0) in zip(marks[1:], marks[:-1])}, flush=True)
     return out_keys, vals, valids, sent_bytes
 
 
-def distributed_join(ops, build, probe, out_cols, group=None):
+def distributed_join(ops, build, probe, out_cols, group=None, xchg=None):
     """Inner equi-join of two sharded relations.  out_cols: list of ("b"|"p", "key"|payload index, type).
-    Returns (n_rows, [(pages tensor, n_pages, type)], stats) for THIS rank's share of the result."""
+    xchg = (PeerExchange for build, PeerExchange for probe) switches the exchange from NCCL all-to-all-v to
+    the fused partition + peer-store kernel.
+    Returns (n_rows, [ResultPages], stats) for THIS rank's share of the result."""
     world = dist.get_world_size(group)
     g = log2_exact(world)
     trace = os.environ.get("RJ_DIST_TRACE") and hasattr(ops, "sync")
@@ -297,10 +405,16 @@ def distributed_join(ops, build, probe, out_cols, group=None):
             ops.sync()
             t.append(time.perf_counter())
 
-    bk, bvals, bvalids, sent_b = shuffle_relation(ops, build, g, group)
-    mark()
-    pk, pvals, pvalids, sent_p = shuffle_relation(ops, probe, g, group)
-    mark()
+    if xchg is not None:
+        bk, bvals, bvalids, sent_b = shuffle_relation_p2p(ops, build, g, xchg[0], group)
+        mark()
+        pk, pvals, pvalids, sent_p = shuffle_relation_p2p(ops, probe, g, xchg[1], group)
+        mark()
+    else:
+        bk, bvals, bvalids, sent_b = shuffle_relation(ops, build, g, group)
+        mark()
+        pk, pvals, pvalids, sent_p = shuffle_relation(ops, probe, g, group)
+        mark()
     if hasattr(ops, "local_join_encode"):
         # whole-path local join (CUDA engine): partition -> build/probe -> carried payloads -> page encode
         ops._types = (tuple(p[2] for p in build.payloads), tuple(p[2] for p in probe.payloads))
@@ -321,7 +435,8 @@ def distributed_join(ops, build, probe, out_cols, group=None):
             cols.append(ResultPages(n_pages, type_, tensor=pages))
         n_rows = int(ob.numel())
     mark()
-    stats = {"sent_bytes": sent_b + sent_p, "owned_build": int(bk.numel()), "owned_probe": int(pk.numel())}
+    stats = {"sent_bytes": sent_b + sent_p, "owned_build": int(bk.numel()), "owned_probe": int(pk.numel()),
+             "exchange": "peer stores (fused into the partition kernel)" if xchg is not None else "collective all-to-all-v"}
     if trace:
         names = ["shuffle_build", "shuffle_probe", "join(+encode)", "encode"]
         stats["phase_ms"] = {n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t[:-1], t[1:])}

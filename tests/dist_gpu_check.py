@@ -26,7 +26,12 @@ def main():
     dt = syn.make_c2_device(ctx, n_b, n_p, rank=rank, world=world)
     build, probe = dist_bench._relations(dt)
     ops = dj.CudaOps(ctx)
-    rows, cols, stats = dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS)
+    xchg = None
+    if os.environ.get("RJ_DIST_EXCHANGE", "p2p") == "p2p":
+        xchg = (dj.PeerExchange(ops.device, n_b, [torch.int64], [True]), dj.PeerExchange(ops.device, n_p, [torch.int64], [True]))
+    rows, cols, stats = dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS, xchg=xchg)
+    if rank == 0:
+        print("exchange:", stats["exchange"], flush=True)
     outdir = os.environ.get("RJ_CHECK_DIR", "/tmp/rj_dist_check")
     os.makedirs(outdir, exist_ok=True)
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
