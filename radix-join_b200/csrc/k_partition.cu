@@ -274,40 +274,94 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
         }
         __syncthreads();
 
-        // 4) stream the runs out: thread -> staged position, neighbours write neighbouring addresses
+        // 4) stream the runs out: thread -> staged position, neighbours write neighbouring addresses.
+        //    Four positions per thread are in flight at once, and the payload slots are unrolled
+        //    statically (a dynamically indexed descriptor lands in local memory: ncu showed the copy-out
+        //    stalled on LDL -> LDG -> STG chains, one position at a time).
         const uint32_t total = s_total;
-        for (uint32_t pos = threadIdx.x; pos < total; pos += kScatterThreads) {
-            const K        k    = s_keys[pos];
-            const uint32_t part = (hash_key(k) >> shift) & mask;
-            const uint32_t dst  = s_gbase[part] + pos;
-            const uint32_t row  = s_idx[pos];
+        for (uint32_t base = 0; base < total; base += 4 * kScatterThreads) {
+            K        kk[4];
+            uint32_t rr[4], dd[4], pp[4];
+            bool     in[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pos = base + j * kScatterThreads + threadIdx.x;
+                in[j] = pos < total;
+                kk[j] = K(0);
+                rr[j] = dd[j] = pp[j] = 0;
+                if (in[j]) {
+                    kk[j] = s_keys[pos];
+                    rr[j] = s_idx[pos];
+                    pp[j] = (hash_key(kk[j]) >> shift) & mask;
+                    dd[j] = s_gbase[pp[j]] + pos;
+                }
+            }
             if (kMulti) {
                 // per-partition bases (peer memory when the partitions are owner ranks)
-                static_cast<K*>(multi->keys_out[part])[dst] = k;
-                if (multi->rows_out[part] != nullptr) multi->rows_out[part][dst] = row;
-                for (uint32_t c = 0; c < multi->n_payload; ++c) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (!in[j]) continue;
+                    static_cast<K*>(multi->keys_out[pp[j]])[dd[j]] = kk[j];
+                    if (multi->rows_out[pp[j]] != nullptr) multi->rows_out[pp[j]][dd[j]] = rr[j];
+                }
+                const uint32_t n_pay = multi->n_payload;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    if (c >= static_cast<int>(n_pay)) break;
                     const int w = multi->pay_width[c];
                     if (w == 8) {
-                        static_cast<uint64_t*>(multi->pay_dst[c][part])[dst] = static_cast<const uint64_t*>(multi->pay_src[c])[row];
+                        uint64_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(multi->pay_src[c])[rr[j]] : 0ull;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint64_t*>(multi->pay_dst[c][pp[j]])[dd[j]] = v[j];
                     } else if (w == 1) {
-                        static_cast<uint8_t*>(multi->pay_dst[c][part])[dst] = test_bit(static_cast<const uint32_t*>(multi->pay_src[c]), row) ? 1 : 0;
+                        uint32_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(multi->pay_src[c])[rr[j] >> 5] : 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint8_t*>(multi->pay_dst[c][pp[j]])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
                     } else {
-                        static_cast<uint32_t*>(multi->pay_dst[c][part])[dst] = static_cast<const uint32_t*>(multi->pay_src[c])[row];
+                        uint32_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(multi->pay_src[c])[rr[j]] : 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint32_t*>(multi->pay_dst[c][pp[j]])[dd[j]] = v[j];
                     }
                 }
                 continue;
             }
-            keys_out[dst] = k;
-            idx_out[dst]  = row;
-            // payload columns ride along: the reads stay inside this tile's row window
-            for (int c = 0; c < pay.n; ++c) {
-                if (pay.width[c] == 8) {
-                    static_cast<uint64_t*>(pay.dst[c])[dst] = static_cast<const uint64_t*>(pay.src[c])[row];
-                } else if (pay.width[c] == 1) {
-                    // a validity bitmap travels as one byte per tuple
-                    static_cast<uint8_t*>(pay.dst[c])[dst] = test_bit(static_cast<const uint32_t*>(pay.src[c]), row) ? 1 : 0;
-                } else {
-                    static_cast<uint32_t*>(pay.dst[c])[dst] = static_cast<const uint32_t*>(pay.src[c])[row];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (in[j]) {
+                    keys_out[dd[j]] = kk[j];
+                    idx_out[dd[j]]  = rr[j];
+                }
+            }
+            // carried payload columns: the reads stay inside this tile's row window (L1/L2 resident)
+#pragma unroll
+            for (int c = 0; c < ScatterPayload::kMax; ++c) {
+                if (c < pay.n) {
+                    const int w = pay.width[c];
+                    if (w == 8) {
+                        uint64_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(pay.src[c])[rr[j]] : 0ull;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = v[j];
+                    } else if (w == 1) { // a validity bitmap travels as one byte per tuple
+                        uint32_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j] >> 5] : 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint8_t*>(pay.dst[c])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
+                    } else {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j]] : 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = v[j];
+                    }
                 }
             }
         }
