@@ -250,6 +250,48 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                 uint32_t slot = 0xffffffffu; // where its cluster walk continues (0xffffffff = home slot)
                 for (;;) {
                     bool stalled = false;
+                    if (unique) {
+                        // ---- fast path: no duplicate build keys in this table --------------------------
+                        // at most one match per probe tuple, so a super-batch stages <= kBatch pairs into a
+                        // buffer that is flushed after every super-batch: no overflow, no resume logic.
+                        // All items are walked first (lockstep per item), then the warp reserves its
+                        // staging slots ONCE: per-item ballots give conflict-free, item-major positions.
+                        uint32_t mrow[kItems];
+                        uint32_t bal[kItems];
+                        uint32_t total = 0;
+#pragma unroll
+                        for (int k = 0; k < kItems; ++k) {
+                            mrow[k] = kEmpty;
+                            if (row[k] != kEmpty) {
+                                uint32_t sl = (hash_key(key[k]) >> part_bits) & kSlotMask;
+                                for (;;) {
+                                    bool           eq;
+                                    const uint32_t r = table.load(sl, key[k], &eq);
+                                    if (r == kEmpty) break;
+                                    if (eq) {
+                                        mrow[k] = r;
+                                        break;
+                                    }
+                                    sl = (sl + 1) & kSlotMask;
+                                }
+                            }
+                            __syncwarp();
+                            bal[k] = __ballot_sync(RJ_FULL_MASK, mrow[k] != kEmpty);
+                            total += __popc(bal[k]);
+                        }
+                        uint32_t off = 0;
+                        if (lane == 0 && total) off = atomicAdd(&s_out_n, total);
+                        off = __shfl_sync(RJ_FULL_MASK, off, 0);
+#pragma unroll
+                        for (int k = 0; k < kItems; ++k) {
+                            if (mrow[k] != kEmpty) {
+                                const uint32_t pos = off + __popc(bal[k] & lt);
+                                s_out_b[pos] = mrow[k];
+                                s_out_p[pos] = row[k];
+                            }
+                            off += __popc(bal[k]);
+                        }
+                    } else {
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
                         // lanes that already finished item k (before a flush), have no tuple, or stalled
@@ -283,7 +325,6 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                                 if (pos < kOutCap) {
                                     s_out_b[pos] = match;
                                     s_out_p[pos] = row[k];
-                                    if (unique) walking = false; // no other build row can match
                                 } else {
                                     // staging buffer full: step back onto the match, resume after the flush
                                     slot = (slot - 1) & kSlotMask;
@@ -297,6 +338,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                             item = k + 1;
                             slot = 0xffffffffu;
                         }
+                    }
                     }
                     const int any_stalled = __syncthreads_or(stalled ? 1 : 0);
                     const uint32_t staged = s_out_n < kOutCap ? s_out_n : kOutCap;
