@@ -395,8 +395,9 @@ struct Attr {
 // `pos` indexes the side's position order (the pass-1 / single-pass scatter output).  Kept lazy: the
 // root encodes carried columns straight from position order and may never need the row ids.
 struct PosSpace {
-    Buf pos;         // [rows]
-    Buf rows_of_pos; // [side rows]
+    Buf      pos;         // [rows]; the top bits may carry validity flags
+    Buf      rows_of_pos; // [side rows]
+    uint32_t mask = 0xffffffffu;
 };
 
 // A column that travelled through the scatter: values_of_pos[pos[i]] is row i's value.
@@ -405,6 +406,8 @@ struct CarriedCol {
     const void* values_of_pos = nullptr;
     Buf         valid_hold;        // one validity byte per position (carried with the values), or null
     Buf         pos;
+    uint32_t    pos_mask = 0xffffffffu;
+    int         valid_bit = -1;     // >= 0: validity of this column rides in that bit of pos
     bool        never_null = false; // a matched join key is never NULL
 };
 
@@ -424,6 +427,7 @@ struct CarryCol {
     Buf         out;           // values by position (filled by the scatter)
     const uint32_t* valid_src = nullptr; // validity bitmap by row (null: no NULLs)
     Buf         valid_out;     // validity bytes by position
+    int         valid_bit = -1; // >= 0: also folded into that bit of the emitted positions
 };
 
 struct JoinSide {
@@ -433,6 +437,7 @@ struct JoinSide {
     std::vector<CarryCol> carry; // columns to move with the tuples (only honoured when partitioned)
     // results
     bool partitioned = false;
+    uint32_t pos_mask = 0xffffffffu; // strips the validity flags pass 2 may fold into the positions
     Buf  pos;          // [M] position (= row when not partitioned)
     Buf  rows_of_pos;  // [n]
     Buf  keys_of_pos;  // [n]
@@ -471,7 +476,7 @@ struct Exec {
     Rel  run(uint64_t n);
     Rel  join(uint64_t n, const Rel& L, const Rel& R);
     void join_keys(JoinSide& b, JoinSide& p, int key_bytes, uint64_t* n_out);
-    Buf  gather_u32(const Buf& src, const Buf& idx, uint64_t n);
+    Buf  gather_u32(const Buf& src, const Buf& idx, uint64_t n, uint32_t idx_mask = 0xffffffffu);
     Buf  side_rows(const JoinSide& sd, uint64_t m);
     Buf  rid_of(const Rel& r, int leaf);
     std::unique_ptr<rj_result> root(uint64_t n, const Rel& r);
@@ -546,10 +551,10 @@ const DecodedCol& Exec::string_hash(uint32_t t, uint32_t c) {
     return d;
 }
 
-Buf Exec::gather_u32(const Buf& src, const Buf& idx, uint64_t n) {
+Buf Exec::gather_u32(const Buf& src, const Buf& idx, uint64_t n, uint32_t idx_mask) {
     Buf out = dev_alloc(n * 4, s);
     StageScope sc(ctx, RJ_ST_GATHER, s, 1, n * 12);
-    launch_gather(src->p, nullptr, idx->as<uint32_t>(), n, 4, out->p, nullptr, ctx->sm_count, s);
+    launch_gather(src->p, nullptr, idx->as<uint32_t>(), n, 4, out->p, nullptr, ctx->sm_count, s, idx_mask);
     return out;
 }
 
@@ -637,10 +642,24 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
             Buf tk_p = dev_alloc(np * key_bytes, s), ti_p = dev_alloc(np * 4, s);
             launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, bits2, bits1, pl.cur1_b, tk_b->p, ti_b->as<uint32_t>(), pay_b, ctx->sm_count, s);
             launch_radix_scatter(pk, pv, nullptr, np, key_bytes, bits2, bits1, pl.cur1_p, tk_p->p, ti_p->as<uint32_t>(), pay_p, ctx->sm_count, s);
+            // validity of up to two carried columns per side rides in bits 30/31 of the positions
+            auto flags_of = [&](JoinSide& sd) {
+                RegionFlags f;
+                if (sd.n >= kPosMask) return f;
+                for (auto& c: sd.carry) {
+                    if (c.valid_out && f.n < 2) {
+                        c.valid_bit = 30 + f.n;
+                        f.src[f.n++] = c.valid_out->as<uint8_t>();
+                    }
+                }
+                if (f.n) sd.pos_mask = kPosMask;
+                return f;
+            };
+            const RegionFlags fl_b = flags_of(B), fl_p = flags_of(P);
             launch_radix_scatter_regions(tk_b->p, nullptr, pl.reg_b, pl.tile_b, 1u << bits1, nb, key_bytes, 0, bits2,
-                                         pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), ctx->sm_count, s);
+                                         pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), fl_b, ctx->sm_count, s);
             launch_radix_scatter_regions(tk_p->p, nullptr, pl.reg_p, pl.tile_p, 1u << bits1, np, key_bytes, 0, bits2,
-                                         pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), ctx->sm_count, s);
+                                         pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), fl_p, ctx->sm_count, s);
             jl.bkeys = keys_b->p; jl.bidx = idx_b->as<uint32_t>(); jl.bvalid = nullptr; // idx = pass-1 position
             jl.pkeys = keys_p->p; jl.pidx = idx_p->as<uint32_t>(); jl.pvalid = nullptr;
             B.rows_of_pos = ti_b; B.keys_of_pos = tk_b;
@@ -701,7 +720,7 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
 
 // row index (into the side's input relation) of every match
 Buf Exec::side_rows(const JoinSide& sd, uint64_t m) {
-    return sd.partitioned ? gather_u32(sd.rows_of_pos, sd.pos, m) : sd.pos;
+    return sd.partitioned ? gather_u32(sd.rows_of_pos, sd.pos, m, sd.pos_mask) : sd.pos;
 }
 
 Buf Exec::rid_of(const Rel& r, int leaf) {
@@ -709,7 +728,7 @@ Buf Exec::rid_of(const Rel& r, int leaf) {
     if (it != r.rid.end()) return it->second;
     auto lz = r.lazy.find(leaf);
     if (lz == r.lazy.end()) throw EngineError("internal: leaf not tracked");
-    Buf rows = gather_u32(lz->second.rows_of_pos, lz->second.pos, r.rows);
+    Buf rows = gather_u32(lz->second.rows_of_pos, lz->second.pos, r.rows, lz->second.mask);
     r.rid[leaf] = rows;
     return rows;
 }
@@ -848,12 +867,13 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
         if (identity) {
             // the child is a scan of this leaf: its row index IS the row id
             if (sd.partitioned) {
-                out.lazy[leaf] = PosSpace{sd.pos, sd.rows_of_pos};
+                out.lazy[leaf] = PosSpace{sd.pos, sd.rows_of_pos, sd.pos_mask};
                 // the join key and the carried columns are available in position order
                 CarriedCol kc;
                 kc.hold = sd.keys_of_pos;
                 kc.values_of_pos = sd.keys_of_pos->p;
                 kc.pos = sd.pos;
+                kc.pos_mask = sd.pos_mask;
                 kc.never_null = true;
                 if (key_type != RJ_VARCHAR && leaf == key_attr.leaf) out.carried[{leaf, key_attr.col}] = kc;
                 for (auto& c: sd.carry) {
@@ -863,6 +883,8 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
                     cc.values_of_pos = c.out->p;
                     cc.valid_hold = c.valid_out;
                     cc.pos = sd.pos;
+                    cc.pos_mask = sd.pos_mask;
+                    cc.valid_bit = c.valid_bit;
                     out.carried[{leaf, c.col}] = cc;
                 }
             } else {
@@ -976,6 +998,8 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
         const uint32_t* idx = nullptr;
         const uint32_t* vidx = nullptr;
         const uint8_t*  valid_bytes = nullptr;
+        uint32_t        idx_mask = 0xffffffffu;
+        int             valid_bit = -1;
         Buf             hold_rid;
         auto carried = r.carried.find({at.leaf, at.col});
         if (carried != r.carried.end()) {
@@ -983,7 +1007,10 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
             values = carried->second.values_of_pos;
             idx = carried->second.pos->as<uint32_t>();
             vidx = idx;
-            if (carried->second.valid_hold) {
+            idx_mask = carried->second.pos_mask;
+            if (carried->second.valid_bit >= 0) {
+                valid_bit = carried->second.valid_bit; // validity rides in the position: no gather at all
+            } else if (carried->second.valid_hold) {
                 valid_bytes = carried->second.valid_hold->as<uint8_t>();
             } else if (col.valid && !carried->second.never_null) {
                 hold_rid = rid_of(r, at.leaf);
@@ -996,7 +1023,7 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
         // M*4 + M*w read + 8192 * pages written
         StageScope sc(ctx, RJ_ST_ENCODE, s, 1, r.rows * (4 + w) + rc.n_pages * uint64_t(RJ_PAGE_SIZE));
         const bool all_valid = carried != r.carried.end() && carried->second.never_null;
-        launch_encode_fixed(values, all_valid ? nullptr : col.valid_ptr(), valid_bytes, idx, vidx, r.rows, rc.type, rc.pages->p, ctx->sm_count, s);
+        launch_encode_fixed(values, all_valid ? nullptr : col.valid_ptr(), valid_bytes, idx, vidx, r.rows, rc.type, rc.pages->p, ctx->sm_count, s, idx_mask, valid_bit);
     }
     return res;
 }

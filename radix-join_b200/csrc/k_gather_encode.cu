@@ -21,7 +21,7 @@ constexpr int kEncThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(256)
     gather_kernel(const T* __restrict__ src, const uint32_t* __restrict__ src_valid, const uint32_t* __restrict__ idx,
-                  uint64_t n, T* __restrict__ out, uint32_t* __restrict__ out_valid) {
+                  uint64_t n, T* __restrict__ out, uint32_t* __restrict__ out_valid, uint32_t idx_mask) {
     // each warp owns 32-row groups so that it can assemble whole validity words
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t gw = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256)
     for (uint64_t g = gw; g < n_groups; g += nw) {
         const uint64_t i  = (g << 5) + lane;
         const bool     in = i < n;
-        uint32_t r = in ? idx[i] : 0u;
+        uint32_t r = in ? (idx[i] & idx_mask) : 0u;
         bool     v = in;
         if (in && src_valid != nullptr) v = test_bit(src_valid, r);
         if (in) out[i] = v ? src[r] : T(0);
@@ -53,7 +53,8 @@ template <typename T>
 __global__ void __launch_bounds__(kEncThreads)
     encode_fixed_kernel(const T* __restrict__ values, const uint32_t* __restrict__ valid,
                         const uint8_t* __restrict__ valid_bytes, const uint32_t* __restrict__ idx,
-                        const uint32_t* __restrict__ vidx, uint64_t n, uint8_t* __restrict__ pages_out) {
+                        const uint32_t* __restrict__ vidx, uint64_t n, uint8_t* __restrict__ pages_out,
+                        uint32_t idx_mask, int valid_bit) {
     constexpr uint32_t kRows  = rows_per_page(sizeof(T));
     constexpr uint32_t kBegin = sizeof(T) == 4 ? 4 : 8;
     constexpr int      kPer   = (kRows + kEncThreads - 1) / kEncThreads; // 8 or 4
@@ -77,16 +78,19 @@ __global__ void __launch_bounds__(kEncThreads)
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
             const bool in = i0 + k < cnt;
-            r[k]  = in ? (idx != nullptr ? idx[j0 + i0 + k] : static_cast<uint32_t>(j0 + i0 + k)) : 0u;
-            vr[k] = r[k];
-            if (valid != nullptr && valid_bytes == nullptr && vidx != idx && in)
+            const uint32_t raw = in ? (idx != nullptr ? idx[j0 + i0 + k] : static_cast<uint32_t>(j0 + i0 + k)) : 0u;
+            r[k]  = raw & idx_mask;
+            vr[k] = valid_bit >= 0 ? ((raw >> valid_bit) & 1u) : r[k]; // flag bit, or the index of the validity lookup
+            if (valid_bit < 0 && valid != nullptr && valid_bytes == nullptr && vidx != idx && in)
                 vr[k] = vidx != nullptr ? vidx[j0 + i0 + k] : static_cast<uint32_t>(j0 + i0 + k);
         }
         uint32_t mine = 0, bits = 0;
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
             ok[k] = i0 + k < cnt;
-            if (valid_bytes != nullptr) {
+            if (valid_bit >= 0) {
+                ok[k] = ok[k] && vr[k] != 0;
+            } else if (valid_bytes != nullptr) {
                 ok[k] = ok[k] && valid_bytes[r[k]] != 0;
             } else if (valid != nullptr) {
                 ok[k] = ok[k] && test_bit(valid, vr[k]);
@@ -162,22 +166,23 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint64_t n) {
 } // namespace
 
 void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* idx, uint64_t n, int elem_bytes,
-                   void* out, uint32_t* out_valid, int sm_count, cudaStream_t s) {
+                   void* out, uint32_t* out_valid, int sm_count, cudaStream_t s, uint32_t idx_mask) {
     if (n == 0) return;
     uint64_t want = (n + 255) / 256;
     unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 16 ? want : static_cast<uint64_t>(sm_count) * 16);
     if (elem_bytes == 4) {
         gather_kernel<uint32_t><<<blocks, 256, 0, s>>>(static_cast<const uint32_t*>(src), src_valid, idx, n,
-                                                       static_cast<uint32_t*>(out), out_valid);
+                                                       static_cast<uint32_t*>(out), out_valid, idx_mask);
     } else {
         gather_kernel<uint64_t><<<blocks, 256, 0, s>>>(static_cast<const uint64_t*>(src), src_valid, idx, n,
-                                                       static_cast<uint64_t*>(out), out_valid);
+                                                       static_cast<uint64_t*>(out), out_valid, idx_mask);
     }
     RJ_LAUNCH_CHECK();
 }
 
 void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_t* valid_bytes, const uint32_t* idx,
-                         const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s) {
+                         const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s,
+                         uint32_t idx_mask, int valid_bit) {
     if (n == 0) return;
     const uint32_t rows = type == RJ_INT32 ? rows_per_page(4) : rows_per_page(8);
     const uint64_t n_pages = (n + rows - 1) / rows;
@@ -186,10 +191,10 @@ void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_
     const unsigned blocks = static_cast<unsigned>(n_pages);
     if (type == RJ_INT32) {
         encode_fixed_kernel<uint32_t><<<blocks, kEncThreads, 0, s>>>(
-            static_cast<const uint32_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out));
+            static_cast<const uint32_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out), idx_mask, valid_bit);
     } else {
         encode_fixed_kernel<uint64_t><<<blocks, kEncThreads, 0, s>>>(
-            static_cast<const uint64_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out));
+            static_cast<const uint64_t*>(values), valid, valid_bytes, idx, vidx, n, static_cast<uint8_t*>(pages_out), idx_mask, valid_bit);
     }
     RJ_LAUNCH_CHECK();
 }

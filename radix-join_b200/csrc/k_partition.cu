@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
                          const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
                          const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
                          uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
-                         ScatterPayload pay, const rj_scatter_multi_t* __restrict__ multi = nullptr) {
+                         ScatterPayload pay, const rj_scatter_multi_t* __restrict__ multi = nullptr,
+                         RegionFlags flags = RegionFlags{}) {
     constexpr int      kScatterItems = ScatterCfg<K>::kItems;
     constexpr uint32_t kTile         = ScatterCfg<K>::kTile;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -269,7 +270,13 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
                 const uint64_t i   = lo + static_cast<uint64_t>(k) * kScatterThreads + threadIdx.x;
                 const uint32_t pos = s_start[pr[k] >> 16] + (pr[k] & 0xffffu);
                 s_keys[pos] = key[k];
-                s_idx[pos]  = idx_in != nullptr ? idx_in[i] : static_cast<uint32_t>(i);
+                uint32_t id = idx_in != nullptr ? idx_in[i] : static_cast<uint32_t>(i);
+                if (kRegions) {
+                    // carried validity bytes of the pass-1 order ride in the top bits of the position
+                    if (flags.n > 0 && flags.src[0][i]) id |= 1u << 30;
+                    if (flags.n > 1 && flags.src[1][i]) id |= 1u << 31;
+                }
+                s_idx[pos]  = id;
             }
         }
         __syncthreads();
@@ -510,7 +517,7 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
 void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,
                                   const uint32_t* tile_start, uint32_t n_regions, uint64_t n_upper, int key_bytes,
                                   int shift, int bits, uint32_t* cursor, void* keys_out, uint32_t* idx_out,
-                                  int sm_count, cudaStream_t s) {
+                                  const RegionFlags& flags, int sm_count, cudaStream_t s) {
     if (n_upper == 0) return;
     // the exact tile count lives on the device (tile_start[n_regions]); size the persistent grid from
     // its upper bound so no host synchronisation is needed
@@ -522,13 +529,13 @@ void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, cons
         scatter_set_attr<uint32_t, true>(smem);
         radix_scatter_kernel<uint32_t, true><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{});
+            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{}, nullptr, flags);
     } else {
         const size_t smem = scatter_smem_bytes<uint64_t>(bits);
         scatter_set_attr<uint64_t, true>(smem);
         radix_scatter_kernel<uint64_t, true><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{});
+            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{}, nullptr, flags);
     }
     RJ_LAUNCH_CHECK();
 }

@@ -105,10 +105,17 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
                                 uint32_t* cursor, const rj_scatter_multi_t& out, int sm_count, cudaStream_t s);
 // segmented scatter (pass 2): region r covers [region_start[r], region_start[r+1]) of the input,
 // tiles are enumerated through tile_start, cursor index = (r << bits) | digit
+// Flags folded into the row index written by the segmented scatter: bit (30 + c) of idx_out is set
+// iff flag_src[c][i] != 0 for input tuple i (carried validity bytes; indices must stay below 2^30).
+struct RegionFlags {
+    int            n = 0;
+    const uint8_t* src[2] = {nullptr, nullptr};
+};
+constexpr uint32_t kPosMask = 0x3fffffffu;
 void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,
                                   const uint32_t* tile_start, uint32_t n_regions, uint64_t n_upper,
                                   int key_bytes, int shift, int bits, uint32_t* cursor, void* keys_out,
-                                  uint32_t* idx_out, int sm_count, cudaStream_t s);
+                                  uint32_t* idx_out, const RegionFlags& flags, int sm_count, cudaStream_t s);
 
 // ---- k_join.cu ------------------------------------------------------------------------------------
 struct JoinLaunch {
@@ -134,12 +141,15 @@ void launch_join(const JoinLaunch& a, int sm_count, cudaStream_t s);
 
 // ---- k_gather_encode.cu ---------------------------------------------------------------------------
 void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* idx, uint64_t n,
-                   int elem_bytes, void* out, uint32_t* out_valid, int sm_count, cudaStream_t s);
+                   int elem_bytes, void* out, uint32_t* out_valid, int sm_count, cudaStream_t s,
+                   uint32_t idx_mask = 0xffffffffu);
 // values are read through idx, validity bits through vidx (both NULL = identity; vidx == idx is the
 // plain row-id case, vidx != idx when the values were carried into a partitioned order);
 // valid_bytes (one byte per value, read through idx) replaces the bitmap when it was carried too
+// idx_mask strips flag bits from idx; valid_bit >= 0: the row is non-NULL iff that bit of idx is set
 void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_t* valid_bytes, const uint32_t* idx,
-                         const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s);
+                         const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s,
+                         uint32_t idx_mask = 0xffffffffu, int valid_bit = -1);
 void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
 void launch_bitmap_to_bytes(const uint32_t* bits, uint64_t n, uint8_t* out, int sm_count, cudaStream_t s);
 void launch_bytes_to_bitmap(const uint8_t* bytes, uint64_t n, uint32_t* out, int sm_count, cudaStream_t s);
