@@ -80,6 +80,30 @@ __device__ __forceinline__ void decode_fixed_page(const uint8_t* pg, uint64_t r0
     const T*       vals = reinterpret_cast<const T*>(pg + kBegin);
     const bool     dense = (n_v == n_r); // no NULL on this page: skip the bitmap
     const uint32_t lt = lanemask_lt();
+    if (dense) {
+        // no NULL on this page: a straight copy, 4 x 32 rows per step (4 independent LDS -> STG)
+        const uint32_t n = n_r < kMaxVals ? n_r : kMaxVals;
+        for (uint32_t base = 0; base < n; base += 128) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * 32 + lane;
+                v[u] = i < n ? vals[i] : T(0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = base + u * 32 + lane;
+                if (i < n) out[r0 + i] = v[u];
+            }
+        }
+        if (out_valid != nullptr) {
+            for (uint32_t base = lane * 32; base < n; base += 32 * 32) {
+                const uint32_t left = n - base;
+                or_valid_word(out_valid, r0 + base, left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+            }
+        }
+        return;
+    }
     uint32_t running = 0;
     for (uint32_t base = 0; base < n_r; base += 32) {
         const uint32_t i  = base + lane;

@@ -207,11 +207,17 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
         // 1) load + rank inside the partition
         K        key[kScatterItems];
         uint32_t pr[kScatterItems]; // partition << 16 | rank (rank < 8192, partition < 512)
+        uint32_t fl = 0;            // 2 carried-validity flags per item (segmented scatter only)
 #pragma unroll
         for (int k = 0; k < kScatterItems; ++k) {
             const uint64_t i = lo + static_cast<uint64_t>(k) * kScatterThreads + threadIdx.x;
             bool ok = i < hi;
             key[k] = ok ? keys[i] : K(0);
+            if (kRegions && ok) {
+                // loaded here, in the same batch of independent loads as the keys
+                if (flags.n > 0 && flags.src[0][i]) fl |= 1u << (2 * k);
+                if (flags.n > 1 && flags.src[1][i]) fl |= 2u << (2 * k);
+            }
             if (ok && valid != nullptr) ok = test_bit(valid, i);
             pr[k]  = ok ? ((hash_key(key[k]) >> shift) & mask) : 0xffffffffu;
         }
@@ -271,11 +277,8 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
                 const uint32_t pos = s_start[pr[k] >> 16] + (pr[k] & 0xffffu);
                 s_keys[pos] = key[k];
                 uint32_t id = idx_in != nullptr ? idx_in[i] : static_cast<uint32_t>(i);
-                if (kRegions) {
-                    // carried validity bytes of the pass-1 order ride in the top bits of the position
-                    if (flags.n > 0 && flags.src[0][i]) id |= 1u << 30;
-                    if (flags.n > 1 && flags.src[1][i]) id |= 1u << 31;
-                }
+                // carried validity bytes of the pass-1 order ride in the top bits of the position
+                if (kRegions) id |= ((fl >> (2 * k)) & 3u) << 30;
                 s_idx[pos]  = id;
             }
         }
