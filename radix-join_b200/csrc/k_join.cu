@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
     uint32_t* s_out_p = s_out_b + kOutCap;
     __shared__ uint32_t           s_out_n;
     __shared__ int                s_dups;
-    __shared__ uint32_t           s_unit;
+    __shared__ uint32_t           s_unit, s_part;
     __shared__ unsigned long long s_flush_base;
 
     const K* __restrict__ bkeys = static_cast<const K*>(a.bkeys);
@@ -151,17 +151,37 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
     for (;;) {
         // ---- next work unit, in global order ---------------------------------------------------------
         __syncthreads();
-        if (threadIdx.x == 0) s_unit = atomicAdd(a.unit_cursor, 1u);
+        if (threadIdx.x < 32) {
+            // warp 0 takes the next unit and finds its partition with a 32-ary search: each lane probes
+            // one splitter per step, so 2^15 partitions take 3 dependent loads instead of 15
+            uint32_t u = 0;
+            if (lane == 0) u = atomicAdd(a.unit_cursor, 1u);
+            u = __shfl_sync(RJ_FULL_MASK, u, 0);
+            uint32_t lo = 0, hi = a.nparts; // unit_start[lo] <= u < unit_start[hi]
+            if (u < n_units) {
+                while (hi - lo > 1) {
+                    const uint32_t span = hi - lo;
+                    const uint32_t step = (span + 31) / 32;
+                    const uint32_t probe = lo + (lane + 1) * step; // splitters lo+step, lo+2*step, ...
+                    const bool     le = probe < hi && a.unit_start[probe] <= u;
+                    const uint32_t m = __ballot_sync(RJ_FULL_MASK, le);
+                    const uint32_t k = __popc(m); // unit_start is non-decreasing: the lanes that hold are a prefix
+                    const uint32_t nlo = lo + k * step;
+                    const uint32_t nhi = (k < 32 && lo + (k + 1) * step < hi) ? lo + (k + 1) * step : hi;
+                    lo = nlo;
+                    hi = nhi;
+                }
+            }
+            if (lane == 0) {
+                s_unit = u;
+                s_part = lo;
+            }
+        }
         __syncthreads();
         const uint32_t u = s_unit;
         if (u >= n_units) break;
         {
-            uint32_t lo = 0, hi = a.nparts;
-            while (hi - lo > 1) {
-                uint32_t m = (lo + hi) >> 1;
-                if (a.unit_start[m] <= u) lo = m; else hi = m;
-            }
-            const uint32_t part = lo;
+            const uint32_t part = s_part;
             const uint32_t local = u - a.unit_start[part];
             const uint32_t b_lo = a.off_b[part], b_hi = a.off_b[part + 1];
             const uint32_t p_lo = a.off_p[part], p_hi = a.off_p[part + 1];

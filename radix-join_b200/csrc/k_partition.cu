@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
     uint32_t* s_gbase = s_start + (1u << bits);   // [nb]  global run start minus s_start
     __shared__ uint32_t s_warp_sums[kScatterThreads / 32];
     __shared__ uint32_t s_total;
+    // segmented scatter: region / tile tables (<= 257 entries each) cached once per CTA, so that the
+    // per-tile region lookup is a shared-memory binary search instead of 8 dependent L2 round trips
+    __shared__ uint32_t s_region_start[kRegions ? 258 : 1];
+    __shared__ uint32_t s_tile_start[kRegions ? 258 : 1];
 
     const uint32_t nb = 1u << bits, mask = nb - 1;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,7 +182,12 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
 
     uint64_t n_tiles;
     if (kRegions) {
-        n_tiles = tile_start[n_regions];
+        for (uint32_t r = threadIdx.x; r <= n_regions; r += kScatterThreads) {
+            s_region_start[r] = region_start[r];
+            s_tile_start[r]   = tile_start[r];
+        }
+        __syncthreads();
+        n_tiles = s_tile_start[n_regions];
     } else {
         n_tiles = (n + kTile - 1) / kTile;
     }
@@ -193,10 +202,10 @@ __global__ void __launch_bounds__(kScatterThreads, 2)
             uint32_t a = 0, b = n_regions;
             while (b - a > 1) {
                 uint32_t m = (a + b) >> 1;
-                if (tile_start[m] <= t) a = m; else b = m;
+                if (s_tile_start[m] <= t) a = m; else b = m;
             }
-            lo = static_cast<uint64_t>(region_start[a]) + (t - tile_start[a]) * kTile;
-            hi = region_start[a + 1];
+            lo = static_cast<uint64_t>(s_region_start[a]) + (t - s_tile_start[a]) * kTile;
+            hi = s_region_start[a + 1];
             if (hi > lo + kTile) hi = lo + kTile;
             cursor_base = a << bits;
         } else {
