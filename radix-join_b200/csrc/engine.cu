@@ -1346,7 +1346,7 @@ int rj_radix_scatter(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid, c
                      int32_t key_bytes, int32_t shift, int32_t bits, uint32_t* d_cursor, void* d_keys_out,
                      uint32_t* d_idx_out, void* stream) {
     return guarded(ctx, [&] {
-        if ((key_bytes != 4 && key_bytes != 8) || bits < 0 || bits > 9) throw EngineError("rj_radix_scatter: bits must be in [0, 9]");
+        if ((key_bytes != 4 && key_bytes != 8) || bits < 0 || bits > 8) throw EngineError("rj_radix_scatter: bits must be in [0, 8]");
         if (n >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
         launch_radix_scatter(d_keys, d_valid, d_idx_in, n, key_bytes, shift, bits, d_cursor, d_keys_out, d_idx_out,
                              ScatterPayload{}, ctx->sm_count, pick_stream(ctx, stream));

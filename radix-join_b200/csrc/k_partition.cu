@@ -21,7 +21,7 @@ namespace rj {
 namespace {
 
 constexpr int kHistThreads    = 512;
-constexpr int kScatterThreads = 512;
+constexpr int kScatterThreads = 256;
 template <typename K>
 struct ScatterCfg {
     // tuples per thread: 16 x 4-byte keys or 8 x 8-byte keys keep the kernel under 64 registers
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kPlanThreads)
 // ---- scatter ----------------------------------------------------------------------------------------
 // kMulti: every partition has its own output bases (`multi`), possibly in another GPU's memory
 template <typename K, bool kRegions, bool kMulti = false>
-__global__ void __launch_bounds__(kScatterThreads, 2)
+__global__ void __launch_bounds__(kScatterThreads, 4)
     radix_scatter_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
                          const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
                          const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
@@ -475,7 +475,7 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
     if (n == 0) return;
     const uint32_t tile = scatter_tile(key_bytes);
     uint64_t n_tiles = (n + tile - 1) / tile;
-    unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 2 ? n_tiles : static_cast<uint64_t>(sm_count) * 2);
+    unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 4 ? n_tiles : static_cast<uint64_t>(sm_count) * 4);
     if (key_bytes == 4) {
         const size_t smem = scatter_smem_bytes<uint32_t>(bits);
         scatter_set_attr<uint32_t, false>(smem);
@@ -501,7 +501,7 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
     RJ_CUDA(cudaMemcpyAsync(d_desc, &out, sizeof(rj_scatter_multi_t), cudaMemcpyHostToDevice, s));
     const uint32_t tile = scatter_tile(key_bytes);
     uint64_t n_tiles = (n + tile - 1) / tile;
-    unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 2 ? n_tiles : static_cast<uint64_t>(sm_count) * 2);
+    unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 4 ? n_tiles : static_cast<uint64_t>(sm_count) * 4);
     if (key_bytes == 4) {
         const size_t smem = scatter_smem_bytes<uint32_t>(bits);
         static size_t configured = 0;
@@ -535,7 +535,7 @@ void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, cons
     // its upper bound so no host synchronisation is needed
     const uint32_t tile = scatter_tile(key_bytes);
     uint64_t tiles_upper = (n_upper + tile - 1) / tile + n_regions;
-    unsigned blocks = static_cast<unsigned>(tiles_upper < static_cast<uint64_t>(sm_count) * 2 ? tiles_upper : static_cast<uint64_t>(sm_count) * 2);
+    unsigned blocks = static_cast<unsigned>(tiles_upper < static_cast<uint64_t>(sm_count) * 4 ? tiles_upper : static_cast<uint64_t>(sm_count) * 4);
     if (key_bytes == 4) {
         const size_t smem = scatter_smem_bytes<uint32_t>(bits);
         scatter_set_attr<uint32_t, true>(smem);

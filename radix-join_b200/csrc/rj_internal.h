@@ -40,8 +40,8 @@ constexpr uint32_t kJoinSlots      = 8192;  // shared-memory hash table slots pe
 constexpr uint32_t kJoinBuildCap   = 6144;  // build tuples per table (75 % fill); larger partitions are chunked
 constexpr uint32_t kJoinTargetFill = 2048;  // partition fan-out aims at <= this many build tuples on average (25 % fill)
 constexpr uint32_t kJoinProbeChunk = 16384; // probe tuples per work unit
-// tuples per scatter tile: 512 threads x 16 (4-byte keys) or x 8 (8-byte keys)
-constexpr uint32_t scatter_tile(int key_bytes) { return key_bytes == 4 ? 8192u : 4096u; }
+// tuples per scatter tile: 256 threads x 16 (4-byte keys) or x 8 (8-byte keys)
+constexpr uint32_t scatter_tile(int key_bytes) { return key_bytes == 4 ? 4096u : 2048u; }
 constexpr int      kMaxPassBits    = 8;     // radix bits per scatter pass
 constexpr int      kMaxTotalBits   = 16;
 
