@@ -27,7 +27,7 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     # rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) out of it
-    os.environ["NCCL_DEBUG"] = os.environ.get("RJ_NCCL_DEBUG", "WARN")
+    os.environ["NCCL_DEBUG"] = os.environ.get("RJ_NCCL_DEBUG", "NONE")  # WARN and above print the banner
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = build_context(local)
     ops = dj.CudaOps(ctx)
