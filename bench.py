@@ -120,7 +120,8 @@ def time_reference(plan, n_tuples, steps, warmup):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        res = orc.execute(plan, impl="ref" if kind == "reference" else "port")
+        # all host threads: torchrun exports OMP_NUM_THREADS=1, so the count is set explicitly
+        res = orc.execute(plan, impl="ref" if kind == "reference" else "port", n_threads=os.cpu_count() or 1)
         dt = orc.last_execute_seconds() if kind == "reference" else time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
