@@ -17,6 +17,8 @@
 #include "rj_common.cuh"
 #include "rj_internal.h"
 
+#include <type_traits>
+
 namespace rj {
 namespace {
 
@@ -388,6 +390,273 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
     }
 }
 
+// ---- scatter, local outputs (flat pass and segmented pass 2) ----------------------------------------
+// Same tile algorithm as above, rewritten around the instruction budget: the first version executed ~170
+// thread instructions per tuple (ncu source view: 64-bit index arithmetic, per-tuple bounds predicates,
+// two bitmap probes through 64-bit addresses, the hash recomputed at copy-out) and was issue-limited at
+// a third of the DRAM bandwidth.  Here
+//   * a tile that is full (all but the last of a relation / region) runs without bounds predicates, and
+//     full copy-out batches run without per-position predicates;
+//   * everything inside a tile is addressed by 32-bit offsets from the tile's base pointers;
+//   * the staged word is  tile offset | partition << kOffBits | flags << 30, so the copy-out neither
+//     re-hashes the key nor loads a separate partition id, and the row id is  tile start + offset;
+//   * validity of the key and of up to two carried columns is read as ONE warp-uniform bitmap word per
+//     (warp, item) in the load phase -- bit = lane -- and carried through the staged word;
+//   * the skew detector runs on every fourth item.
+struct TileFlags {
+    int         n = 0;
+    const void* src[2] = {nullptr, nullptr}; // flat pass: validity bitmaps by row; pass 2: bytes by position
+    uint8_t*    dst[2] = {nullptr, nullptr}; // flat pass: one byte per scattered tuple
+};
+
+template <typename K, bool kRegions>
+__global__ void __launch_bounds__(kScatterThreads, 4)
+    scatter_tile_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
+                        const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
+                        const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
+                        uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
+                        ScatterPayload pay, TileFlags flags) {
+    constexpr int      kItems   = ScatterCfg<K>::kItems;
+    constexpr uint32_t kTile    = ScatterCfg<K>::kTile;
+    constexpr int      kOffBits = sizeof(K) == 4 ? 12 : 11;
+    constexpr int      kWarps   = kScatterThreads / 32;
+    static_assert((1u << kOffBits) == kTile, "tile offset must fit kOffBits");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    K*        s_keys  = reinterpret_cast<K*>(smem_raw);
+    uint32_t* s_idx   = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kTile);
+    uint32_t* s_count = s_idx + kTile;
+    uint32_t* s_start = s_count + (1u << bits);
+    uint32_t* s_gbase = s_start + (1u << bits);
+    __shared__ uint32_t s_warp_sums[kWarps];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_region_start[kRegions ? 258 : 1];
+    __shared__ uint32_t s_tile_start[kRegions ? 258 : 1];
+
+    const uint32_t nb = 1u << bits, mask = nb - 1;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+
+    uint64_t n_tiles;
+    if (kRegions) {
+        for (uint32_t r = tid; r <= n_regions; r += kScatterThreads) {
+            s_region_start[r] = region_start[r];
+            s_tile_start[r]   = tile_start[r];
+        }
+        __syncthreads();
+        n_tiles = s_tile_start[n_regions];
+    } else {
+        n_tiles = (n + kTile - 1) / kTile;
+    }
+    for (uint32_t b = tid; b < nb; b += kScatterThreads) s_count[b] = 0;
+    __syncthreads();
+
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint64_t lo;
+        uint32_t cnt, cursor_base = 0;
+        if (kRegions) {
+            uint32_t a = 0, b = n_regions;
+            while (b - a > 1) {
+                uint32_t m = (a + b) >> 1;
+                if (s_tile_start[m] <= t) a = m; else b = m;
+            }
+            lo = static_cast<uint64_t>(s_region_start[a]) + (t - s_tile_start[a]) * kTile;
+            const uint64_t left = s_region_start[a + 1] - lo;
+            cnt = left < kTile ? static_cast<uint32_t>(left) : kTile;
+            cursor_base = a << bits;
+        } else {
+            lo = t * kTile;
+            cnt = n - lo < kTile ? static_cast<uint32_t>(n - lo) : kTile;
+        }
+        const K* __restrict__ tkeys = keys + lo;
+
+        // 1) load the tile, partition id per tuple
+        K        key[kItems];
+        uint32_t pr[kItems]; // partition, later partition << 16 | rank; ~0 = dropped (NULL key / past the end)
+        uint32_t fl = 0;     // 2 carried-validity flags per item
+        auto load_tile = [&](auto full_c) {
+            constexpr bool kFull = decltype(full_c)::value;
+            bool ok[kItems];
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                const uint32_t off = k * kScatterThreads + tid;
+                ok[k]  = kFull || off < cnt;
+                key[k] = ok[k] ? tkeys[off] : K(0);
+            }
+            if (kRegions) {
+                if (flags.n > 0) {
+                    const uint8_t* __restrict__ f0 = static_cast<const uint8_t*>(flags.src[0]) + lo;
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k)
+                        if (ok[k] && f0[k * kScatterThreads + tid]) fl |= 1u << (2 * k);
+                }
+                if (flags.n > 1) {
+                    const uint8_t* __restrict__ f1 = static_cast<const uint8_t*>(flags.src[1]) + lo;
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k)
+                        if (ok[k] && f1[k * kScatterThreads + tid]) fl |= 2u << (2 * k);
+                }
+            } else {
+                // lo is a multiple of the tile: item k of this warp is bit `lane` of word k * kWarps + warp
+                const uint64_t w0 = (lo >> 5) + warp;
+                if (flags.n > 0) {
+                    const uint32_t* __restrict__ f0 = static_cast<const uint32_t*>(flags.src[0]) + w0;
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k)
+                        if (ok[k]) fl |= ((f0[k * kWarps] >> lane) & 1u) << (2 * k);
+                }
+                if (flags.n > 1) {
+                    const uint32_t* __restrict__ f1 = static_cast<const uint32_t*>(flags.src[1]) + w0;
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k)
+                        if (ok[k]) fl |= ((f1[k * kWarps] >> lane) & 1u) << (2 * k + 1);
+                }
+                if (valid != nullptr) {
+                    const uint32_t* __restrict__ v = valid + w0;
+#pragma unroll
+                    for (int k = 0; k < kItems; ++k)
+                        if (ok[k]) ok[k] = (v[k * kWarps] >> lane) & 1u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kItems; ++k)
+                pr[k] = ok[k] ? ((hash_key(key[k]) >> shift) & mask) : 0xffffffffu;
+        };
+        if (cnt == kTile) load_tile(std::true_type{}); else load_tile(std::false_type{});
+
+        // rank inside the partition: shared-memory atomic, warp-aggregated when the warp is skewed
+        bool skewed = false;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const uint32_t part = pr[k];
+            const bool     ok   = part != 0xffffffffu;
+            if ((k & 3) == 0) {
+                const uint32_t nbr = __shfl_xor_sync(RJ_FULL_MASK, part, 1);
+                skewed = __popc(__ballot_sync(RJ_FULL_MASK, ok && nbr == part)) >= 4;
+            }
+            uint32_t rank = 0;
+            if (skewed) {
+                const uint32_t peers  = __match_any_sync(RJ_FULL_MASK, part);
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (ok && lane == leader) base = atomicAdd(&s_count[part], static_cast<uint32_t>(__popc(peers)));
+                base = __shfl_sync(RJ_FULL_MASK, base, leader);
+                rank = base + __popc(peers & lt);
+            } else if (ok) {
+                rank = atomicAdd(&s_count[part], 1u);
+            }
+            pr[k] = ok ? ((part << 16) | rank) : 0xffffffffu;
+        }
+        __syncthreads();
+
+        // 2) exclusive scan of the per-partition counts (nb <= kScatterThreads), reserve global runs
+        {
+            const uint32_t c = tid < nb ? s_count[tid] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane == 31) s_warp_sums[warp] = inc;
+            __syncthreads();
+            uint32_t prefix = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < kWarps; ++w) prefix += w < warp ? s_warp_sums[w] : 0u;
+            const uint32_t start = prefix + inc - c;
+            if (tid < nb) {
+                s_start[tid] = start;
+                uint32_t g = 0;
+                if (c) g = atomicAdd(&cursor[cursor_base + tid], c);
+                s_gbase[tid] = g - start;
+                s_count[tid] = 0; // ready for the next tile
+            }
+            if (tid == kScatterThreads - 1) s_total = prefix + inc;
+        }
+        __syncthreads();
+
+        // 3) stage the tile in partition order
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            if (pr[k] != 0xffffffffu) {
+                const uint32_t part = pr[k] >> 16;
+                const uint32_t pos  = s_start[part] + (pr[k] & 0xffffu);
+                s_keys[pos] = key[k];
+                s_idx[pos]  = (k * kScatterThreads + tid) | (part << kOffBits) | (((fl >> (2 * k)) & 3u) << 30);
+            }
+        }
+        __syncthreads();
+
+        // 4) stream the runs out: thread -> staged position, four positions per thread in flight
+        const uint32_t total = s_total;
+        const uint32_t lo32  = static_cast<uint32_t>(lo);
+        auto copy_out = [&](auto pred_c, uint32_t base) {
+            constexpr bool kPred = decltype(pred_c)::value;
+            K        kk[4];
+            uint32_t rr[4], dd[4], ww[4];
+            bool     in[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pos = base + j * kScatterThreads + tid;
+                in[j] = !kPred || pos < total;
+                kk[j] = in[j] ? s_keys[pos] : K(0);
+                ww[j] = in[j] ? s_idx[pos] : 0u;
+                dd[j] = s_gbase[(ww[j] >> kOffBits) & 0xffu] + pos;
+                rr[j] = lo32 + (ww[j] & (kTile - 1));
+            }
+            if (!kRegions && idx_in != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rr[j] = in[j] ? idx_in[rr[j]] : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (in[j]) {
+                    keys_out[dd[j]] = kk[j];
+                    idx_out[dd[j]]  = kRegions ? (rr[j] | (ww[j] & 0xc0000000u)) : rr[j];
+                }
+            }
+            if (kRegions) return;
+            if (flags.n > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (in[j]) flags.dst[0][dd[j]] = (ww[j] >> 30) & 1u;
+            }
+            if (flags.n > 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (in[j]) flags.dst[1][dd[j]] = ww[j] >> 31;
+            }
+            // carried payload columns: the reads stay inside this tile's row window (L1/L2 resident)
+#pragma unroll
+            for (int c = 0; c < ScatterPayload::kMax; ++c) {
+                if (c < pay.n) {
+                    const int w = pay.width[c];
+                    if (w == 8) {
+                        uint64_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(pay.src[c])[rr[j]] : 0ull;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = v[j];
+                    } else if (w == 1) { // a validity bitmap travels as one byte per tuple
+                        uint32_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j] >> 5] : 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint8_t*>(pay.dst[c])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
+                    } else {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j]] : 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = v[j];
+                    }
+                }
+            }
+        };
+        uint32_t base = 0;
+        for (; base + 4 * kScatterThreads <= total; base += 4 * kScatterThreads) copy_out(std::false_type{}, base);
+        if (base < total) copy_out(std::true_type{}, base);
+        __syncthreads();
+    }
+}
+
 template <typename K>
 size_t scatter_smem_bytes(int bits) {
     return (sizeof(K) + 4) * ScatterCfg<K>::kTile + 3 * sizeof(uint32_t) * (1u << bits);
@@ -397,7 +666,7 @@ template <typename K, bool kRegions>
 void scatter_set_attr(size_t smem) {
     static size_t configured = 0;
     if (smem > configured) {
-        RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<K, kRegions>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<K, kRegions>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
         configured = smem;
     }
@@ -476,18 +745,34 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
     const uint32_t tile = scatter_tile(key_bytes);
     uint64_t n_tiles = (n + tile - 1) / tile;
     unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 4 ? n_tiles : static_cast<uint64_t>(sm_count) * 4);
+    // row id == input position: up to two carried validity bitmaps take the cheap path (one bitmap word
+    // per warp and item in the load phase) instead of a gather per tuple at copy-out
+    ScatterPayload pay;
+    TileFlags      flags;
+    for (int c = 0; c < payload.n; ++c) {
+        if (payload.width[c] == 1 && idx_in == nullptr && flags.n < 2) {
+            flags.src[flags.n] = payload.src[c];
+            flags.dst[flags.n] = static_cast<uint8_t*>(payload.dst[c]);
+            ++flags.n;
+        } else {
+            pay.src[pay.n] = payload.src[c];
+            pay.dst[pay.n] = payload.dst[c];
+            pay.width[pay.n] = payload.width[c];
+            ++pay.n;
+        }
+    }
     if (key_bytes == 4) {
         const size_t smem = scatter_smem_bytes<uint32_t>(bits);
         scatter_set_attr<uint32_t, false>(smem);
-        radix_scatter_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
+        scatter_tile_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<uint32_t*>(keys_out), idx_out, payload);
+            static_cast<uint32_t*>(keys_out), idx_out, pay, flags);
     } else {
         const size_t smem = scatter_smem_bytes<uint64_t>(bits);
         scatter_set_attr<uint64_t, false>(smem);
-        radix_scatter_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
+        scatter_tile_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<uint64_t*>(keys_out), idx_out, payload);
+            static_cast<uint64_t*>(keys_out), idx_out, pay, flags);
     }
     RJ_LAUNCH_CHECK();
 }
@@ -536,18 +821,21 @@ void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, cons
     const uint32_t tile = scatter_tile(key_bytes);
     uint64_t tiles_upper = (n_upper + tile - 1) / tile + n_regions;
     unsigned blocks = static_cast<unsigned>(tiles_upper < static_cast<uint64_t>(sm_count) * 4 ? tiles_upper : static_cast<uint64_t>(sm_count) * 4);
+    TileFlags tf;
+    tf.n = flags.n;
+    for (int c = 0; c < flags.n; ++c) tf.src[c] = flags.src[c];
     if (key_bytes == 4) {
         const size_t smem = scatter_smem_bytes<uint32_t>(bits);
         scatter_set_attr<uint32_t, true>(smem);
-        radix_scatter_kernel<uint32_t, true><<<blocks, kScatterThreads, smem, s>>>(
-            static_cast<const uint32_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{}, nullptr, flags);
+        scatter_tile_kernel<uint32_t, true><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint32_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start, n_regions, shift,
+            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{}, tf);
     } else {
         const size_t smem = scatter_smem_bytes<uint64_t>(bits);
         scatter_set_attr<uint64_t, true>(smem);
-        radix_scatter_kernel<uint64_t, true><<<blocks, kScatterThreads, smem, s>>>(
-            static_cast<const uint64_t*>(keys), nullptr, idx_in, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{}, nullptr, flags);
+        scatter_tile_kernel<uint64_t, true><<<blocks, kScatterThreads, smem, s>>>(
+            static_cast<const uint64_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start, n_regions, shift,
+            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{}, tf);
     }
     RJ_LAUNCH_CHECK();
 }
