@@ -174,6 +174,7 @@ def run_single_gpu(args):
         res.free()
         return rows, pages
 
+    rows, out_pages = dt.expected_rows, 0
     for _ in range(args.warmup):
         rows, out_pages = step()
     assert rows == dt.expected_rows, (rows, dt.expected_rows)
@@ -187,7 +188,7 @@ def run_single_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
-        step()
+        rows, out_pages = step()
     ev1.record(stream)
     torch.cuda.synchronize()
     ms_total = ev0.elapsed_time(ev1)

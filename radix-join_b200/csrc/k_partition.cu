@@ -415,26 +415,37 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
                         const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
                         const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
                         uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
-                        ScatterPayload pay, TileFlags flags) {
-    constexpr int      kItems   = ScatterCfg<K>::kItems;
-    constexpr uint32_t kTile    = ScatterCfg<K>::kTile;
-    constexpr int      kOffBits = sizeof(K) == 4 ? 12 : 11;
-    constexpr int      kWarps   = kScatterThreads / 32;
-    static_assert((1u << kOffBits) == kTile, "tile offset must fit kOffBits");
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    K*        s_keys  = reinterpret_cast<K*>(smem_raw);
-    uint32_t* s_idx   = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kTile);
-    uint32_t* s_count = s_idx + kTile;
-    uint32_t* s_start = s_count + (1u << bits);
-    uint32_t* s_gbase = s_start + (1u << bits);
+                        ScatterPayload pay, TileFlags flags, int n_tma) {
+    constexpr int      kItems     = ScatterCfg<K>::kItems;
+    constexpr uint32_t kTile      = ScatterCfg<K>::kTile;
+    constexpr int      kPartShift = 12; // staged word: tile offset | bucket << 12 | flags << 30
+    constexpr int      kWarps     = kScatterThreads / 32;
+    constexpr int      kDepth     = 8;  // staged positions per thread in flight at copy-out
+    static_assert(kTile <= (1u << kPartShift), "tile offset and rank must fit 12 bits");
+    // static shared memory: every address below is base + compile-time constant
+    __shared__ __align__(16) K s_keys[kTile];
+    __shared__ uint32_t s_idx[kTile];
+    __shared__ uint32_t s_count[257]; // [nb] tuples of this tile per partition, [nb] = dropped tuples
+    __shared__ uint32_t s_start[257]; // exclusive prefix inside the tile; the dropped ones go last
+    __shared__ uint32_t s_gbase[256]; // global run start minus s_start
     __shared__ uint32_t s_warp_sums[kWarps];
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_region_start[kRegions ? 258 : 1];
     __shared__ uint32_t s_tile_start[kRegions ? 258 : 1];
+    // flat pass: the row windows of the first n_tma carried columns, brought in by one TMA bulk copy per
+    // tile and column (kTile * 8 bytes each).  Gathering them from global memory instead costs one L1
+    // wavefront per tuple (32 distinct lines per warp load) -- that, not DRAM, bounded the pass.
+    extern __shared__ __align__(128) uint8_t s_pay[];
+    __shared__ __align__(8) uint64_t s_bar;
 
     const uint32_t nb = 1u << bits, mask = nb - 1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
+    uint32_t tma_phase = 0;
+    if (!kRegions && n_tma > 0 && tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
 
     uint64_t n_tiles;
     if (kRegions) {
@@ -447,12 +458,13 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
     } else {
         n_tiles = (n + kTile - 1) / kTile;
     }
-    for (uint32_t b = tid; b < nb; b += kScatterThreads) s_count[b] = 0;
+    for (uint32_t b = tid; b <= nb; b += kScatterThreads) s_count[b] = 0;
     __syncthreads();
 
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         uint64_t lo;
         uint32_t cnt, cursor_base = 0;
+        bool     staged = false;
         if (kRegions) {
             uint32_t a = 0, b = n_regions;
             while (b - a > 1) {
@@ -466,12 +478,39 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
         } else {
             lo = t * kTile;
             cnt = n - lo < kTile ? static_cast<uint32_t>(n - lo) : kTile;
+            staged = n_tma > 0 && cnt == kTile;
+            if (staged && tid == 0) {
+                // every read of the previous tile's windows is behind the __syncthreads that ended it
+                uint32_t bytes = 0;
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    if (c < n_tma) bytes += kTile * static_cast<uint32_t>(pay.width[c]);
+                mbar_arrive_expect_tx(&s_bar, bytes);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c < n_tma)
+                        tma_load_1d(s_pay + c * kTile * 8, static_cast<const char*>(pay.src[c]) + lo * pay.width[c],
+                                    kTile * static_cast<uint32_t>(pay.width[c]), &s_bar);
+                }
+            }
+            // the other carried columns are gathered from this tile's row window at copy-out: start
+            // pulling the window into L2 now
+            if (idx_in == nullptr) {
+#pragma unroll
+                for (int c = 0; c < ScatterPayload::kMax; ++c) {
+                    if (c < pay.n && pay.width[c] > 1 && !(staged && c < n_tma)) {
+                        const uint32_t bytes = cnt * static_cast<uint32_t>(pay.width[c]);
+                        const char*    w0    = static_cast<const char*>(pay.src[c]) + lo * pay.width[c];
+                        for (uint32_t o = tid * 128; o < bytes; o += kScatterThreads * 128) prefetch_l2(w0 + o);
+                    }
+                }
+            }
         }
         const K* __restrict__ tkeys = keys + lo;
 
-        // 1) load the tile, partition id per tuple
+        // 1) load the tile; bucket per tuple (nb = dropped: NULL key or past the end of the tile)
         K        key[kItems];
-        uint32_t pr[kItems]; // partition, later partition << 16 | rank; ~0 = dropped (NULL key / past the end)
+        uint32_t pr[kItems]; // bucket, later bucket << 12 | rank inside the bucket
         uint32_t fl = 0;     // 2 carried-validity flags per item
         auto load_tile = [&](auto full_c) {
             constexpr bool kFull = decltype(full_c)::value;
@@ -518,33 +557,36 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
                 }
             }
 #pragma unroll
-            for (int k = 0; k < kItems; ++k)
-                pr[k] = ok[k] ? ((hash_key(key[k]) >> shift) & mask) : 0xffffffffu;
+            for (int k = 0; k < kItems; ++k) {
+                const uint32_t digit = (hash_key(key[k]) >> shift) & mask;
+                pr[k] = ok[k] ? digit : nb;
+            }
         };
         if (cnt == kTile) load_tile(std::true_type{}); else load_tile(std::false_type{});
 
-        // rank inside the partition: shared-memory atomic, warp-aggregated when the warp is skewed
+        // rank inside the bucket: shared-memory atomic, warp-aggregated when the warp is skewed.  Every
+        // tuple takes a rank (the dropped ones in the bucket that is staged last and never copied out),
+        // so neither this loop nor the staging below carries a per-tuple predicate.
         bool skewed = false;
 #pragma unroll
         for (int k = 0; k < kItems; ++k) {
             const uint32_t part = pr[k];
-            const bool     ok   = part != 0xffffffffu;
             if ((k & 3) == 0) {
                 const uint32_t nbr = __shfl_xor_sync(RJ_FULL_MASK, part, 1);
-                skewed = __popc(__ballot_sync(RJ_FULL_MASK, ok && nbr == part)) >= 4;
+                skewed = __popc(__ballot_sync(RJ_FULL_MASK, nbr == part)) >= 4;
             }
-            uint32_t rank = 0;
+            uint32_t rank;
             if (skewed) {
                 const uint32_t peers  = __match_any_sync(RJ_FULL_MASK, part);
                 const uint32_t leader = __ffs(peers) - 1;
                 uint32_t base = 0;
-                if (ok && lane == leader) base = atomicAdd(&s_count[part], static_cast<uint32_t>(__popc(peers)));
+                if (lane == leader) base = atomicAdd(&s_count[part], static_cast<uint32_t>(__popc(peers)));
                 base = __shfl_sync(RJ_FULL_MASK, base, leader);
                 rank = base + __popc(peers & lt);
-            } else if (ok) {
+            } else {
                 rank = atomicAdd(&s_count[part], 1u);
             }
-            pr[k] = ok ? ((part << 16) | rank) : 0xffffffffu;
+            pr[k] = (part << kPartShift) | rank;
         }
         __syncthreads();
 
@@ -570,45 +612,51 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
                 s_gbase[tid] = g - start;
                 s_count[tid] = 0; // ready for the next tile
             }
-            if (tid == kScatterThreads - 1) s_total = prefix + inc;
+            if (tid == kScatterThreads - 1) {
+                s_total     = prefix + inc;
+                s_start[nb] = prefix + inc; // dropped tuples: behind everything that is copied out
+                s_count[nb] = 0;
+            }
         }
         __syncthreads();
 
         // 3) stage the tile in partition order
 #pragma unroll
         for (int k = 0; k < kItems; ++k) {
-            if (pr[k] != 0xffffffffu) {
-                const uint32_t part = pr[k] >> 16;
-                const uint32_t pos  = s_start[part] + (pr[k] & 0xffffu);
-                s_keys[pos] = key[k];
-                s_idx[pos]  = (k * kScatterThreads + tid) | (part << kOffBits) | (((fl >> (2 * k)) & 3u) << 30);
-            }
+            const uint32_t pos = s_start[pr[k] >> kPartShift] + (pr[k] & ((1u << kPartShift) - 1));
+            s_keys[pos] = key[k];
+            s_idx[pos]  = (pr[k] & (0x1ffu << kPartShift)) | (k * kScatterThreads + tid) |
+                          ((fl << (30 - 2 * k)) & 0xc0000000u);
         }
         __syncthreads();
 
-        // 4) stream the runs out: thread -> staged position, four positions per thread in flight
+        // 4) stream the runs out: thread -> staged position, kDepth positions per thread in flight
         const uint32_t total = s_total;
         const uint32_t lo32  = static_cast<uint32_t>(lo);
+        if (!kRegions && staged) {
+            mbar_wait(&s_bar, tma_phase);
+            tma_phase ^= 1;
+        }
         auto copy_out = [&](auto pred_c, uint32_t base) {
             constexpr bool kPred = decltype(pred_c)::value;
-            K        kk[4];
-            uint32_t rr[4], dd[4], ww[4];
-            bool     in[4];
+            K        kk[kDepth];
+            uint32_t rr[kDepth], dd[kDepth], ww[kDepth];
+            bool     in[kDepth];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kDepth; ++j) {
                 const uint32_t pos = base + j * kScatterThreads + tid;
                 in[j] = !kPred || pos < total;
                 kk[j] = in[j] ? s_keys[pos] : K(0);
                 ww[j] = in[j] ? s_idx[pos] : 0u;
-                dd[j] = s_gbase[(ww[j] >> kOffBits) & 0xffu] + pos;
+                dd[j] = s_gbase[(ww[j] >> kPartShift) & 0xffu] + pos;
                 rr[j] = lo32 + (ww[j] & (kTile - 1));
             }
             if (!kRegions && idx_in != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) rr[j] = in[j] ? idx_in[rr[j]] : 0u;
+                for (int j = 0; j < kDepth; ++j) rr[j] = in[j] ? idx_in[rr[j]] : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kDepth; ++j) {
                 if (in[j]) {
                     keys_out[dd[j]] = kk[j];
                     idx_out[dd[j]]  = kRegions ? (rr[j] | (ww[j] & 0xc0000000u)) : rr[j];
@@ -617,41 +665,54 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
             if (kRegions) return;
             if (flags.n > 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (in[j]) flags.dst[0][dd[j]] = (ww[j] >> 30) & 1u;
+                for (int j = 0; j < kDepth; ++j) if (in[j]) flags.dst[0][dd[j]] = (ww[j] >> 30) & 1u;
             }
             if (flags.n > 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (in[j]) flags.dst[1][dd[j]] = ww[j] >> 31;
+                for (int j = 0; j < kDepth; ++j) if (in[j]) flags.dst[1][dd[j]] = ww[j] >> 31;
             }
-            // carried payload columns: the reads stay inside this tile's row window (L1/L2 resident)
+            // carried payload columns: the reads stay inside this tile's row window (prefetched above)
 #pragma unroll
             for (int c = 0; c < ScatterPayload::kMax; ++c) {
                 if (c < pay.n) {
                     const int w = pay.width[c];
-                    if (w == 8) {
-                        uint64_t v[4];
+                    if (c < 2 && staged && c < n_tma) {
+                        // the window is in shared memory: row offset inside the tile = low bits of ww
+                        if (w == 8) {
+                            const uint64_t* win = reinterpret_cast<const uint64_t*>(s_pay + c * kTile * 8);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(pay.src[c])[rr[j]] : 0ull;
+                            for (int j = 0; j < kDepth; ++j)
+                                if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = win[ww[j] & (kTile - 1)];
+                        } else {
+                            const uint32_t* win = reinterpret_cast<const uint32_t*>(s_pay + c * kTile * 8);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = v[j];
+                            for (int j = 0; j < kDepth; ++j)
+                                if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = win[ww[j] & (kTile - 1)];
+                        }
+                    } else if (w == 8) {
+                        uint64_t v[kDepth];
+#pragma unroll
+                        for (int j = 0; j < kDepth; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(pay.src[c])[rr[j]] : 0ull;
+#pragma unroll
+                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = v[j];
                     } else if (w == 1) { // a validity bitmap travels as one byte per tuple
-                        uint32_t v[4];
+                        uint32_t v[kDepth];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j] >> 5] : 0u;
+                        for (int j = 0; j < kDepth; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j] >> 5] : 0u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint8_t*>(pay.dst[c])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
+                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint8_t*>(pay.dst[c])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
                     } else {
-                        uint32_t v[4];
+                        uint32_t v[kDepth];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j]] : 0u;
+                        for (int j = 0; j < kDepth; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j]] : 0u;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = v[j];
+                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = v[j];
                     }
                 }
             }
         };
         uint32_t base = 0;
-        for (; base + 4 * kScatterThreads <= total; base += 4 * kScatterThreads) copy_out(std::false_type{}, base);
+        for (; base + kDepth * kScatterThreads <= total; base += kDepth * kScatterThreads) copy_out(std::false_type{}, base);
         if (base < total) copy_out(std::true_type{}, base);
         __syncthreads();
     }
@@ -662,14 +723,14 @@ size_t scatter_smem_bytes(int bits) {
     return (sizeof(K) + 4) * ScatterCfg<K>::kTile + 3 * sizeof(uint32_t) * (1u << bits);
 }
 
-template <typename K, bool kRegions>
-void scatter_set_attr(size_t smem) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<K, kRegions>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-        configured = smem;
-    }
+// persistent grid = the CTAs that are resident at once (the windows in dynamic shared memory change that)
+template <typename Kern>
+unsigned resident_grid(Kern kern, size_t smem, uint64_t n_tiles, int sm_count) {
+    int per_sm = 0;
+    RJ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScatterThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * per_sm;
+    return static_cast<unsigned>(n_tiles < cap ? n_tiles : cap);
 }
 
 } // namespace
@@ -749,30 +810,58 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
     // per warp and item in the load phase) instead of a gather per tuple at copy-out
     ScatterPayload pay;
     TileFlags      flags;
+    int            n_tma = 0;
+    auto push = [&](int c) {
+        pay.src[pay.n] = payload.src[c];
+        pay.dst[pay.n] = payload.dst[c];
+        pay.width[pay.n] = payload.width[c];
+        ++pay.n;
+    };
+    // up to two value columns travel through shared-memory windows (TMA); they come first
+    auto tma_ok = [&](int c) {
+        return idx_in == nullptr && payload.width[c] >= 4 && reinterpret_cast<uintptr_t>(payload.src[c]) % 16 == 0;
+    };
     for (int c = 0; c < payload.n; ++c) {
-        if (payload.width[c] == 1 && idx_in == nullptr && flags.n < 2) {
-            flags.src[flags.n] = payload.src[c];
-            flags.dst[flags.n] = static_cast<uint8_t*>(payload.dst[c]);
-            ++flags.n;
-        } else {
-            pay.src[pay.n] = payload.src[c];
-            pay.dst[pay.n] = payload.dst[c];
-            pay.width[pay.n] = payload.width[c];
-            ++pay.n;
+        if (tma_ok(c) && n_tma < 2) {
+            push(c);
+            ++n_tma;
         }
     }
+    {
+        int taken = 0;
+        for (int c = 0; c < payload.n; ++c) {
+            if (tma_ok(c) && taken < 2) {
+                ++taken;
+            } else if (payload.width[c] == 1 && idx_in == nullptr && flags.n < 2) {
+                flags.src[flags.n] = payload.src[c];
+                flags.dst[flags.n] = static_cast<uint8_t*>(payload.dst[c]);
+                ++flags.n;
+            } else {
+                push(c);
+            }
+        }
+    }
+    const size_t smem = static_cast<size_t>(n_tma) * tile * 8;
     if (key_bytes == 4) {
-        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
-        scatter_set_attr<uint32_t, false>(smem);
+        static size_t configured = 0;
+        if (smem > configured) {
+            RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        blocks = resident_grid(scatter_tile_kernel<uint32_t, false>, smem, n_tiles, sm_count);
         scatter_tile_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<uint32_t*>(keys_out), idx_out, pay, flags);
+            static_cast<uint32_t*>(keys_out), idx_out, pay, flags, n_tma);
     } else {
-        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
-        scatter_set_attr<uint64_t, false>(smem);
+        static size_t configured = 0;
+        if (smem > configured) {
+            RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        blocks = resident_grid(scatter_tile_kernel<uint64_t, false>, smem, n_tiles, sm_count);
         scatter_tile_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
-            static_cast<uint64_t*>(keys_out), idx_out, pay, flags);
+            static_cast<uint64_t*>(keys_out), idx_out, pay, flags, n_tma);
     }
     RJ_LAUNCH_CHECK();
 }
@@ -825,17 +914,13 @@ void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, cons
     tf.n = flags.n;
     for (int c = 0; c < flags.n; ++c) tf.src[c] = flags.src[c];
     if (key_bytes == 4) {
-        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
-        scatter_set_attr<uint32_t, true>(smem);
-        scatter_tile_kernel<uint32_t, true><<<blocks, kScatterThreads, smem, s>>>(
+        scatter_tile_kernel<uint32_t, true><<<blocks, kScatterThreads, 0, s>>>(
             static_cast<const uint32_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{}, tf);
+            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{}, tf, 0);
     } else {
-        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
-        scatter_set_attr<uint64_t, true>(smem);
-        scatter_tile_kernel<uint64_t, true><<<blocks, kScatterThreads, smem, s>>>(
+        scatter_tile_kernel<uint64_t, true><<<blocks, kScatterThreads, 0, s>>>(
             static_cast<const uint64_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{}, tf);
+            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{}, tf, 0);
     }
     RJ_LAUNCH_CHECK();
 }

@@ -53,6 +53,9 @@ __device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ bitmap, ui
 }
 
 // ---- shared-memory address / mbarrier / TMA bulk copies --------------------------------------------
+// pull one 128-byte line towards L2 without waiting for it
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
