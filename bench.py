@@ -223,31 +223,38 @@ def run_single_gpu(args):
                 "stages": stages}
 
     # ---- end to end: host pages in (pinned, contiguous), host pages out -----------------------------
+    # rj_execute_streamed: the probe table goes through the GPU in row windows, so the upload of window
+    # k+1, the kernels of window k and the download of window k-1 overlap on the PCIe link.
     e2e = None
     if not args.no_e2e:
         import numpy as np
         host_plan, keep = syn.to_host_plan(dt)
-        out_bufs = None
+        root = host_plan.nodes[host_plan.root]
+        # pinned result buffers, sized once: dense page count of every output column + room for the
+        # partly filled last page of each window
+        caps = [-(-dt.expected_rows // int(ctx.lib.rj_fixed_rows_per_page(int(t)))) + 256 for _, t in root.output_attrs]
+        out_bufs = [torch.empty(cap * 8192, dtype=torch.uint8, pin_memory=True).numpy().reshape(-1, 8192) for cap in caps]
+        used = [0] * len(caps)
+
+        def alloc(column, _dtype, n_pages):
+            lo = used[column]
+            used[column] = lo + n_pages
+            return out_bufs[column][lo:lo + n_pages]
+
         e2e_steps = max(1, min(args.steps, 3))
         times = []
         for i in range(1 + e2e_steps):
+            used[:] = [0] * len(caps)
             t0 = time.perf_counter()
-            res = rj.execute_to_device(host_plan, ctx)
-            if out_bufs is None:
-                out_bufs = [torch.empty(res.column_pages(c) * 8192, dtype=torch.uint8, pin_memory=True).numpy().reshape(-1, 8192)
-                            for c in range(res.num_columns)]
-                t0 = None  # the first (warm-up) call also allocates the pinned result buffers
-            for c in range(res.num_columns):
-                res.fetch_column(c, out=out_bufs[c])
-            e_rows = res.num_rows
-            res.free()
-            if t0 is not None and i > 0:
+            e_rows, _chunks = rj.execute_streamed(host_plan, ctx, alloc=alloc)
+            if i > 0:
                 times.append(time.perf_counter() - t0)
         assert e_rows == dt.expected_rows
         sec = sum(times) / len(times)
         e2e = {"value": round((nb + np_) / 1e6 / sec, 2), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-               "d2h_bytes_per_step": int(sum(b.nbytes for b in out_bufs)), "ms_per_step": round(sec * 1e3, 2),
-               "steps": len(times), "host_buffers": "pinned, contiguous per column; timed with the host clock around the call"}
+               "d2h_bytes_per_step": int(sum(used) * 8192), "ms_per_step": round(sec * 1e3, 2),
+               "steps": len(times), "api": "rj_execute_streamed (512 MiB windows of the probe table)",
+               "host_buffers": "pinned, contiguous per column; timed with the host clock around the call"}
         del keep
 
     # ---- CPU baseline: the reference's execute() on a bounded sample, host cores ---------------------

@@ -111,6 +111,20 @@ int         rj_ctx_set_host_threads(rj_ctx* ctx, int n);
 /* Host pages in -> result.  H2D upload, decode, joins, gather+encode all happen inside. */
 int rj_execute(rj_ctx* ctx, const rj_plan_t* plan, rj_result** out);
 
+/* Host pages in -> host pages out, streamed.  Replaces the same call (src/execute.cpp:316-324) for
+ * inputs whose transfer dominates: the plan runs once per row window of its largest table (an inner
+ * join distributes over a union of its inputs; the table must be read by a single ScanNode and its
+ * referenced columns be fixed-width, otherwise the call degrades to upload + execute + download) while
+ * the next window is uploaded and the previous window's result pages are downloaded.  `chunk_bytes` =
+ * page bytes per window (0 = 512 MiB).  Every time result pages of a column are ready, `sink` is asked
+ * for a host buffer of n_pages * 8192 contiguous bytes; the pages are complete when the call returns.
+ * Pages of different windows are independent (a window's last page may be partly filled), the row
+ * order is the engine's usual free order.  Copies overlap only if the host buffers are pinned and the
+ * input columns contiguous. */
+typedef void* (*rj_page_sink_t)(void* user, uint32_t column, int32_t type, uint64_t n_pages);
+int rj_execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, rj_page_sink_t sink,
+                        void* user, uint64_t* num_rows);
+
 /* Same, split so a benchmark can keep the inputs resident in HBM:
  * rj_inputs_upload copies every column of every table once (plan->inputs of the later call is
  * ignored); rj_execute_resident runs decode -> joins -> encode on device only. */

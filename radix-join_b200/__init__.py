@@ -12,12 +12,13 @@ sm_100 device and fails loudly otherwise.
 """
 from ._cabi import PAGE_SIZE, EngineMissing, load_library
 from .engine import (Context, EngineError, ResidentInputs, Result, adopt_device, build_context,
-                     destroy_context, execute, execute_resident, execute_to_device, upload)
+                     destroy_context, execute, execute_resident, execute_streamed,
+                     execute_streamed_columnar, execute_to_device, upload)
 from .plan import (Column, ColumnarTable, DataType, FlatPlan, JoinNode, Plan, PlanNode, ScanNode)
 
 __all__ = [
     "PAGE_SIZE", "EngineMissing", "load_library", "Context", "EngineError", "ResidentInputs", "Result",
     "adopt_device", "build_context", "destroy_context", "execute", "execute_resident",
-    "execute_to_device", "upload", "Column", "ColumnarTable", "DataType", "FlatPlan", "JoinNode",
+    "execute_streamed", "execute_streamed_columnar", "execute_to_device", "upload", "Column", "ColumnarTable", "DataType", "FlatPlan", "JoinNode",
     "Plan", "PlanNode", "ScanNode",
 ]

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <set>
@@ -48,6 +49,9 @@ struct rj_ctx {
     static constexpr size_t kStageBytes = size_t(64) << 20;
     uint8_t*     pinned[2]    = {nullptr, nullptr};
     cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
+    // rj_execute_streamed: uploads and downloads run beside the kernels on their own streams
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t  up_ev[2] = {nullptr, nullptr};
 };
 
 static thread_local std::string g_create_error;
@@ -258,6 +262,11 @@ struct ColumnDev {
     bool            dense = false;
     const void*     dense_values = nullptr;
     const uint32_t* dense_valid = nullptr;
+    // row window of a streamed table (rj_execute_streamed): the pages hold `skip_rows` rows before the
+    // table's first row and possibly rows behind its last one
+    bool            windowed = false;
+    uint64_t        skip_rows = 0;
+    bool            window_nulls = false; // the column holds NULLs somewhere (keep a validity bitmap)
 };
 
 struct TableDev {
@@ -382,6 +391,7 @@ struct DecodedCol {
     Buf             valid;  // null when the column holds no NULL
     const uint8_t*  pages = nullptr;
     Buf             str_hash; // VARCHAR join keys: 64-bit hash per row (lazily)
+    Buf             hold_values, hold_valid; // owners when values / valid are views into a larger decode
     const uint32_t* valid_ptr() const { return valid ? valid->as<uint32_t>() : nullptr; }
 };
 
@@ -413,6 +423,7 @@ struct CarriedCol {
 
 struct Rel {
     uint64_t                rows = 0;
+    bool                    streamed = false; // holds the table that rj_execute_streamed feeds in windows
     mutable std::map<int, Buf> rid;  // leaf -> row ids into that scan's base table; null Buf = identity
     std::map<int, PosSpace>    lazy; // leaf -> row ids not materialised yet
     std::map<std::pair<int, uint32_t>, CarriedCol> carried; // (leaf, column) -> values in position order
@@ -448,7 +459,14 @@ struct Exec {
     const rj_plan_t* plan;
     const rj_inputs* in;
     cudaStream_t     s;
-    std::map<std::pair<uint32_t, uint32_t>, DecodedCol> decoded;
+    using DecodedMap = std::map<std::pair<uint32_t, uint32_t>, DecodedCol>;
+    DecodedMap  own_decoded;
+    // rj_execute_streamed runs the plan once per chunk of one table: the decoded columns of all the
+    // other tables are shared between those runs
+    DecodedMap* shared_decoded = nullptr;
+    uint32_t    streamed_table = 0xffffffffu;
+    double      streamed_scale = 1.0; // whole table / this window: joins choose their sides as the whole job would
+    DecodedMap& decoded_of(uint32_t t) { return shared_decoded && t != streamed_table ? *shared_decoded : own_decoded; }
 
     Exec(rj_ctx* c, const rj_plan_t* p, const rj_inputs* i): ctx(c), plan(p), in(i), s(c->stream) {}
 
@@ -484,8 +502,10 @@ struct Exec {
 };
 
 // ---- page ingest -----------------------------------------------------------------------------------
+// `bias` (< 256) rows of padding precede the first decoded row: a row window that starts in the middle
+// of a page is shifted so that its first row lands on a validity-word boundary.
 void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_pages, int type, uint64_t rows,
-                  bool need_valid, DecodedCol* out) {
+                  bool need_valid, DecodedCol* out, uint32_t bias = 0) {
     out->type = type;
     out->rows = rows;
     out->pages = pages;
@@ -493,13 +513,17 @@ void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_
     out->values = dev_alloc(rows * w, s);
     if (need_valid) out->valid = dev_alloc_zero(((rows + 31) / 32 + 1) * 4, s);
     if (n_pages == 0) return;
-    Buf row_cnt = dev_alloc(n_pages * 4, s);
-    Buf row_start = dev_alloc((n_pages + 1) * 8, s);
-    Buf tmp = dev_alloc(scan_tmp_bytes(n_pages), s);
+    // entry 0 of the count array is the padding; the scan then yields biased row starts
+    Buf row_cnt = dev_alloc((n_pages + 1) * 4, s);
+    Buf row_start_buf = dev_alloc((n_pages + 2) * 8, s);
+    Buf tmp = dev_alloc(scan_tmp_bytes(n_pages + 1), s);
+    const uint64_t* row_start = row_start_buf->as<uint64_t>() + 1;
     {
         StageScope sc(ctx, RJ_ST_ROW_OFFSETS, s, 4, n_pages * 4);
-        launch_page_rows(pages, n_pages, type, row_cnt->as<uint32_t>(), nullptr, s);
-        launch_exclusive_scan_u32_u64(row_cnt->as<uint32_t>(), row_start->as<uint64_t>(), n_pages, tmp->p, s);
+        RJ_CUDA(cudaMemsetAsync(row_cnt->p, 0, 4, s));
+        if (bias) RJ_CUDA(cudaMemsetAsync(row_cnt->p, static_cast<int>(bias), 1, s)); // little-endian low byte
+        launch_page_rows(pages, n_pages, type, row_cnt->as<uint32_t>() + 1, nullptr, s);
+        launch_exclusive_scan_u32_u64(row_cnt->as<uint32_t>(), row_start_buf->as<uint64_t>(), n_pages + 1, tmp->p, s);
     }
     {
         // 8192 * pages read + rows * w + rows / 8 written
@@ -509,10 +533,10 @@ void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_
             RJ_CUDA(cudaMemsetAsync(out->values->p, 0, rows * w, s));
         }
         if (type == RJ_VARCHAR) {
-            launch_decode_varchar(pages, n_pages, row_start->as<uint64_t>(), out->values->as<uint64_t>(),
+            launch_decode_varchar(pages, n_pages, row_start, out->values->as<uint64_t>(),
                                   need_valid ? out->valid->as<uint32_t>() : nullptr, ctx->sm_count, s);
         } else {
-            launch_decode_fixed(pages, n_pages, type, row_start->as<uint64_t>(), out->values->p,
+            launch_decode_fixed(pages, n_pages, type, row_start, out->values->p,
                                 need_valid ? out->valid->as<uint32_t>() : nullptr, ctx->sm_count, s);
         }
     }
@@ -520,10 +544,33 @@ void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_
 
 const DecodedCol& Exec::column(uint32_t t, uint32_t c) {
     auto key = std::make_pair(t, c);
+    DecodedMap& decoded = decoded_of(t);
     auto it = decoded.find(key);
     if (it != decoded.end()) return it->second;
     const TableDev&  td = in->tables[t];
     const ColumnDev& cd = td.cols[c];
+    if (cd.windowed) {
+        // decode every page of the chunk, shifted so that the window's first row starts a validity
+        // word, then expose the window as a view
+        if (cd.type == RJ_VARCHAR) throw EngineError("internal: VARCHAR columns are not streamed");
+        const size_t   w     = type_width(cd.type);
+        const uint32_t bias  = static_cast<uint32_t>((32 - cd.skip_rows % 32) % 32);
+        const uint64_t first = bias + cd.skip_rows; // multiple of 32
+        const uint64_t total = std::max<uint64_t>(bias + cd.page_rows, first + td.num_rows);
+        DecodedCol full;
+        decode_pages(ctx, s, cd.pages, cd.n_pages, cd.type, total, cd.window_nulls, &full, bias);
+        DecodedCol d;
+        d.type = cd.type;
+        d.rows = td.num_rows;
+        d.pages = cd.pages;
+        d.hold_values = full.values;
+        d.values = std::make_shared<DevMem>(full.values->as<uint8_t>() + first * w, td.num_rows * w);
+        if (full.valid) {
+            d.hold_valid = full.valid;
+            d.valid = std::make_shared<DevMem>(full.valid->as<uint32_t>() + first / 32, ((td.num_rows + 31) / 32) * 4);
+        }
+        return decoded.emplace(key, std::move(d)).first->second;
+    }
     if (cd.dense) {
         DecodedCol d;
         d.type = cd.type;
@@ -816,7 +863,11 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
 
     // The hash table goes on the SMALLER side whatever build_left says: the result is the same
     // multiset of (left row, right row) pairs, and a small table side means fewer partitions.
-    const bool table_left = L.rows <= R.rows;
+    // (a window of a streamed table counts as the whole table: a window of a foreign-key side is smaller
+    // than the key side it refers to, but full of duplicates)
+    const double l_size = static_cast<double>(L.rows) * (L.streamed ? streamed_scale : 1.0);
+    const double r_size = static_cast<double>(R.rows) * (R.streamed ? streamed_scale : 1.0);
+    const bool table_left = l_size <= r_size;
     uint64_t m = 0;
     if (table_left) {
         join_keys(ls, rs, lk.key_bytes, &m);
@@ -857,6 +908,7 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
         m = kept;
     }
     out.rows = m;
+    out.streamed = L.streamed || R.streamed;
     if (m == 0) return out;
     // row-id lists of every scan the parents can still see through this node's output_attrs
     std::set<int> needed;
@@ -912,6 +964,7 @@ Rel Exec::run(uint64_t n) {
         if (nd.base_table_id >= in->tables.size()) throw EngineError("base table out of range");
         Rel r;
         r.rows = in->tables[nd.base_table_id].num_rows;
+        r.streamed = nd.base_table_id == streamed_table;
         r.rid[static_cast<int>(n)] = nullptr; // identity
         return r;
     }
@@ -1028,7 +1081,9 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
     return res;
 }
 
-std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in) {
+std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in,
+                                            Exec::DecodedMap* shared_decoded = nullptr, uint32_t streamed_table = 0xffffffffu,
+                                            double streamed_scale = 1.0) {
     if (plan->root >= plan->n_nodes) throw EngineError("plan root out of range");
     static const bool trace = getenv("RJ_TRACE") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
@@ -1037,6 +1092,9 @@ std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, 
     double t_run = 0, t_root = 0;
     {
         Exec ex(ctx, plan, in);
+        ex.shared_decoded = shared_decoded;
+        ex.streamed_table = streamed_table;
+        ex.streamed_scale = streamed_scale;
         Rel  r = ex.run(plan->root);
         t_run = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         res = ex.root(plan->root, r);
@@ -1152,6 +1210,10 @@ void rj_ctx_destroy(rj_ctx* ctx) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->pinned_ev[i]) cudaEventDestroy(ctx->pinned_ev[i]);
     }
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->up_ev[i]) cudaEventDestroy(ctx->up_ev[i]);
     cudaStreamDestroy(ctx->stream);
     if (g_live_contexts[ctx->device].fetch_sub(1) == 1) g_cache[ctx->device].trim(); // last context: release HBM
     delete ctx;
@@ -1251,6 +1313,268 @@ int rj_execute(rj_ctx* ctx, const rj_plan_t* plan, rj_result** out) {
         collect_wanted(plan, &wanted);
         auto in = upload_tables(ctx, plan->inputs, plan->n_inputs, &wanted);
         *out = execute_resident(ctx, plan, in.get()).release();
+    });
+}
+
+
+// ---- streamed execution: host pages in, host pages out, PCIe busy in both directions ----------------
+// An inner join distributes over a union of its inputs, so the plan can run once per row window of ONE
+// base table (the largest, when a single scan reads it) with every other table resident:
+//     upload(k+1)  ||  kernels(k)  ||  download(k-1)
+// on three streams.  With pinned, contiguous host buffers the copies are plain DMAs and the call costs
+// max(upload, download) instead of their sum; pageable or page-by-page buffers still work, without the
+// overlap.  Windows are cut on row boundaries, so the pages of a window's columns start and end at
+// different rows: the decode shifts each column to the window (ColumnDev::skip_rows).
+namespace {
+
+struct StreamCol {
+    uint32_t              col = 0;
+    std::vector<uint64_t> row_prefix; // [n_pages + 1] rows before page p
+    bool                  has_null = false;
+    Buf                   slot[2];
+    uint64_t              slot_pages = 0;
+};
+
+void ensure_copy_streams(rj_ctx* ctx) {
+    if (ctx->h2d_stream) return;
+    RJ_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    RJ_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) RJ_CUDA(cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming));
+}
+
+// pages [p0, p0 + cnt) of a host column -> device, on `stream`
+void copy_pages_h2d(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t cnt, uint8_t* dst, cudaStream_t stream) {
+    if (cnt == 0) return;
+    if (!c.pages) {
+        RJ_CUDA(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(c.contiguous) + p0 * RJ_PAGE_SIZE, cnt * size_t(RJ_PAGE_SIZE),
+                                cudaMemcpyHostToDevice, stream));
+        return;
+    }
+    ensure_pinned(ctx);
+    const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
+    int slot = 0;
+    for (uint64_t q = 0; q < cnt; q += chunk_pages, slot ^= 1) {
+        const uint64_t m = std::min<uint64_t>(chunk_pages, cnt - q);
+        RJ_CUDA(cudaEventSynchronize(ctx->pinned_ev[slot]));
+        uint8_t* stage = ctx->pinned[slot];
+        parallel_for(ctx->host_threads, m, [&](uint64_t b, uint64_t e, int) {
+            for (uint64_t i = b; i < e; ++i) std::memcpy(stage + i * RJ_PAGE_SIZE, host_page(c, p0 + q + i), RJ_PAGE_SIZE);
+        });
+        RJ_CUDA(cudaMemcpyAsync(dst + q * RJ_PAGE_SIZE, stage, m * RJ_PAGE_SIZE, cudaMemcpyHostToDevice, stream));
+        RJ_CUDA(cudaEventRecord(ctx->pinned_ev[slot], stream));
+    }
+}
+
+struct PendingDownload {
+    std::unique_ptr<rj_result> res;
+    cudaEvent_t                done = nullptr;
+};
+
+uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, rj_page_sink_t sink, void* user) {
+    if (!sink) throw EngineError("rj_execute_streamed: no page sink");
+    if (chunk_bytes == 0) chunk_bytes = uint64_t(512) << 20;
+    ensure_copy_streams(ctx);
+    std::set<std::pair<uint32_t, uint32_t>> wanted;
+    collect_wanted(plan, &wanted);
+
+    auto deliver = [&](rj_result* res, cudaStream_t stream) {
+        for (uint32_t c = 0; c < res->cols.size(); ++c) {
+            const ResultColumn& rc = res->cols[c];
+            if (rc.n_pages == 0) continue;
+            void* dst = sink(user, c, rc.type, rc.n_pages);
+            if (!dst) throw EngineError("rj_execute_streamed: the sink returned no buffer");
+            StageScope scope(ctx, RJ_ST_D2H, stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
+            if (getenv("RJ_STREAM_NO_D2H")) continue; // timing experiments only
+            RJ_CUDA(cudaMemcpyAsync(dst, rc.pages->p, rc.n_pages * size_t(RJ_PAGE_SIZE), cudaMemcpyDeviceToHost, stream));
+        }
+    };
+
+    // the table to stream: read by exactly one scan, fixed-width columns only, at least two chunks
+    std::vector<int> scans(plan->n_inputs, 0);
+    for (uint64_t i = 0; i < plan->n_nodes; ++i)
+        if (!plan->nodes[i].is_join && plan->nodes[i].base_table_id < plan->n_inputs) ++scans[plan->nodes[i].base_table_id];
+    int      pick = -1;
+    uint64_t pick_bytes = 0;
+    for (uint32_t t = 0; t < plan->n_inputs; ++t) {
+        if (scans[t] != 1) continue;
+        uint64_t bytes = 0;
+        bool     ok = true;
+        for (uint32_t c = 0; c < plan->inputs[t].n_columns; ++c) {
+            if (!wanted.count({t, c})) continue;
+            if (plan->inputs[t].columns[c].type == RJ_VARCHAR) ok = false;
+            bytes += plan->inputs[t].columns[c].n_pages * uint64_t(RJ_PAGE_SIZE);
+        }
+        if (ok && bytes >= 2 * chunk_bytes && bytes > pick_bytes) {
+            pick = static_cast<int>(t);
+            pick_bytes = bytes;
+        }
+    }
+    if (pick < 0) {
+        // nothing worth streaming: one upload, one execute, one download
+        auto in  = upload_tables(ctx, plan->inputs, plan->n_inputs, &wanted);
+        auto res = execute_resident(ctx, plan, in.get());
+        deliver(res.get(), ctx->stream);
+        RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+        return res->num_rows;
+    }
+
+    const uint32_t    T  = static_cast<uint32_t>(pick);
+    const rj_table_t& ht = plan->inputs[T];
+    // everything else becomes resident
+    std::set<std::pair<uint32_t, uint32_t>> others;
+    for (auto& w: wanted)
+        if (w.first != T) others.insert(w);
+    auto in = upload_tables(ctx, plan->inputs, plan->n_inputs, &others);
+
+    // page headers of the streamed table: rows before every page, per column
+    std::vector<StreamCol> cols;
+    for (uint32_t c = 0; c < ht.n_columns; ++c) {
+        if (!wanted.count({T, c})) continue;
+        const rj_column_t& hc = ht.columns[c];
+        if (hc.n_pages && !hc.pages && !hc.contiguous) throw EngineError("column has pages but no page pointers");
+        StreamCol sc;
+        sc.col = c;
+        sc.row_prefix.assign(hc.n_pages + 1, 0);
+        std::vector<uint64_t> nn(ctx->host_threads, 0);
+        parallel_for(ctx->host_threads, hc.n_pages, [&](uint64_t b, uint64_t e, int t) {
+            for (uint64_t i = b; i < e; ++i) {
+                uint64_t r = 0;
+                page_counts(host_page(hc, i), hc.type, &r, &nn[t]);
+                sc.row_prefix[i + 1] = r;
+            }
+        });
+        for (uint64_t i = 0; i < hc.n_pages; ++i) sc.row_prefix[i + 1] += sc.row_prefix[i];
+        if (sc.row_prefix[hc.n_pages] > ht.num_rows) throw EngineError("row_idx");
+        uint64_t non_null = 0;
+        for (auto v: nn) non_null += v;
+        sc.has_null = non_null != ht.num_rows;
+        cols.push_back(std::move(sc));
+    }
+
+    // row windows: multiples of 4096 rows, about chunk_bytes of pages each
+    uint64_t rows_per_chunk = static_cast<uint64_t>(static_cast<double>(ht.num_rows) * chunk_bytes / pick_bytes);
+    rows_per_chunk = std::max<uint64_t>(4096, (rows_per_chunk + 4095) & ~uint64_t(4095));
+    const uint64_t n_chunks = (ht.num_rows + rows_per_chunk - 1) / rows_per_chunk;
+    // pages of column `sc` that hold rows [r0, r1)
+    auto page_range = [&](const StreamCol& sc, uint64_t r0, uint64_t r1, uint64_t* p0, uint64_t* p1) {
+        const auto& pre = sc.row_prefix;
+        const uint64_t np = pre.size() - 1;
+        *p0 = std::upper_bound(pre.begin(), pre.end(), r0) - pre.begin();
+        *p0 = *p0 ? *p0 - 1 : 0;                     // last page with pre[p] <= r0
+        if (*p0 > np) *p0 = np;
+        *p1 = std::lower_bound(pre.begin(), pre.end(), r1) - pre.begin(); // first p with pre[p] >= r1
+        if (*p1 > np) *p1 = np;
+        if (*p1 < *p0) *p1 = *p0;
+    };
+    for (auto& sc: cols) {
+        for (uint64_t k = 0; k < n_chunks; ++k) {
+            uint64_t p0, p1;
+            page_range(sc, k * rows_per_chunk, std::min(ht.num_rows, (k + 1) * rows_per_chunk), &p0, &p1);
+            sc.slot_pages = std::max(sc.slot_pages, p1 - p0);
+        }
+        for (int i = 0; i < 2; ++i) sc.slot[i] = dev_alloc(std::max<uint64_t>(1, sc.slot_pages) * RJ_PAGE_SIZE, ctx->stream);
+    }
+    RJ_CUDA(cudaStreamSynchronize(ctx->stream)); // resident tables and slots are in place
+
+    auto issue_upload = [&](uint64_t k) {
+        const int      slot = static_cast<int>(k & 1);
+        const uint64_t r0 = k * rows_per_chunk, r1 = std::min(ht.num_rows, r0 + rows_per_chunk);
+        uint64_t       bytes = 0;
+        for (auto& sc: cols) {
+            uint64_t p0, p1;
+            page_range(sc, r0, r1, &p0, &p1);
+            bytes += (p1 - p0) * RJ_PAGE_SIZE;
+        }
+        StageScope scope(ctx, RJ_ST_H2D, ctx->h2d_stream, cols.size(), bytes);
+        for (auto& sc: cols) {
+            uint64_t p0, p1;
+            page_range(sc, r0, r1, &p0, &p1);
+            copy_pages_h2d(ctx, ht.columns[sc.col], p0, p1 - p0, sc.slot[slot]->as<uint8_t>(), ctx->h2d_stream);
+        }
+        RJ_CUDA(cudaEventRecord(ctx->up_ev[slot], ctx->h2d_stream));
+    };
+
+    Exec::DecodedMap             shared;
+    std::deque<PendingDownload>  pending;
+    uint64_t                     total_rows = 0;
+    auto reap = [&](bool all) {
+        while (!pending.empty()) {
+            if (all) RJ_CUDA(cudaEventSynchronize(pending.front().done));
+            else if (cudaEventQuery(pending.front().done) != cudaSuccess) { cudaGetLastError(); break; }
+            cudaEventDestroy(pending.front().done);
+            pending.pop_front();
+        }
+    };
+    static const bool trace = getenv("RJ_TRACE") != nullptr;
+    auto now_ms = [t0 = std::chrono::steady_clock::now()] {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    if (trace) fprintf(stderr, "[rj stream] table %u: %llu rows in %llu windows of %llu rows\n", T, (unsigned long long)ht.num_rows,
+                       (unsigned long long)n_chunks, (unsigned long long)rows_per_chunk);
+    try {
+        issue_upload(0);
+        for (uint64_t k = 0; k < n_chunks; ++k) {
+            const double t_a = now_ms();
+            if (k + 1 < n_chunks) issue_upload(k + 1); // its slot was last read by chunk k-1, which has finished
+            const double t_b = now_ms();
+            const int      slot = static_cast<int>(k & 1);
+            const uint64_t r0 = k * rows_per_chunk, r1 = std::min(ht.num_rows, r0 + rows_per_chunk);
+            double t_w = 0;
+            if (trace) {
+                const double t_w0 = now_ms();
+                RJ_CUDA(cudaEventSynchronize(ctx->up_ev[slot]));
+                t_w = now_ms() - t_w0;
+            }
+            RJ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->up_ev[slot], 0));
+            TableDev& td = in->tables[T];
+            td.num_rows = r1 - r0;
+            for (auto& sc: cols) {
+                uint64_t p0, p1;
+                page_range(sc, r0, r1, &p0, &p1);
+                ColumnDev& cd = td.cols[sc.col];
+                cd.type = ht.columns[sc.col].type;
+                cd.pages = sc.slot[slot]->as<uint8_t>();
+                cd.n_pages = p1 - p0;
+                cd.page_rows = sc.row_prefix[p1] - sc.row_prefix[p0];
+                cd.windowed = true;
+                cd.skip_rows = std::min(r0, sc.row_prefix[p1]) - sc.row_prefix[p0];
+                cd.window_nulls = sc.has_null;
+                cd.non_null = 0;
+            }
+            const double scale = static_cast<double>(ht.num_rows) / static_cast<double>(std::max<uint64_t>(1, r1 - r0));
+            auto res = execute_resident(ctx, plan, in.get(), &shared, T, scale); // returns with the stream idle
+            total_rows += res->num_rows;
+            PendingDownload pd;
+            RJ_CUDA(cudaEventCreateWithFlags(&pd.done, cudaEventDisableTiming));
+            deliver(res.get(), ctx->d2h_stream);
+            RJ_CUDA(cudaEventRecord(pd.done, ctx->d2h_stream));
+            pd.res = std::move(res);
+            pending.push_back(std::move(pd));
+            const double t_c = now_ms();
+            reap(false);
+            if (trace) fprintf(stderr, "[rj stream] window %llu: waited %.2f ms for the upload\n", (unsigned long long)k, t_w);
+            if (trace) fprintf(stderr, "[rj stream] window %llu: issue upload %.2f ms, execute %.2f ms, issue download + reap %.2f ms, %zu downloads pending\n",
+                               (unsigned long long)k, t_b - t_a, t_c - t_b, now_ms() - t_c, pending.size());
+        }
+        reap(true);
+    } catch (...) {
+        cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+        for (auto& pd: pending) cudaEventDestroy(pd.done);
+        throw;
+    }
+    RJ_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+    return total_rows;
+}
+
+} // namespace
+
+int rj_execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, rj_page_sink_t sink, void* user,
+                        uint64_t* num_rows) {
+    return guarded(ctx, [&] {
+        if (!plan) throw EngineError("null plan");
+        const uint64_t n = execute_streamed(ctx, plan, chunk_bytes, sink, user);
+        if (num_rows) *num_rows = n;
     });
 }
 

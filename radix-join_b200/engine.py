@@ -163,6 +163,52 @@ def execute(plan: Plan, ctx: Context) -> ColumnarTable:
         res.free()
 
 
+def execute_streamed(plan: Plan, ctx: Context, chunk_bytes=0, alloc=None):
+    """Host pages in, host pages out, with upload / kernels / download overlapped (rj_execute_streamed).
+
+    `alloc(column, data_type, n_pages)` returns a C-contiguous uint8 array of n_pages * 8192 bytes for
+    one window's result pages of a column (pinned memory makes the download a true DMA); default:
+    numpy.  Returns (num_rows, pages) with pages[column] = list of the arrays that were filled.
+    """
+    flat = FlatPlan(plan)
+    chunks = {}
+    failure = []
+
+    def sink(_user, column, dtype, n_pages):
+        try:
+            if alloc is None:
+                buf = np.empty((n_pages, PAGE_SIZE), dtype=np.uint8)
+            else:
+                buf = alloc(column, DataType(dtype), n_pages)
+            if buf.nbytes < n_pages * PAGE_SIZE or not buf.flags["C_CONTIGUOUS"]:
+                raise ValueError("sink buffer too small or not contiguous")
+            chunks.setdefault(column, []).append(buf)
+            return buf.ctypes.data
+        except Exception as e:  # an exception must not cross the C frame
+            failure.append(e)
+            return None
+
+    cb = _cabi.rj_page_sink_t(sink)
+    n = C.c_uint64(0)
+    rc = ctx.lib.rj_execute_streamed(ctx.handle, flat.pointer(), int(chunk_bytes), cb, None, C.byref(n))
+    if failure:
+        raise failure[0]
+    ctx.check(rc)
+    return int(n.value), chunks
+
+
+def execute_streamed_columnar(plan: Plan, ctx: Context, chunk_bytes=0) -> ColumnarTable:
+    """execute_streamed, collected into an owning ColumnarTable (column types from the root's output_attrs)."""
+    n, chunks = execute_streamed(plan, ctx, chunk_bytes)
+    t = ColumnarTable(num_rows=n)
+    root = plan.nodes[plan.root]
+    for c, (_, dtype) in enumerate(root.output_attrs):
+        parts = [b.reshape(-1, PAGE_SIZE) for b in chunks.get(c, [])]
+        pages = np.concatenate(parts) if parts else None
+        t.columns.append(Column(dtype, pages))
+    return t
+
+
 def upload(plan: Plan, ctx: Context) -> ResidentInputs:
     """Copy every input column's pages into HBM once (bench: inputs resident before the timer)."""
     flat = FlatPlan(plan)

@@ -403,3 +403,89 @@ def test_resident_inputs_and_profile(ctx):
     inputs.free()
     for st in ("decode", "histogram", "scatter", "join", "encode"):
         assert prof[st]["ms"] > 0 and prof[st]["launches"] > 0 and prof[st]["bytes"] > 0, (st, prof)
+
+
+# ---- streamed execution (rj_execute_streamed): row windows of the largest table --------------------------
+def check_streamed(plan, ctx, chunk_bytes, impl=None, min_chunks=2):
+    want = orc.execute(plan, impl=impl or oracle_impl())
+    calls = []
+
+    def alloc(column, dtype, n_pages):
+        calls.append((column, int(dtype), n_pages))
+        return np.empty((n_pages, 8192), dtype=np.uint8)
+
+    n, chunks = rj.execute_streamed(plan, ctx, chunk_bytes, alloc=alloc)
+    assert n == want.num_rows
+    got = rj.execute_streamed_columnar(plan, ctx, chunk_bytes)
+    assert got.num_rows == want.num_rows
+    assert [int(c.type) for c in got.columns] == [int(c.type) for c in want.columns]
+    assert orc.result_equal(got, want)
+    if min_chunks and want.num_rows:
+        per_col = max(sum(1 for c in calls if c[0] == col) for col in range(len(want.columns)))
+        assert per_col >= min_chunks, calls
+    return got
+
+
+@pytest.mark.parametrize("build_left", [True, False])
+def test_streamed_probe_windows_match_the_oracle(ctx, build_left):
+    # the right table is ~64 pages per column; 6-page windows cut every column in the middle of pages,
+    # INT32 and 8-byte columns at different rows, with NULLs in keys and payloads
+    rng = np.random.default_rng(77)
+    lt, rt = [INT32, INT64], [FP64, INT32, INT64]
+    tl, _ = H.random_table(rng, lt, 20_000, key_cols=(0,), key_range=15_000)
+    tr, _ = H.random_table(rng, rt, 60_000, key_cols=(1,), key_range=15_000)
+    plan = H.single_join_plan(tl, tr, lt, rt, 0, 1, build_left, out_cols=[1, 3, 2, 4, 0])
+    check_streamed(plan, ctx, chunk_bytes=6 * 8192 * 3)
+
+
+def test_streamed_build_side_and_multi_join(ctx):
+    # the streamed table sits below two joins, on the build side of the first
+    rng = np.random.default_rng(78)
+    big, _ = H.random_table(rng, [INT32, INT64, INT32], 50_000, key_cols=(0, 2), key_range=3_000)
+    a, _ = H.random_table(rng, [INT32, FP64], 3_000, key_cols=(0,), key_range=3_000)
+    b, _ = H.random_table(rng, [INT32, VARCHAR], 2_000, key_cols=(0,), key_range=3_000)
+    plan = rj.Plan()
+    s_big = plan.new_scan_node(0, [(0, INT32), (1, INT64), (2, INT32)])
+    s_a = plan.new_scan_node(1, [(0, INT32), (1, FP64)])
+    s_b = plan.new_scan_node(2, [(0, INT32), (1, VARCHAR)])
+    j1 = plan.new_join_node(True, s_big, s_a, 0, 0, [(0, INT32), (1, INT64), (2, INT32), (4, FP64)])
+    plan.root = plan.new_join_node(False, j1, s_b, 2, 0, [(5, VARCHAR), (1, INT64), (3, FP64), (0, INT32)])
+    for t in (big, a, b):
+        plan.new_input(t)
+    check_streamed(plan, ctx, chunk_bytes=5 * 8192 * 3)
+
+
+def test_streamed_falls_back_when_the_table_cannot_be_windowed(ctx):
+    rng = np.random.default_rng(79)
+    # (a) the big table carries a VARCHAR column the plan reads, (b) it is scanned twice (self join)
+    lt, rt = [INT32, INT64], [INT32, VARCHAR]
+    tl, _ = H.random_table(rng, lt, 2_000, key_cols=(0,), key_range=1_500)
+    tr, _ = H.random_table(rng, rt, 30_000, key_cols=(0,), key_range=1_500)
+    check_streamed(H.single_join_plan(tl, tr, lt, rt, 0, 0, True), ctx, chunk_bytes=4 * 8192, min_chunks=0)
+    t, _ = H.random_table(rng, [INT32, INT64], 30_000, key_cols=(0,), key_range=20_000)
+    plan = rj.Plan()
+    plan.new_scan_node(0, [(0, INT32), (1, INT64)])
+    plan.new_scan_node(0, [(0, INT32), (1, INT64)])
+    plan.root = plan.new_join_node(True, 0, 1, 0, 0, [(0, INT32), (1, INT64), (3, INT64)])
+    plan.new_input(t)
+    check_streamed(plan, ctx, chunk_bytes=4 * 8192, min_chunks=0)
+
+
+def test_streamed_scan_root_and_larger_join(ctx):
+    rng = np.random.default_rng(80)
+    t, _ = H.random_table(rng, [INT64, INT32], 40_000, null_frac=0.2)
+    plan = rj.Plan()
+    plan.new_input(t)
+    plan.root = plan.new_scan_node(0, [(1, INT32), (0, INT64)])
+    check_streamed(plan, ctx, chunk_bytes=7 * 8192)
+    # two scatter passes inside every window
+    n_build, n_probe = 3_000_000, 6_000_000
+    bk = rng.permutation(n_build).astype(np.int32)
+    ba = orc.Cells(INT64, (rng.random(n_build) > 0.01).astype(np.uint8), values=rng.integers(-2**62, 2**62, n_build))
+    pk = orc.Cells(INT32, (rng.random(n_probe) > 0.02).astype(np.uint8),
+                   values=rng.integers(0, int(n_build * 1.1), n_probe).astype(np.int32))
+    pb = H.random_cells(rng, FP64, n_probe, null_frac=0.01)
+    tl = H.table_from_cells([orc.Cells.from_values(INT32, bk), ba])
+    tr = H.table_from_cells([pk, pb])
+    plan = H.single_join_plan(tl, tr, [INT32, INT64], [INT32, FP64], 0, 0, True, out_cols=[0, 1, 3])
+    check_streamed(plan, ctx, chunk_bytes=24 << 20, impl="port")
