@@ -446,6 +446,7 @@ struct JoinSide {
     const uint32_t* valid = nullptr;
     uint64_t        n = 0;
     std::vector<CarryCol> carry; // columns to move with the tuples (only honoured when partitioned)
+    bool need_rows = true;       // false: nothing downstream asks for row ids, the scatter skips them
     // results
     bool partitioned = false;
     uint32_t pos_mask = 0xffffffffu; // strips the validity flags pass 2 may fold into the positions
@@ -642,10 +643,13 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
             launch_radix_histogram(pk, pv, np, key_bytes, 0, bits, hist_p, ctx->sm_count, s);
         }
         launch_partition_plan(hist_b, hist_p, 0, 0, bits, bits1, key_bytes, pl, s);
+        // the row ids of a side travel only if something downstream will ask for them (two passes: the
+        // final arrays then hold positions, which the join always needs)
+        const bool two_pass = bits1 != 0;
         keys_b = dev_alloc(nb * key_bytes, s);
-        idx_b  = dev_alloc(nb * 4, s);
+        if (two_pass || B.need_rows) idx_b = dev_alloc(nb * 4, s);
         keys_p = dev_alloc(np * key_bytes, s);
-        idx_p  = dev_alloc(np * 4, s);
+        if (two_pass || P.need_rows) idx_p = dev_alloc(np * 4, s);
         auto payload_of = [&](JoinSide& sd) {
             ScatterPayload pay;
             for (auto& c: sd.carry) {
@@ -674,8 +678,8 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
         B.partitioned = P.partitioned = true;
         if (bits1 == 0) {
             // single pass: position order = final partition order
-            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, 0, bits, pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), pay_b, ctx->sm_count, s);
-            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, 0, bits, pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), pay_p, ctx->sm_count, s);
+            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, 0, bits, pl.cur_b, keys_b->p, idx_b ? idx_b->as<uint32_t>() : nullptr, pay_b, ctx->sm_count, s);
+            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, 0, bits, pl.cur_p, keys_p->p, idx_p ? idx_p->as<uint32_t>() : nullptr, pay_p, ctx->sm_count, s);
             jl.bkeys = keys_b->p; jl.bidx = nullptr; jl.bvalid = nullptr; // emit positions
             jl.pkeys = keys_p->p; jl.pidx = nullptr; jl.pvalid = nullptr;
             B.rows_of_pos = idx_b; B.keys_of_pos = keys_b;
@@ -685,10 +689,10 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
             // carried payloads are written once, in regions of |side| / 2^bits1 tuples.  Pass 2 (low
             // bits2 inside each region) only moves (key, POSITION in the pass-1 arrays), so everything a
             // match refers to later lies inside one L2-sized region.
-            Buf tk_b = dev_alloc(nb * key_bytes, s), ti_b = dev_alloc(nb * 4, s);
-            Buf tk_p = dev_alloc(np * key_bytes, s), ti_p = dev_alloc(np * 4, s);
-            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, bits2, bits1, pl.cur1_b, tk_b->p, ti_b->as<uint32_t>(), pay_b, ctx->sm_count, s);
-            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, bits2, bits1, pl.cur1_p, tk_p->p, ti_p->as<uint32_t>(), pay_p, ctx->sm_count, s);
+            Buf tk_b = dev_alloc(nb * key_bytes, s), ti_b = B.need_rows ? dev_alloc(nb * 4, s) : Buf();
+            Buf tk_p = dev_alloc(np * key_bytes, s), ti_p = P.need_rows ? dev_alloc(np * 4, s) : Buf();
+            launch_radix_scatter(bk, bv, nullptr, nb, key_bytes, bits2, bits1, pl.cur1_b, tk_b->p, ti_b ? ti_b->as<uint32_t>() : nullptr, pay_b, ctx->sm_count, s);
+            launch_radix_scatter(pk, pv, nullptr, np, key_bytes, bits2, bits1, pl.cur1_p, tk_p->p, ti_p ? ti_p->as<uint32_t>() : nullptr, pay_p, ctx->sm_count, s);
             // validity of up to two carried columns per side rides in bits 30/31 of the positions
             auto flags_of = [&](JoinSide& sd) {
                 RegionFlags f;
@@ -767,6 +771,7 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
 
 // row index (into the side's input relation) of every match
 Buf Exec::side_rows(const JoinSide& sd, uint64_t m) {
+    if (sd.partitioned && !sd.rows_of_pos) throw EngineError("internal: row ids of a join side were not kept");
     return sd.partitioned ? gather_u32(sd.rows_of_pos, sd.pos, m, sd.pos_mask) : sd.pos;
 }
 
@@ -775,6 +780,7 @@ Buf Exec::rid_of(const Rel& r, int leaf) {
     if (it != r.rid.end()) return it->second;
     auto lz = r.lazy.find(leaf);
     if (lz == r.lazy.end()) throw EngineError("internal: leaf not tracked");
+    if (!lz->second.rows_of_pos) throw EngineError("internal: row ids of a join side were not kept");
     Buf rows = gather_u32(lz->second.rows_of_pos, lz->second.pos, r.rows, lz->second.mask);
     r.rid[leaf] = rows;
     return rows;
@@ -860,6 +866,26 @@ Rel Exec::join(uint64_t n, const Rel& L, const Rel& R) {
     };
     plan_carry(L, la, ls);
     plan_carry(R, ra, rs);
+    // Row ids of a side are needed unless this is the root, the side is a plain scan and every root
+    // output from it is the join key or a column the scatter will carry (same slot budget as join_keys).
+    auto rows_needed = [&](const Rel& rel, const Attr& key_attr, const JoinSide& sd) {
+        if (!is_root || key_type == RJ_VARCHAR || !pure_scan(rel, key_attr)) return true;
+        std::set<uint32_t> moved;
+        int slots = 0;
+        for (auto& c: sd.carry) {
+            const int want = c.valid_src ? 2 : 1;
+            if (slots + want > ScatterPayload::kMax) break;
+            slots += want;
+            moved.insert(c.col);
+        }
+        for (uint32_t a = 0; a < nd.n_output_attrs; ++a) {
+            const Attr at = resolve(n, a);
+            if (at.leaf == key_attr.leaf && at.col != key_attr.col && !moved.count(at.col)) return true;
+        }
+        return false;
+    };
+    ls.need_rows = rows_needed(L, la, ls);
+    rs.need_rows = rows_needed(R, ra, rs);
 
     // The hash table goes on the SMALLER side whatever build_left says: the result is the same
     // multiset of (left row, right row) pairs, and a small table side means fewer partitions.

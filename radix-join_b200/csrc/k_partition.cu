@@ -656,11 +656,12 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
                 for (int j = 0; j < kDepth; ++j) rr[j] = in[j] ? idx_in[rr[j]] : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < kDepth; ++j) {
-                if (in[j]) {
-                    keys_out[dd[j]] = kk[j];
-                    idx_out[dd[j]]  = kRegions ? (rr[j] | (ww[j] & 0xc0000000u)) : rr[j];
-                }
+            for (int j = 0; j < kDepth; ++j)
+                if (in[j]) keys_out[dd[j]] = kk[j];
+            if (kRegions || idx_out != nullptr) { // the flat pass drops the row ids nobody will read
+#pragma unroll
+                for (int j = 0; j < kDepth; ++j)
+                    if (in[j]) idx_out[dd[j]] = kRegions ? (rr[j] | (ww[j] & 0xc0000000u)) : rr[j];
             }
             if (kRegions) return;
             if (flags.n > 0) {
