@@ -2,14 +2,14 @@
 // (src/execute.cpp:85-92 bucket count, :124-132 histogram, :169-184 prefix sum + scatter of row ids).
 //
 // Differences by design (none observable in results):
-//   * the fan-out is sized for SHARED MEMORY, not a 1 MiB CPU L2: partitions target <= 4096 build
+//   * the fan-out is sized for SHARED MEMORY, not a 1 MiB CPU L2: partitions target <= 2048 build
 //     tuples so that the build side of one partition fits an 8192-slot table in one CTA's smem;
 //   * (key, row id) pairs are scattered, not bare row ids, so build/probe never gather keys again;
 //   * up to 16 radix bits in at most two passes of <= 8 bits; ONE histogram kernel over all bits
 //     yields every offset of both passes;
 //   * NULL keys are dropped here (execute.cpp:61-83: a NULL key never matches).
 //
-// Scatter kernel: a CTA takes a tile of 8192 tuples, ranks every tuple inside its partition with a
+// Scatter kernel: a CTA takes a tile of 4096 tuples, ranks every tuple inside its partition with a
 // shared-memory atomic (warp-aggregated through __match_any_sync when a warp is dominated by one
 // partition -- skewed keys), stages the tile in shared memory IN PARTITION ORDER (software
 // write-combining), reserves each partition's run with one global atomic, and streams the runs out
@@ -153,248 +153,10 @@ __global__ void __launch_bounds__(kPlanThreads)
     });
 }
 
-// ---- scatter ----------------------------------------------------------------------------------------
-// kMulti: every partition has its own output bases (`multi`), possibly in another GPU's memory
-template <typename K, bool kRegions, bool kMulti = false>
-__global__ void __launch_bounds__(kScatterThreads, 4)
-    radix_scatter_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
-                         const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
-                         const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
-                         uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
-                         ScatterPayload pay, const rj_scatter_multi_t* __restrict__ multi = nullptr,
-                         RegionFlags flags = RegionFlags{}) {
-    constexpr int      kScatterItems = ScatterCfg<K>::kItems;
-    constexpr uint32_t kTile         = ScatterCfg<K>::kTile;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    K*        s_keys  = reinterpret_cast<K*>(smem_raw);
-    uint32_t* s_idx   = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kTile);
-    uint32_t* s_count = s_idx + kTile;            // [nb]  tuples of this tile per partition
-    uint32_t* s_start = s_count + (1u << bits);   // [nb]  exclusive prefix inside the tile
-    uint32_t* s_gbase = s_start + (1u << bits);   // [nb]  global run start minus s_start
-    __shared__ uint32_t s_warp_sums[kScatterThreads / 32];
-    __shared__ uint32_t s_total;
-    // segmented scatter: region / tile tables (<= 257 entries each) cached once per CTA, so that the
-    // per-tile region lookup is a shared-memory binary search instead of 8 dependent L2 round trips
-    __shared__ uint32_t s_region_start[kRegions ? 258 : 1];
-    __shared__ uint32_t s_tile_start[kRegions ? 258 : 1];
-
-    const uint32_t nb = 1u << bits, mask = nb - 1;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt = lanemask_lt();
-
-    uint64_t n_tiles;
-    if (kRegions) {
-        for (uint32_t r = threadIdx.x; r <= n_regions; r += kScatterThreads) {
-            s_region_start[r] = region_start[r];
-            s_tile_start[r]   = tile_start[r];
-        }
-        __syncthreads();
-        n_tiles = s_tile_start[n_regions];
-    } else {
-        n_tiles = (n + kTile - 1) / kTile;
-    }
-    for (uint32_t b = threadIdx.x; b < nb; b += kScatterThreads) s_count[b] = 0;
-    __syncthreads();
-
-    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        uint64_t lo, hi;
-        uint32_t cursor_base = 0;
-        if (kRegions) {
-            // region of this tile: last r with tile_start[r] <= t
-            uint32_t a = 0, b = n_regions;
-            while (b - a > 1) {
-                uint32_t m = (a + b) >> 1;
-                if (s_tile_start[m] <= t) a = m; else b = m;
-            }
-            lo = static_cast<uint64_t>(s_region_start[a]) + (t - s_tile_start[a]) * kTile;
-            hi = s_region_start[a + 1];
-            if (hi > lo + kTile) hi = lo + kTile;
-            cursor_base = a << bits;
-        } else {
-            lo = t * kTile;
-            hi = lo + kTile < n ? lo + kTile : n;
-        }
-
-        // 1) load + rank inside the partition
-        K        key[kScatterItems];
-        uint32_t pr[kScatterItems]; // partition << 16 | rank (rank < 8192, partition < 512)
-        uint32_t fl = 0;            // 2 carried-validity flags per item (segmented scatter only)
-#pragma unroll
-        for (int k = 0; k < kScatterItems; ++k) {
-            const uint64_t i = lo + static_cast<uint64_t>(k) * kScatterThreads + threadIdx.x;
-            bool ok = i < hi;
-            key[k] = ok ? keys[i] : K(0);
-            if (kRegions && ok) {
-                // loaded here, in the same batch of independent loads as the keys
-                if (flags.n > 0 && flags.src[0][i]) fl |= 1u << (2 * k);
-                if (flags.n > 1 && flags.src[1][i]) fl |= 2u << (2 * k);
-            }
-            if (ok && valid != nullptr) ok = test_bit(valid, i);
-            pr[k]  = ok ? ((hash_key(key[k]) >> shift) & mask) : 0xffffffffu;
-        }
-#pragma unroll
-        for (int k = 0; k < kScatterItems; ++k) {
-            const uint32_t part = pr[k];
-            const bool     ok   = part != 0xffffffffu;
-            // skew detector: how many lanes share the partition of their neighbour?
-            const uint32_t nbr  = __shfl_xor_sync(RJ_FULL_MASK, part, 1);
-            const uint32_t same = __ballot_sync(RJ_FULL_MASK, ok && nbr == part);
-            uint32_t rank = 0;
-            if (__popc(same) >= 4) {
-                // warp dominated by few partitions: one shared-memory atomic per distinct partition
-                const uint32_t peers  = __match_any_sync(RJ_FULL_MASK, part);
-                const uint32_t leader = __ffs(peers) - 1;
-                uint32_t base = 0;
-                if (ok && lane == leader) base = atomicAdd(&s_count[part], static_cast<uint32_t>(__popc(peers)));
-                base = __shfl_sync(RJ_FULL_MASK, base, leader);
-                rank = base + __popc(peers & lt);
-            } else if (ok) {
-                rank = atomicAdd(&s_count[part], 1u);
-            }
-            pr[k] = ok ? ((part << 16) | rank) : 0xffffffffu;
-        }
-        __syncthreads();
-
-        // 2) exclusive scan of the per-partition counts (nb <= kScatterThreads), reserve global runs
-        {
-            const uint32_t c = threadIdx.x < nb ? s_count[threadIdx.x] : 0u;
-            uint32_t inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
-                if (lane >= d) inc += o;
-            }
-            if (lane == 31) s_warp_sums[warp] = inc;
-            __syncthreads();
-            uint32_t prefix = 0;
-            for (uint32_t w = 0; w < warp; ++w) prefix += s_warp_sums[w];
-            const uint32_t start = prefix + inc - c;
-            if (threadIdx.x < nb) {
-                s_start[threadIdx.x] = start;
-                uint32_t g = 0;
-                if (c) g = atomicAdd(&cursor[cursor_base + threadIdx.x], c);
-                s_gbase[threadIdx.x] = g - start;
-                s_count[threadIdx.x] = 0; // ready for the next tile
-            }
-            if (threadIdx.x == kScatterThreads - 1) s_total = prefix + inc;
-        }
-        __syncthreads();
-
-        // 3) stage the tile in partition order
-#pragma unroll
-        for (int k = 0; k < kScatterItems; ++k) {
-            if (pr[k] != 0xffffffffu) {
-                const uint64_t i   = lo + static_cast<uint64_t>(k) * kScatterThreads + threadIdx.x;
-                const uint32_t pos = s_start[pr[k] >> 16] + (pr[k] & 0xffffu);
-                s_keys[pos] = key[k];
-                uint32_t id = idx_in != nullptr ? idx_in[i] : static_cast<uint32_t>(i);
-                // carried validity bytes of the pass-1 order ride in the top bits of the position
-                if (kRegions) id |= ((fl >> (2 * k)) & 3u) << 30;
-                s_idx[pos]  = id;
-            }
-        }
-        __syncthreads();
-
-        // 4) stream the runs out: thread -> staged position, neighbours write neighbouring addresses.
-        //    Four positions per thread are in flight at once, and the payload slots are unrolled
-        //    statically (a dynamically indexed descriptor lands in local memory: ncu showed the copy-out
-        //    stalled on LDL -> LDG -> STG chains, one position at a time).
-        const uint32_t total = s_total;
-        for (uint32_t base = 0; base < total; base += 4 * kScatterThreads) {
-            K        kk[4];
-            uint32_t rr[4], dd[4], pp[4];
-            bool     in[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t pos = base + j * kScatterThreads + threadIdx.x;
-                in[j] = pos < total;
-                kk[j] = K(0);
-                rr[j] = dd[j] = pp[j] = 0;
-                if (in[j]) {
-                    kk[j] = s_keys[pos];
-                    rr[j] = s_idx[pos];
-                    pp[j] = (hash_key(kk[j]) >> shift) & mask;
-                    dd[j] = s_gbase[pp[j]] + pos;
-                }
-            }
-            if (kMulti) {
-                // per-partition bases (peer memory when the partitions are owner ranks)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (!in[j]) continue;
-                    static_cast<K*>(multi->keys_out[pp[j]])[dd[j]] = kk[j];
-                    if (multi->rows_out[pp[j]] != nullptr) multi->rows_out[pp[j]][dd[j]] = rr[j];
-                }
-                const uint32_t n_pay = multi->n_payload;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    if (c >= static_cast<int>(n_pay)) break;
-                    const int w = multi->pay_width[c];
-                    if (w == 8) {
-                        uint64_t v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(multi->pay_src[c])[rr[j]] : 0ull;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint64_t*>(multi->pay_dst[c][pp[j]])[dd[j]] = v[j];
-                    } else if (w == 1) {
-                        uint32_t v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(multi->pay_src[c])[rr[j] >> 5] : 0u;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint8_t*>(multi->pay_dst[c][pp[j]])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
-                    } else {
-                        uint32_t v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(multi->pay_src[c])[rr[j]] : 0u;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint32_t*>(multi->pay_dst[c][pp[j]])[dd[j]] = v[j];
-                    }
-                }
-                continue;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (in[j]) {
-                    keys_out[dd[j]] = kk[j];
-                    idx_out[dd[j]]  = rr[j];
-                }
-            }
-            // carried payload columns: the reads stay inside this tile's row window (L1/L2 resident)
-#pragma unroll
-            for (int c = 0; c < ScatterPayload::kMax; ++c) {
-                if (c < pay.n) {
-                    const int w = pay.width[c];
-                    if (w == 8) {
-                        uint64_t v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(pay.src[c])[rr[j]] : 0ull;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = v[j];
-                    } else if (w == 1) { // a validity bitmap travels as one byte per tuple
-                        uint32_t v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j] >> 5] : 0u;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint8_t*>(pay.dst[c])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
-                    } else {
-                        uint32_t v[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j]] : 0u;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = v[j];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ---- scatter, local outputs (flat pass and segmented pass 2) ----------------------------------------
-// Same tile algorithm as above, rewritten around the instruction budget: the first version executed ~170
-// thread instructions per tuple (ncu source view: 64-bit index arithmetic, per-tuple bounds predicates,
-// two bitmap probes through 64-bit addresses, the hash recomputed at copy-out) and was issue-limited at
-// a third of the DRAM bandwidth.  Here
+// ---- scatter: flat pass, segmented pass 2, multi-GPU exchange ---------------------------------------
+// Written around the instruction budget: the first version of this kernel executed ~170 thread
+// instructions per tuple (ncu source view: 64-bit index arithmetic, per-tuple bounds predicates, two
+// bitmap probes through 64-bit addresses, the hash recomputed at copy-out).  Here
 //   * a tile that is full (all but the last of a relation / region) runs without bounds predicates, and
 //     full copy-out batches run without per-position predicates;
 //   * everything inside a tile is addressed by 32-bit offsets from the tile's base pointers;
@@ -409,13 +171,21 @@ struct TileFlags {
     uint8_t*    dst[2] = {nullptr, nullptr}; // flat pass: one byte per scattered tuple
 };
 
-template <typename K, bool kRegions>
+// kMulti (the multi-GPU exchange, rj_radix_scatter_multi): every partition has its own output bases,
+// possibly in another GPU's memory; `dsts` holds them per output array and partition
+struct MultiDsts {
+    static constexpr int kKeys = 0, kRows = 1, kFlag0 = 2, kPay0 = 4, kArrays = 4 + ScatterPayload::kMax;
+    void* p[kArrays][8];
+};
+
+template <typename K, bool kRegions, bool kMulti = false>
 __global__ void __launch_bounds__(kScatterThreads, 4)
     scatter_tile_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ valid,
                         const uint32_t* __restrict__ idx_in, uint64_t n, const uint32_t* __restrict__ region_start,
                         const uint32_t* __restrict__ tile_start, uint32_t n_regions, int shift, int bits,
                         uint32_t* __restrict__ cursor, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out,
-                        ScatterPayload pay, TileFlags flags, int n_tma) {
+                        ScatterPayload pay, TileFlags flags, int n_tma, const MultiDsts* __restrict__ dsts = nullptr) {
+    static_assert(!(kRegions && kMulti), "the exchange is a flat pass");
     constexpr int      kItems     = ScatterCfg<K>::kItems;
     constexpr uint32_t kTile      = ScatterCfg<K>::kTile;
     constexpr int      kPartShift = 12; // staged word: tile offset | bucket << 12 | flags << 30
@@ -437,6 +207,10 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
     // wavefront per tuple (32 distinct lines per warp load) -- that, not DRAM, bounded the pass.
     extern __shared__ __align__(128) uint8_t s_pay[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ void* s_dst[kMulti ? MultiDsts::kArrays : 1][8];
+    if (kMulti) {
+        for (uint32_t i = threadIdx.x; i < MultiDsts::kArrays * 8; i += kScatterThreads) s_dst[i >> 3][i & 7] = dsts->p[i >> 3][i & 7];
+    }
 
     const uint32_t nb = 1u << bits, mask = nb - 1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -655,22 +429,27 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j) rr[j] = in[j] ? idx_in[rr[j]] : 0u;
             }
+            // destination of array `a` for staged position j: one base, or one base per partition
+            auto out = [&](int a, void* single, int j) -> void* {
+                if (kMulti) return s_dst[a][(ww[j] >> kPartShift) & 7u];
+                return single;
+            };
 #pragma unroll
             for (int j = 0; j < kDepth; ++j)
-                if (in[j]) keys_out[dd[j]] = kk[j];
-            if (kRegions || idx_out != nullptr) { // the flat pass drops the row ids nobody will read
+                if (in[j]) static_cast<K*>(out(MultiDsts::kKeys, keys_out, j))[dd[j]] = kk[j];
+            if (kRegions || (kMulti ? s_dst[MultiDsts::kRows][0] != nullptr : idx_out != nullptr)) { // row ids nobody reads are dropped
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j)
-                    if (in[j]) idx_out[dd[j]] = kRegions ? (rr[j] | (ww[j] & 0xc0000000u)) : rr[j];
+                    if (in[j]) static_cast<uint32_t*>(out(MultiDsts::kRows, idx_out, j))[dd[j]] = kRegions ? (rr[j] | (ww[j] & 0xc0000000u)) : rr[j];
             }
             if (kRegions) return;
             if (flags.n > 0) {
 #pragma unroll
-                for (int j = 0; j < kDepth; ++j) if (in[j]) flags.dst[0][dd[j]] = (ww[j] >> 30) & 1u;
+                for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint8_t*>(out(MultiDsts::kFlag0, flags.dst[0], j))[dd[j]] = (ww[j] >> 30) & 1u;
             }
             if (flags.n > 1) {
 #pragma unroll
-                for (int j = 0; j < kDepth; ++j) if (in[j]) flags.dst[1][dd[j]] = ww[j] >> 31;
+                for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint8_t*>(out(MultiDsts::kFlag0 + 1, flags.dst[1], j))[dd[j]] = ww[j] >> 31;
             }
             // carried payload columns: the reads stay inside this tile's row window (prefetched above)
 #pragma unroll
@@ -683,31 +462,31 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
                             const uint64_t* win = reinterpret_cast<const uint64_t*>(s_pay + c * kTile * 8);
 #pragma unroll
                             for (int j = 0; j < kDepth; ++j)
-                                if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = win[ww[j] & (kTile - 1)];
+                                if (in[j]) static_cast<uint64_t*>(out(MultiDsts::kPay0 + c, pay.dst[c], j))[dd[j]] = win[ww[j] & (kTile - 1)];
                         } else {
                             const uint32_t* win = reinterpret_cast<const uint32_t*>(s_pay + c * kTile * 8);
 #pragma unroll
                             for (int j = 0; j < kDepth; ++j)
-                                if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = win[ww[j] & (kTile - 1)];
+                                if (in[j]) static_cast<uint32_t*>(out(MultiDsts::kPay0 + c, pay.dst[c], j))[dd[j]] = win[ww[j] & (kTile - 1)];
                         }
                     } else if (w == 8) {
                         uint64_t v[kDepth];
 #pragma unroll
                         for (int j = 0; j < kDepth; ++j) v[j] = in[j] ? static_cast<const uint64_t*>(pay.src[c])[rr[j]] : 0ull;
 #pragma unroll
-                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint64_t*>(pay.dst[c])[dd[j]] = v[j];
+                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint64_t*>(out(MultiDsts::kPay0 + c, pay.dst[c], j))[dd[j]] = v[j];
                     } else if (w == 1) { // a validity bitmap travels as one byte per tuple
                         uint32_t v[kDepth];
 #pragma unroll
                         for (int j = 0; j < kDepth; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j] >> 5] : 0u;
 #pragma unroll
-                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint8_t*>(pay.dst[c])[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
+                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint8_t*>(out(MultiDsts::kPay0 + c, pay.dst[c], j))[dd[j]] = (v[j] >> (rr[j] & 31)) & 1u;
                     } else {
                         uint32_t v[kDepth];
 #pragma unroll
                         for (int j = 0; j < kDepth; ++j) v[j] = in[j] ? static_cast<const uint32_t*>(pay.src[c])[rr[j]] : 0u;
 #pragma unroll
-                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint32_t*>(pay.dst[c])[dd[j]] = v[j];
+                        for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint32_t*>(out(MultiDsts::kPay0 + c, pay.dst[c], j))[dd[j]] = v[j];
                     }
                 }
             }
@@ -717,11 +496,6 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
         if (base < total) copy_out(std::true_type{}, base);
         __syncthreads();
     }
-}
-
-template <typename K>
-size_t scatter_smem_bytes(int bits) {
-    return (sizeof(K) + 4) * ScatterCfg<K>::kTile + 3 * sizeof(uint32_t) * (1u << bits);
 }
 
 // persistent grid = the CTAs that are resident at once (the windows in dynamic shared memory change that)
@@ -870,33 +644,68 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
 void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift, int bits,
                                 uint32_t* cursor, const rj_scatter_multi_t& out, int sm_count, cudaStream_t s) {
     if (n == 0) return;
-    // the descriptor (~600 bytes of pointers) lives in device memory for the duration of the launch
-    static thread_local rj_scatter_multi_t* d_desc = nullptr;
-    if (!d_desc) RJ_CUDA(cudaMalloc(&d_desc, sizeof(rj_scatter_multi_t)));
-    RJ_CUDA(cudaMemcpyAsync(d_desc, &out, sizeof(rj_scatter_multi_t), cudaMemcpyHostToDevice, s));
+    // Same slot assignment as the flat pass: up to two value columns through TMA windows (first slots),
+    // up to two validity bitmaps through the per-warp bitmap words, the rest gathered.
+    ScatterPayload pay;
+    TileFlags      flags;
+    MultiDsts      h{};
+    int            n_tma = 0;
+    for (int p = 0; p < 8; ++p) {
+        h.p[MultiDsts::kKeys][p] = out.keys_out[p];
+        h.p[MultiDsts::kRows][p] = out.rows_out[p];
+    }
+    auto push = [&](uint32_t c) {
+        pay.src[pay.n] = out.pay_src[c];
+        pay.width[pay.n] = out.pay_width[c];
+        for (int p = 0; p < 8; ++p) h.p[MultiDsts::kPay0 + pay.n][p] = out.pay_dst[c][p];
+        ++pay.n;
+    };
+    auto tma_ok = [&](uint32_t c) { return out.pay_width[c] >= 4 && reinterpret_cast<uintptr_t>(out.pay_src[c]) % 16 == 0; };
+    for (uint32_t c = 0; c < out.n_payload; ++c) {
+        if (tma_ok(c) && n_tma < 2) {
+            push(c);
+            ++n_tma;
+        }
+    }
+    int taken = 0;
+    for (uint32_t c = 0; c < out.n_payload; ++c) {
+        if (tma_ok(c) && taken < 2) {
+            ++taken;
+        } else if (out.pay_width[c] == 1 && flags.n < 2) {
+            flags.src[flags.n] = out.pay_src[c];
+            for (int p = 0; p < 8; ++p) h.p[MultiDsts::kFlag0 + flags.n][p] = out.pay_dst[c][p];
+            ++flags.n;
+        } else {
+            push(c);
+        }
+    }
+    // the destination table (~900 bytes of pointers) lives in device memory for the duration of the launch
+    static thread_local MultiDsts* d_dsts = nullptr;
+    if (!d_dsts) RJ_CUDA(cudaMalloc(&d_dsts, sizeof(MultiDsts)));
+    RJ_CUDA(cudaMemcpyAsync(d_dsts, &h, sizeof(MultiDsts), cudaMemcpyHostToDevice, s));
     const uint32_t tile = scatter_tile(key_bytes);
-    uint64_t n_tiles = (n + tile - 1) / tile;
-    unsigned blocks = static_cast<unsigned>(n_tiles < static_cast<uint64_t>(sm_count) * 4 ? n_tiles : static_cast<uint64_t>(sm_count) * 4);
+    const uint64_t n_tiles = (n + tile - 1) / tile;
+    const size_t   smem = static_cast<size_t>(n_tma) * tile * 8;
     if (key_bytes == 4) {
-        const size_t smem = scatter_smem_bytes<uint32_t>(bits);
+        auto kern = scatter_tile_kernel<uint32_t, false, true>;
         static size_t configured = 0;
         if (smem > configured) {
-            RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<uint32_t, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        radix_scatter_kernel<uint32_t, false, true><<<blocks, kScatterThreads, smem, s>>>(
-            static_cast<const uint32_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift, bits, cursor, nullptr, nullptr,
-            ScatterPayload{}, d_desc);
+        const unsigned blocks = resident_grid(kern, smem, n_tiles, sm_count);
+        kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift,
+                                                   bits, cursor, nullptr, nullptr, pay, flags, n_tma, d_dsts);
     } else {
-        const size_t smem = scatter_smem_bytes<uint64_t>(bits);
+        auto kern = scatter_tile_kernel<uint64_t, false, true>;
         static size_t configured = 0;
         if (smem > configured) {
-            RJ_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<uint64_t, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
-        radix_scatter_kernel<uint64_t, false, true><<<blocks, kScatterThreads, smem, s>>>(
-            static_cast<const uint64_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift, bits, cursor, nullptr, nullptr,
-            ScatterPayload{}, d_desc);
+        const unsigned blocks = resident_grid(kern, smem, n_tiles, sm_count);
+        kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift,
+                                                   bits, cursor, nullptr, nullptr, pay, flags, n_tma, d_dsts);
     }
     RJ_LAUNCH_CHECK();
 }
