@@ -163,7 +163,7 @@ def run_single_gpu(args):
     torch.cuda.set_device(0)
     nb, np_ = FULL_BUILD // args.scale, FULL_PROBE // args.scale
     ctx = rj.build_context(0)
-    dt = syn.make_c2_device(ctx, nb, np_)
+    dt = syn.make_c2_device(ctx, nb, np_, checksum=True)
     inputs = rj.adopt_device(dt.plan, dt.device_pages, ctx, keep=dt.keep)
     in_bytes = sum(n * 8192 for cols in dt.device_pages for _, n in cols)
     stream = torch.cuda.ExternalStream(ctx.stream)
@@ -198,6 +198,15 @@ def run_single_gpu(args):
     ctx.profile_enable(False)
     ms_per_step = ms_total / args.steps
     value = (nb + np_) / 1e6 / (ms_per_step / 1e3)
+
+    # ---- parity at full size (outside the timed region): multiset checksum of the result pages against
+    #      the value derived from the generator without a join (synthetic.row_hash_torch) -------------
+    res = rj.execute_resident(dt.plan, inputs, ctx)
+    parity = {"rows": res.num_rows == dt.expected_rows,
+              "multiset_checksum": syn.result_checksum(ctx, res) == dt.expected_checksum,
+              "how": "two wrapping 64-bit sums over a per-row hash of the result pages vs the generator's direct-addressing expectation"}
+    res.free()
+    assert parity["rows"] and parity["multiset_checksum"], parity
 
     # ---- roofline of the dominant kernel class (CUDA events recorded around the launches, on the
     #      launching stream, inside the timed region above) -----------------------------------------
@@ -246,10 +255,12 @@ def run_single_gpu(args):
         for i in range(1 + e2e_steps):
             used[:] = [0] * len(caps)
             t0 = time.perf_counter()
-            e_rows, _chunks = rj.execute_streamed(host_plan, ctx, alloc=alloc)
+            e_rows, chunks = rj.execute_streamed(host_plan, ctx, alloc=alloc)
             if i > 0:
                 times.append(time.perf_counter() - t0)
         assert e_rows == dt.expected_rows
+        parity["e2e_multiset_checksum"] = syn.host_chunks_checksum(ctx, [t for _, t in root.output_attrs], chunks) == dt.expected_checksum
+        assert parity["e2e_multiset_checksum"], parity
         sec = sum(times) / len(times)
         e2e = {"value": round((nb + np_) / 1e6 / sec, 2), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                "d2h_bytes_per_step": int(sum(used) * 8192), "ms_per_step": round(sec * 1e3, 2),
@@ -276,7 +287,7 @@ def run_single_gpu(args):
                    "output_pages_bytes": out_pages * 8192,
                    "cache": "inputs (%.1f GB) and every intermediate are far larger than the 126 MB L2; no flush needed" % (in_bytes / 1e9),
                    "tuples": "build rows + probe rows (SURVEY 8d)"},
-        "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity": parity,
     }
     print(json.dumps(line), flush=True)
 

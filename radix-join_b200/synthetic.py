@@ -106,6 +106,7 @@ class DeviceTables:
         self.n_build = 0
         self.n_probe = 0
         self.expected_rows = None
+        self.expected_checksum = None  # multiset checksum of the join result (see row_hash_torch)
 
 
 def _pages_from_dense(ctx, values, valid_words, n, dtype):
@@ -135,9 +136,102 @@ def single_join_plan(payload):
     return plan
 
 
-def make_c2_device(ctx, n_build, n_probe, rank=0, world=1, theta=0.75, null_frac=0.01, device="cuda"):
+# ---- multiset checksum of a result: size-independent parity at full scale ---------------------------
+# A result is a multiset of rows, so it is summarised by two wrapping 64-bit sums over a per-row hash
+# (column order matters, row order does not; NULL hashes apart from every value).  For config 2 the
+# expected checksum is derived from the generator WITHOUT joining: build keys are a permutation, so the
+# build row of a probe key is a direct table lookup.
+_NA = 0x6A09E667F3BCC909
+
+
+def row_hash_torch(cols):
+    """cols: [(int64 tensor, bool tensor or None)] -> int64 hash per row"""
+    import torch
+    h = None
+    for c, (v, ok) in enumerate(cols):
+        x = splitmix64_torch(v ^ _s64(0x9E3779B97F4A7C15 * (c + 1)))
+        if ok is not None:
+            x = torch.where(ok, x, torch.full_like(x, _s64(_NA + c)))
+        h = x if h is None else splitmix64_torch(h + x)
+    return h
+
+
+def checksum_add(acc, h):
+    s1 = (acc[0] + int(h.sum().item())) & _M64
+    s2 = (acc[1] + int(splitmix64_torch(h).sum().item())) & _M64
+    return (s1, s2, acc[2] + h.shape[0])
+
+
+def _unpack_valid_torch(words, lo, hi):
+    import torch
+    idx = torch.arange(lo, hi, device=words.device, dtype=torch.int64)
+    return ((words[idx >> 5].to(torch.int64) >> (idx & 31)) & 1).bool()
+
+
+def decode_fixed_pages(ctx, pages_ptr, n_pages, dtype, num_rows, device="cuda"):
+    """device pages of a fixed-width column -> (values tensor, validity words) via the engine's decode"""
+    import torch
+    row_start = torch.zeros(n_pages + 1, dtype=torch.int64, device=device)
+    values = torch.zeros(max(num_rows, 1), dtype=torch.int32 if int(dtype) == int(DataType.INT32) else torch.int64, device=device)
+    valid = torch.zeros((num_rows + 31) // 32 + 1, dtype=torch.int32, device=device)
+    torch.cuda.synchronize()
+    if n_pages:
+        ctx.check(ctx.lib.rj_page_row_offsets(ctx.handle, pages_ptr, n_pages, int(dtype), row_start.data_ptr(), None, None))
+        ctx.check(ctx.lib.rj_decode_fixed(ctx.handle, pages_ptr, n_pages, int(dtype), row_start.data_ptr(), values.data_ptr(),
+                                          valid.data_ptr(), None))
+    torch.cuda.current_stream().synchronize()
+    torch.cuda.synchronize()
+    rows = int(row_start[-1].item()) if n_pages else 0
+    return values, valid, rows
+
+
+def pages_checksum(ctx, columns, acc=(0, 0, 0), chunk=1 << 25):
+    """columns: [(DataType, device pages pointer, n_pages)] of ONE page list per column, row-aligned.
+    Returns the running (sum, sum of mixed, rows) checksum."""
+    import torch
+    dec, n = [], None
+    for dtype, ptr, n_pages in columns:
+        # rows are not known up front for a window's page list: count them, then decode
+        row_start = torch.zeros(n_pages + 1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        if n_pages:
+            ctx.check(ctx.lib.rj_page_row_offsets(ctx.handle, ptr, n_pages, int(dtype), row_start.data_ptr(), None, None))
+        torch.cuda.synchronize()
+        rows = int(row_start[-1].item()) if n_pages else 0
+        if n is None:
+            n = rows
+        if rows != n:
+            raise AssertionError(f"columns decode to different row counts: {rows} vs {n}")
+        dec.append(decode_fixed_pages(ctx, ptr, n_pages, dtype, rows)[:2])
+    for lo in range(0, n or 0, chunk):
+        hi = min(n, lo + chunk)
+        cols = [(v[lo:hi].to(torch.int64), _unpack_valid_torch(w, lo, hi)) for v, w in dec]
+        acc = checksum_add(acc, row_hash_torch(cols))
+    return acc
+
+
+def result_checksum(ctx, res):
+    """checksum of a device-resident Result (all columns fixed-width)"""
+    cols = [(res.column_type(c), res.column_device_ptr(c), res.column_pages(c)) for c in range(res.num_columns)]
+    return pages_checksum(ctx, cols)
+
+
+def host_chunks_checksum(ctx, types, chunks):
+    """checksum of what rj.execute_streamed delivered: chunks[column] = list of host page arrays; the k-th
+    arrays of all columns belong to the same window"""
+    import torch
+    acc = (0, 0, 0)
+    n_windows = max((len(v) for v in chunks.values()), default=0)
+    for k in range(n_windows):
+        dev = [torch.from_numpy(chunks[c][k]).cuda() for c in range(len(types))]
+        acc = pages_checksum(ctx, [(types[c], dev[c].data_ptr(), dev[c].numel() // 8192) for c in range(len(types))], acc)
+    return acc
+
+
+def make_c2_device(ctx, n_build, n_probe, rank=0, world=1, theta=0.75, null_frac=0.01, device="cuda", checksum=False):
     """Config 2 (or a scaled copy of it) in HBM.  With world > 1 each rank holds rows
-    [rank*n/world, (rank+1)*n/world) of both tables."""
+    [rank*n/world, (rank+1)*n/world) of both tables.  checksum=True (world 1) also derives the expected
+    multiset checksum of the join result from the generator."""
     import torch
     out = DeviceTables()
     g = torch.Generator(device=device)
@@ -164,9 +258,23 @@ def make_c2_device(ctx, n_build, n_probe, rank=0, world=1, theta=0.75, null_frac
         del u, keys
     rows = torch.arange(p_lo, p_hi, device=device, dtype=torch.int64)
     sb = _finite_double_bits_torch(splitmix64_torch(rows))
-    sb_valid = _pack_valid_torch(_not_null_torch(rows, 2044, null_frac))
+    sb_ok = _not_null_torch(rows, 2044, null_frac)
+    sb_valid = _pack_valid_torch(sb_ok)
     del rows
     del perm
+    if checksum and world == 1:
+        # (R.k, R.a, S.b) for every probe row: R.a = splitmix64(k), NULL iff the build row holding k is
+        a_ok_by_key = torch.empty(n_build, dtype=torch.bool, device=device)
+        a_ok_by_key[rk.to(torch.int64)] = _not_null_torch(torch.arange(0, n_build, device=device, dtype=torch.int64), 1043, null_frac)
+        acc = (0, 0, 0)
+        for lo in range(0, n_probe, 1 << 25):
+            hi = min(n_probe, lo + (1 << 25))
+            k = sk[lo:hi].to(torch.int64)
+            acc = checksum_add(acc, row_hash_torch([(k, torch.ones_like(k, dtype=torch.bool)), (splitmix64_torch(k), a_ok_by_key[k]),
+                                                    (sb[lo:hi], sb_ok[lo:hi])]))
+        out.expected_checksum = acc
+        del a_ok_by_key
+    del sb_ok
     tables = []
     for cols in (((rk, None, DataType.INT32), (ra, ra_valid, DataType.INT64)),
                  ((sk, None, DataType.INT32), (sb, sb_valid, DataType.FP64))):

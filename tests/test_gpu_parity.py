@@ -489,3 +489,30 @@ def test_streamed_scan_root_and_larger_join(ctx):
     tr = H.table_from_cells([pk, pb])
     plan = H.single_join_plan(tl, tr, [INT32, INT64], [INT32, FP64], 0, 0, True, out_cols=[0, 1, 3])
     check_streamed(plan, ctx, chunk_bytes=24 << 20, impl="port")
+
+
+# ---- BASELINE.json config 2 at FULL size: parity through a size-independent property ---------------------
+def test_config2_full_size_multiset_checksum(ctx):
+    """64 Mi x 512 Mi rows, Zipf(0.75), INT64 + FP64 payloads with NULLs.  The oracle cannot hold this, so
+    the result is pinned by a multiset checksum (two wrapping sums over a per-row hash) whose expected value
+    is derived from the generator by direct addressing -- no join involved.  Both the resident path and
+    the streamed host-to-host path must reproduce it."""
+    from radix_join_b200 import synthetic as syn
+    free, _ = torch.cuda.mem_get_info()
+    scale = 1 if free > 120 << 30 else 8
+    nb, np_ = (64 << 20) // scale, (512 << 20) // scale
+    dt = syn.make_c2_device(ctx, nb, np_, checksum=True)
+    assert dt.expected_checksum[2] == np_
+    inputs = rj.adopt_device(dt.plan, dt.device_pages, ctx, keep=dt.keep)
+    res = rj.execute_resident(dt.plan, inputs, ctx)
+    assert res.num_rows == np_
+    assert syn.result_checksum(ctx, res) == dt.expected_checksum
+    res.free()
+    # streamed: host pages in, host pages out, 13 windows
+    host_plan, keep = syn.to_host_plan(dt, pinned=False)
+    inputs.free()
+    rows, chunks = rj.execute_streamed(host_plan, ctx)
+    assert rows == np_
+    types = [t for _, t in host_plan.nodes[host_plan.root].output_attrs]
+    assert max(len(v) for v in chunks.values()) >= 2
+    assert syn.host_chunks_checksum(ctx, types, chunks) == dt.expected_checksum
