@@ -31,7 +31,7 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = build_context(local)
     ops = dj.CudaOps(ctx)
-    dt = syn.make_c2_device(ctx, n_build, n_probe, rank=rank, world=world)
+    dt = syn.make_c2_device(ctx, n_build, n_probe, rank=rank, world=world, checksum=True)
     build, probe = _relations(dt)
     in_bytes = sum(n * 8192 for cols in dt.device_pages for _, n in cols)
 
@@ -57,6 +57,19 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     total_rows = torch.tensor([rows], dtype=torch.int64, device="cuda")
     dist.all_reduce(total_rows)
     assert int(total_rows) == n_probe, (int(total_rows), n_probe)
+    # parity at full size: the ranks' result pages add up to the multiset checksum the generator predicts
+    # (a rank's RESULT rows are not its INPUT shard's rows, only the sums over all ranks agree)
+    def pages_of(c):
+        return (c.type, c.tensor.data_ptr() if c.tensor is not None else c.result.column_device_ptr(c.col), c.n_pages)
+    got = syn.pages_checksum(ctx, [pages_of(c) for c in cols])
+    both = [None] * world
+    dist.all_gather_object(both, (got, dt.expected_checksum))
+    m64 = (1 << 64) - 1
+    sum_got = tuple(sum(g[i] for g, _ in both) & m64 for i in range(3))
+    sum_exp = tuple(sum(e[i] for _, e in both) & m64 for i in range(3))
+    parity = {"rows": True, "multiset_checksum": sum_got == sum_exp,
+              "how": "per-rank sums over a per-row hash of the result pages, added over ranks, vs the generator's join-free expectation"}
+    assert parity["multiset_checksum"], (sum_got, sum_exp)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -132,7 +145,7 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
                          "frac": None, "traffic": None,
                          "note": f"max bytes one rank sends per step: {xchg_gbs:.3f} GB (>= {xchg_gbs / 770.0 * 1e3:.2f} ms at the measured 770 GB/s peer bandwidth); "
                                  f"single-GPU kernel rooflines are in the --gpus 1 line; HBM peak {peak} GB/s ({peak_src})"},
-            "e2e": e2e, "cpu_baseline": None,
+            "e2e": e2e, "cpu_baseline": None, "parity": parity,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

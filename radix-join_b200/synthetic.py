@@ -261,20 +261,21 @@ def make_c2_device(ctx, n_build, n_probe, rank=0, world=1, theta=0.75, null_frac
     sb_ok = _not_null_torch(rows, 2044, null_frac)
     sb_valid = _pack_valid_torch(sb_ok)
     del rows
-    del perm
-    if checksum and world == 1:
-        # (R.k, R.a, S.b) for every probe row: R.a = splitmix64(k), NULL iff the build row holding k is
+    if checksum:
+        # (R.k, R.a, S.b) for every probe row of this shard: R.a = splitmix64(k), NULL iff the build row
+        # holding k is (the whole permutation is known to every rank); shards add up to the job's checksum
         a_ok_by_key = torch.empty(n_build, dtype=torch.bool, device=device)
-        a_ok_by_key[rk.to(torch.int64)] = _not_null_torch(torch.arange(0, n_build, device=device, dtype=torch.int64), 1043, null_frac)
+        a_ok_by_key[perm.to(torch.int64)] = _not_null_torch(torch.arange(0, n_build, device=device, dtype=torch.int64), 1043, null_frac)
         acc = (0, 0, 0)
-        for lo in range(0, n_probe, 1 << 25):
-            hi = min(n_probe, lo + (1 << 25))
+        for lo in range(0, p_hi - p_lo, 1 << 25):
+            hi = min(p_hi - p_lo, lo + (1 << 25))
             k = sk[lo:hi].to(torch.int64)
             acc = checksum_add(acc, row_hash_torch([(k, torch.ones_like(k, dtype=torch.bool)), (splitmix64_torch(k), a_ok_by_key[k]),
                                                     (sb[lo:hi], sb_ok[lo:hi])]))
         out.expected_checksum = acc
         del a_ok_by_key
     del sb_ok
+    del perm
     tables = []
     for cols in (((rk, None, DataType.INT32), (ra, ra_valid, DataType.INT64)),
                  ((sk, None, DataType.INT32), (sb, sb_valid, DataType.FP64))):
