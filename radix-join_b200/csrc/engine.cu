@@ -722,11 +722,20 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
 
     Buf counter = dev_alloc(8, s);
     jl.out_count = counter->as<unsigned long long>();
+    // scratch of the duplicate chains (4-byte keys): written before it is read, no initialisation
+    Buf dup_next, dup_head;
+    if (key_bytes == 4) {
+        dup_next = dev_alloc(size_t(join_grid(ctx->sm_count)) * kJoinBuildCap * 4, s);
+        dup_head = dev_alloc(size_t(join_grid(ctx->sm_count)) * kJoinSlots * 4, s);
+        jl.dup_next = dup_next->as<uint32_t>();
+        jl.dup_head = dup_head->as<uint32_t>();
+    }
     // Output cardinality is unknown (non-unique keys on both sides are legal).  Run with room for
     // max(|build|, |probe|) pairs -- enough for every key/foreign-key join -- and let the kernel keep
     // counting when that overflows; the exact count then sizes a second run.
     uint64_t capacity = std::max(nb, np);
     uint64_t matches = 0;
+    auto t_join0 = std::chrono::steady_clock::now();
     for (int attempt = 0; attempt < 2; ++attempt) {
         B.pos = dev_alloc(capacity * 4, s);
         P.pos = dev_alloc(capacity * 4, s);
@@ -735,6 +744,10 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
         jl.capacity = capacity;
         RJ_CUDA(cudaMemsetAsync(counter->p, 0, 8, s));
         RJ_CUDA(cudaMemsetAsync(pl.unit_cursor, 0, 4, s));
+        if (getenv("RJ_TRACE")) {
+            RJ_CUDA(cudaStreamSynchronize(s));
+            t_join0 = std::chrono::steady_clock::now();
+        }
         {
             // N*(w_k+4) read + M*8 written (M is added once known)
             StageScope sc(ctx, RJ_ST_JOIN, s, 1, n_in * (key_bytes + 4));
@@ -747,6 +760,10 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
         capacity = matches;
     }
     if (ctx->profiling) ctx->stats[RJ_ST_JOIN].bytes += matches * 8;
+    static const bool trace_joins = getenv("RJ_TRACE") != nullptr;
+    if (trace_joins) fprintf(stderr, "[rj] join: table side %llu rows, probe side %llu rows, %d radix bits (%d + %d), %llu matches, kernel + sync %.3f ms\n",
+                             (unsigned long long)nb, (unsigned long long)np, bits, bits1, bits2, (unsigned long long)matches,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_join0).count());
     if (getenv("RJ_DEBUG_POS") && matches > (1u << 22)) {
         // development aid: how far apart are the positions referenced by consecutive output rows?
         const size_t cnt = 1u << 21;

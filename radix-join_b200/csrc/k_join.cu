@@ -26,6 +26,8 @@
 #include "rj_common.cuh"
 #include "rj_internal.h"
 
+#include <stdexcept>
+
 namespace rj {
 namespace {
 
@@ -57,9 +59,29 @@ struct JoinArgs {
     uint32_t*       out_p;
     unsigned long long capacity;
     unsigned long long* out_count;
+    uint32_t*       dup_next; // [gridDim.x * kJoinBuildCap] duplicate chains of 4-byte keys: next node + 1, per CTA
+    uint32_t*       dup_head; // [gridDim.x * kJoinSlots]    first node + 1 per table slot, per CTA
 };
 
 // ---- the shared-memory table, specialised on the key width -----------------------------------------
+// Open addressing with DOUBLE hashing: the stride of a key's probe sequence is a second hash of the key
+// (odd, so the sequence visits every slot).
+//
+// Duplicate build keys.  4-byte keys: the table holds every DISTINCT key once (key | row of the tuple
+// that won the slot); the other tuples of that key hang off the slot as a chain through global memory
+// (dup_head: first node per slot, dup_next: next node per build tuple; a node is a build tuple's index
+// inside the unit's build chunk, its row id is re-read from the build arrays; both arrays are private to
+// the CTA, because several CTAs build the same chunk at once -- one per probe chunk -- each in its own
+// order; they are read with ld.cg since the heads are written by atomics, past the L1).  Pushing a node is one atomicExch, so a key with d
+// duplicates costs O(d) to build and only probes of that very key walk them.  The first version stored
+// duplicates as separate entries of a linear-probing table: d duplicates cost O(d^2) CAS attempts on one
+// contended frontier slot and formed a run that every probe hashing into it walked to its end -- JOB
+// plans with 4 000 copies of one movie_id on the table side spent 6-13 ms per join (results unchanged).
+// 8-byte keys (INT64, VARCHAR hashes) still keep duplicates as separate entries along the key's own
+// sequence.
+__device__ __forceinline__ uint32_t probe_step(uint32_t k) { return ((k * 0x9E3779B1u) >> 19) | 1u; }
+__device__ __forceinline__ uint32_t probe_step(uint64_t k) { return probe_step(static_cast<uint32_t>(k ^ (k >> 32))); }
+
 template <typename K>
 struct Table;
 
@@ -72,16 +94,23 @@ struct Table<uint32_t> {
     __device__ void clear() {
         for (uint32_t s = threadIdx.x; s < kJoinSlots; s += kJoinThreads) slots[s] = ~0ull;
     }
-    // returns true when an equal key was met on the way (duplicate build key)
+    // returns true when the key is in the table already: the tuple is NOT inserted (it joins the key's chain)
     __device__ bool insert(uint32_t key, uint32_t row, uint32_t slot) {
         const unsigned long long mine = static_cast<unsigned long long>(key) | (static_cast<unsigned long long>(row) << 32);
-        bool dup = false;
+        const uint32_t step = probe_step(key);
         for (;;) {
-            const unsigned long long old = atomicCAS(&slots[slot], ~0ull, mine);
-            if (old == ~0ull) return dup;
-            dup |= static_cast<uint32_t>(old) == key;
-            slot = (slot + 1) & kSlotMask;
+            unsigned long long cur = slots[slot];
+            if (cur == ~0ull) cur = atomicCAS(&slots[slot], ~0ull, mine);
+            if (cur == ~0ull) return false;
+            if (static_cast<uint32_t>(cur) == key) return true;
+            slot = (slot + step) & kSlotMask;
         }
+    }
+    // slot of a key that is known to be in the table
+    __device__ uint32_t find(uint32_t key, uint32_t slot) const {
+        const uint32_t step = probe_step(key);
+        while (static_cast<uint32_t>(slots[slot]) != key) slot = (slot + step) & kSlotMask;
+        return slot;
     }
     __device__ void post_build(uint32_t, uint32_t, uint32_t, int*) {}
     // row id stored at `slot` (kEmpty if free) and whether its key equals `key`
@@ -104,18 +133,20 @@ struct Table<uint64_t> {
         for (uint32_t s = threadIdx.x; s < kJoinSlots; s += kJoinThreads) rows[s] = kEmpty;
     }
     __device__ bool insert(uint64_t key, uint32_t row, uint32_t slot) {
-        while (atomicCAS(&rows[slot], kEmpty, row) != kEmpty) slot = (slot + 1) & kSlotMask;
+        const uint32_t step = probe_step(key);
+        while (atomicCAS(&rows[slot], kEmpty, row) != kEmpty) slot = (slot + step) & kSlotMask;
         keys[slot] = key;
         return false; // the key of a colliding slot may not be written yet: checked in post_build
     }
     // after the build barrier: did an equal key land between my home slot and my own slot?
     __device__ void post_build(uint64_t key, uint32_t row, uint32_t slot, int* dups) {
+        const uint32_t step = probe_step(key);
         while (rows[slot] != row) {
             if (keys[slot] == key) {
                 *dups = 1;
                 return;
             }
-            slot = (slot + 1) & kSlotMask;
+            slot = (slot + step) & kSlotMask;
         }
     }
     __device__ uint32_t load(uint32_t slot, uint64_t key, bool* equal) const {
@@ -123,12 +154,14 @@ struct Table<uint64_t> {
         *equal = r != kEmpty && keys[slot] == key;
         return r;
     }
+    __device__ uint32_t find(uint64_t, uint32_t slot) const { return slot; } // chains are for 4-byte keys
 };
 
 template <typename K>
 __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
     constexpr int      kItems = Table<K>::kProbeItems;
     constexpr uint32_t kBatch = kItems * kJoinThreads;
+    constexpr bool     kChains = sizeof(K) == 4; // duplicates of a key hang off its slot (see Table)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Table<K>  table(smem_raw);
     uint32_t* s_out_b = reinterpret_cast<uint32_t*>(smem_raw + Table<K>::kBytes);
@@ -224,14 +257,31 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                 table.clear();
                 if (threadIdx.x == 0) s_dups = 0;
                 __syncthreads();
-                bool dup = false;
+                uint32_t dup = 0; // bit k: build item k met its key in the table
 #pragma unroll
                 for (int k = 0; k < kBuildItems; ++k) {
-                    if (brow[k] != kEmpty) dup |= table.insert(bkey[k], brow[k], (hash_key(bkey[k]) >> part_bits) & kSlotMask);
+                    if (brow[k] != kEmpty && table.insert(bkey[k], brow[k], (hash_key(bkey[k]) >> part_bits) & kSlotMask)) dup |= 1u << k;
                     __syncwarp(); // keep the warp converged from one insert to the next
                 }
                 if (dup) s_dups = 1;
                 __syncthreads();
+                if (kChains && s_dups) {
+                    // duplicates exist: reset this CTA's chain heads, then every duplicate pushes itself
+                    // onto the chain of its key's slot (one atomicExch each)
+                    uint32_t* head = a.dup_head + static_cast<size_t>(blockIdx.x) * kJoinSlots;
+                    uint32_t* chain = a.dup_next + static_cast<size_t>(blockIdx.x) * kJoinBuildCap;
+                    for (uint32_t sl = threadIdx.x; sl < kJoinSlots; sl += kJoinThreads) head[sl] = 0;
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < kBuildItems; ++k) {
+                        if (dup & (1u << k)) {
+                            const uint32_t li = k * kJoinThreads + threadIdx.x; // index inside the build chunk
+                            const uint32_t sl = table.find(bkey[k], (hash_key(bkey[k]) >> part_bits) & kSlotMask);
+                            chain[li] = atomicExch(&head[sl], li + 1);
+                        }
+                    }
+                    __syncthreads();
+                }
                 if (sizeof(K) == 8) {
                     int found = 0;
 #pragma unroll
@@ -284,6 +334,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                             mrow[k] = kEmpty;
                             if (row[k] != kEmpty) {
                                 uint32_t sl = (hash_key(key[k]) >> part_bits) & kSlotMask;
+                                const uint32_t step = probe_step(key[k]);
                                 for (;;) {
                                     bool           eq;
                                     const uint32_t r = table.load(sl, key[k], &eq);
@@ -292,7 +343,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                                         mrow[k] = r;
                                         break;
                                     }
-                                    sl = (sl + 1) & kSlotMask;
+                                    sl = (sl + step) & kSlotMask;
                                 }
                             }
                             __syncwarp();
@@ -311,6 +362,64 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                             }
                             off += __popc(bal[k]);
                         }
+                    } else if (kChains) {
+                        // ---- duplicates as chains: find the key once, then follow its nodes ---------------
+                        // `slot` is the lane's position in the chain of item `item`: 0xffffffff = the key has
+                        // not been looked up yet, otherwise the next node + 1 (0 = end of the chain)
+                        const uint32_t* head = a.dup_head + static_cast<size_t>(blockIdx.x) * kJoinSlots;
+                        const uint32_t* chain = a.dup_next + static_cast<size_t>(blockIdx.x) * kJoinBuildCap;
+#pragma unroll
+                        for (int k = 0; k < kItems; ++k) {
+                            bool walking = k >= item && !stalled && row[k] != kEmpty;
+                            for (;;) { // rounds: at most one match per lane per round
+                                uint32_t match = kEmpty, next = 0;
+                                if (walking) {
+                                    if (slot == 0xffffffffu) {
+                                        uint32_t       sl = (hash_key(key[k]) >> part_bits) & kSlotMask;
+                                        const uint32_t step = probe_step(key[k]);
+                                        for (;;) {
+                                            bool           eq;
+                                            const uint32_t r = table.load(sl, key[k], &eq);
+                                            if (r == kEmpty) break; // the key is not in the table
+                                            if (eq) {
+                                                match = r;
+                                                next = __ldcg(&head[sl]);
+                                                break;
+                                            }
+                                            sl = (sl + step) & kSlotMask;
+                                        }
+                                        if (match == kEmpty) walking = false;
+                                    } else {
+                                        const uint32_t gi = bs + slot - 1;
+                                        match = a.bidx != nullptr ? a.bidx[gi] : gi;
+                                        next = __ldcg(&chain[slot - 1]);
+                                    }
+                                }
+                                __syncwarp();
+                                const uint32_t m = __ballot_sync(RJ_FULL_MASK, match != kEmpty);
+                                if (m == 0) break; // every lane reached the end of its chain
+                                uint32_t pos = 0;
+                                if (lane == 0) pos = atomicAdd(&s_out_n, static_cast<uint32_t>(__popc(m)));
+                                pos = __shfl_sync(RJ_FULL_MASK, pos, 0) + __popc(m & lt);
+                                if (match != kEmpty) {
+                                    if (pos < kOutCap) {
+                                        s_out_b[pos] = match;
+                                        s_out_p[pos] = row[k];
+                                        slot = next;
+                                        if (next == 0) walking = false;
+                                    } else {
+                                        // staging buffer full: `slot` still names this match, redo it after the flush
+                                        walking = false;
+                                        stalled = true;
+                                        item = k;
+                                    }
+                                }
+                            }
+                            if (!stalled && k >= item) {
+                                item = k + 1;
+                                slot = 0xffffffffu;
+                            }
+                        }
                     } else {
 #pragma unroll
                     for (int k = 0; k < kItems; ++k) {
@@ -318,6 +427,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                         // on an earlier item sit this item out but keep in step with the warp
                         bool walking = k >= item && !stalled && row[k] != kEmpty;
                         if (walking && slot == 0xffffffffu) slot = (hash_key(key[k]) >> part_bits) & kSlotMask;
+                        const uint32_t step = probe_step(key[k]);
                         for (;;) { // rounds: at most one match per lane per round
                             uint32_t match = kEmpty;
                             if (walking) {
@@ -328,7 +438,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                                         walking = false;
                                         break;
                                     }
-                                    slot = (slot + 1) & kSlotMask;
+                                    slot = (slot + step) & kSlotMask;
                                     if (eq) {
                                         match = r;
                                         break;
@@ -347,7 +457,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                                     s_out_p[pos] = row[k];
                                 } else {
                                     // staging buffer full: step back onto the match, resume after the flush
-                                    slot = (slot - 1) & kSlotMask;
+                                    slot = (slot - step) & kSlotMask;
                                     walking = false;
                                     stalled = true;
                                     item = k;
@@ -400,8 +510,10 @@ void run_join(const JoinLaunch& L, int sm_count, cudaStream_t s) {
     a.off_b = L.off_b; a.off_p = L.off_p; a.unit_start = L.unit_start; a.unit_cursor = L.unit_cursor;
     a.nparts = L.nparts; a.part_bits = L.part_bits;
     a.out_b = L.out_b; a.out_p = L.out_p; a.capacity = L.capacity; a.out_count = L.out_count;
+    a.dup_next = L.dup_next; a.dup_head = L.dup_head;
+    if (sizeof(K) == 4 && (!a.dup_next || !a.dup_head)) throw std::runtime_error("join: duplicate-chain scratch missing");
     // persistent grid: 2 CTAs per SM pull batches of work units in a strided order
-    join_kernel<K><<<static_cast<unsigned>(sm_count) * 2, kJoinThreads, smem, s>>>(a);
+    join_kernel<K><<<join_grid(sm_count), kJoinThreads, smem, s>>>(a);
     RJ_LAUNCH_CHECK();
 }
 

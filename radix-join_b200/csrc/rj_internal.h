@@ -136,7 +136,11 @@ struct JoinLaunch {
     uint32_t*       out_p;
     uint64_t        capacity;
     unsigned long long* out_count; // device counter (zeroed by the caller)
+    // scratch for the duplicate chains of 4-byte keys (k_join.cu): no initialisation needed
+    uint32_t*       dup_next;      // [join_grid(sm_count) * kJoinBuildCap]
+    uint32_t*       dup_head;      // [join_grid(sm_count) * kJoinSlots]
 };
+inline unsigned join_grid(int sm_count) { return static_cast<unsigned>(sm_count) * 2; }
 void launch_join(const JoinLaunch& a, int sm_count, cudaStream_t s);
 
 // ---- k_gather_encode.cu ---------------------------------------------------------------------------
