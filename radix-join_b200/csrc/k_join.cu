@@ -72,7 +72,7 @@ struct JoinArgs {
 // (dup_head: first node per slot, dup_next: next node per build tuple; a node is a build tuple's index
 // inside the unit's build chunk, its row id is re-read from the build arrays; both arrays are private to
 // the CTA, because several CTAs build the same chunk at once -- one per probe chunk -- each in its own
-// order; they are read with ld.cg since the heads are written by atomics, past the L1).  Pushing a node is one atomicExch, so a key with d
+// order; the heads are read with ld.cg since they are written by atomics, past the L1).  Pushing a node is one atomicExch, so a key with d
 // duplicates costs O(d) to build and only probes of that very key walk them.  The first version stored
 // duplicates as separate entries of a linear-probing table: d duplicates cost O(d^2) CAS attempts on one
 // contended frontier slot and formed a run that every probe hashing into it walked to its end -- JOB
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
                                     } else {
                                         const uint32_t gi = bs + slot - 1;
                                         match = a.bidx != nullptr ? a.bidx[gi] : gi;
-                                        next = __ldcg(&chain[slot - 1]);
+                                        next = chain[slot - 1]; // written by this CTA's own stores: L1 is coherent with them
                                     }
                                 }
                                 __syncwarp();
