@@ -116,7 +116,7 @@ int rj_execute(rj_ctx* ctx, const rj_plan_t* plan, rj_result** out);
  * join distributes over a union of its inputs; the table must be read by a single ScanNode and its
  * referenced columns be fixed-width, otherwise the call degrades to upload + execute + download) while
  * the next window is uploaded and the previous window's result pages are downloaded.  `chunk_bytes` =
- * page bytes per window (0 = 512 MiB).  Every time result pages of a column are ready, `sink` is asked
+ * page bytes per window (0 = 256 MiB).  Every time result pages of a column are ready, `sink` is asked
  * for a host buffer of n_pages * 8192 contiguous bytes; the pages are complete when the call returns.
  * Pages of different windows are independent (a window's last page may be partly filled), the row
  * order is the engine's usual free order.  Copies overlap only if the host buffers are pinned and the

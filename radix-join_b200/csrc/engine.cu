@@ -764,24 +764,6 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
     if (trace_joins) fprintf(stderr, "[rj] join: table side %llu rows, probe side %llu rows, %d radix bits (%d + %d), %llu matches, kernel + sync %.3f ms\n",
                              (unsigned long long)nb, (unsigned long long)np, bits, bits1, bits2, (unsigned long long)matches,
                              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_join0).count());
-    if (getenv("RJ_DEBUG_POS") && matches > (1u << 22)) {
-        // development aid: how far apart are the positions referenced by consecutive output rows?
-        const size_t cnt = 1u << 21;
-        std::vector<uint32_t> hp(cnt), hb(cnt);
-        for (uint64_t off: {uint64_t(0), matches / 2}) {
-            RJ_CUDA(cudaMemcpy(hp.data(), P.pos->as<uint32_t>() + off, cnt * 4, cudaMemcpyDeviceToHost));
-            RJ_CUDA(cudaMemcpy(hb.data(), B.pos->as<uint32_t>() + off, cnt * 4, cudaMemcpyDeviceToHost));
-            for (size_t w: {size_t(4096), size_t(1) << 16, cnt}) {
-                uint32_t pmin = ~0u, pmax = 0, bmin = ~0u, bmax = 0;
-                for (size_t i = 0; i < w; ++i) {
-                    pmin = std::min(pmin, hp[i]); pmax = std::max(pmax, hp[i]);
-                    bmin = std::min(bmin, hb[i]); bmax = std::max(bmax, hb[i]);
-                }
-                fprintf(stderr, "[rj pos] off=%llu window=%zu probe span=%u (of %llu) build span=%u (of %llu)\n",
-                        (unsigned long long)off, w, pmax - pmin, (unsigned long long)np, bmax - bmin, (unsigned long long)nb);
-            }
-        }
-    }
     if (matches >= 0xffffffffull) throw EngineError("join result exceeds 2^32-1 rows");
     *n_out = matches;
 }
@@ -1415,7 +1397,7 @@ struct PendingDownload {
 
 uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, rj_page_sink_t sink, void* user) {
     if (!sink) throw EngineError("rj_execute_streamed: no page sink");
-    if (chunk_bytes == 0) chunk_bytes = uint64_t(512) << 20;
+    if (chunk_bytes == 0) chunk_bytes = uint64_t(256) << 20;
     ensure_copy_streams(ctx);
     std::set<std::pair<uint32_t, uint32_t>> wanted;
     collect_wanted(plan, &wanted);
@@ -1427,7 +1409,6 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
             void* dst = sink(user, c, rc.type, rc.n_pages);
             if (!dst) throw EngineError("rj_execute_streamed: the sink returned no buffer");
             StageScope scope(ctx, RJ_ST_D2H, stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
-            if (getenv("RJ_STREAM_NO_D2H")) continue; // timing experiments only
             RJ_CUDA(cudaMemcpyAsync(dst, rc.pages->p, rc.n_pages * size_t(RJ_PAGE_SIZE), cudaMemcpyDeviceToHost, stream));
         }
     };
