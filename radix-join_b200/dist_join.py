@@ -390,10 +390,53 @@ def shuffle_relation(ops, rel, g, group=None):
     return out_keys, vals, valids, sent_bytes
 
 
-def distributed_join(ops, build, probe, out_cols, group=None, xchg=None):
+def local_tuples(ops, rel, g):
+    """this rank's tuples of a relation with NULL keys dropped: (keys, [payload values], [validity bytes or None])"""
+    kp, kn, kt, knull = rel.key
+    keys, kvalid = ops.decode_fixed(kp, kn, kt, rel.n_rows, knull)
+    keys_o, rows_o, _counts = ops.owner_partition(keys, kvalid, g)  # grouped by owner: the order is irrelevant here
+    vals, valids = [], []
+    for (pp, pn, pt, pnull) in rel.payloads:
+        v, vv = ops.decode_fixed(pp, pn, pt, rel.n_rows, pnull)
+        gv, gvalid = ops.gather(v, vv, rows_o)
+        vals.append(gv)
+        valids.append(gvalid)
+    return keys_o, vals, valids
+
+
+def all_gather_v(tensor, group=None):
+    """concatenation of every rank's 1-D tensor (different lengths), in rank order"""
+    world = dist.get_world_size(group)
+    n = int(tensor.numel())
+    recv = exchange_counts(torch.full((world,), n, dtype=torch.int64), group)
+    return all_to_all_v(tensor.repeat(world), [n] * world, recv, group)
+
+
+def broadcast_relation(ops, rel, g, group=None):
+    """Small relation: every rank receives ALL of its tuples (the build side is broadcast when
+    it is small, the probe side then stays where it is and nothing else is exchanged)."""
+    world = dist.get_world_size(group)
+    keys, vals, valids = local_tuples(ops, rel, g)
+    sent = 0
+    out_keys = all_gather_v(keys, group)
+    sent += keys.numel() * keys.element_size() * (world - 1)
+    out_vals, out_valids = [], []
+    for v, vb in zip(vals, valids):
+        out_vals.append(all_gather_v(v, group))
+        sent += v.numel() * v.element_size() * (world - 1)
+        if vb is not None:
+            out_valids.append(all_gather_v(vb, group))
+            sent += vb.numel() * (world - 1)
+        else:
+            out_valids.append(None)
+    return out_keys, out_vals, out_valids, sent
+
+
+def distributed_join(ops, build, probe, out_cols, group=None, xchg=None, broadcast_max_rows=0):
     """Inner equi-join of two sharded relations.  out_cols: list of ("b"|"p", "key"|payload index, type).
     xchg = (PeerExchange for build, PeerExchange for probe) switches the exchange from NCCL all-to-all-v to
-    the fused partition + peer-store kernel.
+    the fused partition + peer-store kernel.  A build side of at most `broadcast_max_rows` rows in total is
+    broadcast instead: every rank joins its own probe rows against the whole build side.
     Returns (n_rows, [ResultPages], stats) for THIS rank's share of the result."""
     world = dist.get_world_size(group)
     g = log2_exact(world)
@@ -405,7 +448,19 @@ def distributed_join(ops, build, probe, out_cols, group=None, xchg=None):
             ops.sync()
             t.append(time.perf_counter())
 
-    if xchg is not None:
+    broadcast = False
+    if broadcast_max_rows:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        total_b = torch.tensor([build.n_rows], dtype=torch.int64, device=device)
+        dist.all_reduce(total_b, group=group)
+        broadcast = int(total_b) <= broadcast_max_rows
+    if broadcast:
+        bk, bvals, bvalids, sent_b = broadcast_relation(ops, build, g, group)
+        mark()
+        pk, pvals, pvalids = local_tuples(ops, probe, g)
+        sent_p = 0
+        mark()
+    elif xchg is not None:
         bk, bvals, bvalids, sent_b = shuffle_relation_p2p(ops, build, g, xchg[0], group)
         mark()
         pk, pvals, pvalids, sent_p = shuffle_relation_p2p(ops, probe, g, xchg[1], group)
@@ -436,7 +491,8 @@ def distributed_join(ops, build, probe, out_cols, group=None, xchg=None):
         n_rows = int(ob.numel())
     mark()
     stats = {"sent_bytes": sent_b + sent_p, "owned_build": int(bk.numel()), "owned_probe": int(pk.numel()),
-             "exchange": "peer stores (fused into the partition kernel)" if xchg is not None else "collective all-to-all-v"}
+             "exchange": "build side broadcast (all-gather), probe side in place" if broadcast
+                         else "peer stores (fused into the partition kernel)" if xchg is not None else "collective all-to-all-v"}
     if trace:
         names = ["shuffle_build", "shuffle_probe", "join(+encode)", "encode"]
         stats["phase_ms"] = {n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t[:-1], t[1:])}

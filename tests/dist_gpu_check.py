@@ -29,31 +29,38 @@ def main():
     xchg = None
     if os.environ.get("RJ_DIST_EXCHANGE", "p2p") == "p2p":
         xchg = (dj.PeerExchange(ops.device, n_b, [torch.int64], [True]), dj.PeerExchange(ops.device, n_p, [torch.int64], [True]))
-    rows, cols, stats = dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS, xchg=xchg)
-    if rank == 0:
-        print("exchange:", stats["exchange"], flush=True)
     outdir = os.environ.get("RJ_CHECK_DIR", "/tmp/rj_dist_check")
     os.makedirs(outdir, exist_ok=True)
-    np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
-    dist.barrier()
     ok = True
-    if rank == 0:
-        from oracle import pyoracle as orc
-        parts = [np.load(os.path.join(outdir, f"rank{r}.npz")) for r in range(world)]
-        total = int(sum(p["rows"] for p in parts))
-        types = [0, 1, 2]
-        got = rj.ColumnarTable(num_rows=total, columns=[
-            rj.Column(t, np.concatenate([p[f"c{i}"].reshape(-1, 8192) for p in parts])) for i, t in enumerate(types)])
-        full = syn.make_c2_device(ctx, n_b, n_p)
-        inputs = rj.adopt_device(full.plan, full.device_pages, ctx, keep=full.keep)
-        res = rj.execute_resident(full.plan, inputs, ctx)
-        single = res.to_columnar()
-        res.free()
-        host_plan, _keep = syn.to_host_plan(full, pinned=False)
-        want = orc.execute(host_plan, impl="port")
-        ok = total == n_p == single.num_rows == want.num_rows
-        ok = ok and orc.result_equal(got, single) and orc.result_equal(single, want)
-        print(f"dist parity ({world} GPUs): rows {total}, sent/rank {stats['sent_bytes']} B ->", "OK" if ok else "MISMATCH", flush=True)
+    single = want = inputs = None
+    # the hash-distributed exchange, then the broadcast of the (here: forced) small build side
+    for mode, kwargs in (("exchange", {"xchg": xchg}), ("broadcast", {"broadcast_max_rows": n_b})):
+        rows, cols, stats = dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS, **kwargs)
+        if rank == 0:
+            print(f"{mode}:", stats["exchange"], flush=True)
+        np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
+        dist.barrier()
+        if rank == 0:
+            from oracle import pyoracle as orc
+            parts = [np.load(os.path.join(outdir, f"rank{r}.npz")) for r in range(world)]
+            total = int(sum(p["rows"] for p in parts))
+            types = [0, 1, 2]
+            got = rj.ColumnarTable(num_rows=total, columns=[
+                rj.Column(t, np.concatenate([p[f"c{i}"].reshape(-1, 8192) for p in parts])) for i, t in enumerate(types)])
+            if single is None:
+                full = syn.make_c2_device(ctx, n_b, n_p)
+                inputs = rj.adopt_device(full.plan, full.device_pages, ctx, keep=full.keep)
+                res = rj.execute_resident(full.plan, inputs, ctx)
+                single = res.to_columnar()
+                res.free()
+                host_plan, _keep = syn.to_host_plan(full, pinned=False)
+                want = orc.execute(host_plan, impl="port")
+            good = total == n_p == single.num_rows == want.num_rows
+            good = good and orc.result_equal(got, single) and orc.result_equal(single, want)
+            print(f"dist parity ({world} GPUs, {mode}): rows {total}, sent/rank {stats['sent_bytes']} B ->", "OK" if good else "MISMATCH", flush=True)
+            ok = ok and good
+        dist.barrier()
+    if inputs is not None:
         inputs.free()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

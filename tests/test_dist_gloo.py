@@ -72,7 +72,7 @@ def slice_cells(c, lo, hi):
     return orc.Cells(c.type, c.valid[lo:hi], values=c.values[lo:hi])
 
 
-def worker(rank, world, port, outdir, n_b, n_p):
+def worker(rank, world, port, outdir, n_b, n_p, broadcast_max_rows=0):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from radix_join_b200 import dist_join as dj
@@ -84,19 +84,21 @@ def worker(rank, world, port, outdir, n_b, n_p):
         rels.append(dj.Relation(hi - lo, (t.columns[0].pages, t.columns[0].n_pages, INT32, True),
                                 [(t.columns[1].pages, t.columns[1].n_pages, vt, True)]))
     out_cols = [("b", "key", INT32), ("b", 0, INT64), ("p", 0, FP64), ("p", "key", INT32)]
-    rows, cols, stats = dj.distributed_join(NumpyOps(), rels[0], rels[1], out_cols)
-    np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, sent=stats["sent_bytes"],
+    rows, cols, stats = dj.distributed_join(NumpyOps(), rels[0], rels[1], out_cols, broadcast_max_rows=broadcast_max_rows)
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, sent=stats["sent_bytes"], exchange=stats["exchange"],
              **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_distributed_join_matches_oracle(world):
+@pytest.mark.parametrize("world,broadcast_max_rows", [(2, 0), (4, 0), (2, 10_000), (4, 10_000), (2, 100)])
+def test_distributed_join_matches_oracle(world, broadcast_max_rows):
+    """hash-distributed exchange, and the broadcast of a small build side; a limit below the
+    build side's size must fall back to the exchange"""
     n_b, n_p = 3000, 9000
-    port = 29500 + os.getpid() % 2000 + world
+    port = 29500 + os.getpid() % 2000 + world + (7 if broadcast_max_rows else 0) + (broadcast_max_rows == 100) * 11
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(worker, args=(world, port, d, n_b, n_p), nprocs=world, join=True)
+        mp.spawn(worker, args=(world, port, d, n_b, n_p, broadcast_max_rows), nprocs=world, join=True)
         parts = [np.load(os.path.join(d, f"rank{r}.npz")) for r in range(world)]
     total = int(sum(p["rows"] for p in parts))
     types = [INT32, INT64, FP64, INT32]
@@ -110,6 +112,8 @@ def test_distributed_join_matches_oracle(world):
     assert want.num_rows == total and total > 0
     assert orc.result_equal(got, want)
     assert all(int(p["sent"]) > 0 for p in parts)
+    used_broadcast = "broadcast" in str(parts[0]["exchange"])
+    assert used_broadcast == (broadcast_max_rows >= n_b)
 
 
 def test_world_size_must_be_power_of_two():
