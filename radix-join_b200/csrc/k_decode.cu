@@ -236,18 +236,16 @@ void launch_decode_fixed(const void* pages, uint64_t n_pages, int type, const ui
     unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 3 ? want : static_cast<uint64_t>(sm_count) * 3);
     const uint8_t* pg = static_cast<const uint8_t*>(pages);
     if (type == RJ_INT32) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(decode_fixed_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
         }
         decode_fixed_kernel<uint32_t><<<blocks, kDecWarps * 32, smem, s>>>(pg, n_pages, row_start,
                                                                           static_cast<uint32_t*>(values), valid);
     } else {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(decode_fixed_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
         }
         decode_fixed_kernel<uint64_t><<<blocks, kDecWarps * 32, smem, s>>>(pg, n_pages, row_start,
                                                                           static_cast<uint64_t*>(values), valid);

@@ -499,11 +499,8 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
 template <typename K>
 void run_join(const JoinLaunch& L, int sm_count, cudaStream_t s) {
     const size_t smem = Table<K>::kBytes + 8 * kOutCap;
-    static bool  configured = false;
-    if (!configured) {
-        RJ_CUDA(cudaFuncSetAttribute(join_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
+    static SmemConfigured cfg;
+    if (cfg.raise(smem)) RJ_CUDA(cudaFuncSetAttribute(join_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     JoinArgs a;
     a.bkeys = L.bkeys; a.bidx = L.bidx; a.bvalid = L.bvalid;
     a.pkeys = L.pkeys; a.pidx = L.pidx; a.pvalid = L.pvalid;

@@ -549,17 +549,15 @@ void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n,
     unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * per_sm ? want : static_cast<uint64_t>(sm_count) * per_sm);
     if (blocks == 0) blocks = 1;
     if (key_bytes == 4) {
-        static size_t configured = 0;
-        if (smem > configured) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
         }
         radix_hist_kernel<uint32_t><<<blocks, threads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, n, shift, bits, hist);
     } else {
-        static size_t configured = 0;
-        if (smem > configured) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
         }
         radix_hist_kernel<uint64_t><<<blocks, threads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, n, shift, bits, hist);
     }
@@ -618,20 +616,18 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
     }
     const size_t smem = static_cast<size_t>(n_tma) * tile * 8;
     if (key_bytes == 4) {
-        static size_t configured = 0;
-        if (smem > configured) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
         }
         blocks = resident_grid(scatter_tile_kernel<uint32_t, false>, smem, n_tiles, sm_count);
         scatter_tile_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
             static_cast<uint32_t*>(keys_out), idx_out, pay, flags, n_tma);
     } else {
-        static size_t configured = 0;
-        if (smem > configured) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
         }
         blocks = resident_grid(scatter_tile_kernel<uint64_t, false>, smem, n_tiles, sm_count);
         scatter_tile_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
@@ -680,7 +676,10 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
         }
     }
     // the destination table (~900 bytes of pointers) lives in device memory for the duration of the launch
-    static thread_local MultiDsts* d_dsts = nullptr;
+    static thread_local MultiDsts* d_dsts_of[64] = {};
+    int dev = 0;
+    RJ_CUDA(cudaGetDevice(&dev));
+    MultiDsts*& d_dsts = d_dsts_of[dev & 63];
     if (!d_dsts) RJ_CUDA(cudaMalloc(&d_dsts, sizeof(MultiDsts)));
     RJ_CUDA(cudaMemcpyAsync(d_dsts, &h, sizeof(MultiDsts), cudaMemcpyHostToDevice, s));
     const uint32_t tile = scatter_tile(key_bytes);
@@ -688,20 +687,18 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
     const size_t   smem = static_cast<size_t>(n_tma) * tile * 8;
     if (key_bytes == 4) {
         auto kern = scatter_tile_kernel<uint32_t, false, true>;
-        static size_t configured = 0;
-        if (smem > configured) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
         }
         const unsigned blocks = resident_grid(kern, smem, n_tiles, sm_count);
         kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift,
                                                    bits, cursor, nullptr, nullptr, pay, flags, n_tma, d_dsts);
     } else {
         auto kern = scatter_tile_kernel<uint64_t, false, true>;
-        static size_t configured = 0;
-        if (smem > configured) {
+        static SmemConfigured cfg;
+        if (cfg.raise(smem)) {
             RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
         }
         const unsigned blocks = resident_grid(kern, smem, n_tiles, sm_count);
         kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift,

@@ -35,6 +35,20 @@ extern std::atomic<uint64_t> g_kernel_launches;
         RJ_CUDA(cudaGetLastError());                       \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember the largest size configured on
+// each one (a process may hold contexts on several GPUs)
+struct SmemConfigured {
+    size_t bytes[64] = {};
+    bool raise(size_t want) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t& have = bytes[dev & 63];
+        if (want <= have) return false;
+        have = want;
+        return true;
+    }
+};
+
 // ---- join geometry (shared by the partition planner and the join kernel) ---------------------------
 constexpr uint32_t kJoinSlots      = 8192;  // shared-memory hash table slots per CTA
 constexpr uint32_t kJoinBuildCap   = 6144;  // build tuples per table (75 % fill); larger partitions are chunked
