@@ -203,7 +203,8 @@ int rj_radix_histogram(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid,
 
 /* Scatter (key, row index) into partition order.  d_idx_in may be NULL (= identity row ids).
  * d_cursor: uint32[1<<bits] holding each partition's start offset (exclusive prefix of the
- * histogram); it is advanced by the kernel.  Output order inside a partition is unspecified. */
+ * histogram); it is advanced by the kernel.  Output order inside a partition is unspecified.
+ * d_idx_out may be NULL when the row ids are not needed (only the keys are scattered). */
 int rj_radix_scatter(rj_ctx* ctx, const void* d_keys, const uint32_t* d_valid,
                      const uint32_t* d_idx_in, uint64_t n, int32_t key_bytes, int32_t shift,
                      int32_t bits, uint32_t* d_cursor, void* d_keys_out, uint32_t* d_idx_out,
