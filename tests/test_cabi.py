@@ -76,3 +76,20 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "rj_oracle" not in text and "libref_oracle" not in text, f
+
+
+def test_header_is_plain_c_and_the_c_example_binds(tmp_path):
+    """The boundary is a C ABI: the header must compile as C11 (no C++), and a C caller written against it
+    (examples/c_abi_join.c) must only need symbols the library exports.  Compile only -- no GPU here."""
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", HEADER],
+                   check=True, capture_output=True)
+    obj = str(tmp_path / "c_abi_join.o")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.dirname(HEADER), "-c",
+                    os.path.join(H.ROOT, "examples", "c_abi_join.c"), "-o", obj], check=True, capture_output=True)
+    wanted = {line.split()[-1] for line in subprocess.run(["nm", obj], capture_output=True, text=True).stdout.splitlines()
+              if " U rj_" in line}
+    assert {"rj_ctx_create", "rj_execute", "rj_execute_streamed", "rj_result_fetch", "rj_ctx_destroy"} <= wanted
+    _build_engine()
+    exported = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    for name in wanted:
+        assert re.search(rf"\bT {name}\b", exported), f"{name} is used by the C example but not exported"
