@@ -3,13 +3,17 @@
 Contest::execute on BASELINE.json config 2 (INT32 join, 64 Mi build x 512 Mi probe, Zipf(0.75),
 INT64 + FP64 payloads with 1 % NULLs; synthetic, generated on device).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|job] [--scale S]
 
 One step = one full pass of the hot path: page decode -> radix partition -> shared-memory build+probe
 -> gather + page encode, input pages resident in HBM when the timed region starts, result pages left in
-HBM.  `e2e` is the same call with HOST pages in and HOST pages out (H2D / D2H inside the timed region).
-`--impl reference` times the UNMODIFIED reference's CPU execute() (oracle/_ref) on a bounded sample of
-the same workload on the host cores.  One JSON line is printed by rank 0.
+HBM (`value`).  `e2e` is `Contest::execute` itself (radix-join_b200/libcontest_b200.so) called by a C++
+harness on a Plan of individually new-ed host pages, returning new-ed host pages: host gather, H2D,
+kernels, D2H and host scatter all inside the timed region (tests/contest_harness.cpp).
+`--impl reference` times the UNMODIFIED reference's CPU `Contest::execute` (oracle/_ref) through the same
+harness on a bounded sample of the same workload on the host cores.  `--workload c1` is BASELINE.json
+configs[0], which both arms run at full size (a same-config ratio); `--workload job` the 113-plan JOB
+suite.  One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -23,9 +27,42 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FULL_BUILD, FULL_PROBE = 1 << 26, 1 << 29  # config 2
-CPU_SAMPLE_DIV = 64                        # the CPU arms run config 2 at 1/64 scale (1 Mi x 8 Mi)
 METRIC, UNIT = "join_throughput", "Mtuples/s"
+# BASELINE.json configs[1] (the headline) and configs[0] (fits both arms at full size: a same-config ratio)
+WORKLOADS = {
+    "c2": {"build": 1 << 26, "probe": 1 << 29, "name": "c2_int32_join_64Mi_x_512Mi_zipf0.75_int64_fp64_payloads"},
+    "c1": {"build": 1_000_000, "probe": 10_000_000, "name": "c1_int32_join_1M_x_10M_unique_fk"},
+}
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "contest_harness")  # tests/contest_harness.cpp, built by csrc/Makefile `contest`
+PARITY_SAMPLE_DIV = 64   # GPU vs reference on the SAME Plan object, outside the timed region
+
+
+def reference_div(workload, steps, warmup):
+    """The reference arm's bounded sample: config 1 runs at full size (about 6-10 s per execute());
+    config 2 needs ~300 GB of host RAM and ~4 min per execute() at full size in the reference's
+    row-of-variants form, so it runs at 1/16 scale unless the requested step
+    count would push the whole run past a few minutes (~15 s per execute() at 1/16)."""
+    if workload == "c1":
+        return 1
+    div = 16
+    while (steps + warmup) * 240.0 / div > 200.0 and div < 256:
+        div *= 2
+    return div
+
+
+def run_harness(*args, timeout=3000):
+    """tests/contest_harness.cpp: Contest::execute on individually new-ed pages (ours or the reference)"""
+    if not os.path.exists(HARNESS):
+        return None, "oracle/_ref/contest_harness is not built (needs the reference headers at build time)"
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference uses OpenMP
+    out = subprocess.run([HARNESS, *args], capture_output=True, text=True, timeout=timeout, env=env)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    if not lines:
+        return None, f"harness exit {out.returncode}: {out.stderr[-400:]}"
+    res = json.loads(lines[-1])
+    res["exit_code"] = out.returncode
+    return res, None
 
 
 def measured_peak():
@@ -87,65 +124,67 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arms: the unmodified reference (oracle/_ref) on a bounded sample of config 2
+# CPU arms: the unmodified reference (oracle/_ref) on a bounded sample of the workload
 # --------------------------------------------------------------------------------------------------
-def cpu_sample_plan(n_build, n_probe):
-    """config 2 at reduced scale, host pages, same distributions (numpy twin of synthetic.make_c2_device)"""
-    import numpy as np
+def reference_run(workload, div, steps, warmup):
+    """-> (Mtuples/s, ms per execute, kind, cores, sample text) of the reference's Contest::execute, timed
+    like the contest harness does (steady_clock around the call only, tests/read_sql.cpp:1234-1236)"""
+    w = WORKLOADS[workload]
+    nb, np_ = w["build"] // div, w["probe"] // div
+    cores = os.cpu_count() or 1
+    res, why = run_harness("bench", workload, "--div", str(div), "--steps", str(steps), "--warmup", str(warmup),
+                           "--impl", "reference")
+    if res is not None and res.get("ok"):
+        sec = res["ms_mean"] / 1e3
+        scale = "full size" if div == 1 else f"1/{div} scale"
+        sample = (f"{w['name']} at {scale}: {nb} x {np_} rows, {res['rows']} output rows, inputs = individually new-ed pages "
+                  f"(ColumnInserter), result checked against the generator's multiset checksum")
+        return (nb + np_) / 1e6 / sec, res["ms_mean"], "reference", cores, sample
+    # no harness binary: the plain-C port of the oracle through ctypes (still the CPU path, kind "port")
     from oracle import pyoracle as orc
     from radix_join_b200 import synthetic as syn
+    import numpy as np
+    if workload != "c2":
+        raise RuntimeError(f"reference arm unavailable: {why}")
     rng = np.random.default_rng(43)
-    perm = rng.permutation(n_build).astype(np.int32)
+    perm = rng.permutation(nb).astype(np.int32)
     ra = syn.splitmix64_numpy(perm.astype(np.int64).view(np.uint64)).view(np.int64)
-    zipf = syn.Zipf(n_build, 0.75)
-    sk = perm[zipf.ranks(np.random.default_rng(44).random(n_probe), np)]
-    bits = syn.splitmix64_numpy(np.arange(n_probe, dtype=np.uint64))
-    inf = ((bits >> np.uint64(52)) & np.uint64(0x7FF)) == np.uint64(0x7FF)
-    bits[inf] &= ~np.uint64(1 << 62)
-    va = (rng.random(n_build) >= 0.01).astype(np.uint8)
-    vb = (rng.random(n_probe) >= 0.01).astype(np.uint8)
-    tl = orc.encode([orc.Cells.from_values(orc.INT32, perm), orc.Cells(orc.INT64, va, values=ra)], impl="port")
-    tr = orc.encode([orc.Cells.from_values(orc.INT32, sk), orc.Cells(orc.FP64, vb, values=bits.view(np.float64))], impl="port")
+    sk = perm[syn.Zipf(nb, 0.75).ranks(np.random.default_rng(44).random(np_), np)]
+    bits = syn.splitmix64_numpy(np.arange(np_, dtype=np.uint64))
+    bits[((bits >> np.uint64(52)) & np.uint64(0x7FF)) == np.uint64(0x7FF)] &= ~np.uint64(1 << 62)
+    va, vb = (rng.random(nb) >= 0.01).astype(np.uint8), (rng.random(np_) >= 0.01).astype(np.uint8)
     plan = syn.single_join_plan(payload=True)
-    plan.new_input(tl)
-    plan.new_input(tr)
-    return plan
-
-
-def time_reference(plan, n_tuples, steps, warmup):
-    """seconds per execute() of the reference, timed like the contest harness does
-    (steady_clock around Contest::execute only, tests/read_sql.cpp:1234-1236)"""
-    from oracle import pyoracle as orc
+    plan.new_input(orc.encode([orc.Cells.from_values(orc.INT32, perm), orc.Cells(orc.INT64, va, values=ra)], impl="port"))
+    plan.new_input(orc.encode([orc.Cells.from_values(orc.INT32, sk), orc.Cells(orc.FP64, vb, values=bits.view(np.float64))], impl="port"))
     kind = "reference" if orc.available("ref") else "port"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        # all host threads: torchrun exports OMP_NUM_THREADS=1, so the count is set explicitly
-        res = orc.execute(plan, impl="ref" if kind == "reference" else "port", n_threads=os.cpu_count() or 1)
+        r = orc.execute(plan, impl="ref" if kind == "reference" else "port", n_threads=cores)
         dt = orc.last_execute_seconds() if kind == "reference" else time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-        rows = res.num_rows
-        del res
-    return kind, times, rows
+        rows = r.num_rows
+        del r
+    sec = sum(times) / len(times)
+    return (nb + np_) / 1e6 / sec, sec * 1e3, kind, cores, f"{w['name']} at 1/{div} scale: {nb} x {np_} rows, {rows} output rows (harness unavailable: {why})"
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the reference is a single-process CPU program: rank 0 alone runs it
-    nb, np_ = FULL_BUILD // CPU_SAMPLE_DIV, FULL_PROBE // CPU_SAMPLE_DIV
-    plan = cpu_sample_plan(nb, np_)
-    kind, times, rows = time_reference(plan, nb + np_, args.steps, args.warmup)
-    sec = sum(times) / len(times)
-    value = (nb + np_) / 1e6 / sec
-    cores = os.cpu_count()
-    sample = f"config 2 at 1/{CPU_SAMPLE_DIV} scale: {nb} x {np_} rows, Zipf(0.75), INT64+FP64 payloads, {rows} output rows"
+    if args.workload == "job":
+        from radix_join_b200 import job_bench
+        return job_bench.run(args, impl="reference")
+    div = reference_div(args.workload, args.steps, args.warmup)
+    value, ms, kind, cores, sample = reference_run(args.workload, div, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "c2_int32_join_64Mi_x_512Mi_zipf0.75_int64_fp64_payloads", "sample": sample},
+        "config": {"workload": WORKLOADS[args.workload]["name"], "sample": sample, "sample_div": div,
+                   "api": "Contest::execute of the unmodified reference (oracle/_ref/libref_oracle.so) via tests/contest_harness.cpp"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -161,12 +200,19 @@ def run_single_gpu(args):
     from radix_join_b200 import synthetic as syn
 
     torch.cuda.set_device(0)
-    nb, np_ = FULL_BUILD // args.scale, FULL_PROBE // args.scale
+    w = WORKLOADS[args.workload]
+    nb, np_ = w["build"] // args.scale, w["probe"] // args.scale
     ctx = rj.build_context(0)
-    dt = syn.make_c2_device(ctx, nb, np_, checksum=True)
+    if args.workload == "c2":
+        dt = syn.make_c2_device(ctx, nb, np_, checksum=True)
+    else:
+        dt = syn.make_c1_device(ctx, nb, np_, checksum=True)
     inputs = rj.adopt_device(dt.plan, dt.device_pages, ctx, keep=dt.keep)
     in_bytes = sum(n * 8192 for cols in dt.device_pages for _, n in cols)
     stream = torch.cuda.ExternalStream(ctx.stream)
+    # config 1 (133 MB in, 81 MB out) would sit in the 126 MB L2 from one step to the next: write a
+    # buffer larger than L2 between timed steps; config 2's 7.4 GB of inputs need no flush
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if in_bytes < (1 << 30) else None
 
     def step():
         res = rj.execute_resident(dt.plan, inputs, ctx)
@@ -185,13 +231,25 @@ def run_single_gpu(args):
     sampler.start()
     launches0 = ctx.kernel_launches()
     torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        rows, out_pages = step()
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = 0.0
+    if flush is None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            rows, out_pages = step()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms_total = ev0.elapsed_time(ev1)
+    else:
+        for _ in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(1)  # 256 MB written: evicts the previous step's lines from L2 (untimed)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            rows, out_pages = step()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms_total += ev0.elapsed_time(ev1)
     launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop()
     prof = ctx.profile_read()
@@ -224,68 +282,65 @@ def run_single_gpu(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"scale{args.scale}", {}).get(dominant)
+            traffic = json.load(f).get(f"{args.workload}_scale{args.scale}", {}).get(dominant)
     except Exception:
         pass
+    alg_total = sum(v["algorithmic_gb_per_step"] for v in stages.values())
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": stages[dominant]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": stages[dominant]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "whole_step": {"algorithmic_gb": round(alg_total, 3), "achieved_gbs": round(alg_total / (ms_per_step / 1e3), 1),
+                               "frac": round(alg_total / (ms_per_step / 1e3) / peak, 4)},
                 "stages": stages}
-
-    # ---- end to end: host pages in (pinned, contiguous), host pages out -----------------------------
-    # rj_execute_streamed: the probe table goes through the GPU in row windows, so the upload of window
-    # k+1, the kernels of window k and the download of window k-1 overlap on the PCIe link.
-    e2e = None
-    if not args.no_e2e:
-        import numpy as np
-        host_plan, keep = syn.to_host_plan(dt)
-        root = host_plan.nodes[host_plan.root]
-        # pinned result buffers, sized once: dense page count of every output column + room for the
-        # partly filled last page of each window
-        caps = [-(-dt.expected_rows // int(ctx.lib.rj_fixed_rows_per_page(int(t)))) + 1024 for _, t in root.output_attrs]
-        out_bufs = [torch.empty(cap * 8192, dtype=torch.uint8, pin_memory=True).numpy().reshape(-1, 8192) for cap in caps]
-        used = [0] * len(caps)
-
-        def alloc(column, _dtype, n_pages):
-            lo = used[column]
-            used[column] = lo + n_pages
-            return out_bufs[column][lo:lo + n_pages]
-
-        e2e_steps = max(1, min(args.steps, 3))
-        times = []
-        for i in range(1 + e2e_steps):
-            used[:] = [0] * len(caps)
-            t0 = time.perf_counter()
-            e_rows, chunks = rj.execute_streamed(host_plan, ctx, alloc=alloc)
-            if i > 0:
-                times.append(time.perf_counter() - t0)
-        assert e_rows == dt.expected_rows
-        parity["e2e_multiset_checksum"] = syn.host_chunks_checksum(ctx, [t for _, t in root.output_attrs], chunks) == dt.expected_checksum
-        assert parity["e2e_multiset_checksum"], parity
-        sec = sum(times) / len(times)
-        e2e = {"value": round((nb + np_) / 1e6 / sec, 2), "unit": UNIT, "h2d_bytes_per_step": in_bytes,
-               "d2h_bytes_per_step": int(sum(used) * 8192), "ms_per_step": round(sec * 1e3, 2),
-               "steps": len(times), "api": "rj_execute_streamed (256 MiB windows of the probe table)",
-               "host_buffers": "pinned, contiguous per column; timed with the host clock around the call"}
-        del keep
-
-    # ---- CPU baseline: the reference's execute() on a bounded sample, host cores ---------------------
-    cpu = None
-    if not args.no_cpu_baseline:
-        cb, cp = FULL_BUILD // CPU_SAMPLE_DIV, FULL_PROBE // CPU_SAMPLE_DIV
-        kind, times, crow = time_reference(cpu_sample_plan(cb, cp), cb + cp, 1, 0)
-        cpu = {"value": round((cb + cp) / 1e6 / times[0], 4), "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
-               "sample": f"config 2 at 1/{CPU_SAMPLE_DIV} scale: {cb} x {cp} rows, {crow} output rows, one execute()"}
 
     inputs.free()
     rj.destroy_context(ctx)
+    del dt, inputs, flush
+    torch.cuda.empty_cache()
+
+    # ---- end to end: Contest::execute on individually new-ed host pages, new-ed host pages out ----------
+    # (a separate process, like a contest harness: tests/contest_harness.cpp links nothing of this repo but
+    # dlopens radix-join_b200/libcontest_b200.so).  Timed with steady_clock around the call, as
+    # tests/read_sql.cpp:1234-1236 does; its result is checked against the generator's multiset checksum.
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 5))
+        hres, why = run_harness("bench", args.workload, "--div", str(args.scale), "--steps", str(e2e_steps), "--warmup", "2")
+        if hres is None or not hres.get("ok"):
+            raise RuntimeError(f"end-to-end run through Contest::execute failed: {why or hres}")
+        sec = hres["ms_mean"] / 1e3
+        e2e = {"value": round((nb + np_) / 1e6 / sec, 2), "unit": UNIT, "h2d_bytes_per_step": hres["input_pages"] * 8192,
+               "d2h_bytes_per_step": hres["output_pages"] * 8192, "ms_per_step": round(hres["ms_mean"], 2),
+               "ms_best": round(hres["ms_best"], 2), "steps": e2e_steps, "warmup": 2,
+               "api": "Contest::execute (libcontest_b200.so -> rj_execute_pages): individually new-ed pages in (ColumnInserter), new Page out",
+               "host_threads": hres["threads"], "build_context_ms": hres["build_context_ms"],
+               "timed": "steady_clock around Contest::execute, mean of the timed calls; the previous result is destroyed before the next call"}
+        parity["e2e_multiset_checksum"] = bool(hres["checked"] and hres["ok"])
+
+    # ---- the SAME Plan object through both implementations (outside the timed region) -------------------
+    if not args.no_cpu_baseline and args.workload == "c2" and args.scale == 1:
+        pres, why = run_harness("parity", "c2", "--div", str(PARITY_SAMPLE_DIV))
+        parity["sample_vs_reference"] = {"ok": bool(pres and pres.get("ok")), "div": PARITY_SAMPLE_DIV,
+                                         "rows": pres.get("rows") if pres else None,
+                                         "how": "Contest::execute of this repo and of the unmodified reference on one Plan; results decoded by the reference's Table::from_columnar, sorted, compared exactly"}
+        assert parity["sample_vs_reference"]["ok"], (pres, why)
+
+    # ---- CPU baseline: the reference's Contest::execute on a bounded sample, host cores ------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        div = 1 if args.workload == "c1" else 16 * args.scale
+        cvalue, cms, kind, cores, sample = reference_run(args.workload, div, 1, 0)
+        cpu = {"value": round(cvalue, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample + ", one execute()",
+               "ms": round(cms, 1)}
+
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "c2_int32_join_64Mi_x_512Mi_zipf0.75_int64_fp64_payloads" + ("" if args.scale == 1 else f"_div{args.scale}"),
+        "config": {"workload": w["name"] + ("" if args.scale == 1 else f"_div{args.scale}"),
                    "build_rows": nb, "probe_rows": np_, "output_rows": rows, "input_pages_bytes": in_bytes,
                    "output_pages_bytes": out_pages * 8192,
-                   "cache": "inputs (%.1f GB) and every intermediate are far larger than the 126 MB L2; no flush needed" % (in_bytes / 1e9),
+                   "cache": ("a 256 MB buffer is written between timed steps (inputs + outputs would fit the 126 MB L2)" if in_bytes < (1 << 30) else
+                             "inputs (%.1f GB) and every intermediate are far larger than the 126 MB L2; no flush needed" % (in_bytes / 1e9)),
                    "tuples": "build rows + probe rows (SURVEY 8d)"},
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity": parity,
     }
@@ -298,15 +353,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=int, default=1, help="divide config 2's row counts (debugging only)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "job"])
+    ap.add_argument("--scale", type=int, default=1, help="divide the workload's row counts (debugging only)")
+    ap.add_argument("--job-scale", type=float, default=1.0, help="--workload job: fraction of the IMDB row counts")
+    ap.add_argument("--job-cpu-plans", type=int, default=12, help="--workload job: plans the CPU reference also runs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "job":
+        from radix_join_b200 import job_bench
+        return job_bench.run(args, impl="ours")
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         from radix_join_b200 import dist_bench
-        return dist_bench.run(args, FULL_BUILD // args.scale, FULL_PROBE // args.scale, METRIC, UNIT, ClockSampler, measured_peak)
+        w = WORKLOADS["c2"]
+        return dist_bench.run(args, w["build"] // args.scale, w["probe"] // args.scale, METRIC, UNIT, ClockSampler, measured_peak)
     return run_single_gpu(args)
 
 

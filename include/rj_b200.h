@@ -125,6 +125,27 @@ typedef void* (*rj_page_sink_t)(void* user, uint32_t column, int32_t type, uint6
 int rj_execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, rj_page_sink_t sink,
                         void* user, uint64_t* num_rows);
 
+/* Host pages in -> host pages out where EVERY page is an individually allocated object -- the shape of
+ * the reference's ColumnarTable (std::vector<Page*> per column, include/plan.h:60-68), whose result
+ * pages must come from `new Page` because Column::~Column deletes them (plan.h:95-99).  This is what
+ * Contest::execute (src/execute.cpp:316-324) calls.  Same windowed pipeline as rj_execute_streamed; in
+ * addition worker threads gather the input pages into pinned staging buffers and scatter the result
+ * pages out of them, so host copies, both DMA directions and the kernels overlap.
+ *   new_pages   allocate n pages of 8192 bytes (8-byte aligned) into out[0..n); called on the calling
+ *               thread only; non-zero = failure
+ *   append      hand over the next n filled pages of result column `column` (ownership passes to the
+ *               caller); called on the calling thread, for every column in the same window order, so
+ *               the columns stay row-aligned; never called for a column without pages
+ *   free_pages  give back pages that were allocated but will not be appended (error paths); may be NULL */
+typedef struct rj_page_alloc_t {
+    void* user;
+    int  (*new_pages)(void* user, uint64_t n, void** out);
+    int  (*append)(void* user, uint32_t column, int32_t type, void* const* pages, uint64_t n);
+    void (*free_pages)(void* user, uint64_t n, void* const* pages);
+} rj_page_alloc_t;
+int rj_execute_pages(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, const rj_page_alloc_t* alloc,
+                     uint64_t* num_rows);
+
 /* Same, split so a benchmark can keep the inputs resident in HBM:
  * rj_inputs_upload copies every column of every table once (plan->inputs of the later call is
  * ignored); rj_execute_resident runs decode -> joins -> encode on device only. */

@@ -93,6 +93,13 @@ _pvp = C.POINTER(C.c_void_p)
 # void* sink(void* user, uint32_t column, int32_t type, uint64_t n_pages)
 rj_page_sink_t = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64)
 
+class rj_page_alloc_t(C.Structure):
+    _fields_ = [("user", C.c_void_p),
+                ("new_pages", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p))),
+                ("append", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p), C.c_uint64)),
+                ("free_pages", C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)))]
+
+
 PROTOTYPES = {
     "rj_ctx_create": (C.c_int, [C.c_int, _pvp]),
     "rj_ctx_destroy": (None, [_vp]),
@@ -104,6 +111,7 @@ PROTOTYPES = {
     "rj_ctx_set_host_threads": (C.c_int, [_vp, C.c_int]),
     "rj_execute": (C.c_int, [_vp, C.POINTER(rj_plan_t), _pvp]),
     "rj_execute_streamed": (C.c_int, [_vp, C.POINTER(rj_plan_t), _u64, rj_page_sink_t, _vp, C.POINTER(_u64)]),
+    "rj_execute_pages": (C.c_int, [_vp, C.POINTER(rj_plan_t), _u64, C.POINTER(rj_page_alloc_t), C.POINTER(_u64)]),
     "rj_inputs_upload": (C.c_int, [_vp, C.POINTER(rj_table_t), _u32, _pvp]),
     "rj_inputs_adopt_device": (C.c_int, [_vp, C.POINTER(rj_table_t), _u32, _pvp]),
     "rj_inputs_adopt_dense": (C.c_int, [_vp, C.POINTER(rj_dense_table_t), _u32, _pvp]),

@@ -6,9 +6,14 @@
 // reference's own headers (-I$REF/include), so Plan / ColumnarTable / Column / Page are byte-compatible
 // by construction.  The adapter only flattens the plan into plain structs and wraps the result pages:
 //   * inputs are borrowed (`const Plan&`): page pointers are passed through, nothing is copied here;
-//   * every output page is `new Page` because Column::~Column deletes them (plan.h:64-68,95-99);
+//   * every output page is `new Page` because Column::~Column deletes them (plan.h:64-68,95-99): the
+//     engine asks for them through rj_page_alloc_t and fills them while the transfers are running
+//     (rj_execute_pages: gather + H2D, kernels, D2H + scatter all overlap);
 //   * engine errors surface as std::runtime_error, the reference's error contract
 //     (src/execute.cpp:280; the harness catches std::exception, tests/read_sql.cpp:1329-1332).
+#include <malloc.h>
+
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -20,6 +25,12 @@
 namespace Contest {
 
 void* build_context() {
+    // Result pages are individually `new`-ed 8 KB objects, millions per large result, freed by the
+    // caller before the next query.  Keep that memory mapped between queries instead of returning it to
+    // the kernel and faulting it in again: the first touch of 11 GB costs more than the join.
+    mallopt(M_TRIM_THRESHOLD, std::numeric_limits<int>::max());
+    mallopt(M_TOP_PAD, 256 << 20);
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
     rj_ctx* ctx = nullptr;
     if (rj_ctx_create(0, &ctx) != 0) {
         throw std::runtime_error(std::string("rj_ctx_create: ") + rj_last_error(nullptr));
@@ -80,34 +91,45 @@ ColumnarTable execute(const Plan& plan, void* context) {
     flat.inputs   = tables.data();
     flat.root     = plan.root;
 
-    // ---- run ---------------------------------------------------------------------------------------
-    rj_result* res = nullptr;
-    if (rj_execute(ctx, &flat, &res) != 0) {
-        throw std::runtime_error(rj_last_error(ctx));
-    }
-    // ---- wrap: typed columns of freshly allocated pages ---------------------------------------------
-    ColumnarTable out;
-    out.num_rows = rj_result_num_rows(res);
-    std::string error;
-    for (uint32_t c = 0; c < rj_result_num_columns(res); ++c) {
-        out.columns.emplace_back(static_cast<DataType>(rj_result_column_type(res, c)));
-        Column&  col     = out.columns.back();
-        uint64_t n_pages = rj_result_column_pages(res, c);
-        col.pages.reserve(n_pages);
-        for (uint64_t p = 0; p < n_pages; ++p) {
-            col.new_page();
+    // ---- run: every result page is a `new Page` (Column::~Column deletes them, plan.h:95-99) ---------
+    // The typed, possibly page-less result columns exist before the engine runs (tests/unit_tests.cpp:24-27).
+    struct Sink {
+        ColumnarTable out;
+        static int new_pages(void*, uint64_t n, void** pages) {
+            uint64_t i = 0;
+            try {
+                for (; i < n; ++i) pages[i] = new Page;
+            } catch (...) {
+                while (i > 0) delete static_cast<Page*>(pages[--i]);
+                return 1;
+            }
+            return 0;
         }
-        if (n_pages != 0
-            && rj_result_fetch(ctx, res, c, reinterpret_cast<void* const*>(col.pages.data()), nullptr) != 0) {
-            error = rj_last_error(ctx);
-            break;
+        static int append(void* user, uint32_t column, int32_t, void* const* pages, uint64_t n) {
+            auto& cols = static_cast<Sink*>(user)->out.columns;
+            if (column >= cols.size()) return 1;
+            auto& v = cols[column].pages;
+            v.reserve(v.size() + n);
+            for (uint64_t i = 0; i < n; ++i) v.push_back(static_cast<Page*>(pages[i]));
+            return 0;
         }
+        static void free_pages(void*, uint64_t n, void* const* pages) {
+            for (uint64_t i = 0; i < n; ++i) delete static_cast<Page*>(pages[i]);
+        }
+    } sink;
+    if (plan.root >= plan.nodes.size()) {
+        throw std::runtime_error("plan root out of range");
     }
-    rj_result_free(ctx, res);
-    if (!error.empty()) {
-        throw std::runtime_error(error);
+    for (auto [idx, type]: plan.nodes[plan.root].output_attrs) {
+        sink.out.columns.emplace_back(type);
     }
-    return out;
+    rj_page_alloc_t alloc{&sink, &Sink::new_pages, &Sink::append, &Sink::free_pages};
+    uint64_t        num_rows = 0;
+    if (rj_execute_pages(ctx, &flat, 0, &alloc, &num_rows) != 0) {
+        throw std::runtime_error(rj_last_error(ctx)); // ~Sink deletes whatever was appended
+    }
+    sink.out.num_rows = num_rows;
+    return std::move(sink.out);
 }
 
 } // namespace Contest

@@ -19,6 +19,7 @@
 #include <set>
 #include <thread>
 
+#include "host_pipe.h"
 #include "rj_internal.h"
 
 using namespace rj;
@@ -35,6 +36,10 @@ struct PendingTiming {
     cudaEvent_t a, b;
 };
 
+namespace {
+struct BlockCache;
+}
+
 struct rj_ctx {
     int          device    = 0;
     int          sm_count  = 0;
@@ -45,10 +50,13 @@ struct rj_ctx {
     rj_stage_stat_t            stats[RJ_ST_COUNT] = {};
     std::vector<PendingTiming> pending;
     std::vector<cudaEvent_t>   free_events;
-    // pinned staging ring for H2D / D2H of individually allocated pages
-    static constexpr size_t kStageBytes = size_t(64) << 20;
-    uint8_t*     pinned[2]    = {nullptr, nullptr};
-    cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
+    // worker pool + pinned staging rings for H2D / D2H of individually allocated pages (host_pipe.h);
+    // created on first use, kept for the life of the context
+    std::unique_ptr<HostPipe> pipe;
+    std::shared_ptr<BlockCache> cache;
+    // RJ_ERR_* bits set by kernels that meet malformed input: mapped pinned memory, read after a sync
+    uint32_t* err_host = nullptr;
+    uint32_t* err_dev = nullptr;
     // rj_execute_streamed: uploads and downloads run beside the kernels on their own streams
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t  up_ev[2] = {nullptr, nullptr};
@@ -104,9 +112,11 @@ struct BlockCache {
         free_blocks.clear();
         cached_bytes = 0;
     }
+    ~BlockCache() { trim(); }
 };
-BlockCache g_cache[64];
-std::atomic<int> g_live_contexts[64];
+// One cache per CONTEXT (blocks released on a context's stream are reused without synchronisation, which
+// is only sound while every user of the cache orders its work on that stream).  Buffers keep their cache
+// alive, so a result may outlive its context.
 
 struct DevMem {
     void*        p = nullptr;
@@ -114,11 +124,11 @@ struct DevMem {
     size_t       block = 0;    // size of the underlying block
     cudaStream_t stream = nullptr;
     cudaStream_t home = nullptr; // the context stream: releases from it need no synchronisation
-    int          device = 0;
-    DevMem(size_t n, cudaStream_t s, cudaStream_t ctx_stream, int dev): bytes(n), stream(s), home(ctx_stream), device(dev) {
+    std::shared_ptr<BlockCache> cache;
+    DevMem(size_t n, cudaStream_t s, cudaStream_t ctx_stream, std::shared_ptr<BlockCache> c): bytes(n), stream(s), home(ctx_stream), cache(std::move(c)) {
         auto t0 = std::chrono::steady_clock::now();
         const size_t want = BlockCache::round(n);
-        p = g_cache[device].take(want, &block);
+        p = cache->take(want, &block);
         if (!p) {
             ++g_alloc_misses;
             block = want;
@@ -126,7 +136,7 @@ struct DevMem {
             if (e == cudaErrorMemoryAllocation) {
                 cudaGetLastError();
                 cudaDeviceSynchronize();
-                g_cache[device].trim(); // give the cached blocks back and retry once
+                cache->trim(); // give the cached blocks back and retry once
                 e = cudaMalloc(&p, block);
             }
             if (e != cudaSuccess) {
@@ -141,7 +151,7 @@ struct DevMem {
     ~DevMem() {
         if (!p || view) return;
         if (stream != home) cudaStreamSynchronize(stream);
-        g_cache[device].give(p, block);
+        cache->give(p, block);
     }
     // non-owning view of caller memory (adopted dense columns)
     DevMem(void* ptr, size_t n): p(ptr), bytes(n), view(true) {}
@@ -154,9 +164,12 @@ struct DevMem {
 using Buf = std::shared_ptr<DevMem>;
 
 thread_local cudaStream_t t_home_stream = nullptr; // set by guarded() for the duration of an API call
-thread_local int          t_device = 0;
+thread_local std::shared_ptr<BlockCache> t_cache;
 
-Buf dev_alloc(size_t bytes, cudaStream_t s) { return std::make_shared<DevMem>(bytes, s, t_home_stream, t_device); }
+Buf dev_alloc(size_t bytes, cudaStream_t s) {
+    if (!t_cache) throw CudaError("internal: device allocation outside an engine call");
+    return std::make_shared<DevMem>(bytes, s, t_home_stream, t_cache);
+}
 
 Buf dev_alloc_zero(size_t bytes, cudaStream_t s) {
     Buf b = dev_alloc(bytes, s);
@@ -207,24 +220,6 @@ void profile_collect(rj_ctx* ctx) {
 }
 
 // ---- host helpers ------------------------------------------------------------------------------
-template <class F>
-void parallel_for(int n_threads, uint64_t n, F fn) {
-    // static split of [0, n) over up to n_threads host threads; fn(begin, end, thread)
-    if (n == 0) return;
-    uint64_t per = 512; // do not spawn a thread for less than this many items
-    int t = static_cast<int>(std::min<uint64_t>(n_threads, (n + per - 1) / per));
-    if (t <= 1) {
-        fn(uint64_t(0), n, 0);
-        return;
-    }
-    std::vector<std::thread> th;
-    for (int i = 0; i < t; ++i) {
-        uint64_t b = n * i / t, e = n * (i + 1) / t;
-        th.emplace_back([=] { fn(b, e, i); });
-    }
-    for (auto& x: th) x.join();
-}
-
 size_t type_width(int t) { return t == RJ_INT32 ? 4 : 8; }
 
 const uint8_t* host_page(const rj_column_t& c, uint64_t i) {
@@ -291,63 +286,112 @@ struct rj_result {
 
 namespace {
 
-void ensure_pinned(rj_ctx* ctx) {
-    for (int i = 0; i < 2; ++i) {
-        if (!ctx->pinned[i]) {
-            RJ_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->pinned[i]), rj_ctx::kStageBytes));
-            RJ_CUDA(cudaEventCreateWithFlags(&ctx->pinned_ev[i], cudaEventDisableTiming));
-        }
+HostPipe* ensure_pipe(rj_ctx* ctx) {
+    if (!ctx->pipe) {
+        // RJ_PIPE_BUFS caps each staging ring (tests: a ring of 2 buffers wraps after 1024 pages)
+        const char* env = getenv("RJ_PIPE_BUFS");
+        const int   cap = env && atoi(env) > 0 ? atoi(env) : 0;
+        ctx->pipe = std::make_unique<HostPipe>(ctx->host_threads, ctx->device, cap);
     }
+    return ctx->pipe.get();
 }
 
-// H2D of one column: pages are gathered into a pinned ring by host threads while the previous chunk
-// is in flight.  Returns per-column totals computed from the page headers on the way.
-void upload_column(rj_ctx* ctx, const rj_column_t& c, ColumnDev* out) {
-    out->type = c.type;
-    out->n_pages = c.n_pages;
-    out->owned = dev_alloc(c.n_pages * size_t(RJ_PAGE_SIZE), ctx->stream);
-    out->pages = out->owned->as<uint8_t>();
-    if (c.n_pages == 0) return;
-    if (!c.pages && !c.contiguous) throw EngineError("column has pages but no page pointers");
-    if (!c.pages) {
-        // contiguous host buffer: one DMA straight from the caller's memory (full PCIe rate when it is
-        // pinned); the page headers are scanned on the host meanwhile for the row / non-NULL totals
-        RJ_CUDA(cudaMemcpyAsync(out->owned->p, c.contiguous, c.n_pages * size_t(RJ_PAGE_SIZE), cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<uint64_t> rows(ctx->host_threads, 0), vals(ctx->host_threads, 0);
-        parallel_for(ctx->host_threads, c.n_pages, [&](uint64_t b, uint64_t e, int t) {
-            for (uint64_t i = b; i < e; ++i) page_counts(host_page(c, i), c.type, &rows[t], &vals[t]);
+void ensure_copy_streams(rj_ctx* ctx) {
+    if (ctx->h2d_stream) return;
+    RJ_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    RJ_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) RJ_CUDA(cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming));
+}
+
+// fn(begin, end) over [0, n) on the context's worker pool; returns when every piece has run
+template <class F>
+void pool_for(rj_ctx* ctx, uint64_t n, uint64_t grain, F fn) {
+    if (n == 0) return;
+    HostPipe* hp = ensure_pipe(ctx);
+    const uint64_t pieces = std::min<uint64_t>((n + grain - 1) / grain, uint64_t(hp->pool.size()) * 4);
+    if (pieces <= 1) {
+        fn(uint64_t(0), n);
+        return;
+    }
+    TaskGroup g;
+    g.open();
+    for (uint64_t i = 0; i < pieces; ++i) {
+        const uint64_t b = n * i / pieces, e = n * (i + 1) / pieces;
+        g.add();
+        hp->pool.submit([&g, &fn, b, e] {
+            try {
+                fn(b, e);
+                g.done();
+            } catch (...) {
+                g.fail(std::current_exception());
+            }
         });
-        for (int t = 0; t < ctx->host_threads; ++t) {
-            out->page_rows += rows[t];
-            out->non_null += vals[t];
+    }
+    g.seal();
+    g.wait();
+}
+
+struct ColCounters {
+    std::atomic<uint64_t> rows{0}, vals{0};
+};
+
+// H2D of pages [p0, p0 + cnt) of one host column, asynchronously: the copies are ISSUED on `stream` by
+// the time `group` completes.  Individually allocated pages (plan.h:60-68) are gathered into pinned
+// ring buffers by pool workers, 512 pages per task; each task issues its own DMA, so the gather of
+// one buffer overlaps the transfer of the previous ones.  A contiguous host buffer is one DMA straight
+// from the caller's memory.  `counters` (optional) receives the row / non-NULL totals of the page headers.
+void upload_pages_async(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t cnt, uint8_t* dst, cudaStream_t stream,
+                        TaskGroup* group, ColCounters* counters) {
+    if (cnt == 0) return;
+    if (!c.pages && !c.contiguous) throw EngineError("column has pages but no page pointers");
+    HostPipe* hp = ensure_pipe(ctx);
+    const int type = c.type;
+    if (!c.pages) {
+        const uint8_t* src = static_cast<const uint8_t*>(c.contiguous) + p0 * RJ_PAGE_SIZE;
+        RJ_CUDA(cudaMemcpyAsync(dst, src, cnt * size_t(RJ_PAGE_SIZE), cudaMemcpyHostToDevice, stream));
+        if (counters) {
+            const uint64_t grain = 8192;
+            for (uint64_t q = 0; q < cnt; q += grain) {
+                const uint64_t m = std::min<uint64_t>(grain, cnt - q);
+                group->add();
+                hp->pool.submit([=] {
+                    uint64_t r = 0, v = 0;
+                    for (uint64_t i = 0; i < m; ++i) page_counts(src + (q + i) * RJ_PAGE_SIZE, type, &r, &v);
+                    counters->rows.fetch_add(r, std::memory_order_relaxed);
+                    counters->vals.fetch_add(v, std::memory_order_relaxed);
+                    group->done();
+                });
+            }
         }
         return;
     }
-    ensure_pinned(ctx);
-    const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
-    std::vector<uint64_t> rows(ctx->host_threads, 0), vals(ctx->host_threads, 0);
-    int slot = 0;
-    for (uint64_t p0 = 0; p0 < c.n_pages; p0 += chunk_pages, slot ^= 1) {
-        const uint64_t cnt = std::min<uint64_t>(chunk_pages, c.n_pages - p0);
-        RJ_CUDA(cudaEventSynchronize(ctx->pinned_ev[slot])); // the copy that last used this slot is done
-        uint8_t* stage = ctx->pinned[slot];
-        parallel_for(ctx->host_threads, cnt, [&](uint64_t b, uint64_t e, int t) {
-            uint64_t r = 0, v = 0;
-            for (uint64_t i = b; i < e; ++i) {
-                const uint8_t* pg = host_page(c, p0 + i);
-                std::memcpy(stage + i * RJ_PAGE_SIZE, pg, RJ_PAGE_SIZE);
-                page_counts(pg, c.type, &r, &v);
+    const void* const* pages = c.pages + p0;
+    const uint64_t per = HostPipe::kBufBytes / RJ_PAGE_SIZE;
+    for (uint64_t q = 0; q < cnt; q += per) {
+        const uint64_t m = std::min<uint64_t>(per, cnt - q);
+        group->add();
+        hp->pool.submit([=] {
+            try {
+                PinnedBuf* buf = hp->up.acquire();
+                uint64_t r = 0, v = 0;
+                for (uint64_t i = 0; i < m; ++i) {
+                    const uint8_t* pg = static_cast<const uint8_t*>(pages[q + i]);
+                    std::memcpy(buf->p + i * RJ_PAGE_SIZE, pg, RJ_PAGE_SIZE);
+                    if (counters) page_counts(pg, type, &r, &v);
+                }
+                if (counters) {
+                    counters->rows.fetch_add(r, std::memory_order_relaxed);
+                    counters->vals.fetch_add(v, std::memory_order_relaxed);
+                }
+                cudaError_t e = cudaMemcpyAsync(dst + q * RJ_PAGE_SIZE, buf->p, m * RJ_PAGE_SIZE, cudaMemcpyHostToDevice, stream);
+                if (e == cudaSuccess) e = cudaEventRecord(buf->ev, stream);
+                hp->up.release(buf);
+                if (e != cudaSuccess) throw CudaError(std::string("page upload: ") + cudaGetErrorString(e));
+                group->done();
+            } catch (...) {
+                group->fail(std::current_exception());
             }
-            rows[t] += r;
-            vals[t] += v;
         });
-        RJ_CUDA(cudaMemcpyAsync(out->owned->as<uint8_t>() + p0 * RJ_PAGE_SIZE, stage, cnt * RJ_PAGE_SIZE,
-                                cudaMemcpyHostToDevice, ctx->stream));
-        RJ_CUDA(cudaEventRecord(ctx->pinned_ev[slot], ctx->stream));
-    }
-    for (int t = 0; t < ctx->host_threads; ++t) {
-        out->page_rows += rows[t];
-        out->non_null += vals[t];
     }
 }
 
@@ -356,6 +400,8 @@ void check_column_rows(const TableDev& t, const ColumnDev& c) {
     if (c.page_rows > t.num_rows) throw EngineError("row_idx");
 }
 
+// Upload of whole columns: every wanted column's copies are in flight together; returns once they are
+// issued on `stream` (the kernels that follow on the context stream are ordered behind them).
 std::unique_ptr<rj_inputs> upload_tables(rj_ctx* ctx, const rj_table_t* tables, uint32_t n, const std::set<std::pair<uint32_t, uint32_t>>* wanted) {
     auto in = std::make_unique<rj_inputs>();
     in->tables.resize(n);
@@ -367,16 +413,39 @@ std::unique_ptr<rj_inputs> upload_tables(rj_ctx* ctx, const rj_table_t* tables, 
                 ++copies;
             }
     StageScope scope(ctx, RJ_ST_H2D, ctx->stream, copies, bytes);
-    for (uint32_t t = 0; t < n; ++t) {
-        TableDev& td = in->tables[t];
-        td.num_rows = tables[t].num_rows;
-        td.cols.resize(tables[t].n_columns);
-        for (uint32_t c = 0; c < tables[t].n_columns; ++c) {
-            td.cols[c].type = tables[t].columns[c].type;
-            if (wanted && !wanted->count({t, c})) continue; // never referenced by the plan
-            upload_column(ctx, tables[t].columns[c], &td.cols[c]);
-            check_column_rows(td, td.cols[c]);
+    TaskGroup group;
+    std::deque<ColCounters> counters; // stable addresses
+    std::vector<std::pair<TableDev*, ColumnDev*>> cols;
+    group.open();
+    try {
+        for (uint32_t t = 0; t < n; ++t) {
+            TableDev& td = in->tables[t];
+            td.num_rows = tables[t].num_rows;
+            td.cols.resize(tables[t].n_columns);
+            for (uint32_t c = 0; c < tables[t].n_columns; ++c) {
+                const rj_column_t& hc = tables[t].columns[c];
+                ColumnDev& cd = td.cols[c];
+                cd.type = hc.type;
+                if (wanted && !wanted->count({t, c})) continue; // never referenced by the plan
+                cd.n_pages = hc.n_pages;
+                cd.owned = dev_alloc(hc.n_pages * size_t(RJ_PAGE_SIZE), ctx->stream);
+                cd.pages = cd.owned->as<uint8_t>();
+                counters.emplace_back();
+                cols.emplace_back(&td, &cd);
+                upload_pages_async(ctx, hc, 0, hc.n_pages, cd.owned->as<uint8_t>(), ctx->stream, &group, &counters.back());
+            }
         }
+    } catch (...) {
+        group.seal();
+        try { group.wait(); } catch (...) {}
+        throw;
+    }
+    group.seal();
+    group.wait();
+    for (size_t i = 0; i < cols.size(); ++i) {
+        cols[i].second->page_rows = counters[i].rows.load();
+        cols[i].second->non_null = counters[i].vals.load();
+        check_column_rows(*cols[i].first, *cols[i].second);
     }
     return in;
 }
@@ -535,7 +604,7 @@ void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_
         }
         if (type == RJ_VARCHAR) {
             launch_decode_varchar(pages, n_pages, row_start, out->values->as<uint64_t>(),
-                                  need_valid ? out->valid->as<uint32_t>() : nullptr, ctx->sm_count, s);
+                                  need_valid ? out->valid->as<uint32_t>() : nullptr, ctx->sm_count, s, ctx->err_dev);
         } else {
             launch_decode_fixed(pages, n_pages, type, row_start, out->values->p,
                                 need_valid ? out->valid->as<uint32_t>() : nullptr, ctx->sm_count, s);
@@ -1057,9 +1126,31 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
         }
         const Attr at = resolve(n, a);
         if (in->tables[at.table].cols[at.col].type != rc.type) {
-            // the reference silently drops mistyped cells (build_table.cpp:484-501) or throws for
-            // VARCHAR (:667-669); a plan like that is malformed, refuse it
-            throw EngineError(rc.type == RJ_VARCHAR ? "not string or null" : "output attribute type does not match the column");
+            // The column does not physically hold the declared type.  Table::to_columnar visits every
+            // cell: a fixed-width column keeps the NULL cells and silently SKIPS the others
+            // (build_table.cpp:484-501, :527-544, :570-587), so it comes out holding only the NULL rows;
+            // a VARCHAR column throws "not string or null" at the first non-NULL cell (:667-669).
+            const DecodedCol& col = column(at.table, at.col);
+            if (!r.has_leaf(at.leaf)) throw EngineError("internal: root leaf not tracked");
+            uint64_t n_null = 0;
+            if (col.valid) {
+                Buf rid = rid_of(r, at.leaf);
+                Buf cnt = dev_alloc_zero(8, s);
+                launch_count_nulls(col.valid_ptr(), rid ? rid->as<uint32_t>() : nullptr, r.rows, 0xffffffffu,
+                                   cnt->as<unsigned long long>(), ctx->sm_count, s);
+                RJ_CUDA(cudaMemcpyAsync(&n_null, cnt->p, 8, cudaMemcpyDeviceToHost, s));
+                RJ_CUDA(cudaStreamSynchronize(s));
+            }
+            if (rc.type == RJ_VARCHAR && n_null != r.rows) throw EngineError("not string or null");
+            // n_null all-NULL rows: header n_r, n_v = 0, zero bitmap -- the same bytes for every type
+            const uint32_t rpp = rj_fixed_rows_per_page(RJ_INT32);
+            rc.n_pages = (n_null + rpp - 1) / rpp;
+            if (n_null == 0) continue;
+            rc.pages = dev_alloc(rc.n_pages * size_t(RJ_PAGE_SIZE), s);
+            Buf no_valid = dev_alloc_zero(((n_null + 31) / 32 + 1) * 4, s);
+            StageScope sc(ctx, RJ_ST_ENCODE, s, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
+            launch_encode_fixed(no_valid->p, no_valid->as<uint32_t>(), nullptr, nullptr, nullptr, n_null, RJ_INT32, rc.pages->p, ctx->sm_count, s);
+            continue;
         }
         const DecodedCol& col = column(at.table, at.col);
         if (!r.has_leaf(at.leaf)) throw EngineError("internal: root leaf not tracked");
@@ -1124,6 +1215,11 @@ std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, 
         t_run = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         res = ex.root(plan->root, r);
         RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (const uint32_t bad = *static_cast<volatile uint32_t*>(ctx->err_host)) {
+            *ctx->err_host = 0;
+            if (bad & RJ_ERR_ORPHAN_LONG_PAGE) throw EngineError("long string page 0xfffe must follows a string"); // build_table.cpp:401-402
+            throw EngineError("malformed input pages");
+        }
         t_root = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     if (trace) {
@@ -1174,7 +1270,7 @@ int guarded(rj_ctx* ctx, F f) {
     try {
         cudaSetDevice(ctx->device);
         t_home_stream = ctx->stream;
-        t_device = ctx->device;
+        t_cache = ctx->cache;
         f();
         return 0;
     } catch (const std::exception& e) {
@@ -1213,8 +1309,10 @@ int rj_ctx_create(int device, rj_ctx** out) {
         ctx->device = device;
         ctx->sm_count = prop.multiProcessorCount;
         RJ_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        if (device >= 64) throw EngineError("device index out of range");
-        g_live_contexts[device].fetch_add(1);
+        ctx->cache = std::make_shared<BlockCache>();
+        RJ_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->err_host), 64, cudaHostAllocMapped));
+        std::memset(ctx->err_host, 0, 64);
+        RJ_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->err_dev), ctx->err_host, 0));
         unsigned hc = std::thread::hardware_concurrency();
         ctx->host_threads = hc ? static_cast<int>(std::min(hc, 32u)) : 8;
         *out = ctx.release();
@@ -1231,16 +1329,14 @@ void rj_ctx_destroy(rj_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     profile_collect(ctx);
     for (auto e: ctx->free_events) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
-        if (ctx->pinned_ev[i]) cudaEventDestroy(ctx->pinned_ev[i]);
-    }
+    ctx->pipe.reset(); // joins the workers, frees the pinned rings
+    if (ctx->err_host) cudaFreeHost(ctx->err_host);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (int i = 0; i < 2; ++i)
         if (ctx->up_ev[i]) cudaEventDestroy(ctx->up_ev[i]);
     cudaStreamDestroy(ctx->stream);
-    if (g_live_contexts[ctx->device].fetch_sub(1) == 1) g_cache[ctx->device].trim(); // last context: release HBM
+    ctx->cache->trim(); // release the cached HBM; blocks still held by live results follow when those are freed
     delete ctx;
 }
 
@@ -1345,11 +1441,12 @@ int rj_execute(rj_ctx* ctx, const rj_plan_t* plan, rj_result** out) {
 // ---- streamed execution: host pages in, host pages out, PCIe busy in both directions ----------------
 // An inner join distributes over a union of its inputs, so the plan can run once per row window of ONE
 // base table (the largest, when a single scan reads it) with every other table resident:
-//     upload(k+1)  ||  kernels(k)  ||  download(k-1)
-// on three streams.  With pinned, contiguous host buffers the copies are plain DMAs and the call costs
-// max(upload, download) instead of their sum; pageable or page-by-page buffers still work, without the
-// overlap.  Windows are cut on row boundaries, so the pages of a window's columns start and end at
-// different rows: the decode shifts each column to the window (ColumnDev::skip_rows).
+//     gather + upload(k+1)  ||  kernels(k)  ||  download + scatter(k-1)
+// The copies run on their own streams; individually allocated pages (the contest's ColumnarTable,
+// plan.h:60-68) are gathered into / scattered out of pinned ring buffers by the worker pool
+// (host_pipe.h), contiguous pinned buffers are plain DMAs.  Windows are cut on row boundaries, so the
+// pages of a window's columns start and end at different rows: the decode shifts each column to the
+// window (ColumnDev::skip_rows).
 namespace {
 
 struct StreamCol {
@@ -1360,49 +1457,21 @@ struct StreamCol {
     uint64_t              slot_pages = 0;
 };
 
-void ensure_copy_streams(rj_ctx* ctx) {
-    if (ctx->h2d_stream) return;
-    RJ_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
-    RJ_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) RJ_CUDA(cudaEventCreateWithFlags(&ctx->up_ev[i], cudaEventDisableTiming));
-}
-
-// pages [p0, p0 + cnt) of a host column -> device, on `stream`
-void copy_pages_h2d(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t cnt, uint8_t* dst, cudaStream_t stream) {
-    if (cnt == 0) return;
-    if (!c.pages) {
-        RJ_CUDA(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(c.contiguous) + p0 * RJ_PAGE_SIZE, cnt * size_t(RJ_PAGE_SIZE),
-                                cudaMemcpyHostToDevice, stream));
-        return;
-    }
-    ensure_pinned(ctx);
-    const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
-    int slot = 0;
-    for (uint64_t q = 0; q < cnt; q += chunk_pages, slot ^= 1) {
-        const uint64_t m = std::min<uint64_t>(chunk_pages, cnt - q);
-        RJ_CUDA(cudaEventSynchronize(ctx->pinned_ev[slot]));
-        uint8_t* stage = ctx->pinned[slot];
-        parallel_for(ctx->host_threads, m, [&](uint64_t b, uint64_t e, int) {
-            for (uint64_t i = b; i < e; ++i) std::memcpy(stage + i * RJ_PAGE_SIZE, host_page(c, p0 + q + i), RJ_PAGE_SIZE);
-        });
-        RJ_CUDA(cudaMemcpyAsync(dst + q * RJ_PAGE_SIZE, stage, m * RJ_PAGE_SIZE, cudaMemcpyHostToDevice, stream));
-        RJ_CUDA(cudaEventRecord(ctx->pinned_ev[slot], stream));
-    }
-}
-
-struct PendingDownload {
-    std::unique_ptr<rj_result> res;
-    cudaEvent_t                done = nullptr;
+// Where result pages go.  deliver() issues the D2H copies of one window's result on `stream` (the
+// result stays alive until they have run); finish() returns once every page is in host memory.
+struct OutputSink {
+    virtual ~OutputSink() = default;
+    virtual void deliver(rj_ctx* ctx, rj_result* res, cudaStream_t stream) = 0;
+    virtual void finish() = 0;
+    virtual void abort() {}
 };
 
-uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, rj_page_sink_t sink, void* user) {
-    if (!sink) throw EngineError("rj_execute_streamed: no page sink");
-    if (chunk_bytes == 0) chunk_bytes = uint64_t(256) << 20;
-    ensure_copy_streams(ctx);
-    std::set<std::pair<uint32_t, uint32_t>> wanted;
-    collect_wanted(plan, &wanted);
-
-    auto deliver = [&](rj_result* res, cudaStream_t stream) {
+// rj_execute_streamed: the caller hands out one contiguous host buffer per (window, column)
+struct ContiguousSink: OutputSink {
+    rj_page_sink_t sink;
+    void*          user;
+    ContiguousSink(rj_page_sink_t s, void* u): sink(s), user(u) {}
+    void deliver(rj_ctx* ctx, rj_result* res, cudaStream_t stream) override {
         for (uint32_t c = 0; c < res->cols.size(); ++c) {
             const ResultColumn& rc = res->cols[c];
             if (rc.n_pages == 0) continue;
@@ -1411,7 +1480,103 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
             StageScope scope(ctx, RJ_ST_D2H, stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
             RJ_CUDA(cudaMemcpyAsync(dst, rc.pages->p, rc.n_pages * size_t(RJ_PAGE_SIZE), cudaMemcpyDeviceToHost, stream));
         }
+    }
+    void finish() override {}
+};
+
+// rj_execute_pages: every result page is an individually allocated page of the caller (`new Page`,
+// plan.h:64-68).  Pages are allocated on the calling thread (one allocator arena, so the memory of the
+// previous result is reused), filled by the worker pool behind the D2H copies, and handed over column by
+// column in window order at the end -- the same order for every column, which keeps rows aligned.
+struct PageSink: OutputSink {
+    const rj_page_alloc_t* alloc;
+    HostPipe*              hp;
+    struct Piece {
+        uint32_t           column;
+        int32_t            type;
+        std::vector<void*> pages;
     };
+    std::deque<Piece> pieces;
+    TaskGroup         group;
+    bool              open = true;
+    PageSink(const rj_page_alloc_t* a, HostPipe* h): alloc(a), hp(h) { group.open(); }
+    void deliver(rj_ctx* ctx, rj_result* res, cudaStream_t stream) override {
+        for (uint32_t c = 0; c < res->cols.size(); ++c) {
+            const ResultColumn& rc = res->cols[c];
+            if (rc.n_pages == 0) continue;
+            pieces.emplace_back();
+            Piece& pc = pieces.back();
+            pc.column = c;
+            pc.type = rc.type;
+            pc.pages.assign(rc.n_pages, nullptr);
+            if (alloc->new_pages(alloc->user, rc.n_pages, pc.pages.data()) != 0) {
+                pc.pages.clear();
+                throw EngineError("rj_execute_pages: the page allocator failed");
+            }
+            StageScope scope(ctx, RJ_ST_D2H, stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
+            void* const*   dst = pc.pages.data();
+            const uint8_t* src = rc.pages->as<uint8_t>();
+            const uint64_t per = HostPipe::kBufBytes / RJ_PAGE_SIZE;
+            for (uint64_t q = 0; q < rc.n_pages; q += per) {
+                const uint64_t m = std::min<uint64_t>(per, rc.n_pages - q);
+                PinnedBuf* buf = hp->down.acquire(); // blocks while all staging buffers are being scattered
+                cudaError_t e = cudaMemcpyAsync(buf->p, src + q * RJ_PAGE_SIZE, m * RJ_PAGE_SIZE, cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaEventRecord(buf->ev, stream);
+                if (e != cudaSuccess) {
+                    hp->down.release(buf);
+                    throw CudaError(std::string("page download: ") + cudaGetErrorString(e));
+                }
+                group.add();
+                HostPipe*  pipe = hp;
+                TaskGroup* g = &group;
+                hp->waiter.after(buf->ev, [=] {
+                    for (uint64_t i = 0; i < m; ++i) std::memcpy(dst[q + i], buf->p + i * RJ_PAGE_SIZE, RJ_PAGE_SIZE);
+                    pipe->down.release(buf);
+                    g->done();
+                });
+            }
+        }
+    }
+    void drain() {
+        if (open) {
+            open = false;
+            group.seal();
+        }
+        group.wait();
+    }
+    void finish() override {
+        drain();
+        while (!pieces.empty()) {
+            Piece& pc = pieces.front();
+            if (alloc->append(alloc->user, pc.column, pc.type, pc.pages.data(), pc.pages.size()) != 0)
+                throw EngineError("rj_execute_pages: the caller refused result pages");
+            pieces.pop_front(); // handed over: no longer ours to free
+        }
+    }
+    void abort() override {
+        try { drain(); } catch (...) {}
+        for (auto& pc: pieces)
+            if (alloc->free_pages && !pc.pages.empty()) alloc->free_pages(alloc->user, pc.pages.size(), pc.pages.data());
+        pieces.clear();
+    }
+};
+
+struct PendingDownload {
+    std::unique_ptr<rj_result> res;
+    cudaEvent_t                done = nullptr;
+};
+
+uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, OutputSink& out) {
+    if (chunk_bytes == 0) {
+        // RJ_WINDOW_BYTES: window size of callers that cannot pass one (Contest::execute); tests use it to
+        // cut small inputs into many windows
+        const char* env = getenv("RJ_WINDOW_BYTES");
+        chunk_bytes = env && atoll(env) > 0 ? static_cast<uint64_t>(atoll(env)) : uint64_t(256) << 20;
+    }
+    ensure_copy_streams(ctx);
+    ensure_pipe(ctx);
+    std::set<std::pair<uint32_t, uint32_t>> wanted;
+    collect_wanted(plan, &wanted);
 
     // the table to stream: read by exactly one scan, fixed-width columns only, at least two chunks
     std::vector<int> scans(plan->n_inputs, 0);
@@ -1437,18 +1602,14 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
         // nothing worth streaming: one upload, one execute, one download
         auto in  = upload_tables(ctx, plan->inputs, plan->n_inputs, &wanted);
         auto res = execute_resident(ctx, plan, in.get());
-        deliver(res.get(), ctx->stream);
+        out.deliver(ctx, res.get(), ctx->stream);
         RJ_CUDA(cudaStreamSynchronize(ctx->stream));
+        out.finish();
         return res->num_rows;
     }
 
     const uint32_t    T  = static_cast<uint32_t>(pick);
     const rj_table_t& ht = plan->inputs[T];
-    // everything else becomes resident
-    std::set<std::pair<uint32_t, uint32_t>> others;
-    for (auto& w: wanted)
-        if (w.first != T) others.insert(w);
-    auto in = upload_tables(ctx, plan->inputs, plan->n_inputs, &others);
 
     // page headers of the streamed table: rows before every page, per column
     std::vector<StreamCol> cols;
@@ -1459,19 +1620,19 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
         StreamCol sc;
         sc.col = c;
         sc.row_prefix.assign(hc.n_pages + 1, 0);
-        std::vector<uint64_t> nn(ctx->host_threads, 0);
-        parallel_for(ctx->host_threads, hc.n_pages, [&](uint64_t b, uint64_t e, int t) {
+        std::atomic<uint64_t> non_null{0};
+        pool_for(ctx, hc.n_pages, 4096, [&](uint64_t b, uint64_t e) {
+            uint64_t nn = 0;
             for (uint64_t i = b; i < e; ++i) {
                 uint64_t r = 0;
-                page_counts(host_page(hc, i), hc.type, &r, &nn[t]);
+                page_counts(host_page(hc, i), hc.type, &r, &nn);
                 sc.row_prefix[i + 1] = r;
             }
+            non_null.fetch_add(nn, std::memory_order_relaxed);
         });
         for (uint64_t i = 0; i < hc.n_pages; ++i) sc.row_prefix[i + 1] += sc.row_prefix[i];
         if (sc.row_prefix[hc.n_pages] > ht.num_rows) throw EngineError("row_idx");
-        uint64_t non_null = 0;
-        for (auto v: nn) non_null += v;
-        sc.has_null = non_null != ht.num_rows;
+        sc.has_null = non_null.load() != ht.num_rows;
         cols.push_back(std::move(sc));
     }
 
@@ -1498,8 +1659,11 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
         }
         for (int i = 0; i < 2; ++i) sc.slot[i] = dev_alloc(std::max<uint64_t>(1, sc.slot_pages) * RJ_PAGE_SIZE, ctx->stream);
     }
-    RJ_CUDA(cudaStreamSynchronize(ctx->stream)); // resident tables and slots are in place
+    RJ_CUDA(cudaStreamSynchronize(ctx->stream)); // the slots are in place
 
+    // window k's pages: gathered / copied on the upload stream; up_group[k] completes when every copy
+    // of the window has been issued, and its last task records up_ev[k & 1] behind them
+    std::vector<std::unique_ptr<TaskGroup>> up_group(n_chunks);
     auto issue_upload = [&](uint64_t k) {
         const int      slot = static_cast<int>(k & 1);
         const uint64_t r0 = k * rows_per_chunk, r1 = std::min(ht.num_rows, r0 + rows_per_chunk);
@@ -1510,12 +1674,25 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
             bytes += (p1 - p0) * RJ_PAGE_SIZE;
         }
         StageScope scope(ctx, RJ_ST_H2D, ctx->h2d_stream, cols.size(), bytes);
-        for (auto& sc: cols) {
-            uint64_t p0, p1;
-            page_range(sc, r0, r1, &p0, &p1);
-            copy_pages_h2d(ctx, ht.columns[sc.col], p0, p1 - p0, sc.slot[slot]->as<uint8_t>(), ctx->h2d_stream);
+        up_group[k] = std::make_unique<TaskGroup>();
+        TaskGroup* g = up_group[k].get();
+        cudaEvent_t  ev = ctx->up_ev[slot];
+        cudaStream_t hs = ctx->h2d_stream;
+        g->on_complete = [ev, hs] {
+            if (cudaEventRecord(ev, hs) != cudaSuccess) throw CudaError("window upload: cudaEventRecord failed");
+        };
+        g->open();
+        try {
+            for (auto& sc: cols) {
+                uint64_t p0, p1;
+                page_range(sc, r0, r1, &p0, &p1);
+                upload_pages_async(ctx, ht.columns[sc.col], p0, p1 - p0, sc.slot[slot]->as<uint8_t>(), ctx->h2d_stream, g, nullptr);
+            }
+        } catch (...) {
+            g->seal();
+            throw;
         }
-        RJ_CUDA(cudaEventRecord(ctx->up_ev[slot], ctx->h2d_stream));
+        g->seal();
     };
 
     Exec::DecodedMap             shared;
@@ -1535,20 +1712,22 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
     };
     if (trace) fprintf(stderr, "[rj stream] table %u: %llu rows in %llu windows of %llu rows\n", T, (unsigned long long)ht.num_rows,
                        (unsigned long long)n_chunks, (unsigned long long)rows_per_chunk);
+    std::unique_ptr<rj_inputs> in;
     try {
+        // the first window's gather runs beside the upload of the resident tables
         issue_upload(0);
+        std::set<std::pair<uint32_t, uint32_t>> others;
+        for (auto& w: wanted)
+            if (w.first != T) others.insert(w);
+        in = upload_tables(ctx, plan->inputs, plan->n_inputs, &others);
         for (uint64_t k = 0; k < n_chunks; ++k) {
             const double t_a = now_ms();
             if (k + 1 < n_chunks) issue_upload(k + 1); // its slot was last read by chunk k-1, which has finished
             const double t_b = now_ms();
             const int      slot = static_cast<int>(k & 1);
             const uint64_t r0 = k * rows_per_chunk, r1 = std::min(ht.num_rows, r0 + rows_per_chunk);
-            double t_w = 0;
-            if (trace) {
-                const double t_w0 = now_ms();
-                RJ_CUDA(cudaEventSynchronize(ctx->up_ev[slot]));
-                t_w = now_ms() - t_w0;
-            }
+            up_group[k]->wait(); // every copy of the window is on the upload stream, the event behind them
+            const double t_w = now_ms() - t_b;
             RJ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->up_ev[slot], 0));
             TableDev& td = in->tables[T];
             td.num_rows = r1 - r0;
@@ -1567,24 +1746,27 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
             }
             const double scale = static_cast<double>(ht.num_rows) / static_cast<double>(std::max<uint64_t>(1, r1 - r0));
             auto res = execute_resident(ctx, plan, in.get(), &shared, T, scale); // returns with the stream idle
+            const double t_c = now_ms();
             total_rows += res->num_rows;
             PendingDownload pd;
             RJ_CUDA(cudaEventCreateWithFlags(&pd.done, cudaEventDisableTiming));
-            deliver(res.get(), ctx->d2h_stream);
+            out.deliver(ctx, res.get(), ctx->d2h_stream);
             RJ_CUDA(cudaEventRecord(pd.done, ctx->d2h_stream));
             pd.res = std::move(res);
             pending.push_back(std::move(pd));
-            const double t_c = now_ms();
             reap(false);
-            if (trace) fprintf(stderr, "[rj stream] window %llu: waited %.2f ms for the upload\n", (unsigned long long)k, t_w);
-            if (trace) fprintf(stderr, "[rj stream] window %llu: issue upload %.2f ms, execute %.2f ms, issue download + reap %.2f ms, %zu downloads pending\n",
-                               (unsigned long long)k, t_b - t_a, t_c - t_b, now_ms() - t_c, pending.size());
+            if (trace) fprintf(stderr, "[rj stream] window %llu: issue upload %.2f ms, wait for own upload %.2f ms, execute %.2f ms, issue download + reap %.2f ms, %zu downloads pending\n",
+                               (unsigned long long)k, t_b - t_a, t_w, t_c - t_b - t_w, now_ms() - t_c, pending.size());
         }
         reap(true);
+        out.finish();
     } catch (...) {
+        for (auto& g: up_group)
+            if (g) { try { g->wait(); } catch (...) {} }
         cudaStreamSynchronize(ctx->h2d_stream);
         cudaStreamSynchronize(ctx->d2h_stream);
         for (auto& pd: pending) cudaEventDestroy(pd.done);
+        out.abort();
         throw;
     }
     RJ_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
@@ -1597,7 +1779,25 @@ int rj_execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes
                         uint64_t* num_rows) {
     return guarded(ctx, [&] {
         if (!plan) throw EngineError("null plan");
-        const uint64_t n = execute_streamed(ctx, plan, chunk_bytes, sink, user);
+        if (!sink) throw EngineError("rj_execute_streamed: no page sink");
+        ContiguousSink out(sink, user);
+        const uint64_t n = execute_streamed(ctx, plan, chunk_bytes, out);
+        if (num_rows) *num_rows = n;
+    });
+}
+
+int rj_execute_pages(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, const rj_page_alloc_t* alloc, uint64_t* num_rows) {
+    return guarded(ctx, [&] {
+        if (!plan) throw EngineError("null plan");
+        if (!alloc || !alloc->new_pages || !alloc->append) throw EngineError("rj_execute_pages: no page allocator");
+        PageSink out(alloc, ensure_pipe(ctx));
+        uint64_t n = 0;
+        try {
+            n = execute_streamed(ctx, plan, chunk_bytes, out);
+        } catch (...) {
+            out.abort();
+            throw;
+        }
         if (num_rows) *num_rows = n;
     });
 }
@@ -1623,30 +1823,37 @@ int rj_result_fetch(rj_ctx* ctx, const rj_result* r, uint32_t col, void* const* 
             RJ_CUDA(cudaStreamSynchronize(ctx->stream));
             return;
         }
-        ensure_pinned(ctx);
-        const uint64_t chunk_pages = rj_ctx::kStageBytes / RJ_PAGE_SIZE;
-        // two-slot ring: the D2H copy of chunk k+1 overlaps the host scatter of chunk k
-        auto issue = [&](uint64_t p0, int slot) {
-            const uint64_t cnt = std::min<uint64_t>(chunk_pages, rc.n_pages - p0);
-            RJ_CUDA(cudaMemcpyAsync(ctx->pinned[slot], rc.pages->as<uint8_t>() + p0 * RJ_PAGE_SIZE, cnt * RJ_PAGE_SIZE,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-            RJ_CUDA(cudaEventRecord(ctx->pinned_ev[slot], ctx->stream));
-        };
-        issue(0, 0);
-        int slot = 0;
-        for (uint64_t p0 = 0; p0 < rc.n_pages; p0 += chunk_pages, slot ^= 1) {
-            const uint64_t cnt = std::min<uint64_t>(chunk_pages, rc.n_pages - p0);
-            if (p0 + chunk_pages < rc.n_pages) issue(p0 + chunk_pages, slot ^ 1);
-            RJ_CUDA(cudaEventSynchronize(ctx->pinned_ev[slot]));
-            const uint8_t* stage = ctx->pinned[slot];
-            parallel_for(ctx->host_threads, cnt, [&](uint64_t b, uint64_t e, int) {
-                for (uint64_t i = b; i < e; ++i) {
-                    void* dst = dst_pages ? dst_pages[p0 + i] : static_cast<uint8_t*>(dst_contiguous) + (p0 + i) * RJ_PAGE_SIZE;
-                    std::memcpy(dst, stage + i * RJ_PAGE_SIZE, RJ_PAGE_SIZE);
+        // individually allocated destination pages: D2H into pinned ring buffers, scattered by the pool
+        HostPipe*      hp = ensure_pipe(ctx);
+        TaskGroup      group;
+        const uint8_t* src = rc.pages->as<uint8_t>();
+        const uint64_t per = HostPipe::kBufBytes / RJ_PAGE_SIZE;
+        group.open();
+        try {
+            for (uint64_t q = 0; q < rc.n_pages; q += per) {
+                const uint64_t m = std::min<uint64_t>(per, rc.n_pages - q);
+                PinnedBuf* buf = hp->down.acquire();
+                cudaError_t e = cudaMemcpyAsync(buf->p, src + q * RJ_PAGE_SIZE, m * RJ_PAGE_SIZE, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(buf->ev, ctx->stream);
+                if (e != cudaSuccess) {
+                    hp->down.release(buf);
+                    throw CudaError(std::string("page download: ") + cudaGetErrorString(e));
                 }
-            });
+                group.add();
+                TaskGroup* g = &group;
+                hp->waiter.after(buf->ev, [=] {
+                    for (uint64_t i = 0; i < m; ++i) std::memcpy(dst_pages[q + i], buf->p + i * RJ_PAGE_SIZE, RJ_PAGE_SIZE);
+                    hp->down.release(buf);
+                    g->done();
+                });
+            }
+        } catch (...) {
+            group.seal();
+            try { group.wait(); } catch (...) {}
+            throw;
         }
-        // the upload path waits on these events before reusing a slot; they are complete here
+        group.seal();
+        group.wait();
     });
 }
 

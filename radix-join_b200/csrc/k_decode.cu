@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kDecWarps * 32)
 // stay in the page buffer and are addressed through the descriptor (late materialisation).
 __global__ void __launch_bounds__(128)
     decode_varchar_kernel(const uint8_t* __restrict__ pages, uint64_t n_pages, const uint64_t* __restrict__ row_start,
-                          uint64_t* __restrict__ desc, uint32_t* __restrict__ out_valid) {
+                          uint64_t* __restrict__ desc, uint32_t* __restrict__ out_valid, uint32_t* __restrict__ err_flags) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t gw = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nw = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -175,7 +175,26 @@ __global__ void __launch_bounds__(128)
         const uint32_t hdr = *reinterpret_cast<const uint32_t*>(pg);
         const uint32_t n_r = hdr & 0xffffu, n_v = hdr >> 16;
         const uint64_t r0  = row_start[p];
-        if (n_r == 0xfffeu) continue; // continuation: belongs to the preceding 0xffff page
+        if (n_r == 0xfffeu) {
+            // continuation: its chars belong to the row BEFORE it (build_table.cpp:392-405).  After a
+            // 0xffff / 0xfffe page that is the long string being assembled; after a regular page the
+            // reference appends to that page's last row if it is a string (handled below, where that
+            // page is decoded) and throws "long string page 0xfffe must follows a string" if it is NULL.
+            if (lane == 0 && err_flags != nullptr) {
+                bool ok = p > 0;
+                if (ok) {
+                    const uint8_t* pv  = pg - RJ_PAGE;
+                    const uint32_t ph  = *reinterpret_cast<const uint32_t*>(pv);
+                    const uint32_t pnr = ph & 0xffffu, pnv = ph >> 16;
+                    if (pnr < 0xfffeu) {
+                        const uint8_t* pbm = pv + RJ_PAGE - ((pnr + 7) >> 3);
+                        ok = pnr > 0 && pnv > 0 && ((pbm[(pnr - 1) >> 3] >> ((pnr - 1) & 7)) & 1u);
+                    }
+                }
+                if (!ok) atomicOr(err_flags, RJ_ERR_ORPHAN_LONG_PAGE);
+            }
+            continue;
+        }
         if (n_r == 0xffffu) {
             if (lane == 0) {
                 // total length = this page's chars + every following 0xfffe page (build_table.cpp:392-405)
@@ -214,6 +233,23 @@ __global__ void __launch_bounds__(128)
             running += __popc(word);
             if (out_valid != nullptr && lane == 0 && word) or_valid_word(out_valid, r0 + base, word);
         }
+        // a 0xfffe page right behind this one continues its LAST row (see above): that row becomes a chain
+        __syncwarp();
+        if (lane == 0 && n_r > 0 && n_v > 0 && n_v <= 4094 && p + 1 < n_pages) {
+            const uint32_t h2 = *reinterpret_cast<const uint32_t*>(pg + RJ_PAGE);
+            if ((h2 & 0xffffu) == 0xfffeu && ((bm[(n_r - 1) >> 3] >> ((n_r - 1) & 7)) & 1u)) {
+                const uint32_t end   = offs[n_v - 1];
+                const uint32_t start = n_v > 1 ? offs[n_v - 2] : 0u;
+                uint64_t total = end - start;
+                for (uint64_t q = p + 1; q < n_pages; ++q) {
+                    const uint32_t hq = *reinterpret_cast<const uint32_t*>(pages + q * RJ_PAGE);
+                    if ((hq & 0xffffu) != 0xfffeu) break;
+                    total += hq >> 16;
+                }
+                if (total > RJ_DESC_LEN_MASK) total = RJ_DESC_LEN_MASK;
+                desc[r0 + n_r - 1] = (data + start) | (total << RJ_DESC_LEN_SHIFT) | RJ_DESC_LONG;
+            }
+        }
     }
 }
 
@@ -237,16 +273,12 @@ void launch_decode_fixed(const void* pages, uint64_t n_pages, int type, const ui
     const uint8_t* pg = static_cast<const uint8_t*>(pages);
     if (type == RJ_INT32) {
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(decode_fixed_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(decode_fixed_kernel<uint32_t>, smem);
         decode_fixed_kernel<uint32_t><<<blocks, kDecWarps * 32, smem, s>>>(pg, n_pages, row_start,
                                                                           static_cast<uint32_t*>(values), valid);
     } else {
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(decode_fixed_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(decode_fixed_kernel<uint64_t>, smem);
         decode_fixed_kernel<uint64_t><<<blocks, kDecWarps * 32, smem, s>>>(pg, n_pages, row_start,
                                                                           static_cast<uint64_t*>(values), valid);
     }
@@ -254,11 +286,11 @@ void launch_decode_fixed(const void* pages, uint64_t n_pages, int type, const ui
 }
 
 void launch_decode_varchar(const void* pages, uint64_t n_pages, const uint64_t* row_start, uint64_t* desc,
-                           uint32_t* valid, int sm_count, cudaStream_t s) {
+                           uint32_t* valid, int sm_count, cudaStream_t s, uint32_t* err_flags) {
     if (n_pages == 0) return;
     uint64_t want = (n_pages + 3) / 4;
     unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 8 ? want : static_cast<uint64_t>(sm_count) * 8);
-    decode_varchar_kernel<<<blocks, 128, 0, s>>>(static_cast<const uint8_t*>(pages), n_pages, row_start, desc, valid);
+    decode_varchar_kernel<<<blocks, 128, 0, s>>>(static_cast<const uint8_t*>(pages), n_pages, row_start, desc, valid, err_flags);
     RJ_LAUNCH_CHECK();
 }
 

@@ -158,6 +158,19 @@ __global__ void __launch_bounds__(256) bytes_to_bitmap_kernel(const uint8_t* __r
     }
 }
 
+__global__ void __launch_bounds__(256) count_nulls_kernel(const uint32_t* __restrict__ valid, const uint32_t* __restrict__ idx, uint64_t n,
+                                                          uint32_t idx_mask, unsigned long long* __restrict__ out) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    uint32_t mine = 0;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t r = idx != nullptr ? (idx[i] & idx_mask) : i;
+        mine += test_bit(valid, r) ? 0u : 1u;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(RJ_FULL_MASK, mine, d);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, static_cast<unsigned long long>(mine));
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint64_t n) {
     uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -212,6 +225,15 @@ void launch_bytes_to_bitmap(const uint8_t* bytes, uint64_t n, uint32_t* out, int
     uint64_t want = (n + 255) / 256;
     unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 16 ? want : static_cast<uint64_t>(sm_count) * 16);
     bytes_to_bitmap_kernel<<<blocks, 256, 0, s>>>(bytes, n, out);
+    RJ_LAUNCH_CHECK();
+}
+
+void launch_count_nulls(const uint32_t* valid, const uint32_t* idx, uint64_t n, uint32_t idx_mask, unsigned long long* out,
+                        int sm_count, cudaStream_t s) {
+    if (n == 0 || valid == nullptr) return;
+    uint64_t want = (n + 255) / 256;
+    unsigned blocks = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 8 ? want : static_cast<uint64_t>(sm_count) * 8);
+    count_nulls_kernel<<<blocks, 256, 0, s>>>(valid, idx, n, idx_mask, out);
     RJ_LAUNCH_CHECK();
 }
 

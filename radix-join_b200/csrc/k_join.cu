@@ -500,7 +500,7 @@ template <typename K>
 void run_join(const JoinLaunch& L, int sm_count, cudaStream_t s) {
     const size_t smem = Table<K>::kBytes + 8 * kOutCap;
     static SmemConfigured cfg;
-    if (cfg.raise(smem)) RJ_CUDA(cudaFuncSetAttribute(join_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cfg.ensure(join_kernel<K>, smem);
     JoinArgs a;
     a.bkeys = L.bkeys; a.bidx = L.bidx; a.bvalid = L.bvalid;
     a.pkeys = L.pkeys; a.pidx = L.pidx; a.pvalid = L.pvalid;

@@ -550,15 +550,11 @@ void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n,
     if (blocks == 0) blocks = 1;
     if (key_bytes == 4) {
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(radix_hist_kernel<uint32_t>, smem);
         radix_hist_kernel<uint32_t><<<blocks, threads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, n, shift, bits, hist);
     } else {
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(radix_hist_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(radix_hist_kernel<uint64_t>, smem);
         radix_hist_kernel<uint64_t><<<blocks, threads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, n, shift, bits, hist);
     }
     RJ_LAUNCH_CHECK();
@@ -617,18 +613,14 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
     const size_t smem = static_cast<size_t>(n_tma) * tile * 8;
     if (key_bytes == 4) {
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(scatter_tile_kernel<uint32_t, false>, smem);
         blocks = resident_grid(scatter_tile_kernel<uint32_t, false>, smem, n_tiles, sm_count);
         scatter_tile_kernel<uint32_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint32_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
             static_cast<uint32_t*>(keys_out), idx_out, pay, flags, n_tma);
     } else {
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(scatter_tile_kernel<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(scatter_tile_kernel<uint64_t, false>, smem);
         blocks = resident_grid(scatter_tile_kernel<uint64_t, false>, smem, n_tiles, sm_count);
         scatter_tile_kernel<uint64_t, false><<<blocks, kScatterThreads, smem, s>>>(
             static_cast<const uint64_t*>(keys), valid, idx_in, n, nullptr, nullptr, 0, shift, bits, cursor,
@@ -688,18 +680,14 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
     if (key_bytes == 4) {
         auto kern = scatter_tile_kernel<uint32_t, false, true>;
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(kern, smem);
         const unsigned blocks = resident_grid(kern, smem, n_tiles, sm_count);
         kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint32_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift,
                                                    bits, cursor, nullptr, nullptr, pay, flags, n_tma, d_dsts);
     } else {
         auto kern = scatter_tile_kernel<uint64_t, false, true>;
         static SmemConfigured cfg;
-        if (cfg.raise(smem)) {
-            RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        cfg.ensure(kern, smem);
         const unsigned blocks = resident_grid(kern, smem, n_tiles, sm_count);
         kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint64_t*>(keys), valid, nullptr, n, nullptr, nullptr, 0, shift,
                                                    bits, cursor, nullptr, nullptr, pay, flags, n_tma, d_dsts);

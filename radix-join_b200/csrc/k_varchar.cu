@@ -46,15 +46,28 @@ __device__ __forceinline__ void for_each_piece(const uint8_t* __restrict__ pages
         if (b > a) f(pages + s.addr + a, b - a, a);
         return;
     }
-    // chain of pages: chars of page q start at q*8192+4, their count is the page's n_v
-    uint64_t q   = (s.addr - 4) / RJ_PAGE;
+    // chain of pages.  Its head is a 0xffff page (n_v chars at +4) or -- malformed input the reference
+    // nevertheless decodes by appending (build_table.cpp:392-405) -- the last string of a regular page,
+    // which runs from its address to the end of that page's character data; every following 0xfffe page
+    // adds its n_v chars at +4.
+    uint64_t q   = s.addr / RJ_PAGE;
     uint32_t pos = 0;
+    bool     head = true;
     while (pos < b) {
-        const uint8_t* pg = pages + q * RJ_PAGE;
-        const uint32_t n  = *reinterpret_cast<const uint32_t*>(pg) >> 16;
+        const uint8_t* pg  = pages + q * RJ_PAGE;
+        const uint32_t hdr = *reinterpret_cast<const uint32_t*>(pg);
+        const uint8_t* src = pg + 4;
+        uint32_t       n   = hdr >> 16;
+        if (head && (hdr & 0xffffu) != 0xffffu) {
+            const uint32_t n_v = hdr >> 16;
+            const uint32_t end = 4 + 2 * n_v + (n_v ? reinterpret_cast<const uint16_t*>(pg + 4)[n_v - 1] : 0u);
+            src = pages + s.addr;
+            n   = end - static_cast<uint32_t>(s.addr - q * RJ_PAGE);
+        }
+        head = false;
         const uint32_t lo = pos > a ? pos : a;
         const uint32_t hi = pos + n < b ? pos + n : b;
-        if (hi > lo) f(pg + 4 + (lo - pos), hi - lo, lo);
+        if (hi > lo) f(src + (lo - pos), hi - lo, lo);
         pos += n;
         ++q;
         if (n == 0) break; // malformed chain

@@ -14,6 +14,7 @@
 #define RJ_DESC_LEN_MASK  0x7FFFFFull
 #define RJ_DESC_LONG      (1ull << 63)
 
+
 namespace rj {
 
 // ---- hashing --------------------------------------------------------------------------------------

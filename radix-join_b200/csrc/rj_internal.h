@@ -12,6 +12,9 @@
 
 #include "../../include/rj_b200.h"
 
+// bits of the context's device-visible error word (malformed input detected by a kernel)
+#define RJ_ERR_ORPHAN_LONG_PAGE 1u
+
 namespace rj {
 
 struct CudaError: std::runtime_error {
@@ -39,13 +42,16 @@ extern std::atomic<uint64_t> g_kernel_launches;
 // each one (a process may hold contexts on several GPUs)
 struct SmemConfigured {
     size_t bytes[64] = {};
-    bool raise(size_t want) {
+    // raise the kernel's dynamic shared-memory limit to `want` if it is below; the new size is recorded
+    // only once the attribute call has succeeded, so a refused request does not poison later ones
+    template <class Kern>
+    void ensure(Kern kern, size_t want) {
         int dev = 0;
         cudaGetDevice(&dev);
         size_t& have = bytes[dev & 63];
-        if (want <= have) return false;
+        if (want <= have) return;
+        RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(want)));
         have = want;
-        return true;
     }
 };
 
@@ -57,7 +63,7 @@ constexpr uint32_t kJoinProbeChunk = 16384; // probe tuples per work unit
 // tuples per scatter tile: 256 threads x 16 (4-byte keys) or x 8 (8-byte keys)
 constexpr uint32_t scatter_tile(int key_bytes) { return key_bytes == 4 ? 4096u : 2048u; }
 constexpr int      kMaxPassBits    = 8;     // radix bits per scatter pass
-constexpr int      kMaxTotalBits   = 16;
+constexpr int      kMaxTotalBits   = 15;    // 2^15 histogram bins = 128 KB of shared memory (2^16 would not fit one CTA)
 
 // Device-resident partition plan, filled by launch_partition_plan (single small kernel, no host sync)
 struct PartitionPlanDev {
@@ -91,8 +97,9 @@ void launch_page_rows(const void* pages, uint64_t n_pages, int type, uint32_t* r
                       cudaStream_t s);
 void launch_decode_fixed(const void* pages, uint64_t n_pages, int type, const uint64_t* row_start,
                          void* values, uint32_t* valid, int sm_count, cudaStream_t s);
+// err_flags (may be NULL): device-visible word that collects RJ_ERR_* bits of malformed input
 void launch_decode_varchar(const void* pages, uint64_t n_pages, const uint64_t* row_start, uint64_t* desc,
-                           uint32_t* valid, int sm_count, cudaStream_t s);
+                           uint32_t* valid, int sm_count, cudaStream_t s, uint32_t* err_flags = nullptr);
 
 // ---- k_partition.cu -------------------------------------------------------------------------------
 void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift,
@@ -169,6 +176,9 @@ void launch_encode_fixed(const void* values, const uint32_t* valid, const uint8_
                          const uint32_t* vidx, uint64_t n, int type, void* pages_out, int sm_count, cudaStream_t s,
                          uint32_t idx_mask = 0xffffffffu, int valid_bit = -1);
 void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
+// *out += number of NULL cells among rows idx[0..n) of a column (idx NULL = identity; valid NULL = no NULLs)
+void launch_count_nulls(const uint32_t* valid, const uint32_t* idx, uint64_t n, uint32_t idx_mask, unsigned long long* out,
+                        int sm_count, cudaStream_t s);
 void launch_bitmap_to_bytes(const uint32_t* bits, uint64_t n, uint8_t* out, int sm_count, cudaStream_t s);
 void launch_bytes_to_bitmap(const uint8_t* bytes, uint64_t n, uint32_t* out, int sm_count, cudaStream_t s);
 

@@ -345,6 +345,9 @@ class Relation:
 
     def __init__(self, n_rows, key, payloads):
         # key / payloads: (pages_ptr, n_pages, type, has_nulls)
+        if int(key[2]) != 0:
+            # the exchange, the owner histogram and the local join all move 4-byte keys
+            raise ValueError("distributed joins take INT32 keys only (got key type %d)" % int(key[2]))
         self.n_rows, self.key, self.payloads = n_rows, key, payloads
 
 

@@ -296,8 +296,9 @@ def make_c2_device(ctx, n_build, n_probe, rank=0, world=1, theta=0.75, null_frac
     return out
 
 
-def make_c1_device(ctx, n_build, n_probe, device="cuda"):
-    """Config 1: single INT32 equi-join, unique foreign keys, no payload."""
+def make_c1_device(ctx, n_build, n_probe, device="cuda", checksum=False):
+    """Config 1: single INT32 equi-join, unique foreign keys, no payload.  checksum=True also derives the
+    expected multiset checksum of the result (k, k) for every probe key, without joining."""
     import torch
     out = DeviceTables()
     g = torch.Generator(device=device)
@@ -315,6 +316,13 @@ def make_c1_device(ctx, n_build, n_probe, device="cuda"):
     for t in tables:
         out.plan.new_input(t)
     out.n_build, out.n_probe, out.expected_rows = n_build, n_probe, n_probe
+    if checksum:
+        acc = (0, 0, 0)
+        for lo in range(0, n_probe, 1 << 25):
+            k = sk[lo:lo + (1 << 25)].to(torch.int64)
+            ok = torch.ones_like(k, dtype=torch.bool)
+            acc = checksum_add(acc, row_hash_torch([(k, ok), (k, ok)]))
+        out.expected_checksum = acc
     return out
 
 

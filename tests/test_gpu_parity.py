@@ -172,6 +172,93 @@ def test_errors_surface_as_engine_errors(ctx):
     check_plan(H.single_join_plan(t, t, [INT32], [INT32], 0, 0, True), ctx, expect_rows=1)
 
 
+def _mistyped_plan(declared):
+    tl = H.table_from_python([INT32, INT64], [(1, 10), (2, None), (3, 30), (4, None)])
+    tr = H.table_from_python([INT32], [(1,), (2,), (3,), (4,), (2,)])
+    plan = rj.Plan()
+    plan.new_scan_node(0, [(0, INT32), (1, declared)])  # column 1 physically holds INT64
+    plan.new_scan_node(1, [(0, INT32)])
+    plan.new_join_node(True, 0, 1, 0, 0, [(0, INT32), (1, declared)])
+    plan.new_input(tl)
+    plan.new_input(tr)
+    plan.root = 2
+    return plan
+
+
+def test_mistyped_root_attribute_keeps_only_the_null_rows(ctx):
+    """Table::to_columnar silently skips cells whose alternative is not the column type and keeps the
+    NULLs (src/build_table.cpp:484-501): the column comes out shorter than num_rows.  Same here."""
+    plan = _mistyped_plan(INT32)
+    got = rj.execute(plan, ctx)
+    for impl in (["ref"] if orc.available("ref") else []) + ["port"]:
+        want = orc.execute(plan, impl=impl)
+        assert got.num_rows == want.num_rows == 5
+        assert [int(c.type) for c in got.columns] == [int(c.type) for c in want.columns] == [INT32, INT32]
+        for gc, wc in zip(got.columns, want.columns):
+            n = sum(int(pg[0]) | int(pg[1]) << 8 for pg in wc.pages)
+            assert n == sum(int(pg[0]) | int(pg[1]) << 8 for pg in gc.pages)
+            assert orc.decode(gc, n).to_python() == orc.decode(wc, n).to_python()
+    assert orc.decode(got.columns[1], 3).to_python() == [None, None, None]
+    # no NULL among the selected rows: the column has no page at all
+    plan.inputs[1] = H.table_from_python([INT32], [(1,), (3,)])
+    got = rj.execute(plan, ctx)
+    want = orc.execute(plan, impl="port")
+    assert got.num_rows == want.num_rows == 2 and got.columns[1].n_pages == want.columns[1].n_pages == 0
+
+
+def test_mistyped_varchar_root_attribute_throws_like_the_reference(ctx):
+    """src/build_table.cpp:667-669: 'not string or null' at the first non-NULL cell; all-NULL passes"""
+    plan = _mistyped_plan(VARCHAR)
+    with pytest.raises(orc.OracleError, match="not string or null"):
+        orc.execute(plan, impl="port")
+    with pytest.raises(rj.EngineError, match="not string or null"):
+        rj.execute(plan, ctx)
+    plan.inputs[1] = H.table_from_python([INT32], [(2,), (4,), (4,)])  # only rows whose INT64 cell is NULL
+    check_plan(plan, ctx, expect_rows=3)
+
+
+def _with_orphan_page(rows):
+    t = H.table_from_python([INT32, VARCHAR], rows)
+    orphan = np.zeros((1, 8192), np.uint8)
+    orphan[0, 0], orphan[0, 1], orphan[0, 2] = 0xfe, 0xff, 3
+    orphan[0, 4:7] = [120, 121, 122]
+    t.columns[1] = rj.Column(VARCHAR, np.concatenate([t.columns[1].pages, orphan]))
+    plan = rj.Plan()
+    plan.new_scan_node(0, [(0, INT32), (1, VARCHAR)])
+    plan.new_input(t)
+    plan.root = 0
+    return plan
+
+
+def test_continuation_page_after_a_regular_string_is_appended(ctx):
+    """a 0xfffe page extends the row before it, whatever page that row came from
+    (src/build_table.cpp:392-405)"""
+    plan = _with_orphan_page([(1, None), (2, "bb")])
+    got = check_plan(plan, ctx, expect_rows=2)
+    assert H.rows_of(got) == [(1, None), (2, b"bbxyz")]
+    # ... and through a join, where the string is re-encoded from its descriptor
+    t2 = H.table_from_python([INT32], [(2,), (2,), (1,)])
+    p2 = rj.Plan()
+    p2.new_scan_node(0, [(0, INT32), (1, VARCHAR)])
+    p2.new_scan_node(1, [(0, INT32)])
+    p2.new_join_node(False, 0, 1, 0, 0, [(1, VARCHAR), (2, INT32)])
+    p2.new_input(plan.inputs[0])
+    p2.new_input(t2)
+    p2.root = 2
+    check_plan(p2, ctx, expect_rows=3)
+
+
+def test_continuation_page_after_a_null_row_is_an_error(ctx):
+    """the reference throws 'long string page 0xfffe must follows a string' (build_table.cpp:401-402;
+    from a pool thread, so its process terminates); the engine raises the same message"""
+    plan = _with_orphan_page([(1, "aa"), (2, None)])
+    with pytest.raises(orc.OracleError, match="0xfffe must follows a string"):
+        orc.execute(plan, impl="port")
+    with pytest.raises(rj.EngineError, match="0xfffe must follows a string"):
+        rj.execute(plan, ctx)
+    check_plan(_with_orphan_page([(1, None), (2, "bb")]), ctx, expect_rows=2)  # the context survives
+
+
 def test_duplicates_on_both_sides_overflow_the_first_guess(ctx):
     """M >> max(|build|, |probe|): the speculative output buffer overflows and the exact count sizes
     the second run ('unknown, possibly exploding output cardinality')"""
