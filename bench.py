@@ -74,53 +74,76 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs a few hundred
+    ms to produce its first line, longer than a short timed region lasts, so the sampler starts before the
+    warm-up steps and mark() / stop() bracket the timed region: samples whose timestamp falls inside it are
+    used; if the region was too short to catch two samples, the samples of the warm-up steps (the same
+    kernels, same load) are used as well and the line says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
+        self.t_start = self.t_mark = None
 
     def start(self):
+        self.t_start = time.time()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """the timed region starts now"""
+        self.t_mark = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
+        t_end = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lo, hi):
+            sm, mx, reasons = [], [], set()
+            for t, ln in self.lines:
+                if not (lo <= t <= hi):
+                    continue
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        t0 = self.t_mark if self.t_mark is not None else self.t_start
+        sm, mx, reasons = parse(t0, t_end + 0.06)  # a sample is stamped when it is read: allow one period
+        window = "timed region"
+        if len(sm) < 2:
+            sm, mx, reasons = parse(self.t_start, t_end + 0.06)
+            window = "warm-up + timed region (the timed region alone is shorter than two sampling periods)"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -175,8 +198,8 @@ def run_reference_arm(args):
     if rank != 0:
         return  # the reference is a single-process CPU program: rank 0 alone runs it
     if args.workload == "job":
-        from radix_join_b200 import job_bench
-        return job_bench.run(args, impl="reference")
+        import bench_job
+        return bench_job.run(args, impl="reference")
     div = reference_div(args.workload, args.steps, args.warmup)
     value, ms, kind, cores, sample = reference_run(args.workload, div, args.steps, args.warmup)
     line = {
@@ -221,16 +244,17 @@ def run_single_gpu(args):
         return rows, pages
 
     rows, out_pages = dt.expected_rows, 0
+    sampler = ClockSampler(0)
+    sampler.start()
     for _ in range(args.warmup):
         rows, out_pages = step()
     assert rows == dt.expected_rows, (rows, dt.expected_rows)
 
     ctx.profile_enable(True)
     ctx.profile_reset()
-    sampler = ClockSampler(0)
-    sampler.start()
     launches0 = ctx.kernel_launches()
     torch.cuda.synchronize()
+    sampler.mark()
     ms_total = 0.0
     if flush is None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,7 +294,7 @@ def run_single_gpu(args):
     #      launching stream, inside the timed region above) -----------------------------------------
     peak, peak_src = measured_peak()
     stages = {}
-    for name in ("row_offsets", "decode", "histogram", "scatter", "join", "gather", "encode"):
+    for name in ("row_offsets", "decode", "histogram", "scatter", "join", "join_emit", "gather", "encode"):
         st = prof[name]
         if st["launches"] == 0:
             continue
@@ -363,8 +387,8 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.workload == "job":
-        from radix_join_b200 import job_bench
-        return job_bench.run(args, impl="ours")
+        import bench_job
+        return bench_job.run(args, impl="ours")
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         from radix_join_b200 import dist_bench
         w = WORKLOADS["c2"]

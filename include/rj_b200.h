@@ -131,8 +131,9 @@ int rj_execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes
  * Contest::execute (src/execute.cpp:316-324) calls.  Same windowed pipeline as rj_execute_streamed; in
  * addition worker threads gather the input pages into pinned staging buffers and scatter the result
  * pages out of them, so host copies, both DMA directions and the kernels overlap.
- *   new_pages   allocate n pages of 8192 bytes (8-byte aligned) into out[0..n); called on the calling
- *               thread only; non-zero = failure
+ *   new_pages   allocate n pages of 8192 bytes (8-byte aligned) into out[0..n); non-zero = failure.
+ *               Called from the engine's WORKER threads, several at a time (the worker that fills a
+ *               batch of pages allocates it), so it must be thread-safe -- `new Page` is
  *   append      hand over the next n filled pages of result column `column` (ownership passes to the
  *               caller); called on the calling thread, for every column in the same window order, so
  *               the columns stay row-aligned; never called for a column without pages
@@ -314,6 +315,7 @@ enum rj_stage {
     RJ_ST_GATHER,        /* row-id / key gathers                           */
     RJ_ST_ENCODE,        /* gather + page encode                           */
     RJ_ST_D2H,           /* D2H copies + host page scatter                 */
+    RJ_ST_JOIN_EMIT,     /* root join fused with page output               */
     RJ_ST_COUNT
 };
 typedef struct rj_stage_stat_t {

@@ -80,8 +80,8 @@ class rj_stage_stat_t(C.Structure):
     _fields_ = [("ms", C.c_double), ("launches", C.c_uint64), ("bytes", C.c_uint64)]
 
 
-RJ_ST_COUNT = 9
-STAGE_NAMES = ["h2d", "row_offsets", "decode", "histogram", "scatter", "join", "gather", "encode", "d2h"]
+RJ_ST_COUNT = 10
+STAGE_NAMES = ["h2d", "row_offsets", "decode", "histogram", "scatter", "join", "gather", "encode", "d2h", "join_emit"]
 
 _vp = C.c_void_p
 _u64 = C.c_uint64

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <deque>
+#include <emmintrin.h>
 #include <map>
 #include <mutex>
 #include <set>
@@ -340,6 +341,29 @@ struct ColCounters {
 // ring buffers by pool workers, 512 pages per task; each task issues its own DMA, so the gather of
 // one buffer overlaps the transfer of the previous ones.  A contiguous host buffer is one DMA straight
 // from the caller's memory.  `counters` (optional) receives the row / non-NULL totals of the page headers.
+// One 8 KB page, host to host.  Neither the staging buffers (read next by the DMA engine) nor fresh
+// result pages (read next by the caller, much later) are wanted in the cache, and a plain store makes
+// the core read the destination line first: 16-byte non-temporal stores cut the memory traffic of every
+// page copy by a third.  RJ_NT_COPY=0 falls back to memcpy.
+inline void copy_page(void* dst, const void* src) {
+    static const bool nt = !(getenv("RJ_NT_COPY") && atoi(getenv("RJ_NT_COPY")) == 0);
+    if (!nt || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u)) {
+        std::memcpy(dst, src, RJ_PAGE_SIZE);
+        return;
+    }
+    const __m128i* s = static_cast<const __m128i*>(src);
+    __m128i*       d = static_cast<__m128i*>(dst);
+    for (int i = 0; i < static_cast<int>(RJ_PAGE_SIZE / 16); i += 4) {
+        const __m128i a = _mm_load_si128(s + i), b = _mm_load_si128(s + i + 1), c = _mm_load_si128(s + i + 2), e = _mm_load_si128(s + i + 3);
+        _mm_stream_si128(d + i, a);
+        _mm_stream_si128(d + i + 1, b);
+        _mm_stream_si128(d + i + 2, c);
+        _mm_stream_si128(d + i + 3, e);
+    }
+}
+// non-temporal stores are weakly ordered: fence before another agent (DMA engine, another thread) reads
+inline void copy_fence() { _mm_sfence(); }
+
 void upload_pages_async(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t cnt, uint8_t* dst, cudaStream_t stream,
                         TaskGroup* group, ColCounters* counters) {
     if (cnt == 0) return;
@@ -376,13 +400,14 @@ void upload_pages_async(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t
                 uint64_t r = 0, v = 0;
                 for (uint64_t i = 0; i < m; ++i) {
                     const uint8_t* pg = static_cast<const uint8_t*>(pages[q + i]);
-                    std::memcpy(buf->p + i * RJ_PAGE_SIZE, pg, RJ_PAGE_SIZE);
+                    copy_page(buf->p + i * RJ_PAGE_SIZE, pg);
                     if (counters) page_counts(pg, type, &r, &v);
                 }
                 if (counters) {
                     counters->rows.fetch_add(r, std::memory_order_relaxed);
                     counters->vals.fetch_add(v, std::memory_order_relaxed);
                 }
+                copy_fence();
                 cudaError_t e = cudaMemcpyAsync(dst + q * RJ_PAGE_SIZE, buf->p, m * RJ_PAGE_SIZE, cudaMemcpyHostToDevice, stream);
                 if (e == cudaSuccess) e = cudaEventRecord(buf->ev, stream);
                 hp->up.release(buf);
@@ -568,6 +593,7 @@ struct Exec {
     Buf  side_rows(const JoinSide& sd, uint64_t m);
     Buf  rid_of(const Rel& r, int leaf);
     std::unique_ptr<rj_result> root(uint64_t n, const Rel& r);
+    std::unique_ptr<rj_result> root_fused(uint64_t n);
     ResultColumn encode_varchar(const DecodedCol& col, const uint32_t* idx, uint64_t n);
 };
 
@@ -575,7 +601,7 @@ struct Exec {
 // `bias` (< 256) rows of padding precede the first decoded row: a row window that starts in the middle
 // of a page is shifted so that its first row lands on a validity-word boundary.
 void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_pages, int type, uint64_t rows,
-                  bool need_valid, DecodedCol* out, uint32_t bias = 0) {
+                  bool need_valid, DecodedCol* out, uint32_t bias = 0, uint64_t covered_rows = 0) {
     out->type = type;
     out->rows = rows;
     out->pages = pages;
@@ -599,8 +625,12 @@ void decode_pages(rj_ctx* ctx, cudaStream_t s, const uint8_t* pages, uint64_t n_
         // 8192 * pages read + rows * w + rows / 8 written
         StageScope sc(ctx, RJ_ST_DECODE, s, 1, n_pages * uint64_t(RJ_PAGE_SIZE) + rows * w + rows / 8);
         if (need_valid && rows * w) {
-            // rows the pages do not cover stay NULL; covered NULL rows must read as 0
-            RJ_CUDA(cudaMemsetAsync(out->values->p, 0, rows * w, s));
+            // rows the pages do not cover stay NULL and read as 0 (the decode kernel itself stores 0 for the
+            // NULL rows it covers): only the uncovered head / tail is cleared, not the whole array
+            uint8_t* v = out->values->as<uint8_t>();
+            const uint64_t lo = std::min<uint64_t>(bias, rows), hi = std::min<uint64_t>(rows, bias + covered_rows);
+            if (lo) RJ_CUDA(cudaMemsetAsync(v, 0, lo * w, s));
+            if (hi < rows) RJ_CUDA(cudaMemsetAsync(v + hi * w, 0, (rows - hi) * w, s));
         }
         if (type == RJ_VARCHAR) {
             launch_decode_varchar(pages, n_pages, row_start, out->values->as<uint64_t>(),
@@ -628,7 +658,7 @@ const DecodedCol& Exec::column(uint32_t t, uint32_t c) {
         const uint64_t first = bias + cd.skip_rows; // multiple of 32
         const uint64_t total = std::max<uint64_t>(bias + cd.page_rows, first + td.num_rows);
         DecodedCol full;
-        decode_pages(ctx, s, cd.pages, cd.n_pages, cd.type, total, cd.window_nulls, &full, bias);
+        decode_pages(ctx, s, cd.pages, cd.n_pages, cd.type, total, cd.window_nulls, &full, bias, cd.page_rows);
         DecodedCol d;
         d.type = cd.type;
         d.rows = td.num_rows;
@@ -653,7 +683,7 @@ const DecodedCol& Exec::column(uint32_t t, uint32_t c) {
     if (cd.n_pages && !cd.pages) throw EngineError("column was not uploaded");
     DecodedCol d;
     const bool need_valid = cd.non_null != td.num_rows;
-    decode_pages(ctx, s, cd.pages, cd.n_pages, cd.type, td.num_rows, need_valid, &d);
+    decode_pages(ctx, s, cd.pages, cd.n_pages, cd.type, td.num_rows, need_valid, &d, 0, cd.page_rows);
     return decoded.emplace(key, std::move(d)).first->second;
 }
 
@@ -676,6 +706,13 @@ Buf Exec::gather_u32(const Buf& src, const Buf& idx, uint64_t n, uint32_t idx_ma
 }
 
 // ---- the join pipeline: histogram -> plan -> scatter (1 or 2 passes) -> shared-memory build+probe ------
+// radix bits of the first of two scatter passes (RJ_PASS1_BITS overrides: profiling experiments)
+int pass1_bits_of(int total_bits) {
+    static const int forced = getenv("RJ_PASS1_BITS") ? atoi(getenv("RJ_PASS1_BITS")) : 0;
+    if (forced > 0 && forced <= kMaxPassBits && total_bits - forced > 0 && total_bits - forced <= kMaxPassBits) return forced;
+    return (total_bits + 1) / 2;
+}
+
 int choose_total_bits(uint64_t n_build) {
     if (n_build <= kJoinBuildCap) return 0; // small build side: one table, no partitioning
     int b = 0;
@@ -688,7 +725,7 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
     const void* pk = P.keys; const uint32_t* pv = P.valid; const uint64_t np = P.n;
     if (nb >= 0xffffffffull || np >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
     const int      bits  = choose_total_bits(nb);
-    const int      bits1 = bits > kMaxPassBits ? (bits + 1) / 2 : 0; // two passes above 8 bits
+    const int      bits1 = bits > kMaxPassBits ? pass1_bits_of(bits) : 0; // two passes above 8 bits
     const int      bits2 = bits - bits1;
     const uint32_t nparts = 1u << bits;
     Buf plan_mem = dev_alloc(partition_plan_words(bits, bits1) * 4, s);
@@ -777,9 +814,9 @@ void Exec::join_keys(JoinSide& B, JoinSide& P, int key_bytes, uint64_t* n_out) {
             };
             const RegionFlags fl_b = flags_of(B), fl_p = flags_of(P);
             launch_radix_scatter_regions(tk_b->p, nullptr, pl.reg_b, pl.tile_b, 1u << bits1, nb, key_bytes, 0, bits2,
-                                         pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), fl_b, ctx->sm_count, s);
+                                         pl.cur_b, keys_b->p, idx_b->as<uint32_t>(), fl_b, ScatterPayload{}, ctx->sm_count, s);
             launch_radix_scatter_regions(tk_p->p, nullptr, pl.reg_p, pl.tile_p, 1u << bits1, np, key_bytes, 0, bits2,
-                                         pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), fl_p, ctx->sm_count, s);
+                                         pl.cur_p, keys_p->p, idx_p->as<uint32_t>(), fl_p, ScatterPayload{}, ctx->sm_count, s);
             jl.bkeys = keys_b->p; jl.bidx = idx_b->as<uint32_t>(); jl.bvalid = nullptr; // idx = pass-1 position
             jl.pkeys = keys_p->p; jl.pidx = idx_p->as<uint32_t>(); jl.pvalid = nullptr;
             B.rows_of_pos = ti_b; B.keys_of_pos = tk_b;
@@ -1197,6 +1234,222 @@ std::unique_ptr<rj_result> Exec::root(uint64_t n, const Rel& r) {
     return res;
 }
 
+// ---- root join with page output fused into the join kernel (k_join_emit.cu) -----------------------------
+// Taken when the root is a join of two scans on an INT32 key whose output columns are the key and at most
+// kEmitMaxPay fixed-width columns per side: both sides are partitioned to their final order WITH those
+// columns beside the keys (two scatter passes carry values and validity bytes), and the join kernel
+// writes result pages itself.  Returns null when the plan does not qualify or a table met a duplicate
+// build key; the caller then runs the general path.
+std::unique_ptr<rj_result> Exec::root_fused(uint64_t n) {
+    if (getenv("RJ_NO_FUSED_ROOT") != nullptr) return nullptr; // tests and profiling: force the general path
+    const rj_node_t& nd = node(n);
+    if (!nd.is_join || nd.left >= plan->n_nodes || nd.right >= plan->n_nodes) return nullptr;
+    const rj_node_t &ln = node(nd.left), &rn = node(nd.right);
+    if (ln.is_join || rn.is_join) return nullptr;
+    if (nd.n_output_attrs < 1 || nd.n_output_attrs > static_cast<uint32_t>(kEmitMaxOut)) return nullptr;
+    if (nd.left_attr >= ln.n_output_attrs || nd.right_attr >= rn.n_output_attrs) return nullptr;
+    const rj_node_t& bnode = nd.build_left ? ln : rn;
+    if (bnode.output_attrs[nd.build_left ? nd.left_attr : nd.right_attr].type != RJ_INT32) return nullptr; // key type, :271-273
+    if (ln.base_table_id >= in->tables.size() || rn.base_table_id >= in->tables.size()) return nullptr;
+    for (uint32_t a = 0; a < nd.n_output_attrs; ++a) {
+        const uint64_t src = nd.output_attrs[a].index;
+        if (src >= uint64_t(ln.n_output_attrs) + rn.n_output_attrs) return nullptr;
+    }
+    const Attr la = resolve(nd.left, nd.left_attr), ra = resolve(nd.right, nd.right_attr);
+    const TableDev &tl = in->tables[la.table], &tr = in->tables[ra.table];
+    if (tl.num_rows == 0 || tr.num_rows == 0) return nullptr;
+    if (tl.cols[la.col].type != RJ_INT32 || tr.cols[ra.col].type != RJ_INT32) return nullptr;
+    if (tl.num_rows >= 0xffffffffull || tr.num_rows >= 0xffffffffull) return nullptr;
+    // the table goes on the smaller side, as in the general path
+    const double l_size = static_cast<double>(tl.num_rows) * (la.table == streamed_table ? streamed_scale : 1.0);
+    const double r_size = static_cast<double>(tr.num_rows) * (ra.table == streamed_table ? streamed_scale : 1.0);
+    const bool   table_left = l_size <= r_size;
+    const Attr&  ba = table_left ? la : ra;
+    const Attr&  pa = table_left ? ra : la;
+    const uint64_t nb = (table_left ? tl : tr).num_rows, np = (table_left ? tr : tl).num_rows;
+    int bits = 0;
+    while ((nb >> bits) > kJoinTargetFill && bits < kMaxTotalBits) ++bits;
+    if (bits == 0) return nullptr; // a single small table: nothing to win
+
+    // output columns -> the key or a carried column of one side
+    struct Carry {
+        uint32_t col;
+        int      width;
+    };
+    std::vector<Carry> bcols, pcols;
+    JoinEmitLaunch L;
+    L.n_out = static_cast<int>(nd.n_output_attrs);
+    for (uint32_t a = 0; a < nd.n_output_attrs; ++a) {
+        const Attr at = resolve(n, a);
+        const int  t  = in->tables[at.table].cols[at.col].type;
+        if (t == RJ_VARCHAR || t != nd.output_attrs[a].type) return nullptr;
+        const bool on_build = at.leaf == ba.leaf;
+        if (!on_build && at.leaf != pa.leaf) return nullptr;
+        L.out_width[a] = t == RJ_INT32 ? 4 : 8;
+        if (at.col == (on_build ? ba.col : pa.col)) {
+            L.out_src[a] = 0; // the join key: equal on both sides, never NULL in a match
+            continue;
+        }
+        auto& list = on_build ? bcols : pcols;
+        size_t i = 0;
+        while (i < list.size() && list[i].col != at.col) ++i;
+        if (i == list.size()) {
+            if (list.size() == static_cast<size_t>(kEmitMaxPay)) return nullptr;
+            list.push_back({at.col, L.out_width[a]});
+        }
+        L.out_src[a] = on_build ? 1 : 2;
+        L.out_idx[a] = static_cast<int>(i);
+    }
+    const uint32_t bt = ba.table, pt = pa.table;
+    const DecodedCol& bkey = column(bt, ba.col);
+    const DecodedCol& pkey = column(pt, pa.col);
+    std::vector<const DecodedCol*> bdec, pdec;
+    for (auto& c: bcols) bdec.push_back(&column(bt, c.col));
+    for (auto& c: pcols) pdec.push_back(&column(pt, c.col));
+    L.n_bpay = static_cast<int>(bcols.size());
+    L.n_ppay = static_cast<int>(pcols.size());
+    for (int c = 0; c < L.n_bpay; ++c) {
+        L.bwidth[c] = bcols[c].width;
+        L.bvalid[c] = bdec[c]->valid ? reinterpret_cast<const uint8_t*>(1) : nullptr; // placeholder: "has NULLs" (for the layout)
+    }
+    for (int c = 0; c < L.n_ppay; ++c) L.pwidth[c] = pcols[c].width;
+    for (int a = 0; a < L.n_out; ++a) {
+        const DecodedCol* d = L.out_src[a] == 1 ? bdec[L.out_idx[a]] : (L.out_src[a] == 2 ? pdec[L.out_idx[a]] : nullptr);
+        L.out_nullable[a] = d && d->valid ? 1 : 0;
+    }
+    if (!join_emit_fits(L)) return nullptr;
+
+    // ---- histogram, plan, scatter both sides with their columns to the final partition order -------------
+    const int      bits1 = bits > kMaxPassBits ? pass1_bits_of(bits) : 0;
+    const int      bits2 = bits - bits1;
+    const uint32_t nparts = 1u << bits;
+    Buf plan_mem = dev_alloc(partition_plan_words(bits, bits1) * 4, s);
+    PartitionPlanDev pl;
+    partition_plan_carve(plan_mem->as<uint32_t>(), bits, bits1, &pl);
+    Buf hist = dev_alloc_zero(size_t(2) * nparts * 4, s);
+    {
+        StageScope sc(ctx, RJ_ST_HISTOGRAM, s, 2, (nb + np) * 4);
+        launch_radix_histogram(bkey.values->p, bkey.valid_ptr(), nb, 4, 0, bits, hist->as<uint32_t>(), ctx->sm_count, s);
+        launch_radix_histogram(pkey.values->p, pkey.valid_ptr(), np, 4, 0, bits, hist->as<uint32_t>() + nparts, ctx->sm_count, s);
+    }
+    launch_partition_plan(hist->as<uint32_t>(), hist->as<uint32_t>() + nparts, 0, 0, bits, bits1, 4, pl, s, kEmitBuildCap);
+
+    struct SideOut {
+        Buf keys;
+        Buf val[kEmitMaxPay], ok[kEmitMaxPay];
+    };
+    uint64_t carried_bytes = 0;
+    auto scatter_side = [&](const DecodedCol& key, uint64_t rows, const std::vector<Carry>& cols, const std::vector<const DecodedCol*>& dec,
+                            uint32_t* cur1, uint32_t* cur2, const uint32_t* reg, const uint32_t* tile) {
+        SideOut o;
+        o.keys = dev_alloc(rows * 4 + 64, s);
+        ScatterPayload pay; // values first, then the validity bitmaps (they become one byte per tuple)
+        for (size_t c = 0; c < cols.size(); ++c) {
+            o.val[c] = dev_alloc(rows * cols[c].width + 64, s);
+            pay.src[pay.n] = dec[c]->values->p;
+            pay.dst[pay.n] = o.val[c]->p;
+            pay.width[pay.n++] = cols[c].width;
+            carried_bytes += 2 * rows * cols[c].width;
+        }
+        for (size_t c = 0; c < cols.size(); ++c) {
+            if (!dec[c]->valid) continue;
+            o.ok[c] = dev_alloc(rows + 64, s);
+            pay.src[pay.n] = dec[c]->valid_ptr();
+            pay.dst[pay.n] = o.ok[c]->p;
+            pay.width[pay.n++] = 1;
+            carried_bytes += 2 * rows;
+        }
+        if (bits1 == 0) {
+            launch_radix_scatter(key.values->p, key.valid_ptr(), nullptr, rows, 4, 0, bits, cur2, o.keys->p, nullptr, pay, ctx->sm_count, s);
+            return o;
+        }
+        // pass 1 into temporaries, pass 2 (inside each region) to the final order; nothing but keys, values
+        // and validity bytes moves: the join needs neither row ids nor positions
+        SideOut t = std::move(o);
+        SideOut f;
+        f.keys = dev_alloc(rows * 4 + 64, s);
+        launch_radix_scatter(key.values->p, key.valid_ptr(), nullptr, rows, 4, bits2, bits1, cur1, t.keys->p, nullptr, pay, ctx->sm_count, s);
+        ScatterPayload pay2;
+        RegionFlags    fl;
+        for (size_t c = 0; c < cols.size(); ++c) {
+            f.val[c] = dev_alloc(rows * cols[c].width + 64, s);
+            pay2.src[pay2.n] = t.val[c]->p;
+            pay2.dst[pay2.n] = f.val[c]->p;
+            pay2.width[pay2.n++] = cols[c].width;
+            if (t.ok[c]) {
+                f.ok[c] = dev_alloc(rows + 64, s);
+                fl.src[fl.n] = t.ok[c]->as<uint8_t>();
+                fl.dst[fl.n++] = f.ok[c]->as<uint8_t>();
+            }
+        }
+        launch_radix_scatter_regions(t.keys->p, nullptr, reg, tile, 1u << bits1, rows, 4, 0, bits2, cur2, f.keys->p, nullptr, fl, pay2,
+                                     ctx->sm_count, s);
+        return f;
+    };
+    SideOut B, P;
+    {
+        StageScope sc(ctx, RJ_ST_SCATTER, s, bits1 ? 4 : 2, 0);
+        B = scatter_side(bkey, nb, bcols, bdec, pl.cur1_b, pl.cur_b, pl.reg_b, pl.tile_b);
+        P = scatter_side(pkey, np, pcols, pdec, pl.cur1_p, pl.cur_p, pl.reg_p, pl.tile_p);
+        // SURVEY 8d numerator: one-pass scatter = N*w_k read + N*(w_k+4) written, whatever the pass count, plus
+        // the carried columns once (read + written)
+        if (ctx->profiling) ctx->stats[RJ_ST_SCATTER].bytes += (nb + np) * 12 + carried_bytes;
+    }
+
+    // ---- join + page output -------------------------------------------------------------------------------
+    const uint64_t max_chunks = join_emit_max_chunks(np, ctx->sm_count);
+    auto res = std::make_unique<rj_result>();
+    res->cols.resize(nd.n_output_attrs);
+    Buf counters = dev_alloc_zero(32, s); // chunk counter @0, abort flag @4, rows @8
+    L.bkeys = B.keys->as<uint32_t>();
+    L.pkeys = P.keys->as<uint32_t>();
+    L.off_b = pl.off_b; L.off_p = pl.off_p; L.unit_start = pl.unit_start; L.unit_cursor = pl.unit_cursor;
+    L.nparts = nparts; L.part_bits = bits;
+    for (int c = 0; c < L.n_bpay; ++c) {
+        L.bpay[c] = B.val[c]->p;
+        L.bvalid[c] = B.ok[c] ? B.ok[c]->as<uint8_t>() : nullptr;
+    }
+    for (int c = 0; c < L.n_ppay; ++c) {
+        L.ppay[c] = P.val[c]->p;
+        L.pvalid[c] = P.ok[c] ? P.ok[c]->as<uint8_t>() : nullptr;
+    }
+    uint64_t out_page_bytes = 0;
+    for (int a = 0; a < L.n_out; ++a) {
+        ResultColumn& rc = res->cols[a];
+        rc.type = nd.output_attrs[a].type;
+        const uint64_t pages = max_chunks * (L.out_width[a] == 4 ? 1 : 2);
+        rc.pages = dev_alloc(pages * size_t(RJ_PAGE_SIZE), s);
+        L.out_pages[a] = rc.pages->as<uint8_t>();
+    }
+    L.chunk_counter = counters->as<uint32_t>();
+    L.abort_flag = counters->as<uint32_t>() + 1;
+    L.row_counter = reinterpret_cast<unsigned long long*>(counters->as<uint8_t>() + 8);
+    RJ_CUDA(cudaMemsetAsync(pl.unit_cursor, 0, 4, s));
+    uint32_t h[4] = {0, 0, 0, 0};
+    {
+        uint64_t in_bytes = (nb + np) * 4;
+        for (int c = 0; c < L.n_bpay; ++c) in_bytes += nb * (L.bwidth[c] + (L.bvalid[c] ? 1 : 0));
+        for (int c = 0; c < L.n_ppay; ++c) in_bytes += np * (L.pwidth[c] + (L.pvalid[c] ? 1 : 0));
+        StageScope sc(ctx, RJ_ST_JOIN_EMIT, s, 1, in_bytes);
+        launch_join_emit(L, ctx->sm_count, s);
+    }
+    RJ_CUDA(cudaMemcpyAsync(h, counters->p, 16, cudaMemcpyDeviceToHost, s));
+    RJ_CUDA(cudaStreamSynchronize(s));
+    if (h[1] != 0) return nullptr; // duplicate build keys: the general path handles them
+    const uint64_t chunks = h[0];
+    const uint64_t rows = static_cast<uint64_t>(h[2]) | (static_cast<uint64_t>(h[3]) << 32);
+    if (chunks > max_chunks) throw EngineError("internal: the fused root join produced more chunks than planned");
+    res->num_rows = rows;
+    for (int a = 0; a < L.n_out; ++a) {
+        ResultColumn& rc = res->cols[a];
+        rc.n_pages = chunks * (L.out_width[a] == 4 ? 1 : 2);
+        out_page_bytes += rc.n_pages * uint64_t(RJ_PAGE_SIZE);
+        if (rc.n_pages == 0) rc.pages.reset();
+    }
+    if (ctx->profiling) ctx->stats[RJ_ST_JOIN_EMIT].bytes += out_page_bytes;
+    return res;
+}
+
 std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, const rj_inputs* in,
                                             Exec::DecodedMap* shared_decoded = nullptr, uint32_t streamed_table = 0xffffffffu,
                                             double streamed_scale = 1.0) {
@@ -1211,9 +1464,12 @@ std::unique_ptr<rj_result> execute_resident(rj_ctx* ctx, const rj_plan_t* plan, 
         ex.shared_decoded = shared_decoded;
         ex.streamed_table = streamed_table;
         ex.streamed_scale = streamed_scale;
-        Rel  r = ex.run(plan->root);
-        t_run = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        res = ex.root(plan->root, r);
+        if (plan->nodes[plan->root].is_join) res = ex.root_fused(plan->root); // null: not eligible / duplicate build keys
+        if (!res) {
+            Rel r = ex.run(plan->root);
+            t_run = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            res = ex.root(plan->root, r);
+        }
         RJ_CUDA(cudaStreamSynchronize(ctx->stream));
         if (const uint32_t bad = *static_cast<volatile uint32_t*>(ctx->err_host)) {
             *ctx->err_host = 0;
@@ -1499,8 +1755,13 @@ struct PageSink: OutputSink {
     std::deque<Piece> pieces;
     TaskGroup         group;
     bool              open = true;
+    std::atomic<bool> alloc_failed{false};
+    // RJ_TRACE: where the host side of the download spends its time (ns, summed over threads)
+    std::atomic<uint64_t> ns_alloc{0}, ns_copy{0}, ns_acquire{0};
     PageSink(const rj_page_alloc_t* a, HostPipe* h): alloc(a), hp(h) { group.open(); }
     void deliver(rj_ctx* ctx, rj_result* res, cudaStream_t stream) override {
+        using clk = std::chrono::steady_clock;
+        auto ns_since = [](clk::time_point t) { return static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - t).count()); };
         for (uint32_t c = 0; c < res->cols.size(); ++c) {
             const ResultColumn& rc = res->cols[c];
             if (rc.n_pages == 0) continue;
@@ -1509,17 +1770,15 @@ struct PageSink: OutputSink {
             pc.column = c;
             pc.type = rc.type;
             pc.pages.assign(rc.n_pages, nullptr);
-            if (alloc->new_pages(alloc->user, rc.n_pages, pc.pages.data()) != 0) {
-                pc.pages.clear();
-                throw EngineError("rj_execute_pages: the page allocator failed");
-            }
             StageScope scope(ctx, RJ_ST_D2H, stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
-            void* const*   dst = pc.pages.data();
+            void**         dst = pc.pages.data(); // the deque never moves a Piece, the vector is never resized
             const uint8_t* src = rc.pages->as<uint8_t>();
             const uint64_t per = HostPipe::kBufBytes / RJ_PAGE_SIZE;
             for (uint64_t q = 0; q < rc.n_pages; q += per) {
                 const uint64_t m = std::min<uint64_t>(per, rc.n_pages - q);
+                const auto t0 = clk::now();
                 PinnedBuf* buf = hp->down.acquire(); // blocks while all staging buffers are being scattered
+                ns_acquire.fetch_add(ns_since(t0), std::memory_order_relaxed);
                 cudaError_t e = cudaMemcpyAsync(buf->p, src + q * RJ_PAGE_SIZE, m * RJ_PAGE_SIZE, cudaMemcpyDeviceToHost, stream);
                 if (e == cudaSuccess) e = cudaEventRecord(buf->ev, stream);
                 if (e != cudaSuccess) {
@@ -1527,12 +1786,22 @@ struct PageSink: OutputSink {
                     throw CudaError(std::string("page download: ") + cudaGetErrorString(e));
                 }
                 group.add();
-                HostPipe*  pipe = hp;
-                TaskGroup* g = &group;
-                hp->waiter.after(buf->ev, [=] {
-                    for (uint64_t i = 0; i < m; ++i) std::memcpy(dst[q + i], buf->p + i * RJ_PAGE_SIZE, RJ_PAGE_SIZE);
-                    pipe->down.release(buf);
-                    g->done();
+                hp->waiter.after(buf->ev, [this, buf, dst, q, m, ns_since] {
+                    // the pages of this piece are allocated here, by the worker that fills them: a serial
+                    // `new Page` per result page on the calling thread was the longest stage of the pipeline
+                    const auto t1 = clk::now();
+                    const bool ok = !alloc_failed.load(std::memory_order_relaxed) && alloc->new_pages(alloc->user, m, dst + q) == 0;
+                    const auto t2 = clk::now();
+                    if (ok) {
+                        for (uint64_t i = 0; i < m; ++i) copy_page(dst[q + i], buf->p + i * RJ_PAGE_SIZE);
+                        copy_fence();
+                    } else {
+                        alloc_failed.store(true, std::memory_order_relaxed);
+                    }
+                    ns_alloc.fetch_add(static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count()), std::memory_order_relaxed);
+                    ns_copy.fetch_add(ns_since(t2), std::memory_order_relaxed);
+                    hp->down.release(buf);
+                    group.done();
                 });
             }
         }
@@ -1546,6 +1815,10 @@ struct PageSink: OutputSink {
     }
     void finish() override {
         drain();
+        if (getenv("RJ_TRACE") != nullptr)
+            fprintf(stderr, "[rj pages] download side: staging-buffer waits %.1f ms (calling thread), page allocation %.1f ms, page copies %.1f ms (summed over workers)\n",
+                    ns_acquire.load() / 1e6, ns_alloc.load() / 1e6, ns_copy.load() / 1e6);
+        if (alloc_failed.load()) throw EngineError("rj_execute_pages: the page allocator failed");
         while (!pieces.empty()) {
             Piece& pc = pieces.front();
             if (alloc->append(alloc->user, pc.column, pc.type, pc.pages.data(), pc.pages.size()) != 0)
@@ -1555,8 +1828,14 @@ struct PageSink: OutputSink {
     }
     void abort() override {
         try { drain(); } catch (...) {}
-        for (auto& pc: pieces)
-            if (alloc->free_pages && !pc.pages.empty()) alloc->free_pages(alloc->user, pc.pages.size(), pc.pages.data());
+        for (auto& pc: pieces) {
+            if (!alloc->free_pages) continue;
+            // pages are allocated batch by batch: give back whatever exists
+            std::vector<void*> have;
+            for (void* p: pc.pages)
+                if (p) have.push_back(p);
+            if (!have.empty()) alloc->free_pages(alloc->user, have.size(), have.data());
+        }
         pieces.clear();
     }
 };
@@ -2060,7 +2339,7 @@ int rj_profile_read(rj_ctx* ctx, rj_stage_stat_t* stats) {
 
 const char* rj_stage_name(int stage) {
     static const char* names[RJ_ST_COUNT] = {"h2d", "row_offsets", "decode", "histogram", "scatter",
-                                             "join", "gather", "encode", "d2h"};
+                                             "join", "gather", "encode", "d2h", "join_emit"};
     return stage >= 0 && stage < RJ_ST_COUNT ? names[stage] : "?";
 }
 

@@ -105,7 +105,7 @@ __device__ void block_exclusive_scan(uint32_t n, uint32_t* out, F f) {
 
 __global__ void __launch_bounds__(kPlanThreads)
     partition_plan_kernel(const uint32_t* __restrict__ hist_b, const uint32_t* __restrict__ hist_p, uint32_t flat_b,
-                          uint32_t flat_p, int total_bits, int pass1_bits, uint32_t tile, PartitionPlanDev plan) {
+                          uint32_t flat_p, int total_bits, int pass1_bits, uint32_t tile, PartitionPlanDev plan, uint32_t build_cap) {
     const uint32_t nparts = 1u << total_bits;
     // final offsets (partition-major layout of the fully partitioned relations)
     if (total_bits == 0) {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kPlanThreads)
         const uint32_t nb = plan.off_b[i + 1] - plan.off_b[i];
         const uint32_t np = plan.off_p[i + 1] - plan.off_p[i];
         if (nb == 0 || np == 0) return 0u;
-        return ((nb + kJoinBuildCap - 1) / kJoinBuildCap) * ((np + kJoinProbeChunk - 1) / kJoinProbeChunk);
+        return ((nb + build_cap - 1) / build_cap) * ((np + kJoinProbeChunk - 1) / kJoinProbeChunk);
     });
 }
 
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
     constexpr int      kPartShift = 12; // staged word: tile offset | bucket << 12 | flags << 30
     constexpr int      kWarps     = kScatterThreads / 32;
     constexpr int      kDepth     = 8;  // staged positions per thread in flight at copy-out
+    constexpr uint32_t kWinBytes  = kTile * 8 + 16; // one TMA window in s_pay (16 bytes of slack: unaligned region tiles)
     static_assert(kTile <= (1u << kPartShift), "tile offset and rank must fit 12 bits");
     // static shared memory: every address below is base + compile-time constant
     __shared__ __align__(16) K s_keys[kTile];
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
     uint32_t tma_phase = 0;
-    if (!kRegions && n_tma > 0 && tid == 0) {
+    if (n_tma > 0 && tid == 0) {
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
@@ -252,31 +253,40 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
         } else {
             lo = t * kTile;
             cnt = n - lo < kTile ? static_cast<uint32_t>(n - lo) : kTile;
-            staged = n_tma > 0 && cnt == kTile;
-            if (staged && tid == 0) {
+        }
+        // carried value columns: the tile's row window of the first n_tma of them arrives by one TMA bulk
+        // copy each.  A region tile starts at an arbitrary tuple, so its window starts at the 16-byte
+        // boundary below it (win_off[c] = elements skipped) and is 16 bytes longer.
+        uint32_t win_off[2] = {0, 0};
+        staged = n_tma > 0 && cnt == kTile;
+        if (staged) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                if (c < n_tma) win_off[c] = kRegions ? static_cast<uint32_t>(lo & (16u / static_cast<uint32_t>(pay.width[c]) - 1u)) : 0u;
+            if (tid == 0) {
                 // every read of the previous tile's windows is behind the __syncthreads that ended it
                 uint32_t bytes = 0;
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
-                    if (c < n_tma) bytes += kTile * static_cast<uint32_t>(pay.width[c]);
+                    if (c < n_tma) bytes += kTile * static_cast<uint32_t>(pay.width[c]) + (kRegions ? 16u : 0u);
                 mbar_arrive_expect_tx(&s_bar, bytes);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     if (c < n_tma)
-                        tma_load_1d(s_pay + c * kTile * 8, static_cast<const char*>(pay.src[c]) + lo * pay.width[c],
-                                    kTile * static_cast<uint32_t>(pay.width[c]), &s_bar);
+                        tma_load_1d(s_pay + c * kWinBytes, static_cast<const char*>(pay.src[c]) + (lo - win_off[c]) * pay.width[c],
+                                    kTile * static_cast<uint32_t>(pay.width[c]) + (kRegions ? 16u : 0u), &s_bar);
                 }
             }
-            // the other carried columns are gathered from this tile's row window at copy-out: start
-            // pulling the window into L2 now
-            if (idx_in == nullptr) {
+        }
+        // the other carried columns are gathered from this tile's row window at copy-out: start
+        // pulling the window into L2 now
+        if (idx_in == nullptr) {
 #pragma unroll
-                for (int c = 0; c < ScatterPayload::kMax; ++c) {
-                    if (c < pay.n && pay.width[c] > 1 && !(staged && c < n_tma)) {
-                        const uint32_t bytes = cnt * static_cast<uint32_t>(pay.width[c]);
-                        const char*    w0    = static_cast<const char*>(pay.src[c]) + lo * pay.width[c];
-                        for (uint32_t o = tid * 128; o < bytes; o += kScatterThreads * 128) prefetch_l2(w0 + o);
-                    }
+            for (int c = 0; c < ScatterPayload::kMax; ++c) {
+                if (c < pay.n && pay.width[c] > 1 && !(staged && c < n_tma)) {
+                    const uint32_t bytes = cnt * static_cast<uint32_t>(pay.width[c]);
+                    const char*    w0    = static_cast<const char*>(pay.src[c]) + lo * pay.width[c];
+                    for (uint32_t o = tid * 128; o < bytes; o += kScatterThreads * 128) prefetch_l2(w0 + o);
                 }
             }
         }
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
         // 4) stream the runs out: thread -> staged position, kDepth positions per thread in flight
         const uint32_t total = s_total;
         const uint32_t lo32  = static_cast<uint32_t>(lo);
-        if (!kRegions && staged) {
+        if (staged) {
             mbar_wait(&s_bar, tma_phase);
             tma_phase ^= 1;
         }
@@ -437,17 +447,16 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
 #pragma unroll
             for (int j = 0; j < kDepth; ++j)
                 if (in[j]) static_cast<K*>(out(MultiDsts::kKeys, keys_out, j))[dd[j]] = kk[j];
-            if (kRegions || (kMulti ? s_dst[MultiDsts::kRows][0] != nullptr : idx_out != nullptr)) { // row ids nobody reads are dropped
+            if (kMulti ? s_dst[MultiDsts::kRows][0] != nullptr : idx_out != nullptr) { // row ids / positions nobody reads are dropped
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j)
                     if (in[j]) static_cast<uint32_t*>(out(MultiDsts::kRows, idx_out, j))[dd[j]] = kRegions ? (rr[j] | (ww[j] & 0xc0000000u)) : rr[j];
             }
-            if (kRegions) return;
-            if (flags.n > 0) {
+            if (flags.n > 0 && (kMulti || flags.dst[0] != nullptr)) {
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint8_t*>(out(MultiDsts::kFlag0, flags.dst[0], j))[dd[j]] = (ww[j] >> 30) & 1u;
             }
-            if (flags.n > 1) {
+            if (flags.n > 1 && (kMulti || flags.dst[1] != nullptr)) {
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j) if (in[j]) static_cast<uint8_t*>(out(MultiDsts::kFlag0 + 1, flags.dst[1], j))[dd[j]] = ww[j] >> 31;
             }
@@ -459,12 +468,12 @@ __global__ void __launch_bounds__(kScatterThreads, 4)
                     if (c < 2 && staged && c < n_tma) {
                         // the window is in shared memory: row offset inside the tile = low bits of ww
                         if (w == 8) {
-                            const uint64_t* win = reinterpret_cast<const uint64_t*>(s_pay + c * kTile * 8);
+                            const uint64_t* win = reinterpret_cast<const uint64_t*>(s_pay + c * kWinBytes) + win_off[c];
 #pragma unroll
                             for (int j = 0; j < kDepth; ++j)
                                 if (in[j]) static_cast<uint64_t*>(out(MultiDsts::kPay0 + c, pay.dst[c], j))[dd[j]] = win[ww[j] & (kTile - 1)];
                         } else {
-                            const uint32_t* win = reinterpret_cast<const uint32_t*>(s_pay + c * kTile * 8);
+                            const uint32_t* win = reinterpret_cast<const uint32_t*>(s_pay + c * kWinBytes) + win_off[c];
 #pragma unroll
                             for (int j = 0; j < kDepth; ++j)
                                 if (in[j]) static_cast<uint32_t*>(out(MultiDsts::kPay0 + c, pay.dst[c], j))[dd[j]] = win[ww[j] & (kTile - 1)];
@@ -562,9 +571,9 @@ void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n,
 
 void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint32_t flat_b, uint32_t flat_p,
                            int total_bits, int pass1_bits, int key_bytes, const PartitionPlanDev& plan,
-                           cudaStream_t s) {
+                           cudaStream_t s, uint32_t build_cap) {
     partition_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist_b, hist_p, flat_b, flat_p, total_bits, pass1_bits,
-                                                     scatter_tile(key_bytes), plan);
+                                                     scatter_tile(key_bytes), plan, build_cap);
     RJ_LAUNCH_CHECK();
 }
 
@@ -610,7 +619,7 @@ void launch_radix_scatter(const void* keys, const uint32_t* valid, const uint32_
             }
         }
     }
-    const size_t smem = static_cast<size_t>(n_tma) * tile * 8;
+    const size_t smem = static_cast<size_t>(n_tma) * (tile * 8 + 16);
     if (key_bytes == 4) {
         static SmemConfigured cfg;
         cfg.ensure(scatter_tile_kernel<uint32_t, false>, smem);
@@ -676,7 +685,7 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
     RJ_CUDA(cudaMemcpyAsync(d_dsts, &h, sizeof(MultiDsts), cudaMemcpyHostToDevice, s));
     const uint32_t tile = scatter_tile(key_bytes);
     const uint64_t n_tiles = (n + tile - 1) / tile;
-    const size_t   smem = static_cast<size_t>(n_tma) * tile * 8;
+    const size_t   smem = static_cast<size_t>(n_tma) * (tile * 8 + 16);
     if (key_bytes == 4) {
         auto kern = scatter_tile_kernel<uint32_t, false, true>;
         static SmemConfigured cfg;
@@ -698,26 +707,58 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
 void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,
                                   const uint32_t* tile_start, uint32_t n_regions, uint64_t n_upper, int key_bytes,
                                   int shift, int bits, uint32_t* cursor, void* keys_out, uint32_t* idx_out,
-                                  const RegionFlags& flags, int sm_count, cudaStream_t s) {
+                                  const RegionFlags& flags, const ScatterPayload& payload, int sm_count, cudaStream_t s) {
     if (n_upper == 0) return;
     // the exact tile count lives on the device (tile_start[n_regions]); size the persistent grid from
     // its upper bound so no host synchronisation is needed
     const uint32_t tile = scatter_tile(key_bytes);
     uint64_t tiles_upper = (n_upper + tile - 1) / tile + n_regions;
-    unsigned blocks = static_cast<unsigned>(tiles_upper < static_cast<uint64_t>(sm_count) * 4 ? tiles_upper : static_cast<uint64_t>(sm_count) * 4);
     TileFlags tf;
     tf.n = flags.n;
-    for (int c = 0; c < flags.n; ++c) tf.src[c] = flags.src[c];
+    for (int c = 0; c < flags.n; ++c) {
+        tf.src[c] = flags.src[c];
+        tf.dst[c] = flags.dst[c];
+    }
+    // value columns that move with the tuples (positions are the input order of this pass): the first
+    // two whose source is 8-byte aligned go through TMA windows, the rest is gathered from the tile's window
+    ScatterPayload pay;
+    int            n_tma = 0;
+    auto push = [&](int c) {
+        pay.src[pay.n] = payload.src[c];
+        pay.dst[pay.n] = payload.dst[c];
+        pay.width[pay.n] = payload.width[c];
+        ++pay.n;
+    };
+    auto tma_ok = [&](int c) { return payload.width[c] >= 4 && reinterpret_cast<uintptr_t>(payload.src[c]) % 16 == 0; };
+    for (int c = 0; c < payload.n; ++c)
+        if (tma_ok(c) && n_tma < 2) {
+            push(c);
+            ++n_tma;
+        }
+    {
+        int taken = 0;
+        for (int c = 0; c < payload.n; ++c) {
+            if (tma_ok(c) && taken < 2) ++taken; else push(c);
+        }
+    }
+    const size_t smem = static_cast<size_t>(n_tma) * (tile * 8 + 16);
     if (key_bytes == 4) {
-        scatter_tile_kernel<uint32_t, true><<<blocks, kScatterThreads, 0, s>>>(
-            static_cast<const uint32_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, ScatterPayload{}, tf, 0);
+        auto kern = scatter_tile_kernel<uint32_t, true>;
+        static SmemConfigured cfg;
+        cfg.ensure(kern, smem);
+        const unsigned blocks = resident_grid(kern, smem, tiles_upper, sm_count);
+        kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint32_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start,
+                                                   n_regions, shift, bits, cursor, static_cast<uint32_t*>(keys_out), idx_out, pay, tf, n_tma, nullptr);
     } else {
-        scatter_tile_kernel<uint64_t, true><<<blocks, kScatterThreads, 0, s>>>(
-            static_cast<const uint64_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start, n_regions, shift,
-            bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, ScatterPayload{}, tf, 0);
+        auto kern = scatter_tile_kernel<uint64_t, true>;
+        static SmemConfigured cfg;
+        cfg.ensure(kern, smem);
+        const unsigned blocks = resident_grid(kern, smem, tiles_upper, sm_count);
+        kern<<<blocks, kScatterThreads, smem, s>>>(static_cast<const uint64_t*>(keys), nullptr, nullptr, n_upper, region_start, tile_start,
+                                                   n_regions, shift, bits, cursor, static_cast<uint64_t*>(keys_out), idx_out, pay, tf, n_tma, nullptr);
     }
     RJ_LAUNCH_CHECK();
+    (void)idx_in;
 }
 
 } // namespace rj

@@ -104,9 +104,10 @@ void launch_decode_varchar(const void* pages, uint64_t n_pages, const uint64_t* 
 // ---- k_partition.cu -------------------------------------------------------------------------------
 void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift,
                             int bits, uint32_t* hist, int sm_count, cudaStream_t s);
+// build_cap: build tuples per join work unit (kJoinBuildCap for join_kernel, kEmitBuildCap for join_emit_kernel)
 void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint32_t flat_b, uint32_t flat_p,
                            int total_bits, int pass1_bits, int key_bytes, const PartitionPlanDev& plan,
-                           cudaStream_t s);
+                           cudaStream_t s, uint32_t build_cap = kJoinBuildCap);
 // Payload columns that travel with the tuples of a flat scatter: dst[c][pos] = src[c][row of the tuple].
 // The source is read inside the tile's own row window (sequential DRAM traffic), so a later gather
 // through positions of the scattered order stays inside one partition / region instead of the table.
@@ -131,12 +132,39 @@ void launch_radix_scatter_multi(const void* keys, const uint32_t* valid, uint64_
 struct RegionFlags {
     int            n = 0;
     const uint8_t* src[2] = {nullptr, nullptr};
+    uint8_t*       dst[2] = {nullptr, nullptr}; // optional: the bytes again, in the order this pass produces
 };
 constexpr uint32_t kPosMask = 0x3fffffffu;
 void launch_radix_scatter_regions(const void* keys, const uint32_t* idx_in, const uint32_t* region_start,
                                   const uint32_t* tile_start, uint32_t n_regions, uint64_t n_upper,
                                   int key_bytes, int shift, int bits, uint32_t* cursor, void* keys_out,
-                                  uint32_t* idx_out, const RegionFlags& flags, int sm_count, cudaStream_t s);
+                                  uint32_t* idx_out, const RegionFlags& flags, const ScatterPayload& payload, int sm_count,
+                                  cudaStream_t s);
+
+// ---- k_scatter_carry.cu: scatter of whole tuples (4-byte key + the columns the root outputs) ------------
+// Flat pass: region_start == NULL; `valid` = key validity bitmap (tuples with a NULL key are dropped),
+// flag_src = validity BITMAPS of the carried columns by row.  Region pass (second pass): the input is the
+// flat pass's output, flag_src = validity BYTES by position, tiles never straddle a region.  flag_dst is
+// one byte per tuple in both.  Keys and value sources must be 16-byte aligned (1-D TMA).
+struct CarryScatter {
+    const uint32_t* keys = nullptr;
+    const uint32_t* valid = nullptr;
+    uint64_t        n = 0; // tuples (region pass: an upper bound, the exact count is region_start[n_regions])
+    const uint32_t* region_start = nullptr;
+    const uint32_t* tile_start = nullptr;
+    uint32_t        n_regions = 0;
+    int             shift = 0, bits = 0;
+    uint32_t*       cursor = nullptr;
+    uint32_t*       keys_out = nullptr;
+    int             n_val = 0;
+    const void*     val_src[2] = {nullptr, nullptr};
+    void*           val_dst[2] = {nullptr, nullptr};
+    int             val_width[2] = {0, 0}; // 4 or 8
+    int             n_flag = 0;
+    const void*     flag_src[2] = {nullptr, nullptr};
+    uint8_t*        flag_dst[2] = {nullptr, nullptr};
+};
+void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s);
 
 // ---- k_join.cu ------------------------------------------------------------------------------------
 struct JoinLaunch {
@@ -163,6 +191,44 @@ struct JoinLaunch {
 };
 inline unsigned join_grid(int sm_count) { return static_cast<unsigned>(sm_count) * 2; }
 void launch_join(const JoinLaunch& a, int sm_count, cudaStream_t s);
+
+// ---- k_join_emit.cu: root join fused with page output ------------------------------------------------
+constexpr uint32_t kEmitSlots     = 4096;  // table slots per CTA (two CTAs of ~100 KB per SM)
+constexpr uint32_t kEmitBuildCap  = 3072;  // build tuples per table; larger partitions are chunked
+constexpr uint32_t kEmitChunkRows = 1984;  // rows per output chunk: 1 page per 4-byte column, 2 x 992 rows per 8-byte column
+constexpr int      kEmitMaxPay    = 2;     // carried columns per side
+constexpr int      kEmitMaxOut    = 4;     // output columns
+struct JoinEmitLaunch {
+    const uint32_t* bkeys = nullptr; // both sides fully partitioned, 4-byte keys, NULL keys already dropped
+    const uint32_t* pkeys = nullptr;
+    const uint32_t* off_b = nullptr; // [nparts+1]
+    const uint32_t* off_p = nullptr;
+    const uint32_t* unit_start = nullptr; // [nparts+1], units of (kEmitBuildCap build) x (kJoinProbeChunk probe) tuples
+    uint32_t*       unit_cursor = nullptr;
+    uint32_t        nparts = 1;
+    int             part_bits = 0;
+    int             n_bpay = 0, n_ppay = 0;
+    const void*     bpay[kEmitMaxPay] = {};
+    const uint8_t*  bvalid[kEmitMaxPay] = {};
+    int             bwidth[kEmitMaxPay] = {};
+    const void*     ppay[kEmitMaxPay] = {};
+    const uint8_t*  pvalid[kEmitMaxPay] = {};
+    int             pwidth[kEmitMaxPay] = {};
+    int             n_out = 0;
+    int             out_src[kEmitMaxOut] = {};      // 0 = join key, 1 = build payload, 2 = probe payload
+    int             out_idx[kEmitMaxOut] = {};
+    int             out_width[kEmitMaxOut] = {};
+    int             out_nullable[kEmitMaxOut] = {};
+    uint8_t*        out_pages[kEmitMaxOut] = {};    // room for join_emit_max_chunks() chunks each
+    uint32_t*           chunk_counter = nullptr;    // zeroed by the caller
+    unsigned long long* row_counter = nullptr;
+    uint32_t*           abort_flag = nullptr;
+};
+inline unsigned join_emit_grid(int sm_count) { return static_cast<unsigned>(sm_count) * 2; }
+// chunks a launch can produce: every probe tuple matches at most once, every CTA ends with a partial chunk
+inline uint64_t join_emit_max_chunks(uint64_t n_probe, int sm_count) { return n_probe / kEmitChunkRows + join_emit_grid(sm_count) + 1; }
+bool join_emit_fits(const JoinEmitLaunch& L);
+void launch_join_emit(const JoinEmitLaunch& L, int sm_count, cudaStream_t s);
 
 // ---- k_gather_encode.cu ---------------------------------------------------------------------------
 void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* idx, uint64_t n,

@@ -52,6 +52,9 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     def step():
         return dj.distributed_join(ops, build, probe, OUT_COLS, xchg=xchg)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # before the warm-up steps: nvidia-smi takes longer to start than a short timed region lasts
     for _ in range(args.warmup):
         rows, cols, stats = step()
     total_rows = torch.tensor([rows], dtype=torch.int64, device="cuda")
@@ -71,12 +74,11 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
               "how": "per-rank sums over a per-row hash of the result pages, added over ranks, vs the generator's join-free expectation"}
     assert parity["multiset_checksum"], (sum_got, sum_exp)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.kernel_launches()
     dist.barrier()
     torch.cuda.synchronize()
+    if rank == 0:
+        sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):

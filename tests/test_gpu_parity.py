@@ -297,6 +297,77 @@ def test_partitioned_join_with_payloads(ctx, n_build, n_probe):
     check_plan(plan, ctx, impl="port")
 
 
+def _fused_launches(ctx, plan, impl="port", expect_fused=True):
+    """run the plan with stage profiling on; returns the result after checking it against the oracle and that
+    the root join did (or did not) take the fused join + page-output kernel"""
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    try:
+        got = check_plan(plan, ctx, impl=impl)
+        prof = ctx.profile_read()
+    finally:
+        ctx.profile_enable(False)
+    assert (prof["join_emit"]["launches"] > 0) == expect_fused, prof
+    return got, prof
+
+
+@pytest.mark.parametrize("n_build,n_probe", [(40_000, 300_000), (2_500_000, 3_000_000)])  # one / two scatter passes
+def test_fused_root_join_two_payloads_per_side(ctx, n_build, n_probe):
+    """root join of two scans, INT32 key, 4- and 8-byte payloads with and without NULLs on both sides, the key
+    taken from either side, one column twice: the join kernel writes the result pages itself"""
+    rng = np.random.default_rng(n_build + 1)
+    bk = orc.Cells(INT32, (rng.random(n_build) > 0.01).astype(np.uint8), values=rng.permutation(n_build).astype(np.int32))
+    b1 = orc.Cells(INT64, (rng.random(n_build) > 0.05).astype(np.uint8), values=rng.integers(-2**62, 2**62, n_build))
+    b2 = orc.Cells.from_values(INT32, rng.integers(-2**31, 2**31 - 1, n_build).astype(np.int32))
+    pk = orc.Cells(INT32, (rng.random(n_probe) > 0.02).astype(np.uint8),
+                   values=rng.integers(0, int(n_build * 1.2), n_probe).astype(np.int32))
+    p1 = H.random_cells(rng, FP64, n_probe, null_frac=0.3)
+    p2 = H.random_cells(rng, INT32, n_probe, null_frac=0.0)
+    tl = H.table_from_cells([b1, bk, b2])
+    tr = H.table_from_cells([p1, p2, pk])
+    lt, rt = [INT64, INT32, INT32], [FP64, INT32, INT32]
+    for build_left in (True, False):
+        plan = H.single_join_plan(tl, tr, lt, rt, 1, 2, build_left, out_cols=[3, 1, 0, 4])
+        _fused_launches(ctx, plan)
+        plan = H.single_join_plan(tl, tr, lt, rt, 1, 2, build_left, out_cols=[5, 2, 3, 3])
+        _fused_launches(ctx, plan)
+    # the same plan on the general path gives the same multiset
+    os.environ["RJ_NO_FUSED_ROOT"] = "1"
+    try:
+        _fused_launches(ctx, plan, expect_fused=False)
+    finally:
+        del os.environ["RJ_NO_FUSED_ROOT"]
+
+
+def test_fused_root_join_gives_way_to_duplicate_build_keys(ctx):
+    """the fused kernel needs distinct keys per table; a duplicate raises its flag and the general path
+    (duplicate chains) produces the result"""
+    rng = np.random.default_rng(9)
+    n_b, n_p = 50_000, 200_000
+    bkeys = rng.integers(0, 30_000, n_b).astype(np.int32)  # many duplicates
+    tl = H.table_from_cells([orc.Cells.from_values(INT32, bkeys), H.random_cells(rng, INT64, n_b, null_frac=0.1)])
+    tr = H.table_from_cells([orc.Cells.from_values(INT32, rng.integers(0, 30_000, n_p).astype(np.int32))])
+    plan = H.single_join_plan(tl, tr, [INT32, INT64], [INT32], 0, 0, True)
+    got, prof = _fused_launches(ctx, plan, expect_fused=True)  # it is tried first ...
+    assert prof["join"]["launches"] > 0 and prof["encode"]["launches"] > 0  # ... then the general path ran
+
+
+def test_fused_root_join_not_taken_for_varchar_or_wide_outputs(ctx):
+    rng = np.random.default_rng(10)
+    n_b, n_p = 20_000, 60_000
+    tl = H.table_from_cells([orc.Cells.from_values(INT32, rng.permutation(n_b).astype(np.int32)),
+                             H.random_cells(rng, VARCHAR, n_b, null_frac=0.1, max_len=12)])
+    tr = H.table_from_cells([orc.Cells.from_values(INT32, rng.integers(0, n_b, n_p).astype(np.int32)),
+                             H.random_cells(rng, INT64, n_p), H.random_cells(rng, INT64, n_p), H.random_cells(rng, FP64, n_p)])
+    _fused_launches(ctx, H.single_join_plan(tl, tr, [INT32, VARCHAR], [INT32, INT64, INT64, FP64], 0, 0, True, out_cols=[0, 1, 3]),
+                    expect_fused=False)
+    # three carried columns on one side: more than the kernel stages
+    _fused_launches(ctx, H.single_join_plan(tl, tr, [INT32, VARCHAR], [INT32, INT64, INT64, FP64], 0, 0, True, out_cols=[3, 4, 5]),
+                    expect_fused=False)
+    _fused_launches(ctx, H.single_join_plan(tl, tr, [INT32, VARCHAR], [INT32, INT64, INT64, FP64], 0, 0, True, out_cols=[0, 3, 5]),
+                    expect_fused=True)
+
+
 def test_config1_shape_1m_x_10m(ctx):
     """BASELINE config 1: single INT32 equi-join, 1 M build x 10 M probe, unique FK keys"""
     rng = np.random.default_rng(42)

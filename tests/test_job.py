@@ -82,11 +82,14 @@ def test_job_1a_on_the_oracles():
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,scale,long_strings", [("1a", 0.05, False), ("13a", 0.05, True), ("33a", 0.1, True),
                                                      ("24a", 0.01, False), ("31c", 0.01, True), ("17e", 0.01, False),
-                                                     ("16b", 0.004, False)])
+                                                     ("16b", 0.004, False),
+                                                     # BASELINE.json configs 3 and 4 "at IMDB row counts"
+                                                     ("1a", 1.0, False), ("13a", 1.0, True), ("33a", 1.0, True)])
 def test_job_plans_match_the_oracle_on_gpu(name, scale, long_strings):
     """configs 3 and 4: JOB 1a (5-way), 13a (9 scans, depth 6), 33a (14 scans), 24a / 31c (12 / 11 scans,
     non-empty) with NULL bitmaps and long-string page chains in the VARCHAR columns; bit-exact multiset
-    equality with the CPU oracle"""
+    equality with the CPU oracle.  The scale-1.0 cases run at the IMDB row counts of plans.json (largest
+    scan: movie_info, 14.8 M rows)."""
     plan, root_cols, scan_rows = job.make_job(name, scale=scale, seed=3, long_strings=long_strings)
     ctx = rj.build_context(0)
     try:
