@@ -14,7 +14,6 @@
 #include <cstring>
 #include <functional>
 #include <deque>
-#include <emmintrin.h>
 #include <map>
 #include <mutex>
 #include <set>
@@ -341,29 +340,7 @@ struct ColCounters {
 // ring buffers by pool workers, 512 pages per task; each task issues its own DMA, so the gather of
 // one buffer overlaps the transfer of the previous ones.  A contiguous host buffer is one DMA straight
 // from the caller's memory.  `counters` (optional) receives the row / non-NULL totals of the page headers.
-// One 8 KB page, host to host.  Neither the staging buffers (read next by the DMA engine) nor fresh
-// result pages (read next by the caller, much later) are wanted in the cache, and a plain store makes
-// the core read the destination line first: 16-byte non-temporal stores cut the memory traffic of every
-// page copy by a third.  RJ_NT_COPY=0 falls back to memcpy.
-inline void copy_page(void* dst, const void* src) {
-    static const bool nt = !(getenv("RJ_NT_COPY") && atoi(getenv("RJ_NT_COPY")) == 0);
-    if (!nt || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u)) {
-        std::memcpy(dst, src, RJ_PAGE_SIZE);
-        return;
-    }
-    const __m128i* s = static_cast<const __m128i*>(src);
-    __m128i*       d = static_cast<__m128i*>(dst);
-    for (int i = 0; i < static_cast<int>(RJ_PAGE_SIZE / 16); i += 4) {
-        const __m128i a = _mm_load_si128(s + i), b = _mm_load_si128(s + i + 1), c = _mm_load_si128(s + i + 2), e = _mm_load_si128(s + i + 3);
-        _mm_stream_si128(d + i, a);
-        _mm_stream_si128(d + i + 1, b);
-        _mm_stream_si128(d + i + 2, c);
-        _mm_stream_si128(d + i + 3, e);
-    }
-}
-// non-temporal stores are weakly ordered: fence before another agent (DMA engine, another thread) reads
-inline void copy_fence() { _mm_sfence(); }
-
+// host_copy.cpp: one 8 KB page, host to host, with non-temporal stores
 void upload_pages_async(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t cnt, uint8_t* dst, cudaStream_t stream,
                         TaskGroup* group, ColCounters* counters) {
     if (cnt == 0) return;
@@ -1318,6 +1295,14 @@ std::unique_ptr<rj_result> Exec::root_fused(uint64_t n) {
         L.out_nullable[a] = d && d->valid ? 1 : 0;
     }
     if (!join_emit_fits(L)) return nullptr;
+    {
+        // 1-D TMA windows of the scatter need 16-byte aligned sources (adopted dense columns may not be)
+        auto aligned = [](const DecodedCol& d) { return reinterpret_cast<uintptr_t>(d.values->p) % 16 == 0; };
+        bool ok = aligned(bkey) && aligned(pkey);
+        for (auto* d: bdec) ok = ok && aligned(*d);
+        for (auto* d: pdec) ok = ok && aligned(*d);
+        if (!ok) return nullptr;
+    }
 
     // ---- histogram, plan, scatter both sides with their columns to the final partition order -------------
     const int      bits1 = bits > kMaxPassBits ? pass1_bits_of(bits) : 0;
@@ -1332,7 +1317,7 @@ std::unique_ptr<rj_result> Exec::root_fused(uint64_t n) {
         launch_radix_histogram(bkey.values->p, bkey.valid_ptr(), nb, 4, 0, bits, hist->as<uint32_t>(), ctx->sm_count, s);
         launch_radix_histogram(pkey.values->p, pkey.valid_ptr(), np, 4, 0, bits, hist->as<uint32_t>() + nparts, ctx->sm_count, s);
     }
-    launch_partition_plan(hist->as<uint32_t>(), hist->as<uint32_t>() + nparts, 0, 0, bits, bits1, 4, pl, s, kEmitBuildCap);
+    launch_partition_plan(hist->as<uint32_t>(), hist->as<uint32_t>() + nparts, 0, 0, bits, bits1, 4, pl, s, kEmitBuildCap, kEmitProbeChunk);
 
     struct SideOut {
         Buf keys;
@@ -1341,49 +1326,57 @@ std::unique_ptr<rj_result> Exec::root_fused(uint64_t n) {
     uint64_t carried_bytes = 0;
     auto scatter_side = [&](const DecodedCol& key, uint64_t rows, const std::vector<Carry>& cols, const std::vector<const DecodedCol*>& dec,
                             uint32_t* cur1, uint32_t* cur2, const uint32_t* reg, const uint32_t* tile) {
+        // k_scatter_carry.cu: keys, values and validity move together; nothing else does (the join needs
+        // neither row ids nor positions)
         SideOut o;
         o.keys = dev_alloc(rows * 4 + 64, s);
-        ScatterPayload pay; // values first, then the validity bitmaps (they become one byte per tuple)
+        CarryScatter c1;
+        c1.keys = key.values->as<uint32_t>();
+        c1.valid = key.valid_ptr();
+        c1.n = rows;
+        c1.keys_out = o.keys->as<uint32_t>();
         for (size_t c = 0; c < cols.size(); ++c) {
             o.val[c] = dev_alloc(rows * cols[c].width + 64, s);
-            pay.src[pay.n] = dec[c]->values->p;
-            pay.dst[pay.n] = o.val[c]->p;
-            pay.width[pay.n++] = cols[c].width;
+            c1.val_src[c1.n_val] = dec[c]->values->p;
+            c1.val_dst[c1.n_val] = o.val[c]->p;
+            c1.val_width[c1.n_val++] = cols[c].width;
             carried_bytes += 2 * rows * cols[c].width;
-        }
-        for (size_t c = 0; c < cols.size(); ++c) {
-            if (!dec[c]->valid) continue;
-            o.ok[c] = dev_alloc(rows + 64, s);
-            pay.src[pay.n] = dec[c]->valid_ptr();
-            pay.dst[pay.n] = o.ok[c]->p;
-            pay.width[pay.n++] = 1;
-            carried_bytes += 2 * rows;
-        }
-        if (bits1 == 0) {
-            launch_radix_scatter(key.values->p, key.valid_ptr(), nullptr, rows, 4, 0, bits, cur2, o.keys->p, nullptr, pay, ctx->sm_count, s);
-            return o;
-        }
-        // pass 1 into temporaries, pass 2 (inside each region) to the final order; nothing but keys, values
-        // and validity bytes moves: the join needs neither row ids nor positions
-        SideOut t = std::move(o);
-        SideOut f;
-        f.keys = dev_alloc(rows * 4 + 64, s);
-        launch_radix_scatter(key.values->p, key.valid_ptr(), nullptr, rows, 4, bits2, bits1, cur1, t.keys->p, nullptr, pay, ctx->sm_count, s);
-        ScatterPayload pay2;
-        RegionFlags    fl;
-        for (size_t c = 0; c < cols.size(); ++c) {
-            f.val[c] = dev_alloc(rows * cols[c].width + 64, s);
-            pay2.src[pay2.n] = t.val[c]->p;
-            pay2.dst[pay2.n] = f.val[c]->p;
-            pay2.width[pay2.n++] = cols[c].width;
-            if (t.ok[c]) {
-                f.ok[c] = dev_alloc(rows + 64, s);
-                fl.src[fl.n] = t.ok[c]->as<uint8_t>();
-                fl.dst[fl.n++] = f.ok[c]->as<uint8_t>();
+            if (dec[c]->valid) {
+                o.ok[c] = dev_alloc(rows + 64, s);
+                c1.flag_src[c1.n_flag] = dec[c]->valid_ptr(); // a bitmap by row becomes one byte per tuple
+                c1.flag_dst[c1.n_flag++] = o.ok[c]->as<uint8_t>();
+                carried_bytes += 2 * rows;
             }
         }
-        launch_radix_scatter_regions(t.keys->p, nullptr, reg, tile, 1u << bits1, rows, 4, 0, bits2, cur2, f.keys->p, nullptr, fl, pay2,
-                                     ctx->sm_count, s);
+        if (bits1 == 0) {
+            c1.shift = 0; c1.bits = bits; c1.cursor = cur2;
+            launch_scatter_carry(c1, ctx->sm_count, s);
+            return o;
+        }
+        c1.shift = bits2; c1.bits = bits1; c1.cursor = cur1;
+        launch_scatter_carry(c1, ctx->sm_count, s);
+        // pass 2, inside each pass-1 region, to the final order
+        SideOut f;
+        f.keys = dev_alloc(rows * 4 + 64, s);
+        CarryScatter c2;
+        c2.keys = o.keys->as<uint32_t>();
+        c2.n = rows;
+        c2.region_start = reg; c2.tile_start = tile; c2.n_regions = 1u << bits1;
+        c2.shift = 0; c2.bits = bits2; c2.cursor = cur2;
+        c2.keys_out = f.keys->as<uint32_t>();
+        for (size_t c = 0; c < cols.size(); ++c) {
+            f.val[c] = dev_alloc(rows * cols[c].width + 64, s);
+            c2.val_src[c2.n_val] = o.val[c]->p;
+            c2.val_dst[c2.n_val] = f.val[c]->p;
+            c2.val_width[c2.n_val++] = cols[c].width;
+            if (o.ok[c]) {
+                f.ok[c] = dev_alloc(rows + 64, s);
+                c2.flag_src[c2.n_flag] = o.ok[c]->p;
+                c2.flag_dst[c2.n_flag++] = f.ok[c]->as<uint8_t>();
+            }
+        }
+        launch_scatter_carry(c2, ctx->sm_count, s);
+        // (the pass-1 arrays go back to the block cache here: blocks are reused in stream order)
         return f;
     };
     SideOut B, P;

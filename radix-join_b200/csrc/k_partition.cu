@@ -105,7 +105,8 @@ __device__ void block_exclusive_scan(uint32_t n, uint32_t* out, F f) {
 
 __global__ void __launch_bounds__(kPlanThreads)
     partition_plan_kernel(const uint32_t* __restrict__ hist_b, const uint32_t* __restrict__ hist_p, uint32_t flat_b,
-                          uint32_t flat_p, int total_bits, int pass1_bits, uint32_t tile, PartitionPlanDev plan, uint32_t build_cap) {
+                          uint32_t flat_p, int total_bits, int pass1_bits, uint32_t tile, PartitionPlanDev plan, uint32_t build_cap,
+                          uint32_t probe_chunk) {
     const uint32_t nparts = 1u << total_bits;
     // final offsets (partition-major layout of the fully partitioned relations)
     if (total_bits == 0) {
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kPlanThreads)
         const uint32_t nb = plan.off_b[i + 1] - plan.off_b[i];
         const uint32_t np = plan.off_p[i + 1] - plan.off_p[i];
         if (nb == 0 || np == 0) return 0u;
-        return ((nb + build_cap - 1) / build_cap) * ((np + kJoinProbeChunk - 1) / kJoinProbeChunk);
+        return ((nb + build_cap - 1) / build_cap) * ((np + probe_chunk - 1) / probe_chunk);
     });
 }
 
@@ -571,9 +572,9 @@ void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n,
 
 void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint32_t flat_b, uint32_t flat_p,
                            int total_bits, int pass1_bits, int key_bytes, const PartitionPlanDev& plan,
-                           cudaStream_t s, uint32_t build_cap) {
+                           cudaStream_t s, uint32_t build_cap, uint32_t probe_chunk) {
     partition_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist_b, hist_p, flat_b, flat_p, total_bits, pass1_bits,
-                                                     scatter_tile(key_bytes), plan, build_cap);
+                                                     scatter_tile(key_bytes), plan, build_cap, probe_chunk);
     RJ_LAUNCH_CHECK();
 }
 

@@ -15,6 +15,8 @@
 //     is, and the copy-out reads keys, values and validity out of the windows through it.
 //   * the global reservation of the partitions' runs (one atomic per non-empty partition) is issued
 //     before the staging loop and consumed after it.
+//   * 512 threads per CTA, two CTAs per SM: 32 warps hide the shared-memory latency of the ranking atomics and
+//     of the permuted reads (the 256-thread version sat on short-scoreboard stalls at 31 % issue).
 // Output stores are runs of consecutive tuples per partition (software write combining); L2 merges the
 // partial lines of neighbouring runs.
 //
@@ -30,11 +32,11 @@
 namespace rj {
 namespace {
 
-constexpr int      kT     = 256;
-constexpr int      kItems = 16;
+constexpr int      kT     = 512;
+constexpr int      kItems = 8;
 constexpr uint32_t kTile  = kItems * kT; // 4096 tuples
 constexpr int      kWarps = kT / 32;
-constexpr int      kDepth = 8;           // output positions per thread in flight at copy-out
+constexpr int      kDepth = 4;           // output positions per thread in flight at copy-out
 constexpr int      kOffBits = 12;
 static_assert(kTile == (1u << kOffBits), "tile offset must fill kOffBits");
 
@@ -69,7 +71,7 @@ struct Layout {
     static constexpr uint32_t kKeyWin  = kTile * 4 + 16;
     static constexpr uint32_t kV0      = W0 ? kTile * W0 + 16 : 0;
     static constexpr uint32_t kV1      = W1 ? kTile * W1 + 16 : 0;
-    static constexpr uint32_t kFlagWin = kRegions ? kTile + 16 : kTile / 8;
+    static constexpr uint32_t kFlagWin = kRegions ? kTile + 16 : 0; // flat pass: validity bits ride in registers
     static constexpr uint32_t oKey     = 0;
     static constexpr uint32_t oV0      = 2 * kKeyWin;
     static constexpr uint32_t oV1      = oV0 + kV0;
@@ -193,14 +195,16 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
         const uint32_t cnt = cur.cnt;
         mbar_wait(&s_kbar[b], (it >> 1) & 1);
 
-        // flat pass: the validity bitmaps of the carried columns (128 words per tile and column; a window of a
-        // streamed table starts on a word, not a 16-byte, boundary, so these do not come by TMA) are loaded now
-        // and parked in shared memory after the ranking; the copy-out picks bits out of them by tile offset
+        // flat pass: validity of the carried columns.  Item k of this warp covers the 32 rows of bitmap word
+        // k * kWarps + warp of the tile (lo is a multiple of the tile), bit = lane: lane k fetches that word now
+        // (a window of a streamed table starts on a word, not a 16-byte, boundary: no TMA here) and hands it
+        // round at staging time.
         uint32_t fword[2] = {0u, 0u};
         if (!kRegions) {
 #pragma unroll
             for (int f = 0; f < 2; ++f)
-                if (f < n_flag && tid < kTile / 32 && tid * 32 < cnt) fword[f] = static_cast<const uint32_t*>(a.flag_src[f])[(cur.lo >> 5) + tid];
+                if (f < n_flag && lane < kItems && (lane * kWarps + warp) * 32 < cnt)
+                    fword[f] = static_cast<const uint32_t*>(a.flag_src[f])[(cur.lo >> 5) + lane * kWarps + warp];
         }
 
         // 1) partition of every tuple (nb = dropped: NULL key, or past the end of a partial tile) and its
@@ -244,11 +248,6 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
             }
             pr[k] = (part << kOffBits) | rank;
         }
-        if (!kRegions) {
-#pragma unroll
-            for (int f = 0; f < 2; ++f)
-                if (f < n_flag && tid < kTile / 32) reinterpret_cast<uint32_t*>(smem + L::oFlag + f * L::kFlagWin)[tid] = fword[f];
-        }
         __syncthreads();
 
         // 2) exclusive scan of the counts; the global runs are reserved now and their bases used after staging
@@ -280,25 +279,34 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
         }
         __syncthreads();
 
-        // 3) the permutation: output position inside the tile -> (tile offset | partition)
+        // 3) the permutation: output position inside the tile -> (tile offset | partition << 12 | validity << 30)
+        if (kRegions && has_win && n_flag > 0) mbar_wait(&s_vbar, it & 1); // the validity bytes are read here
+        const uint32_t fsk = skew(cur.lo, 1);
 #pragma unroll
         for (int k = 0; k < kItems; ++k) {
             const uint32_t part = pr[k] >> kOffBits;
             const uint32_t pos  = s_start[part] + (pr[k] & (kTile - 1));
-            perm[pos] = (part << kOffBits) | (k * kT + tid);
+            uint32_t fl = 0;
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                if (f < n_flag) {
+                    if (kRegions) fl |= (smem[L::oFlag + f * L::kFlagWin + fsk + k * kT + tid] ? 1u : 0u) << f;
+                    else fl |= ((__shfl_sync(RJ_FULL_MASK, fword[f], k) >> lane) & 1u) << f;
+                }
+            }
+            perm[pos] = (fl << 30) | (part << kOffBits) | (k * kT + tid);
         }
         if (tid < nb) s_gbase[tid] = g - start;
         __syncthreads();
 
         // 4) copy out: consecutive threads write consecutive positions of a partition's run
         const uint32_t total = s_total;
-        if (has_win) mbar_wait(&s_vbar, it & 1);
+        if (has_win && !(kRegions && n_flag > 0)) mbar_wait(&s_vbar, it & 1);
         const T0* __restrict__ v0 = reinterpret_cast<const T0*>(smem + L::oV0) + (W0 ? skew(cur.lo, W0 ? W0 : 4) : 0u);
         const T1* __restrict__ v1 = reinterpret_cast<const T1*>(smem + L::oV1) + (W1 ? skew(cur.lo, W1 ? W1 : 4) : 0u);
-        const uint32_t fsk = skew(cur.lo, 1);
         auto copy_out = [&](auto pred_c, uint32_t base) {
             constexpr bool kPred = decltype(pred_c)::value;
-            uint32_t off[kDepth], dd[kDepth];
+            uint32_t off[kDepth], dd[kDepth], fl[kDepth];
             bool     in[kDepth];
 #pragma unroll
             for (int j = 0; j < kDepth; ++j) {
@@ -306,6 +314,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
                 in[j] = !kPred || pos < total;
                 const uint32_t w = in[j] ? perm[pos] : 0u;
                 off[j] = w & (kTile - 1);
+                fl[j]  = w >> 30;
                 dd[j]  = s_gbase[(w >> kOffBits) & 0xffu] + pos;
             }
             {
@@ -335,19 +344,9 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
                 if (f < n_flag) {
-                    uint8_t bb[kDepth];
-                    if (kRegions) {
-                        const uint8_t* fw = smem + L::oFlag + f * L::kFlagWin + fsk;
-#pragma unroll
-                        for (int j = 0; j < kDepth; ++j) bb[j] = fw[off[j]];
-                    } else {
-                        const uint32_t* fw = reinterpret_cast<const uint32_t*>(smem + L::oFlag + f * L::kFlagWin);
-#pragma unroll
-                        for (int j = 0; j < kDepth; ++j) bb[j] = static_cast<uint8_t>((fw[off[j] >> 5] >> (off[j] & 31u)) & 1u);
-                    }
 #pragma unroll
                     for (int j = 0; j < kDepth; ++j)
-                        if (in[j]) a.flag_dst[f][dd[j]] = bb[j];
+                        if (in[j]) a.flag_dst[f][dd[j]] = static_cast<uint8_t>((fl[j] >> f) & 1u);
                 }
             }
         };

@@ -84,6 +84,10 @@ struct PartitionPlanDev {
 size_t partition_plan_words(int total_bits, int pass1_bits);
 void   partition_plan_carve(uint32_t* base, int total_bits, int pass1_bits, PartitionPlanDev* plan);
 
+// ---- host_copy.cpp ---------------------------------------------------------------------------------
+void copy_page(void* dst, const void* src); // 8192 bytes, non-temporal stores when dst is 16-byte aligned
+void copy_fence();                          // before another agent reads what copy_page wrote
+
 // ---- k_scan.cu ------------------------------------------------------------------------------------
 size_t scan_tmp_bytes(uint64_t n);
 // out[i] = sum_{k<i} in[k], out[n] = total
@@ -104,10 +108,11 @@ void launch_decode_varchar(const void* pages, uint64_t n_pages, const uint64_t* 
 // ---- k_partition.cu -------------------------------------------------------------------------------
 void launch_radix_histogram(const void* keys, const uint32_t* valid, uint64_t n, int key_bytes, int shift,
                             int bits, uint32_t* hist, int sm_count, cudaStream_t s);
-// build_cap: build tuples per join work unit (kJoinBuildCap for join_kernel, kEmitBuildCap for join_emit_kernel)
+// build_cap x probe_chunk: tuples per join work unit (kJoinBuildCap x kJoinProbeChunk for join_kernel,
+// kEmitBuildCap x kEmitProbeChunk for join_emit_kernel)
 void launch_partition_plan(const uint32_t* hist_b, const uint32_t* hist_p, uint32_t flat_b, uint32_t flat_p,
                            int total_bits, int pass1_bits, int key_bytes, const PartitionPlanDev& plan,
-                           cudaStream_t s, uint32_t build_cap = kJoinBuildCap);
+                           cudaStream_t s, uint32_t build_cap = kJoinBuildCap, uint32_t probe_chunk = kJoinProbeChunk);
 // Payload columns that travel with the tuples of a flat scatter: dst[c][pos] = src[c][row of the tuple].
 // The source is read inside the tile's own row window (sequential DRAM traffic), so a later gather
 // through positions of the scattered order stays inside one partition / region instead of the table.
@@ -195,6 +200,7 @@ void launch_join(const JoinLaunch& a, int sm_count, cudaStream_t s);
 // ---- k_join_emit.cu: root join fused with page output ------------------------------------------------
 constexpr uint32_t kEmitSlots     = 4096;  // table slots per CTA (two CTAs of ~100 KB per SM)
 constexpr uint32_t kEmitBuildCap  = 3072;  // build tuples per table; larger partitions are chunked
+constexpr uint32_t kEmitProbeChunk = 65536; // probe tuples per work unit (a table is built once per unit)
 constexpr uint32_t kEmitChunkRows = 1984;  // rows per output chunk: 1 page per 4-byte column, 2 x 992 rows per 8-byte column
 constexpr int      kEmitMaxPay    = 2;     // carried columns per side
 constexpr int      kEmitMaxOut    = 4;     // output columns
@@ -203,7 +209,7 @@ struct JoinEmitLaunch {
     const uint32_t* pkeys = nullptr;
     const uint32_t* off_b = nullptr; // [nparts+1]
     const uint32_t* off_p = nullptr;
-    const uint32_t* unit_start = nullptr; // [nparts+1], units of (kEmitBuildCap build) x (kJoinProbeChunk probe) tuples
+    const uint32_t* unit_start = nullptr; // [nparts+1], units of (kEmitBuildCap build) x (kEmitProbeChunk probe) tuples
     uint32_t*       unit_cursor = nullptr;
     uint32_t        nparts = 1;
     int             part_bits = 0;
@@ -225,8 +231,9 @@ struct JoinEmitLaunch {
     uint32_t*           abort_flag = nullptr;
 };
 inline unsigned join_emit_grid(int sm_count) { return static_cast<unsigned>(sm_count) * 2; }
-// chunks a launch can produce: every probe tuple matches at most once, every CTA ends with a partial chunk
-inline uint64_t join_emit_max_chunks(uint64_t n_probe, int sm_count) { return n_probe / kEmitChunkRows + join_emit_grid(sm_count) + 1; }
+// chunks a launch can produce: every probe tuple matches at most once; every CTA ends with a partial chunk
+// and the two (empty) chunks it held in reserve
+inline uint64_t join_emit_max_chunks(uint64_t n_probe, int sm_count) { return n_probe / kEmitChunkRows + 3 * join_emit_grid(sm_count) + 1; }
 bool join_emit_fits(const JoinEmitLaunch& L);
 void launch_join_emit(const JoinEmitLaunch& L, int sm_count, cudaStream_t s);
 
