@@ -302,6 +302,57 @@ void rj_encode_varchar_free(rj_ctx* ctx, rj_varchar_layout* layout);
 int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n,
                        int32_t type, void* d_pages_out, uint64_t* n_pages_out, void* stream);
 
+/* -- pre-filter evaluation (harness side: Statement::eval on InnerColumns, src/statement.cpp:46-133,
+ *    186-200; include/inner_column.h:170-325,386-562) and filter + emit (src/build_table.cpp:94-119,
+ *    247-303) ------------------------------------------------------------------------------------- */
+
+/* operators of a comparison: the values of the reference's Comparison::Op (include/statement.h:54-65) */
+enum rj_cmp_op {
+    RJ_OP_EQ = 0, RJ_OP_NEQ, RJ_OP_LT, RJ_OP_GT, RJ_OP_LEQ, RJ_OP_GEQ, RJ_OP_LIKE, RJ_OP_NOT_LIKE,
+    RJ_OP_IS_NULL, RJ_OP_IS_NOT_NULL
+};
+/* logical operators: the values of LogicalOperation::Type (include/statement.h:186-190) */
+enum rj_logic_op { RJ_LOGIC_AND = 0, RJ_LOGIC_OR, RJ_LOGIC_NOT };
+
+/* Result of every predicate: one bit per row in uint32 words, LSB first (= the reference's
+ * std::vector<uint8_t> on a little-endian host); bit = "not NULL and the comparison holds".  Bits past
+ * row n are zero.  d_out holds (n + 31) / 32 words.
+ * Fixed-width columns (decoded values + validity bitmap, rj_decode_fixed): ops EQ..GEQ; the literal is
+ * rhs_i for INT32 (narrowed with static_cast<int32_t>, statement.cpp:55) and INT64, rhs_d for FP64. */
+int rj_filter_compare(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n, int32_t type,
+                      int32_t op, int64_t rhs_i, double rhs_d, uint32_t* d_out, void* stream);
+/* VARCHAR columns (descriptors over the page buffer, rj_decode_varchar): ops EQ..GEQ compare bytes like
+ * std::string_view, LIKE / NOT_LIKE follow statement.h:118-161 ('%' = ".*", '_' = ".", full match, '.'
+ * never matches a newline).  `rhs` is a HOST pointer to rhs_len bytes. */
+int rj_filter_varchar(rj_ctx* ctx, const void* d_pages, const uint64_t* d_desc, const uint32_t* d_valid,
+                      uint64_t n, int32_t op, const char* rhs, uint64_t rhs_len, uint32_t* d_out, void* stream);
+/* IS NULL (is_null != 0) / IS NOT NULL: the complement of / the validity bitmap (NULL = no NULLs) */
+int rj_filter_null(rj_ctx* ctx, const uint32_t* d_valid, uint64_t n, int32_t is_null, uint32_t* d_out, void* stream);
+/* AND / OR / NOT of result bitmaps (bitmap_and / bitmap_or / bitmap_not, statement.cpp:8-44); NOT ignores
+ * d_b and, like the reference, turns a NULL row's false into true. */
+int rj_bitmap_logic(rj_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint64_t n, int32_t op,
+                    uint32_t* d_out, void* stream);
+/* Row ids of the set bits, ascending (what from_inner_to_column's loop visits, build_table.cpp:94-119):
+ * d_row_ids must hold n entries; *count (host) receives how many were written (synchronises). */
+int rj_bitmap_select(rj_ctx* ctx, const uint32_t* d_bits, uint64_t n, uint32_t* d_row_ids, uint64_t* count,
+                     void* stream);
+
+/* A filter as a postfix program over the columns of ONE table: comparisons push a bitmap, AND / OR pop
+ * two and push one, NOT pops one and pushes one; exactly one bitmap must remain. */
+typedef struct rj_pred_t {
+    int32_t     kind;      /* 0 = comparison, 1 = logical operator                                  */
+    int32_t     op;        /* rj_cmp_op or rj_logic_op                                               */
+    uint32_t    column;    /* comparison: column of the table                                        */
+    int32_t     lit_type;  /* literal: RJ_INT64 (rhs_i), RJ_FP64 (rhs_d), RJ_VARCHAR (rhs_s), or -1   */
+    int64_t     rhs_i;
+    double      rhs_d;
+    const char* rhs_s;     /* host pointer */
+    uint64_t    rhs_s_len;
+} rj_pred_t;
+/* Filter + emit (Table::from_csv's tail, build_table.cpp:247-303): the rows of `table` (host pages) that
+ * pass the program, in row order, as result pages of ALL its columns; n_prog = 0 keeps every row. */
+int rj_filter_table(rj_ctx* ctx, const rj_table_t* table, const rj_pred_t* prog, uint32_t n_prog, rj_result** out);
+
 /* ------------------------------------------------------------------------------------------------
  * Profiling: per-kernel-class CUDA-event timings accumulated by the whole-path functions.
  * ---------------------------------------------------------------------------------------------- */

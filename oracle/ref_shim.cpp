@@ -15,6 +15,7 @@
 
 #include <omp.h>
 
+#include <inner_column.h>
 #include <plan.h>
 #include <table.h>
 
@@ -211,6 +212,79 @@ int ref_decode_fill(const rj_column_t* col, uint64_t num_rows, uint8_t* valid, v
         if (col->type == RJ_VARCHAR) {
             str_off[num_rows] = pos;
         }
+        return 0;
+    } catch (const std::exception& e) {
+        set_err(err, errlen, e.what());
+        return 1;
+    }
+}
+
+// Pre-filter oracle: the reference's own COLUMN-WISE evaluation (Comparison::eval / LogicalOperation::eval
+// over InnerColumns, src/statement.cpp:46-133,186-200 -- what Table::from_csv runs, build_table.cpp:255)
+// on the decoded table.  `prog` is the postfix program of include/rj_b200.h; selected[i] = result bit i.
+int ref_filter(const rj_table_t* t, const rj_pred_t* prog, uint32_t n_prog, uint8_t* selected, char* err, size_t errlen) {
+    try {
+        Table tab = Table::from_columnar(make_table(*t));
+        std::vector<std::unique_ptr<InnerColumnBase>> owned;
+        std::vector<const InnerColumnBase*>           cols;
+        for (uint32_t c = 0; c < t->n_columns; ++c) {
+            switch (static_cast<DataType>(t->columns[c].type)) {
+            case DataType::INT32: {
+                auto col = std::make_unique<InnerColumn<int32_t>>();
+                for (auto& row: tab.table()) { if (auto* v = std::get_if<int32_t>(&row[c])) col->push_back(*v); else col->push_back_null(); }
+                owned.push_back(std::move(col));
+                break;
+            }
+            case DataType::INT64: {
+                auto col = std::make_unique<InnerColumn<int64_t>>();
+                for (auto& row: tab.table()) { if (auto* v = std::get_if<int64_t>(&row[c])) col->push_back(*v); else col->push_back_null(); }
+                owned.push_back(std::move(col));
+                break;
+            }
+            case DataType::FP64: {
+                auto col = std::make_unique<InnerColumn<double>>();
+                for (auto& row: tab.table()) { if (auto* v = std::get_if<double>(&row[c])) col->push_back(*v); else col->push_back_null(); }
+                owned.push_back(std::move(col));
+                break;
+            }
+            case DataType::VARCHAR: {
+                auto col = std::make_unique<InnerColumn<std::string>>();
+                for (auto& row: tab.table()) { if (auto* v = std::get_if<std::string>(&row[c])) col->push_back(*v); else col->push_back_null(); }
+                owned.push_back(std::move(col));
+                break;
+            }
+            }
+            cols.push_back(owned.back().get());
+        }
+        std::vector<std::unique_ptr<Statement>> stack;
+        for (uint32_t i = 0; i < n_prog; ++i) {
+            const rj_pred_t& e = prog[i];
+            if (e.kind == 0) {
+                Literal lit = std::monostate{};
+                if (e.lit_type == RJ_INT64) lit = e.rhs_i;
+                else if (e.lit_type == RJ_FP64) lit = e.rhs_d;
+                else if (e.lit_type == RJ_VARCHAR) lit = std::string(e.rhs_s ? e.rhs_s : "", e.rhs_s_len);
+                stack.push_back(std::make_unique<Comparison>(e.column, static_cast<Comparison::Op>(e.op), std::move(lit)));
+            } else {
+                if (e.op == RJ_LOGIC_NOT) {
+                    if (stack.empty()) throw std::runtime_error("malformed program");
+                    auto c = std::move(stack.back());
+                    stack.pop_back();
+                    stack.push_back(LogicalOperation::makeNot(std::move(c)));
+                } else {
+                    if (stack.size() < 2) throw std::runtime_error("malformed program");
+                    auto r = std::move(stack.back());
+                    stack.pop_back();
+                    auto l = std::move(stack.back());
+                    stack.pop_back();
+                    stack.push_back(e.op == RJ_LOGIC_AND ? LogicalOperation::makeAnd(std::move(l), std::move(r))
+                                                         : LogicalOperation::makeOr(std::move(l), std::move(r)));
+                }
+            }
+        }
+        if (stack.size() != 1) throw std::runtime_error("malformed program");
+        const std::vector<uint8_t> bits = stack.back()->eval(cols);
+        for (uint64_t i = 0; i < t->num_rows; ++i) selected[i] = (bits[i / 8] >> (i % 8)) & 1u;
         return 0;
     } catch (const std::exception& e) {
         set_err(err, errlen, e.what());

@@ -76,6 +76,11 @@ class rj_plan_t(C.Structure):
     ]
 
 
+class rj_pred_t(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("column", C.c_uint32), ("lit_type", C.c_int32),
+                ("rhs_i", C.c_int64), ("rhs_d", C.c_double), ("rhs_s", C.c_char_p), ("rhs_s_len", C.c_uint64)]
+
+
 class rj_stage_stat_t(C.Structure):
     _fields_ = [("ms", C.c_double), ("launches", C.c_uint64), ("bytes", C.c_uint64)]
 
@@ -141,6 +146,12 @@ PROTOTYPES = {
     "rj_encode_varchar_write": (C.c_int, [_vp, _vp, _vp, _vp]),
     "rj_encode_varchar_free": (None, [_vp, _vp]),
     "rj_gen_fixed_pages": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, C.POINTER(_u64), _vp]),
+    "rj_filter_compare": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, C.c_int64, C.c_double, _vp, _vp]),
+    "rj_filter_varchar": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, C.c_char_p, _u64, _vp, _vp]),
+    "rj_filter_null": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp]),
+    "rj_bitmap_logic": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, _vp]),
+    "rj_bitmap_select": (C.c_int, [_vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
+    "rj_filter_table": (C.c_int, [_vp, C.POINTER(rj_table_t), C.POINTER(rj_pred_t), _u32, _pvp]),
     "rj_profile_enable": (C.c_int, [_vp, C.c_int]),
     "rj_profile_reset": (C.c_int, [_vp]),
     "rj_profile_read": (C.c_int, [_vp, C.POINTER(rj_stage_stat_t)]),

@@ -2308,6 +2308,128 @@ int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_vali
     });
 }
 
+// ---- pre-filters ----------------------------------------------------------------------------------------
+int rj_filter_compare(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n, int32_t type, int32_t op,
+                      int64_t rhs_i, double rhs_d, uint32_t* d_out, void* stream) {
+    return guarded(ctx, [&] { launch_filter_compare(d_values, d_valid, n, type, op, rhs_i, rhs_d, d_out, ctx->sm_count, pick_stream(ctx, stream)); });
+}
+
+int rj_filter_varchar(rj_ctx* ctx, const void* d_pages, const uint64_t* d_desc, const uint32_t* d_valid, uint64_t n, int32_t op,
+                      const char* rhs, uint64_t rhs_len, uint32_t* d_out, void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t st = pick_stream(ctx, stream);
+        if (rhs_len > 0xffffffffull) throw EngineError("rj_filter_varchar: literal too long");
+        Buf lit = dev_alloc(rhs_len + 16, st);
+        if (rhs_len) RJ_CUDA(cudaMemcpyAsync(lit->p, rhs, rhs_len, cudaMemcpyHostToDevice, st)); // pageable source: staged before the call returns
+        launch_filter_varchar(d_pages, d_desc, d_valid, n, op, lit->as<uint8_t>(), static_cast<uint32_t>(rhs_len), d_out, ctx->sm_count, st);
+    });
+}
+
+int rj_filter_null(rj_ctx* ctx, const uint32_t* d_valid, uint64_t n, int32_t is_null, uint32_t* d_out, void* stream) {
+    return guarded(ctx, [&] { launch_filter_null(d_valid, n, is_null != 0, d_out, ctx->sm_count, pick_stream(ctx, stream)); });
+}
+
+int rj_bitmap_logic(rj_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint64_t n, int32_t op, uint32_t* d_out, void* stream) {
+    return guarded(ctx, [&] { launch_bitmap_logic(d_a, d_b, n, op, d_out, ctx->sm_count, pick_stream(ctx, stream)); });
+}
+
+namespace {
+// row ids of the set bits, ascending; returns their number (synchronises the stream)
+uint64_t bitmap_select(rj_ctx* ctx, const uint32_t* bits, uint64_t n, uint32_t* ids, cudaStream_t st) {
+    const uint64_t n_words = (n + 31) / 32;
+    if (n_words == 0) return 0;
+    Buf counts = dev_alloc(n_words * 4, st);
+    Buf start = dev_alloc((n_words + 1) * 8, st);
+    Buf tmp = dev_alloc(scan_tmp_bytes(n_words), st);
+    launch_bitmap_popc(bits, n_words, counts->as<uint32_t>(), ctx->sm_count, st);
+    launch_exclusive_scan_u32_u64(counts->as<uint32_t>(), start->as<uint64_t>(), n_words, tmp->p, st);
+    launch_bitmap_expand(bits, start->as<uint64_t>(), n_words, ids, ctx->sm_count, st);
+    uint64_t total = 0;
+    RJ_CUDA(cudaMemcpyAsync(&total, start->as<uint64_t>() + n_words, 8, cudaMemcpyDeviceToHost, st));
+    RJ_CUDA(cudaStreamSynchronize(st));
+    return total;
+}
+} // namespace
+
+int rj_bitmap_select(rj_ctx* ctx, const uint32_t* d_bits, uint64_t n, uint32_t* d_row_ids, uint64_t* count, void* stream) {
+    return guarded(ctx, [&] {
+        const uint64_t m = bitmap_select(ctx, d_bits, n, d_row_ids, pick_stream(ctx, stream));
+        if (count) *count = m;
+    });
+}
+
+int rj_filter_table(rj_ctx* ctx, const rj_table_t* table, const rj_pred_t* prog, uint32_t n_prog, rj_result** out) {
+    return guarded(ctx, [&] {
+        if (!table || !out) throw EngineError("rj_filter_table: null argument");
+        if (n_prog && !prog) throw EngineError("rj_filter_table: null program");
+        if (table->num_rows >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
+        // a one-node plan: Scan(table 0) with every column as output, in order
+        std::vector<rj_attr_t> attrs(table->n_columns);
+        for (uint32_t c = 0; c < table->n_columns; ++c) attrs[c] = rj_attr_t{c, table->columns[c].type, 0};
+        rj_node_t scan{};
+        scan.n_output_attrs = table->n_columns;
+        scan.output_attrs = attrs.data();
+        rj_plan_t plan{};
+        plan.n_nodes = 1;
+        plan.n_inputs = 1;
+        plan.nodes = &scan;
+        plan.inputs = table;
+        plan.root = 0;
+        auto in = upload_tables(ctx, table, 1, nullptr);
+        Exec ex(ctx, &plan, in.get());
+        cudaStream_t st = ctx->stream;
+        const uint64_t n = table->num_rows;
+        const uint64_t words = (n + 31) / 32;
+        Rel r;
+        r.rows = n;
+        r.rid[0] = nullptr; // identity: no filter keeps every row
+        if (n_prog) {
+            std::vector<Buf> stack;
+            for (uint32_t i = 0; i < n_prog; ++i) {
+                const rj_pred_t& pr = prog[i];
+                Buf res = dev_alloc(words * 4 + 16, st);
+                if (pr.kind == 0) {
+                    if (pr.column >= table->n_columns) throw EngineError("rj_filter_table: predicate column out of range");
+                    const DecodedCol& col = ex.column(0, pr.column);
+                    if (pr.op == RJ_OP_IS_NULL || pr.op == RJ_OP_IS_NOT_NULL) {
+                        launch_filter_null(col.valid_ptr(), n, pr.op == RJ_OP_IS_NULL, res->as<uint32_t>(), ctx->sm_count, st);
+                    } else if (col.type == RJ_VARCHAR) {
+                        if (pr.lit_type != RJ_VARCHAR) throw EngineError("rj_filter_table: a VARCHAR column is compared with a string literal");
+                        if (pr.rhs_s_len > 0xffffffffull) throw EngineError("rj_filter_table: literal too long");
+                        Buf lit = dev_alloc(pr.rhs_s_len + 16, st);
+                        if (pr.rhs_s_len) RJ_CUDA(cudaMemcpyAsync(lit->p, pr.rhs_s, pr.rhs_s_len, cudaMemcpyHostToDevice, st));
+                        launch_filter_varchar(col.pages, col.values->as<uint64_t>(), col.valid_ptr(), n, pr.op, lit->as<uint8_t>(),
+                                              static_cast<uint32_t>(pr.rhs_s_len), res->as<uint32_t>(), ctx->sm_count, st);
+                    } else {
+                        // std::get<int64_t> / std::get<double> of the literal (statement.cpp:55,74,93): the wrong
+                        // alternative throws in the reference
+                        if (col.type == RJ_FP64 ? pr.lit_type != RJ_FP64 : pr.lit_type != RJ_INT64) throw EngineError("bad_variant_access");
+                        launch_filter_compare(col.values->p, col.valid_ptr(), n, col.type, pr.op, pr.rhs_i, pr.rhs_d, res->as<uint32_t>(), ctx->sm_count, st);
+                    }
+                } else if (pr.kind == 1) {
+                    const size_t need = pr.op == RJ_LOGIC_NOT ? 1 : 2;
+                    if (stack.size() < need) throw EngineError("rj_filter_table: malformed program (stack underflow)");
+                    Buf b = pr.op == RJ_LOGIC_NOT ? nullptr : stack.back();
+                    if (need == 2) stack.pop_back();
+                    Buf a = stack.back();
+                    stack.pop_back();
+                    launch_bitmap_logic(a->as<uint32_t>(), b ? b->as<uint32_t>() : nullptr, n, pr.op, res->as<uint32_t>(), ctx->sm_count, st);
+                } else {
+                    throw EngineError("rj_filter_table: unknown program entry");
+                }
+                stack.push_back(std::move(res));
+            }
+            if (stack.size() != 1) throw EngineError("rj_filter_table: malformed program (one bitmap must remain)");
+            Buf ids = dev_alloc(std::max<uint64_t>(n, 1) * 4, st);
+            r.rows = bitmap_select(ctx, stack.back()->as<uint32_t>(), n, ids->as<uint32_t>(), st);
+            r.rid[0] = ids;
+        }
+        auto res = ex.root(0, r);
+        RJ_CUDA(cudaStreamSynchronize(st));
+        *out = res.release();
+    });
+}
+
 // ---- profiling -------------------------------------------------------------------------------------
 int rj_profile_enable(rj_ctx* ctx, int on) {
     if (!ctx) return 1;

@@ -191,18 +191,24 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const EmitArgs a
         }
     };
 
-    // Chunk A is full: write its bitmaps and headers, then B becomes A.  Whole CTA, behind a barrier that
-    // ended the round's stores into the shared bitmaps; `reserved` = rows handed out so far (<= 3968 placed).
+    // Chunk A is full: write its bitmaps and headers, then B becomes A.  Runs behind the barrier that ended
+    // the round's stores into the shared bitmaps.  Only the first two warps work (62 bitmap words per
+    // chunk); they synchronise among themselves with a named barrier, and the rest of the CTA meets them at
+    // the barrier in front of the next reservation -- probing the next batch in the meantime.
+    // `reserved` = rows handed out so far (<= 3968 placed).
     auto close_full_chunk = [&](uint32_t reserved) {
+        if (tid >= kMetaThreads) return;
+        asm volatile("bar.sync 1, 64;" ::: "memory"); // an earlier close of this round is complete
         uint32_t nv1[kMaxNull], nv2[kMaxNull];
 #pragma unroll
         for (int nn = 0; nn < kMaxNull; ++nn) {
             nv1[nn] = nn < NN ? s_nvb[1][nn] : 0u;
             nv2[nn] = nn < NN ? s_nvb[2][nn] : 0u;
         }
+        const uint32_t nv3 = tid < NN ? s_nvb[3][tid] : 0u, nv4 = tid < NN ? s_nvb[4][tid] : 0u;
         write_chunk_meta(s_chunk[0], kChunkRows, nv1, nv2);
-        __syncthreads(); // the bitmaps, s_nvb and s_chunk have been read by everybody
-        // B's words move down (thread w alone touches words w and 62 + w of a bitmap)
+        asm volatile("bar.sync 1, 64;" ::: "memory"); // both warps have read the bitmaps, s_nvb and s_chunk
+        // B's words move down
         if (tid < kBitmapWords) {
 #pragma unroll
             for (int nn = 0; nn < NN; ++nn) {
@@ -229,17 +235,19 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const EmitArgs a
             chunk_ahead = atomicAdd(a.chunk_counter, 1u); // consumed at the next close
         }
         if (tid < NN) {
-            s_nvb[1][tid] = s_nvb[3][tid] - nv2[tid]; // meaningful once a row beyond the boundary exists
-            s_nvb[2][tid] = s_nvb[4][tid] - nv2[tid];
+            const uint32_t mine2 = s_nvb[2][tid];
+            s_nvb[1][tid] = nv3 - mine2; // meaningful once a row beyond the boundary exists
+            s_nvb[2][tid] = nv4 - mine2;
         }
-        __syncthreads();
     };
 
+    bool     close_pending = false; // a chunk was closed since the last CTA-wide barrier
     uint32_t u_next = 0;
     if (tid == 0) u_next = atomicAdd(a.unit_cursor, 1u);
     for (;;) {
         // ---- next work unit, in global order (see k_join.cu); the cursor was advanced one unit ahead --------
         __syncthreads();
+        close_pending = false;
         if (tid < 32) {
             uint32_t u = __shfl_sync(RJ_FULL_MASK, u_next, 0);
             if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(a.abort_flag)) u = 0xffffffffu; // somebody met a duplicate key
@@ -402,6 +410,10 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const EmitArgs a
             // place the matches as rows of the open chunks (A: positions 0..1983, B: 1984..3967)
             for (;;) {
                 // -- phase A: row range and value-slot ranges of this warp, from one packed atomic
+                if (close_pending) {
+                    __syncthreads(); // the chunk closed after the last round has been written and B has become A
+                    close_pending = false;
+                }
                 // (counts are summed over the warp with REDUX: this thread's matches, and how many of them are
                 // non-NULL in each nullable column)
                 const uint32_t total = __reduce_add_sync(RJ_FULL_MASK, static_cast<uint32_t>(__popc(pending)));
@@ -450,10 +462,32 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const EmitArgs a
                 if (total && off < kOpenRows) {
                     uint32_t pos[kItems];               // kNone: not placed in this round
                     uint32_t slot[NN > 0 ? NN : 1][kItems];
-                    uint32_t* bmp[NN > 0 ? NN : 1];
+                    const uint32_t sbase = smem_u32(smem);
+                    if (total == kItems * 32u && off + total <= kOpenRows) {
+                        // dense round (every lane matched in every item -- the rule in a foreign-key join -- and all
+                        // of it fits): rows are lanes in order, a column's validity bits are its four ballots
+                        // shifted to the warp's first row, OR-ed in by five lanes with one atomic each
 #pragma unroll
-                    for (int nn = 0; nn < NN; ++nn) bmp[nn] = reinterpret_cast<uint32_t*>(smem + a.sm_bitmap[nn]);
-                    {
+                        for (int k = 0; k < kItems; ++k) pos[k] = off + 32u * k + lane;
+#pragma unroll
+                        for (int nn = 0; nn < NN; ++nn) {
+                            uint32_t vo = static_cast<uint32_t>(old >> (kFieldBits * (nn + 1))) & kFieldMask;
+                            uint32_t prev = 0u, mine_lo = 0u, mine_hi = 0u; // lane i ORs word (off >> 5) + i = vb[i-1] : vb[i] funnel-shifted
+#pragma unroll
+                            for (int k = 0; k < kItems; ++k) {
+                                const uint32_t vb = __ballot_sync(RJ_FULL_MASK, (okbits >> (nn * kItems + k)) & 1u);
+                                slot[nn][k] = vo + __popc(vb & lt);
+                                vo += __popc(vb);
+                                if (lane == static_cast<uint32_t>(k)) { mine_hi = vb; mine_lo = prev; }
+                                prev = vb;
+                            }
+                            if (lane == kItems) mine_lo = prev; // the last word: only what the shift carries over
+                            const uint32_t word = __funnelshift_l(mine_lo, mine_hi, off & 31u);
+                            if (lane <= kItems && word)
+                                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sbase + a.sm_bitmap[nn] + ((off >> 5) + lane) * 4u), "r"(word) : "memory");
+                        }
+                        pending = 0;
+                    } else {
                         uint32_t ro = off;
                         uint32_t vo[NN > 0 ? NN : 1];
 #pragma unroll
@@ -488,87 +522,102 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const EmitArgs a
                                         lo = __reduce_or_sync(RJ_FULL_MASK, (p >> 5) == word0 ? bit : 0u);
                                         hi = __reduce_or_sync(RJ_FULL_MASK, (p >> 5) == word0 ? 0u : bit);
                                     }
-                                    if (lane == 0 && lo) atomicOr(&bmp[nn][word0], lo);
-                                    if (lane == 1 && hi) atomicOr(&bmp[nn][word0 + 1], hi);
+                                    const uint32_t w = lane == 0 ? lo : hi;
+                                    if (lane < 2 && w)
+                                        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sbase + a.sm_bitmap[nn] + (word0 + lane) * 4u), "r"(w) : "memory");
                                 }
                             }
                             ro += cntk;
                             if (fits) pending &= ~(1u << k);
                         }
                     }
-                    // column by column: the column's description and page pointers are set up once, four stores follow
-#pragma unroll
-                    for (int j = 0; j < kEmitMaxOut; ++j) {
-                        if (j >= a.n_out) continue;
-                        const int      src = a.out_src[j], c = a.out_idx[j], nn = (NN > 0) ? a.out_null[j] : -1;
-                        const bool     wide = a.out_width[j] == 8;
-                        const uint8_t* vsrc = nullptr; // shared-memory column the values come from (nullptr: the key)
-                        bool           v8 = false;
-                        if (src == 1 && NB > 0) {
-                            const int cc = NB > 1 ? c : 0;
-                            v8 = a.bwidth[cc] == 8;
-                            vsrc = smem + a.sm_bpay[cc] + bskew[cc] * (v8 ? 8u : 4u);
-                        } else if (src == 2 && NP > 0) {
-                            const int cc = NP > 1 ? c : 0;
-                            v8 = a.pwidth[cc] == 8;
-                            vsrc = smem + a.sm_ppay[sb][cc] + (v8 ? (base & 1u) * 8u : (base & 3u) * 4u);
-                        }
-                        // validity of this column for item k: bit k of okc
-                        const uint32_t okc = nn >= 0 ? (okbits >> (nn * kItems)) : 0xffffffffu;
-                        // value slot of a row at position p: p, or the packed slot; minus what precedes its page
-                        uint32_t sub[4] = {0u, kHalfRows, 2 * kHalfRows, 3 * kHalfRows};
-                        if (nn >= 0) {
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) sub[h] = s_nvb[h][nn]; // s_nvb[0] = 0
-                        }
-                        if (!wide) {
-                            uint32_t* const pgA = reinterpret_cast<uint32_t*>(a.out_pages[j] + static_cast<uint64_t>(cA) * RJ_PAGE + 4);
-                            uint32_t* const pgB = reinterpret_cast<uint32_t*>(a.out_pages[j] + static_cast<uint64_t>(cB) * RJ_PAGE + 4);
+
+                    // A column's four values go to their pages.  N = index among the nullable carried columns
+                    // (-1: the column holds no NULL), WIDE = 8-byte values: pages 2 cA, 2 cA + 1 for positions below
+                    // 1984, then 2 cB, 2 cB + 1; the slot inside a page = the row's value slot minus the values
+                    // that precede the page (s_nvb), or row position minus the rows that precede it.
+                    auto emit = [&](auto n_c, auto wide_c, int j, const uint64_t (&v)[kItems]) {
+                        constexpr int  N    = decltype(n_c)::value;
+                        constexpr bool WIDE = decltype(wide_c)::value;
+                        uint8_t* const pages = a.out_pages[j];
+                        if constexpr (!WIDE) {
+                            uint32_t* const pgA = reinterpret_cast<uint32_t*>(pages + static_cast<uint64_t>(cA) * RJ_PAGE + 4);
+                            uint32_t* const pgB = reinterpret_cast<uint32_t*>(pages + static_cast<uint64_t>(cB) * RJ_PAGE + 4);
+                            const uint32_t subB = N >= 0 ? s_nvb[2][N >= 0 ? N : 0] : kChunkRows;
 #pragma unroll
                             for (int k = 0; k < kItems; ++k) {
                                 const uint32_t p = pos[k];
-                                if (p == kNone || !((okc >> k) & 1u)) continue; // not placed, or NULL: no value stored
-                                uint32_t v = key[k];
-                                if (vsrc != nullptr) {
-                                    const uint32_t e = src == 1 ? lidx[k] : k * kThreads + tid;
-                                    v = v8 ? static_cast<uint32_t>(reinterpret_cast<const uint64_t*>(vsrc)[e]) : reinterpret_cast<const uint32_t*>(vsrc)[e];
-                                }
-                                uint32_t sl = p;
-                                if (nn >= 0) {
-                                    sl = slot[0][k];
-#pragma unroll
-                                    for (int q = 1; q < NN; ++q)
-                                        if (nn == q) sl = slot[q][k];
-                                }
-                                const bool inB = p >= kChunkRows;
-                                (inB ? pgB : pgA)[sl - (inB ? sub[2] : 0u)] = v;
+                                if (p == kNone) continue;
+                                if (N >= 0 && !((okbits >> ((N >= 0 ? N : 0) * kItems + k)) & 1u)) continue; // NULL: no value stored
+                                const uint32_t sl  = N >= 0 ? slot[N >= 0 ? N : 0][k] : p;
+                                const bool     inB = p >= kChunkRows;
+                                (inB ? pgB : pgA)[sl - (inB ? subB : 0u)] = static_cast<uint32_t>(v[k]);
                             }
                         } else {
-                            // pages 2 cA, 2 cA + 1 for positions below 1984, then 2 cB, 2 cB + 1
-                            uint64_t* const pgA = reinterpret_cast<uint64_t*>(a.out_pages[j] + 2ull * cA * RJ_PAGE + 8);
-                            uint64_t* const pgB = reinterpret_cast<uint64_t*>(a.out_pages[j] + 2ull * cB * RJ_PAGE + 8);
+                            uint64_t* const pgA = reinterpret_cast<uint64_t*>(pages + 2ull * cA * RJ_PAGE + 8);
+                            uint64_t* const pgB = reinterpret_cast<uint64_t*>(pages + 2ull * cB * RJ_PAGE + 8) - 2 * (RJ_PAGE / 8); // indexed with h = 2, 3
 #pragma unroll
                             for (int k = 0; k < kItems; ++k) {
                                 const uint32_t p = pos[k];
-                                if (p == kNone || !((okc >> k) & 1u)) continue;
-                                uint64_t v = key[k];
-                                if (vsrc != nullptr) {
-                                    const uint32_t e = src == 1 ? lidx[k] : k * kThreads + tid;
-                                    v = v8 ? reinterpret_cast<const uint64_t*>(vsrc)[e] : static_cast<uint64_t>(reinterpret_cast<const uint32_t*>(vsrc)[e]);
-                                }
-                                uint32_t sl = p;
-                                if (nn >= 0) {
-                                    sl = slot[0][k];
-#pragma unroll
-                                    for (int q = 1; q < NN; ++q)
-                                        if (nn == q) sl = slot[q][k];
-                                }
-                                const uint32_t h  = (p >= kHalfRows ? 1u : 0u) + (p >= 2 * kHalfRows ? 1u : 0u) + (p >= 3 * kHalfRows ? 1u : 0u);
-                                const uint32_t sb8 = h == 0 ? sub[0] : (h == 1 ? sub[1] : (h == 2 ? sub[2] : sub[3]));
-                                // (h & 1) selects the second page of the pair: + 8192 bytes = 1024 slots
-                                (h < 2 ? pgA : pgB)[(h & 1u) * (RJ_PAGE / 8) + sl - sb8] = v;
+                                if (p == kNone) continue;
+                                if (N >= 0 && !((okbits >> ((N >= 0 ? N : 0) * kItems + k)) & 1u)) continue;
+                                const uint32_t sl  = N >= 0 ? slot[N >= 0 ? N : 0][k] : p;
+                                const uint32_t h   = ((p >> 5) * 2115u) >> 16; // p / 992 for p < 4096
+                                const uint32_t sub = N >= 0 ? s_nvb[h][N >= 0 ? N : 0] : h * kHalfRows;
+                                (h < 2 ? pgA : pgB)[h * (RJ_PAGE / 8) + sl - sub] = v[k];
                             }
                         }
+                    };
+                    // every output column that shows source `src`, column `c`
+                    auto emit_source = [&](int src, int c, const uint64_t (&v)[kItems]) {
+#pragma unroll
+                        for (int j = 0; j < kEmitMaxOut; ++j) {
+                            if (j >= a.n_out || a.out_src[j] != src || (src != 0 && a.out_idx[j] != c)) continue;
+                            const int  nn   = NN > 0 ? a.out_null[j] : -1;
+                            const bool wide = a.out_width[j] == 8;
+                            auto with_n = [&](auto n_c) {
+                                if (wide) emit(n_c, std::true_type{}, j, v); else emit(n_c, std::false_type{}, j, v);
+                            };
+                            if (nn < 0) with_n(std::integral_constant<int, -1>{});
+                            if constexpr (NN > 0) { if (nn == 0) with_n(std::integral_constant<int, 0>{}); }
+                            if constexpr (NN > 1) { if (nn == 1) with_n(std::integral_constant<int, 1>{}); }
+                            if constexpr (NN > 2) { if (nn == 2) with_n(std::integral_constant<int, 2>{}); }
+                            if constexpr (NN > 3) { if (nn == 3) with_n(std::integral_constant<int, 3>{}); }
+                        }
+                    };
+                    // the values are fetched once per source: the key, the build columns (by table index), the
+                    // probe columns (by batch offset)
+                    {
+                        uint64_t v[kItems];
+#pragma unroll
+                        for (int k = 0; k < kItems; ++k) v[k] = key[k];
+                        emit_source(0, 0, v);
+                    }
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) {
+                        uint64_t v[kItems];
+                        const uint8_t* col = smem + a.sm_bpay[c];
+                        if (a.bwidth[c] == 8) {
+#pragma unroll
+                            for (int k = 0; k < kItems; ++k) v[k] = pos[k] != kNone ? (reinterpret_cast<const uint64_t*>(col) + bskew[c])[lidx[k]] : 0ull;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kItems; ++k) v[k] = pos[k] != kNone ? (reinterpret_cast<const uint32_t*>(col) + bskew[c])[lidx[k]] : 0u;
+                        }
+                        emit_source(1, c, v);
+                    }
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) {
+                        uint64_t v[kItems];
+                        const uint8_t* col = smem + a.sm_ppay[sb][c];
+                        if (a.pwidth[c] == 8) {
+#pragma unroll
+                            for (int k = 0; k < kItems; ++k) v[k] = (reinterpret_cast<const uint64_t*>(col) + (base & 1u))[k * kThreads + tid];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kItems; ++k) v[k] = (reinterpret_cast<const uint32_t*>(col) + (base & 3u))[k * kThreads + tid];
+                        }
+                        emit_source(2, c, v);
                     }
                 }
                 __syncthreads(); // the bitmaps of this round are complete; s_ctr, s_chunk and s_nvb have been read
@@ -576,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const EmitArgs a
                 while (reserved >= kChunkRows) {
                     close_full_chunk(reserved);
                     reserved = (reserved > kOpenRows ? kOpenRows : reserved) - kChunkRows;
+                    close_pending = true; // everybody meets the closing warps before the next reservation
                 }
                 if (!again) break;
             }

@@ -55,6 +55,15 @@ struct CarryArgs {
     int             n_flag;
     const void*     flag_src[2]; // flat: bitmaps by row; regions: bytes by position
     uint8_t*        flag_dst[2];
+    // kMulti (the multi-GPU exchange): partition p belongs to owner p >> owner_shift, whose arrays -- possibly
+    // in another GPU's memory, mapped through NVLink -- are listed in `dsts`; cursor[p] indexes the owner's arrays
+    const struct MultiCarryDsts* dsts;
+    int             owner_shift;
+};
+
+struct MultiCarryDsts {
+    static constexpr int kKeys = 0, kVal0 = 1, kFlag0 = 3, kArrays = 5;
+    void* p[kArrays][8];
 };
 
 template <int W>
@@ -84,8 +93,9 @@ struct Tile {
     uint32_t lo, cnt, cbase;
 };
 
-template <bool kRegions, int W0, int W1>
+template <bool kRegions, int W0, int W1, bool kMulti = false>
 __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kernel(const CarryArgs a) {
+    static_assert(!(kRegions && kMulti), "the exchange is a flat pass");
     using L  = Layout<kRegions, W0, W1>;
     using T0 = typename ValT<W0>::type;
     using T1 = typename ValT<W1>::type;
@@ -100,6 +110,10 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
     __shared__ uint32_t s_tile_start[kRegions ? 258 : 1];
     __shared__ __align__(8) uint64_t s_kbar[2];
     __shared__ __align__(8) uint64_t s_vbar;
+    __shared__ void* s_dst[kMulti ? MultiCarryDsts::kArrays : 1][8];
+    if (kMulti) {
+        for (uint32_t i = threadIdx.x; i < MultiCarryDsts::kArrays * 8; i += kT) s_dst[i >> 3][i & 7] = a.dsts->p[i >> 3][i & 7];
+    }
 
     const uint32_t nb = 1u << a.bits, mask = nb - 1;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -306,7 +320,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
         const T1* __restrict__ v1 = reinterpret_cast<const T1*>(smem + L::oV1) + (W1 ? skew(cur.lo, W1 ? W1 : 4) : 0u);
         auto copy_out = [&](auto pred_c, uint32_t base) {
             constexpr bool kPred = decltype(pred_c)::value;
-            uint32_t off[kDepth], dd[kDepth], fl[kDepth];
+            uint32_t off[kDepth], dd[kDepth], fl[kDepth], own[kDepth];
             bool     in[kDepth];
 #pragma unroll
             for (int j = 0; j < kDepth; ++j) {
@@ -316,6 +330,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
                 off[j] = w & (kTile - 1);
                 fl[j]  = w >> 30;
                 dd[j]  = s_gbase[(w >> kOffBits) & 0xffu] + pos;
+                own[j] = kMulti ? (((w >> kOffBits) & 0xffu) >> a.owner_shift) & 7u : 0u;
             }
             {
                 uint32_t kk[kDepth];
@@ -323,7 +338,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
                 for (int j = 0; j < kDepth; ++j) kk[j] = kw[off[j]];
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j)
-                    if (in[j]) a.keys_out[dd[j]] = kk[j];
+                    if (in[j]) (kMulti ? static_cast<uint32_t*>(s_dst[MultiCarryDsts::kKeys][own[j]]) : a.keys_out)[dd[j]] = kk[j];
             }
             if (W0) {
                 T0 vv[kDepth];
@@ -331,7 +346,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
                 for (int j = 0; j < kDepth; ++j) vv[j] = v0[off[j]];
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j)
-                    if (in[j]) static_cast<T0*>(a.val_dst[0])[dd[j]] = vv[j];
+                    if (in[j]) static_cast<T0*>(kMulti ? s_dst[MultiCarryDsts::kVal0][own[j]] : a.val_dst[0])[dd[j]] = vv[j];
             }
             if (W1) {
                 T1 vv[kDepth];
@@ -339,14 +354,14 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
                 for (int j = 0; j < kDepth; ++j) vv[j] = v1[off[j]];
 #pragma unroll
                 for (int j = 0; j < kDepth; ++j)
-                    if (in[j]) static_cast<T1*>(a.val_dst[1])[dd[j]] = vv[j];
+                    if (in[j]) static_cast<T1*>(kMulti ? s_dst[MultiCarryDsts::kVal0 + 1][own[j]] : a.val_dst[1])[dd[j]] = vv[j];
             }
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
                 if (f < n_flag) {
 #pragma unroll
                     for (int j = 0; j < kDepth; ++j)
-                        if (in[j]) a.flag_dst[f][dd[j]] = static_cast<uint8_t>((fl[j] >> f) & 1u);
+                        if (in[j]) (kMulti ? static_cast<uint8_t*>(s_dst[MultiCarryDsts::kFlag0 + f][own[j]]) : a.flag_dst[f])[dd[j]] = static_cast<uint8_t>((fl[j] >> f) & 1u);
                 }
             }
         };
@@ -359,9 +374,9 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
     }
 }
 
-template <bool kRegions, int W0, int W1>
+template <bool kRegions, int W0, int W1, bool kMulti = false>
 void launch_one(const CarryArgs& a, uint64_t tiles_upper, int sm_count, cudaStream_t s) {
-    auto         kern = scatter_carry_kernel<kRegions, W0, W1>;
+    auto         kern = scatter_carry_kernel<kRegions, W0, W1, kMulti>;
     const size_t smem = Layout<kRegions, W0, W1>::kBytes;
     static SmemConfigured cfg;
     cfg.ensure(kern, smem);
@@ -374,16 +389,16 @@ void launch_one(const CarryArgs& a, uint64_t tiles_upper, int sm_count, cudaStre
     RJ_LAUNCH_CHECK();
 }
 
-template <bool kRegions>
+template <bool kRegions, bool kMulti = false>
 void dispatch(const CarryArgs& a, int w0, int w1, uint64_t tiles_upper, int sm_count, cudaStream_t s) {
     const int code = w0 * 10 + w1;
     switch (code) {
-    case 0:  launch_one<kRegions, 0, 0>(a, tiles_upper, sm_count, s); break;
-    case 40: launch_one<kRegions, 4, 0>(a, tiles_upper, sm_count, s); break;
-    case 80: launch_one<kRegions, 8, 0>(a, tiles_upper, sm_count, s); break;
-    case 44: launch_one<kRegions, 4, 4>(a, tiles_upper, sm_count, s); break;
-    case 84: launch_one<kRegions, 8, 4>(a, tiles_upper, sm_count, s); break;
-    case 88: launch_one<kRegions, 8, 8>(a, tiles_upper, sm_count, s); break;
+    case 0:  launch_one<kRegions, 0, 0, kMulti>(a, tiles_upper, sm_count, s); break;
+    case 40: launch_one<kRegions, 4, 0, kMulti>(a, tiles_upper, sm_count, s); break;
+    case 80: launch_one<kRegions, 8, 0, kMulti>(a, tiles_upper, sm_count, s); break;
+    case 44: launch_one<kRegions, 4, 4, kMulti>(a, tiles_upper, sm_count, s); break;
+    case 84: launch_one<kRegions, 8, 4, kMulti>(a, tiles_upper, sm_count, s); break;
+    case 88: launch_one<kRegions, 8, 8, kMulti>(a, tiles_upper, sm_count, s); break;
     default: throw CudaError("scatter_carry: unsupported column widths");
     }
 }
@@ -419,6 +434,30 @@ void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s) {
     const bool regions = c.region_start != nullptr;
     // regions: the exact tile count lives on the device (tile_start[n_regions]); size the grid from its upper bound
     const uint64_t tiles_upper = (c.n + kTile - 1) / kTile + (regions ? c.n_regions : 0);
+    if (c.n_owners > 0) {
+        // the multi-GPU exchange: the destination table (~320 bytes of pointers) lives in device memory for the launch
+        if (regions) throw CudaError("scatter_carry: the exchange is a flat pass");
+        if (c.n_owners > 8) throw CudaError("scatter_carry: at most 8 owners");
+        MultiCarryDsts h{};
+        for (int o = 0; o < c.n_owners; ++o) {
+            h.p[MultiCarryDsts::kKeys][o] = c.keys_dst_multi[o];
+            for (int i = 0; i < c.n_val; ++i) h.p[MultiCarryDsts::kVal0 + i][o] = c.val_dst_multi[order[i]][o];
+            for (int f = 0; f < c.n_flag; ++f) h.p[MultiCarryDsts::kFlag0 + f][o] = c.flag_dst_multi[f][o];
+        }
+        static thread_local MultiCarryDsts* d_dsts_of[64] = {};
+        int dev = 0;
+        RJ_CUDA(cudaGetDevice(&dev));
+        MultiCarryDsts*& d_dsts = d_dsts_of[dev & 63];
+        if (!d_dsts) RJ_CUDA(cudaMalloc(&d_dsts, 2 * sizeof(MultiCarryDsts)));
+        // two slots, used alternately: the previous launch may still be reading its table
+        static thread_local unsigned flip[64] = {};
+        MultiCarryDsts* slot = d_dsts + (flip[dev & 63]++ & 1u);
+        RJ_CUDA(cudaMemcpyAsync(slot, &h, sizeof(MultiCarryDsts), cudaMemcpyHostToDevice, s));
+        a.dsts = slot;
+        a.owner_shift = c.owner_shift;
+        dispatch<false, true>(a, w[0], w[1], tiles_upper, sm_count, s);
+        return;
+    }
     if (regions) dispatch<true>(a, w[0], w[1], tiles_upper, sm_count, s);
     else dispatch<false>(a, w[0], w[1], tiles_upper, sm_count, s);
 }

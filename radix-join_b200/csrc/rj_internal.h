@@ -168,8 +168,25 @@ struct CarryScatter {
     int             n_flag = 0;
     const void*     flag_src[2] = {nullptr, nullptr};
     uint8_t*        flag_dst[2] = {nullptr, nullptr};
+    // multi-GPU exchange (flat pass only): n_owners > 0 -> partition p goes to owner p >> owner_shift, whose
+    // arrays (peer-mapped) are listed here; cursor[p] indexes the owner's arrays; keys_out / val_dst / flag_dst unused
+    int             n_owners = 0;
+    int             owner_shift = 0;
+    void*           keys_dst_multi[8] = {};
+    void*           val_dst_multi[2][8] = {};
+    void*           flag_dst_multi[2][8] = {};
 };
 void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s);
+
+// ---- k_filter.cu: predicates on decoded columns, bitmap algebra, bitmap -> row ids -------------------------
+void launch_filter_compare(const void* values, const uint32_t* valid, uint64_t n, int type, int op, int64_t rhs_i, double rhs_d,
+                           uint32_t* out, int sm_count, cudaStream_t s);
+void launch_filter_null(const uint32_t* valid, uint64_t n, bool want_null, uint32_t* out, int sm_count, cudaStream_t s);
+void launch_bitmap_logic(const uint32_t* a, const uint32_t* b, uint64_t n, int op, uint32_t* out, int sm_count, cudaStream_t s);
+void launch_filter_varchar(const void* pages, const uint64_t* desc, const uint32_t* valid, uint64_t n, int op, const uint8_t* d_rhs,
+                           uint32_t rhs_len, uint32_t* out, int sm_count, cudaStream_t s);
+void launch_bitmap_popc(const uint32_t* bits, uint64_t n_words, uint32_t* counts, int sm_count, cudaStream_t s);
+void launch_bitmap_expand(const uint32_t* bits, const uint64_t* start, uint64_t n_words, uint32_t* ids, int sm_count, cudaStream_t s);
 
 // ---- k_join.cu ------------------------------------------------------------------------------------
 struct JoinLaunch {
