@@ -302,6 +302,70 @@ void rj_encode_varchar_free(rj_ctx* ctx, rj_varchar_layout* layout);
 int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n,
                        int32_t type, void* d_pages_out, uint64_t* n_pages_out, void* stream);
 
+/* -- whole-tuple scatter and the join on partitioned inputs: the two halves of the fused root join
+ *    (k_scatter_carry.cu, k_join_emit.cu), exposed so that the multi-GPU driver can run the FIRST scatter
+ *    pass as the exchange (every pass-1 region lives on the GPU that owns its hash range) and the rest
+ *    locally.  Replaces src/execute.cpp:169-261 + src/build_table.cpp:456-594 like the fused root join. -- */
+
+/* Radix scatter of (4-byte key, up to two 4/8-byte value columns, up to two validity flags per tuple).
+ *   flat pass    d_region_start == NULL: rows in input order; d_valid = key validity bitmap (tuples with a
+ *                NULL key are dropped); flag_src = validity BITMAPS by row; flag_dst = one BYTE per tuple
+ *   region pass  d_region_start / d_tile_start [n_regions + 1] (device): the input is a flat pass's output,
+ *                flag_src = validity BYTES by position; tiles never straddle a region; cursor[region << bits | digit]
+ *   exchange     n_owners > 0 (flat pass only): digit d goes to owner d >> owner_shift, whose arrays are
+ *                keys_dst_multi / val_dst_multi / flag_dst_multi [owner] (peer-mapped device memory);
+ *                cursor[d] indexes the owner's arrays.
+ * digit = (hash(key) >> shift) & (2^bits - 1), bits <= 8; d_cursor [2^bits] (per region in a region pass) holds
+ * the first output index of every digit and is advanced.  Keys and value sources must be 16-byte aligned. */
+typedef struct rj_carry_scatter_t {
+    const void*     d_keys;
+    const uint32_t* d_valid;
+    uint64_t        n;
+    const uint32_t* d_region_start;
+    const uint32_t* d_tile_start;
+    uint32_t        n_regions;
+    int32_t         shift, bits;
+    uint32_t*       d_cursor;
+    void*           d_keys_out;
+    uint32_t        n_val;
+    const void*     val_src[2];
+    void*           val_dst[2];
+    int32_t         val_width[2];
+    uint32_t        n_flag;
+    const void*     flag_src[2];
+    void*           flag_dst[2];
+    uint32_t        n_owners;
+    int32_t         owner_shift;
+    void*           keys_dst_multi[8];
+    void*           val_dst_multi[2][8];
+    void*           flag_dst_multi[2][8];
+} rj_carry_scatter_t;
+int rj_scatter_carry(rj_ctx* ctx, const rj_carry_scatter_t* desc, void* stream);
+
+/* One side of a join whose tuples are already grouped by the first `pass1_bits` of their partition number
+ * (or by all of it): INT32 keys, value columns and one validity byte per tuple beside them. */
+typedef struct rj_part_side_t {
+    const void*    d_keys;
+    uint64_t       n;
+    uint32_t       n_cols;             /* <= 2 */
+    const void*    d_vals[2];
+    int32_t        types[2];           /* RJ_INT32 / RJ_INT64 / RJ_FP64 */
+    const uint8_t* d_valid_bytes[2];   /* NULL: the column holds no NULL */
+} rj_part_side_t;
+typedef struct rj_part_out_t {
+    int32_t side;                      /* 0 = build side, 1 = probe side */
+    int32_t col;                       /* column of that side, -1 = the join key */
+} rj_part_out_t;
+/* Finish a partitioned key / foreign-key join: second scatter pass inside every pass-1 region (skipped when
+ * local_pass1_bits == 0: the inputs are fully partitioned), then build + probe + page output in one kernel.
+ * d_hist_build / d_hist_probe [2^local_bits]: tuples per local partition, in partition order = the order of the
+ * inputs' groups; hash_bits = radix bits of the WHOLE job (the table slot is taken from the hash bits above).
+ * *out = NULL (and 0 returned) when a table met a duplicate build key: run the general path instead. */
+int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_side_t* probe,
+                        const uint32_t* d_hist_build, const uint32_t* d_hist_probe, int32_t local_bits,
+                        int32_t local_pass1_bits, int32_t hash_bits, const rj_part_out_t* outs, uint32_t n_out,
+                        rj_result** out);
+
 /* -- pre-filter evaluation (harness side: Statement::eval on InnerColumns, src/statement.cpp:46-133,
  *    186-200; include/inner_column.h:170-325,386-562) and filter + emit (src/build_table.cpp:94-119,
  *    247-303) ------------------------------------------------------------------------------------- */
@@ -352,6 +416,13 @@ typedef struct rj_pred_t {
 /* Filter + emit (Table::from_csv's tail, build_table.cpp:247-303): the rows of `table` (host pages) that
  * pass the program, in row order, as result pages of ALL its columns; n_prog = 0 keeps every row. */
 int rj_filter_table(rj_ctx* ctx, const rj_table_t* table, const rj_pred_t* prog, uint32_t n_prog, rj_result** out);
+
+/* VARCHAR pages from dense device strings (the role of ColumnInserter<std::string>, plan.h:230-335):
+ * row i = bytes [d_offsets[i], d_offsets[i+1]) of one character buffer (n + 1 offsets).  This call turns the
+ * offsets into string descriptors over that buffer; rj_encode_varchar_plan(d_chars as the source "pages",
+ * d_desc, d_valid, NULL, n) + rj_encode_varchar_write then produce the pages (strings longer than 8185 bytes
+ * become 0xffff / 0xfffe chains).  Strings are limited to 2^23 - 1 bytes, the buffer to 2^40 bytes. */
+int rj_varchar_descriptors(rj_ctx* ctx, const uint64_t* d_offsets, uint64_t n, uint64_t* d_desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Profiling: per-kernel-class CUDA-event timings accumulated by the whole-path functions.

@@ -76,6 +76,25 @@ class rj_plan_t(C.Structure):
     ]
 
 
+class rj_carry_scatter_t(C.Structure):
+    _fields_ = [("d_keys", C.c_void_p), ("d_valid", C.c_void_p), ("n", C.c_uint64),
+                ("d_region_start", C.c_void_p), ("d_tile_start", C.c_void_p), ("n_regions", C.c_uint32),
+                ("shift", C.c_int32), ("bits", C.c_int32), ("d_cursor", C.c_void_p), ("d_keys_out", C.c_void_p),
+                ("n_val", C.c_uint32), ("val_src", C.c_void_p * 2), ("val_dst", C.c_void_p * 2), ("val_width", C.c_int32 * 2),
+                ("n_flag", C.c_uint32), ("flag_src", C.c_void_p * 2), ("flag_dst", C.c_void_p * 2),
+                ("n_owners", C.c_uint32), ("owner_shift", C.c_int32), ("keys_dst_multi", C.c_void_p * 8),
+                ("val_dst_multi", (C.c_void_p * 8) * 2), ("flag_dst_multi", (C.c_void_p * 8) * 2)]
+
+
+class rj_part_side_t(C.Structure):
+    _fields_ = [("d_keys", C.c_void_p), ("n", C.c_uint64), ("n_cols", C.c_uint32), ("d_vals", C.c_void_p * 2),
+                ("types", C.c_int32 * 2), ("d_valid_bytes", C.c_void_p * 2)]
+
+
+class rj_part_out_t(C.Structure):
+    _fields_ = [("side", C.c_int32), ("col", C.c_int32)]
+
+
 class rj_pred_t(C.Structure):
     _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("column", C.c_uint32), ("lit_type", C.c_int32),
                 ("rhs_i", C.c_int64), ("rhs_d", C.c_double), ("rhs_s", C.c_char_p), ("rhs_s_len", C.c_uint64)]
@@ -146,12 +165,16 @@ PROTOTYPES = {
     "rj_encode_varchar_write": (C.c_int, [_vp, _vp, _vp, _vp]),
     "rj_encode_varchar_free": (None, [_vp, _vp]),
     "rj_gen_fixed_pages": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, C.POINTER(_u64), _vp]),
+    "rj_scatter_carry": (C.c_int, [_vp, C.POINTER(rj_carry_scatter_t), _vp]),
+    "rj_join_partitioned": (C.c_int, [_vp, C.POINTER(rj_part_side_t), C.POINTER(rj_part_side_t), _vp, _vp, _i32, _i32, _i32,
+                                      C.POINTER(rj_part_out_t), _u32, _pvp]),
     "rj_filter_compare": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _i32, C.c_int64, C.c_double, _vp, _vp]),
     "rj_filter_varchar": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _i32, C.c_char_p, _u64, _vp, _vp]),
     "rj_filter_null": (C.c_int, [_vp, _vp, _u64, _i32, _vp, _vp]),
     "rj_bitmap_logic": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, _vp]),
     "rj_bitmap_select": (C.c_int, [_vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
     "rj_filter_table": (C.c_int, [_vp, C.POINTER(rj_table_t), C.POINTER(rj_pred_t), _u32, _pvp]),
+    "rj_varchar_descriptors": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "rj_profile_enable": (C.c_int, [_vp, C.c_int]),
     "rj_profile_reset": (C.c_int, [_vp]),
     "rj_profile_read": (C.c_int, [_vp, C.POINTER(rj_stage_stat_t)]),

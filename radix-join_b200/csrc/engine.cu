@@ -2308,6 +2308,199 @@ int rj_gen_fixed_pages(rj_ctx* ctx, const void* d_values, const uint32_t* d_vali
     });
 }
 
+// ---- whole-tuple scatter / join on partitioned inputs (multi-GPU: pass 1 is the exchange) -----------------
+int rj_scatter_carry(rj_ctx* ctx, const rj_carry_scatter_t* d, void* stream) {
+    return guarded(ctx, [&] {
+        if (!d) throw EngineError("rj_scatter_carry: null descriptor");
+        if (d->n_val > 2 || d->n_flag > 2 || d->n_owners > 8) throw EngineError("rj_scatter_carry: at most two value columns, two flags, eight owners");
+        CarryScatter c;
+        c.keys = static_cast<const uint32_t*>(d->d_keys);
+        c.valid = d->d_valid;
+        c.n = d->n;
+        c.region_start = d->d_region_start;
+        c.tile_start = d->d_tile_start;
+        c.n_regions = d->n_regions;
+        c.shift = d->shift;
+        c.bits = d->bits;
+        c.cursor = d->d_cursor;
+        c.keys_out = static_cast<uint32_t*>(d->d_keys_out);
+        c.n_val = static_cast<int>(d->n_val);
+        c.n_flag = static_cast<int>(d->n_flag);
+        for (int i = 0; i < 2; ++i) {
+            c.val_src[i] = d->val_src[i];
+            c.val_dst[i] = d->val_dst[i];
+            c.val_width[i] = d->val_width[i];
+            c.flag_src[i] = d->flag_src[i];
+            c.flag_dst[i] = static_cast<uint8_t*>(d->flag_dst[i]);
+        }
+        c.n_owners = static_cast<int>(d->n_owners);
+        c.owner_shift = d->owner_shift;
+        for (int o = 0; o < 8; ++o) {
+            c.keys_dst_multi[o] = d->keys_dst_multi[o];
+            for (int i = 0; i < 2; ++i) {
+                c.val_dst_multi[i][o] = d->val_dst_multi[i][o];
+                c.flag_dst_multi[i][o] = d->flag_dst_multi[i][o];
+            }
+        }
+        launch_scatter_carry(c, ctx->sm_count, pick_stream(ctx, stream));
+    });
+}
+
+int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_side_t* probe, const uint32_t* d_hist_build,
+                        const uint32_t* d_hist_probe, int32_t local_bits, int32_t local_pass1_bits, int32_t hash_bits,
+                        const rj_part_out_t* outs, uint32_t n_out, rj_result** out) {
+    return guarded(ctx, [&] {
+        if (!build || !probe || !outs || !out) throw EngineError("rj_join_partitioned: null argument");
+        *out = nullptr;
+        if (local_bits < 0 || local_bits > kMaxTotalBits || local_pass1_bits < 0 || local_pass1_bits > kMaxPassBits ||
+            local_bits - local_pass1_bits > kMaxPassBits || (local_pass1_bits && local_bits <= local_pass1_bits))
+            throw EngineError("rj_join_partitioned: radix bits out of range");
+        if (n_out < 1 || n_out > static_cast<uint32_t>(kEmitMaxOut) || build->n_cols > static_cast<uint32_t>(kEmitMaxPay) ||
+            probe->n_cols > static_cast<uint32_t>(kEmitMaxPay))
+            throw EngineError("rj_join_partitioned: too many columns for the fused join");
+        if (build->n >= 0xffffffffull || probe->n >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
+        cudaStream_t s = ctx->stream;
+        const uint64_t nb = build->n, np = probe->n;
+        auto width_of = [](int32_t t) {
+            if (t == RJ_INT32) return 4;
+            if (t == RJ_INT64 || t == RJ_FP64) return 8;
+            throw EngineError("rj_join_partitioned: fixed-width columns only");
+        };
+        JoinEmitLaunch L;
+        L.n_out = static_cast<int>(n_out);
+        L.n_bpay = static_cast<int>(build->n_cols);
+        L.n_ppay = static_cast<int>(probe->n_cols);
+        for (int c = 0; c < L.n_bpay; ++c) {
+            L.bwidth[c] = width_of(build->types[c]);
+            L.bvalid[c] = build->d_valid_bytes[c];
+        }
+        for (int c = 0; c < L.n_ppay; ++c) {
+            L.pwidth[c] = width_of(probe->types[c]);
+            L.pvalid[c] = probe->d_valid_bytes[c];
+        }
+        auto res = std::make_unique<rj_result>();
+        res->cols.resize(n_out);
+        for (uint32_t a = 0; a < n_out; ++a) {
+            const rj_part_side_t* sd = outs[a].side == 0 ? build : probe;
+            if (outs[a].side != 0 && outs[a].side != 1) throw EngineError("rj_join_partitioned: output side is 0 or 1");
+            if (outs[a].col < 0) {
+                L.out_src[a] = 0;
+                L.out_width[a] = 4;
+                res->cols[a].type = RJ_INT32;
+            } else {
+                if (static_cast<uint32_t>(outs[a].col) >= sd->n_cols) throw EngineError("rj_join_partitioned: output column out of range");
+                L.out_src[a] = outs[a].side == 0 ? 1 : 2;
+                L.out_idx[a] = outs[a].col;
+                L.out_width[a] = width_of(sd->types[outs[a].col]);
+                L.out_nullable[a] = sd->d_valid_bytes[outs[a].col] != nullptr;
+                res->cols[a].type = sd->types[outs[a].col];
+            }
+        }
+        if (!join_emit_fits(L)) throw EngineError("rj_join_partitioned: the columns do not fit shared memory");
+        if (nb == 0 || np == 0) { // src/execute.cpp:50: an empty side gives typed, page-less columns
+            *out = res.release();
+            return;
+        }
+        const uint32_t nparts = 1u << local_bits;
+        const int      bits2 = local_bits - local_pass1_bits;
+        Buf plan_mem = dev_alloc(partition_plan_words(local_bits, local_pass1_bits) * 4, s);
+        PartitionPlanDev pl;
+        partition_plan_carve(plan_mem->as<uint32_t>(), local_bits, local_pass1_bits, &pl);
+        launch_partition_plan(d_hist_build, d_hist_probe, static_cast<uint32_t>(nb), static_cast<uint32_t>(np), local_bits, local_pass1_bits, 4,
+                              pl, s, kEmitBuildCap, kEmitProbeChunk);
+        struct SideFinal {
+            const uint32_t* keys;
+            const void*     val[kEmitMaxPay];
+            const uint8_t*  ok[kEmitMaxPay];
+            Buf             hold[1 + 2 * kEmitMaxPay];
+        };
+        auto finish_side = [&](const rj_part_side_t& sd, const int* widths, uint32_t* cur, const uint32_t* reg, const uint32_t* tile) {
+            SideFinal f{};
+            f.keys = static_cast<const uint32_t*>(sd.d_keys);
+            for (uint32_t c = 0; c < sd.n_cols; ++c) {
+                f.val[c] = sd.d_vals[c];
+                f.ok[c] = sd.d_valid_bytes[c];
+            }
+            if (local_pass1_bits == 0) return f; // fully partitioned already
+            CarryScatter c2;
+            c2.keys = f.keys;
+            c2.n = sd.n;
+            c2.region_start = reg; c2.tile_start = tile; c2.n_regions = 1u << local_pass1_bits;
+            c2.shift = 0; c2.bits = bits2; c2.cursor = cur;
+            f.hold[0] = dev_alloc(sd.n * 4 + 64, s);
+            c2.keys_out = f.hold[0]->as<uint32_t>();
+            for (uint32_t c = 0; c < sd.n_cols; ++c) {
+                f.hold[1 + c] = dev_alloc(sd.n * widths[c] + 64, s);
+                c2.val_src[c2.n_val] = sd.d_vals[c];
+                c2.val_dst[c2.n_val] = f.hold[1 + c]->p;
+                c2.val_width[c2.n_val++] = widths[c];
+                if (sd.d_valid_bytes[c]) {
+                    f.hold[1 + kEmitMaxPay + c] = dev_alloc(sd.n + 64, s);
+                    c2.flag_src[c2.n_flag] = sd.d_valid_bytes[c];
+                    c2.flag_dst[c2.n_flag++] = f.hold[1 + kEmitMaxPay + c]->as<uint8_t>();
+                }
+            }
+            launch_scatter_carry(c2, ctx->sm_count, s);
+            f.keys = f.hold[0]->as<uint32_t>();
+            for (uint32_t c = 0; c < sd.n_cols; ++c) {
+                f.val[c] = f.hold[1 + c]->p;
+                f.ok[c] = sd.d_valid_bytes[c] ? f.hold[1 + kEmitMaxPay + c]->as<uint8_t>() : nullptr;
+            }
+            return f;
+        };
+        SideFinal B, P;
+        {
+            uint64_t carried = 0;
+            for (int c = 0; c < L.n_bpay; ++c) carried += 2 * nb * (L.bwidth[c] + (L.bvalid[c] ? 1 : 0));
+            for (int c = 0; c < L.n_ppay; ++c) carried += 2 * np * (L.pwidth[c] + (L.pvalid[c] ? 1 : 0));
+            StageScope sc(ctx, RJ_ST_SCATTER, s, local_pass1_bits ? 2 : 0, local_pass1_bits ? (nb + np) * 8 + carried : 0);
+            B = finish_side(*build, L.bwidth, pl.cur_b, pl.reg_b, pl.tile_b);
+            P = finish_side(*probe, L.pwidth, pl.cur_p, pl.reg_p, pl.tile_p);
+        }
+        const uint64_t max_chunks = join_emit_max_chunks(np, ctx->sm_count);
+        Buf counters = dev_alloc_zero(32, s); // chunk counter @0, abort flag @4, rows @8
+        L.bkeys = B.keys;
+        L.pkeys = P.keys;
+        L.off_b = pl.off_b; L.off_p = pl.off_p; L.unit_start = pl.unit_start; L.unit_cursor = pl.unit_cursor;
+        L.nparts = nparts;
+        L.part_bits = hash_bits;
+        for (int c = 0; c < L.n_bpay; ++c) { L.bpay[c] = B.val[c]; L.bvalid[c] = B.ok[c]; }
+        for (int c = 0; c < L.n_ppay; ++c) { L.ppay[c] = P.val[c]; L.pvalid[c] = P.ok[c]; }
+        for (int a = 0; a < L.n_out; ++a) {
+            ResultColumn& rc = res->cols[a];
+            rc.pages = dev_alloc(max_chunks * (L.out_width[a] == 4 ? 1 : 2) * size_t(RJ_PAGE_SIZE), s);
+            L.out_pages[a] = rc.pages->as<uint8_t>();
+        }
+        L.chunk_counter = counters->as<uint32_t>();
+        L.abort_flag = counters->as<uint32_t>() + 1;
+        L.row_counter = reinterpret_cast<unsigned long long*>(counters->as<uint8_t>() + 8);
+        RJ_CUDA(cudaMemsetAsync(pl.unit_cursor, 0, 4, s));
+        uint64_t in_bytes = (nb + np) * 4;
+        for (int c = 0; c < L.n_bpay; ++c) in_bytes += nb * (L.bwidth[c] + (L.bvalid[c] ? 1 : 0));
+        for (int c = 0; c < L.n_ppay; ++c) in_bytes += np * (L.pwidth[c] + (L.pvalid[c] ? 1 : 0));
+        {
+            StageScope sc(ctx, RJ_ST_JOIN_EMIT, s, 1, in_bytes);
+            launch_join_emit(L, ctx->sm_count, s);
+        }
+        uint32_t h[4] = {0, 0, 0, 0};
+        RJ_CUDA(cudaMemcpyAsync(h, counters->p, 16, cudaMemcpyDeviceToHost, s));
+        RJ_CUDA(cudaStreamSynchronize(s));
+        if (h[1] != 0) return; // duplicate build keys: *out stays NULL
+        const uint64_t chunks = h[0];
+        if (chunks > max_chunks) throw EngineError("internal: the fused join produced more chunks than planned");
+        res->num_rows = static_cast<uint64_t>(h[2]) | (static_cast<uint64_t>(h[3]) << 32);
+        uint64_t out_page_bytes = 0;
+        for (int a = 0; a < L.n_out; ++a) {
+            ResultColumn& rc = res->cols[a];
+            rc.n_pages = chunks * (L.out_width[a] == 4 ? 1 : 2);
+            out_page_bytes += rc.n_pages * uint64_t(RJ_PAGE_SIZE);
+            if (rc.n_pages == 0) rc.pages.reset();
+        }
+        if (ctx->profiling) ctx->stats[RJ_ST_JOIN_EMIT].bytes += out_page_bytes;
+        *out = res.release();
+    });
+}
+
 // ---- pre-filters ----------------------------------------------------------------------------------------
 int rj_filter_compare(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n, int32_t type, int32_t op,
                       int64_t rhs_i, double rhs_d, uint32_t* d_out, void* stream) {
@@ -2428,6 +2621,10 @@ int rj_filter_table(rj_ctx* ctx, const rj_table_t* table, const rj_pred_t* prog,
         RJ_CUDA(cudaStreamSynchronize(st));
         *out = res.release();
     });
+}
+
+int rj_varchar_descriptors(rj_ctx* ctx, const uint64_t* d_offsets, uint64_t n, uint64_t* d_desc, void* stream) {
+    return guarded(ctx, [&] { launch_varchar_desc_from_offsets(d_offsets, n, d_desc, ctx->sm_count, pick_stream(ctx, stream)); });
 }
 
 // ---- profiling -------------------------------------------------------------------------------------

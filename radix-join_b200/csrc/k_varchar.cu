@@ -404,4 +404,25 @@ void launch_varchar_write(const VarcharLayoutDev& L, uint8_t* pages_out, int sm_
     RJ_LAUNCH_CHECK();
 }
 
+
+namespace {
+__global__ void __launch_bounds__(256)
+    varchar_desc_from_offsets_kernel(const uint64_t* __restrict__ off, uint64_t n, uint64_t* __restrict__ desc) {
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t a = off[i], len = off[i + 1] - a;
+        desc[i] = (a & RJ_DESC_ADDR_MASK) | ((len & RJ_DESC_LEN_MASK) << RJ_DESC_LEN_SHIFT);
+    }
+}
+} // namespace
+
+// Descriptors of strings that lie back to back in one buffer (row i = bytes [off[i], off[i+1])): what the page
+// writer (launch_varchar_plan / write) takes, so dense strings on the device become pages without a host pass --
+// the role of ColumnInserter<std::string> (reference include/plan.h:230-335).
+void launch_varchar_desc_from_offsets(const uint64_t* off, uint64_t n, uint64_t* desc, int sm_count, cudaStream_t s) {
+    if (n == 0) return;
+    const uint64_t want = (n + 255) / 256, cap = static_cast<uint64_t>(sm_count) * 8;
+    varchar_desc_from_offsets_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, s>>>(off, n, desc);
+    RJ_LAUNCH_CHECK();
+}
+
 } // namespace rj

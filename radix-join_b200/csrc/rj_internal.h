@@ -178,6 +178,8 @@ struct CarryScatter {
 };
 void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s);
 
+void launch_varchar_desc_from_offsets(const uint64_t* off, uint64_t n, uint64_t* desc, int sm_count, cudaStream_t s); // k_varchar.cu
+
 // ---- k_filter.cu: predicates on decoded columns, bitmap algebra, bitmap -> row ids -------------------------
 void launch_filter_compare(const void* values, const uint32_t* valid, uint64_t n, int type, int op, int64_t rhs_i, double rhs_d,
                            uint32_t* out, int sm_count, cudaStream_t s);

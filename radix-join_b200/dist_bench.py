@@ -50,6 +50,10 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
                 print("[rj dist] falling back to the NCCL exchange:", xchg_note, flush=True)
 
     def step():
+        if xchg is not None and os.environ.get("RJ_DIST_FUSED", "1") != "0":
+            out = dj.distributed_join_fused(ops, build, probe, OUT_COLS, xchg, total_build_rows=n_build)
+            if out is not None:
+                return out
         return dj.distributed_join(ops, build, probe, OUT_COLS, xchg=xchg)
 
     sampler = ClockSampler(local)

@@ -166,6 +166,59 @@ class CudaOps:
         self.ctx.check(self.lib.rj_radix_scatter_multi(self.h, self._p(keys), self._p(valid), keys.numel(), 4, 32 - g, g,
                                                        self._p(cursor), C.byref(desc), self.stream))
 
+    def histogram(self, keys, valid, bits, out):
+        """tuples per radix digit (the low `bits` hash bits) of this rank's slice, NULL keys excluded -> out[2**bits] (int32, zeroed by the caller)"""
+        self.ctx.check(self.lib.rj_radix_histogram(self.h, self._p(keys), self._p(valid), keys.numel(), 4, 0, bits, self._p(out), self.stream))
+
+    def exchange_scatter(self, keys, valid, payloads, shift, bits, cursor, g, xchg):
+        """The FIRST scatter pass of the join, run as the exchange (k_scatter_carry.cu, peer destinations): digit d of
+        the pass belongs to owner d >> (bits - g); keys, values and one validity byte per tuple are stored straight
+        into the owner's receive arrays at cursor[d] -- coalesced runs over NVLink, no collective moves the data."""
+        d = _cabi.rj_carry_scatter_t()
+        d.d_keys, d.d_valid, d.n = self._p(keys), self._p(valid), keys.numel()
+        d.shift, d.bits, d.d_cursor = shift, bits, self._p(cursor)
+        G = 1 << g
+        d.n_owners, d.owner_shift = G, bits - g
+        for o in range(G):
+            d.keys_dst_multi[o] = xchg.keys.ptrs[o]
+        nv = nf = 0
+        for i, (values, vbits) in enumerate(payloads):
+            d.val_src[nv], d.val_width[nv] = self._p(values), values.element_size()
+            for o in range(G):
+                d.val_dst_multi[nv][o] = xchg.vals[i].ptrs[o]
+            nv += 1
+            if vbits is not None:
+                d.flag_src[nf] = self._p(vbits)
+                for o in range(G):
+                    d.flag_dst_multi[nf][o] = xchg.valids[i].ptrs[o]
+                nf += 1
+        d.n_val, d.n_flag = nv, nf
+        self.ctx.check(self.lib.rj_scatter_carry(self.h, C.byref(d), self.stream))
+
+    def join_partitioned(self, sides, hists, local_bits, local_pass1_bits, hash_bits, out_cols):
+        """sides = ((keys, [values], [validity bytes or None], [types]) for build, probe), grouped by their pass-1
+        digit (or fully partitioned); hists = per-local-partition tuple counts (int32 tensors).
+        -> (n_rows, [ResultPages]) or None when a table met duplicate build keys"""
+        from .engine import Result
+        cs = []
+        for keys, vals, valids, types in sides:
+            sd = _cabi.rj_part_side_t()
+            sd.d_keys, sd.n, sd.n_cols = self._p(keys), keys.numel(), len(vals)
+            for i, (v, vb, t) in enumerate(zip(vals, valids, types)):
+                sd.d_vals[i], sd.types[i], sd.d_valid_bytes[i] = self._p(v), int(t), self._p(vb)
+            cs.append(sd)
+        outs = (_cabi.rj_part_out_t * len(out_cols))()
+        for i, (side, which, _type) in enumerate(out_cols):
+            outs[i].side, outs[i].col = (0 if side == "b" else 1), (-1 if which == "key" else int(which))
+        h = C.c_void_p()
+        self.ctx.check(self.lib.rj_join_partitioned(self.h, C.byref(cs[0]), C.byref(cs[1]), self._p(hists[0]), self._p(hists[1]),
+                                                    local_bits, local_pass1_bits, hash_bits, outs, len(out_cols), C.byref(h)))
+        if not h.value:
+            return None
+        res = Result(self.ctx, h)
+        cols = [ResultPages(res.column_pages(c), int(res.column_type(c)), result=res, col=c) for c in range(res.num_columns)]
+        return res.num_rows, cols
+
     def gather(self, values, valid, rows):
         """values[rows], valid bits -> (gathered values, uint8 validity per row or None)"""
         n = rows.numel()
@@ -433,6 +486,130 @@ def broadcast_relation(ops, rel, g, group=None):
         else:
             out_valids.append(None)
     return out_keys, out_vals, out_valids, sent
+
+
+# --------------------------------------------------------------------------------------------------
+# The fused path: the join's first scatter pass IS the exchange
+# --------------------------------------------------------------------------------------------------
+JOIN_TARGET_FILL = 2048   # kJoinTargetFill (csrc/rj_internal.h): build tuples per final partition
+MAX_TOTAL_BITS, MAX_PASS_BITS = 15, 8
+
+
+def choose_bits(n_build_total):
+    """radix bits of the whole job, exactly as the single-GPU engine picks them (engine.cu: root_fused)"""
+    bits = 0
+    while (n_build_total >> bits) > JOIN_TARGET_FILL and bits < MAX_TOTAL_BITS:
+        bits += 1
+    return bits
+
+
+def exchange_layout(H, me, g, bits, p1):
+    """Where everything goes, from the all-gathered histograms alone (device tensor math, no host round trip).
+
+    H[s, side, f] = tuples of relation `side` (0 build, 1 probe) on rank s whose final partition (the low `bits`
+    hash bits) is f.  The exchange moves tuples by their top `p1` bits of f (the pass-1 digit d, or all of f when
+    the join needs one pass); digit d is owned by rank d >> (p1 - g), so a rank ends up with a contiguous range of
+    final partitions.  Inside an owner's receive arrays the digits lie in order, and inside a digit the senders'
+    runs lie in rank order.  Returns
+        cursor[side, d]      first index, in the owner's arrays, of THIS rank's run of digit d
+        local_hist[side, :]  tuples per final partition of the range this rank owns (input of the local plan)
+        owned[side]          tuples this rank receives
+        per_owner[side, o]   tuples rank o receives (capacity check)
+        sent[side]           tuples this rank stores into OTHER ranks' arrays"""
+    G, nfin, ndig = H.shape[0], 1 << bits, 1 << p1
+    per = ndig >> g
+    Cnt = H.view(G, 2, ndig, nfin // ndig).sum(-1)          # [G, 2, ndig]
+    tot = Cnt.sum(0).view(2, G, per)
+    base = (torch.cumsum(tot, -1) - tot).view(2, ndig)      # start of digit d inside its owner's arrays
+    cursor = base + Cnt[:me].sum(0)
+    lo = me * (nfin >> g)
+    local_hist = H.sum(0)[:, lo: lo + (nfin >> g)].contiguous()
+    mine = Cnt[me].view(2, G, per).sum(-1)                  # what I send to each owner
+    sent = mine.sum(-1) - mine[:, me]
+    return cursor, local_hist, local_hist.sum(-1), tot.sum(-1), sent
+
+
+def distributed_join_fused(ops, build, probe, out_cols, xchg, group=None, total_build_rows=None):
+    """Key / foreign-key join of two sharded relations where the first scatter pass of the single-GPU algorithm is
+    the exchange: every rank histograms its slice over the job's radix digits, the histograms are all-gathered,
+    each rank derives from them where its runs start in every owner's receive arrays, ONE kernel per relation
+    scatters keys + carried columns into the owners' memory over NVLink, and each rank then runs the second pass
+    and the fused build / probe / page-output kernel on the range of partitions it owns.  Host round trips: one
+    (the owned tuple counts).  Returns None when the shape is not eligible (INT32 keys, at most two fixed-width
+    carried columns per side, at least as many radix bits as ranks' bits) or a table met duplicate build keys --
+    the caller then runs `distributed_join`."""
+    world, me = dist.get_world_size(group), dist.get_rank(group)
+    g = log2_exact(world)
+    if len(build.payloads) > 2 or len(probe.payloads) > 2:
+        return None
+    if total_build_rows is None:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        tb = torch.tensor([build.n_rows], dtype=torch.int64, device=device)
+        dist.all_reduce(tb, group=group)
+        total_build_rows = int(tb)
+    bits = choose_bits(total_build_rows)
+    two = bits > MAX_PASS_BITS
+    p1 = (bits + 1) // 2 if two else bits
+    if p1 < g or bits - g < 0 or g == 0:
+        return None
+    trace = os.environ.get("RJ_DIST_TRACE") and hasattr(ops, "sync")
+    t = [time.perf_counter()]
+
+    def mark():
+        if trace:
+            ops.sync()
+            t.append(time.perf_counter())
+
+    # 1. decode, histogram over the job's digits
+    rels, hist = [], ops.zeros(2 << bits, torch.int32)
+    for side, rel in enumerate((build, probe)):
+        kp, kn, kt, knull = rel.key
+        keys, kvalid = ops.decode_fixed(kp, kn, kt, rel.n_rows, knull)
+        pays = [ops.decode_fixed(pp, pn, pt, rel.n_rows, pnull) for (pp, pn, pt, pnull) in rel.payloads]
+        ops.histogram(keys, kvalid, bits, hist[side << bits: (side + 1) << bits])
+        rels.append((keys, kvalid, pays))
+    mark()
+    # 2. all ranks' histograms -> layout (device math), one small read-back
+    H = torch.empty(world * (2 << bits), dtype=torch.int32, device=hist.device)
+    dist.all_gather_into_tensor(H, hist, group=group)
+    cursor, local_hist, owned, per_owner, sent = exchange_layout(H.view(world, 2, 1 << bits).to(torch.int64), me, g, bits, p1)
+    cursor32, local_hist32 = cursor.to(torch.int32).contiguous(), local_hist.to(torch.int32).contiguous()
+    info = torch.cat([owned, per_owner.max(-1).values, sent]).cpu()
+    n_own, worst, n_sent = [int(x) for x in info[:2]], [int(x) for x in info[2:4]], [int(x) for x in info[4:6]]
+    if worst[0] > xchg[0].cap or worst[1] > xchg[1].cap:
+        raise RuntimeError("peer exchange buffers too small for this key distribution")
+    mark()
+    # 3. the exchange = scatter pass 1 into the owners' arrays
+    xchg[0].barrier()                      # every rank is done with the previous contents of its receive arrays
+    for side, (keys, kvalid, pays) in enumerate(rels):
+        ops.exchange_scatter(keys, kvalid, pays, bits - p1, p1, cursor32[side], g, xchg[side])
+    xchg[0].barrier()                      # every rank's stores have landed
+    mark()
+    # 4. local: pass 2 inside every received region, then build + probe + page output
+    sides, sent_bytes = [], 0
+    for side, (rel, x) in enumerate(zip((build, probe), xchg)):
+        n = n_own[side]
+        vals = [x.vals[i].tensor[:n] for i in range(len(rel.payloads))]
+        valids = [x.valids[i].tensor[:n] if rel.payloads[i][3] else None for i in range(len(rel.payloads))]
+        types = [p[2] for p in rel.payloads]
+        sides.append((x.keys.tensor[:n], vals, valids, types))
+        sent_bytes += n_sent[side] * (4 + sum((4 if p[2] == INT32 else 8) + (1 if p[3] else 0) for p in rel.payloads))
+    got = ops.join_partitioned(sides, (local_hist32[0], local_hist32[1]), bits - g, (p1 - g) if two else 0, bits, out_cols)
+    mark()
+    if got is None:
+        # duplicate build keys: the general local join on what was received (any order will do)
+        ops._types = (tuple(p[2] for p in build.payloads), tuple(p[2] for p in probe.payloads))
+        (bk, bvals, bvalids, _), (pk, pvals, pvalids, _) = sides
+        got = ops.local_join_encode(bk, bvals, bvalids, pk, pvals, pvalids, out_cols)
+    n_rows, cols = got
+    stats = {"sent_bytes": sent_bytes, "owned_build": n_own[0], "owned_probe": n_own[1],
+             "exchange": f"scatter pass 1 of the join written into the owners' memory (peer stores, {p1} of {bits} radix bits)"}
+    if trace:
+        names = ["decode+histogram", "layout", "exchange", "pass 2 + join + pages"]
+        stats["phase_ms"] = {n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t[:-1], t[1:])}
+        if me == 0:
+            print("[rj dist fused]", stats["phase_ms"], flush=True)
+    return n_rows, cols, stats
 
 
 def distributed_join(ops, build, probe, out_cols, group=None, xchg=None, broadcast_max_rows=0):

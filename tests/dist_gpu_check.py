@@ -21,47 +21,59 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_b, n_p = 1 << 19, 1 << 22
     ctx = rj.build_context(local)
-    dt = syn.make_c2_device(ctx, n_b, n_p, rank=rank, world=world)
-    build, probe = dist_bench._relations(dt)
     ops = dj.CudaOps(ctx)
-    xchg = None
-    if os.environ.get("RJ_DIST_EXCHANGE", "p2p") == "p2p":
-        xchg = (dj.PeerExchange(ops.device, n_b, [torch.int64], [True]), dj.PeerExchange(ops.device, n_p, [torch.int64], [True]))
     outdir = os.environ.get("RJ_CHECK_DIR", "/tmp/rj_dist_check")
     os.makedirs(outdir, exist_ok=True)
     ok = True
-    single = want = inputs = None
-    # the hash-distributed exchange, then the broadcast of the (here: forced) small build side
-    for mode, kwargs in (("exchange", {"xchg": xchg}), ("broadcast", {"broadcast_max_rows": n_b})):
-        rows, cols, stats = dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS, **kwargs)
-        if rank == 0:
-            print(f"{mode}:", stats["exchange"], flush=True)
-        np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
-        dist.barrier()
-        if rank == 0:
-            from oracle import pyoracle as orc
-            parts = [np.load(os.path.join(outdir, f"rank{r}.npz")) for r in range(world)]
-            total = int(sum(p["rows"] for p in parts))
-            types = [0, 1, 2]
-            got = rj.ColumnarTable(num_rows=total, columns=[
-                rj.Column(t, np.concatenate([p[f"c{i}"].reshape(-1, 8192) for p in parts])) for i, t in enumerate(types)])
-            if single is None:
-                full = syn.make_c2_device(ctx, n_b, n_p)
-                inputs = rj.adopt_device(full.plan, full.device_pages, ctx, keep=full.keep)
-                res = rj.execute_resident(full.plan, inputs, ctx)
-                single = res.to_columnar()
-                res.free()
-                host_plan, _keep = syn.to_host_plan(full, pinned=False)
-                want = orc.execute(host_plan, impl="port")
-            good = total == n_p == single.num_rows == want.num_rows
-            good = good and orc.result_equal(got, single) and orc.result_equal(single, want)
-            print(f"dist parity ({world} GPUs, {mode}): rows {total}, sent/rank {stats['sent_bytes']} B ->", "OK" if good else "MISMATCH", flush=True)
-            ok = ok and good
-        dist.barrier()
-    if inputs is not None:
-        inputs.free()
+    p2p = os.environ.get("RJ_DIST_EXCHANGE", "p2p") == "p2p"
+    # 2^19 build rows: 8 radix bits, one scatter pass (the exchange delivers final partitions); 2^21: 10 bits, two passes
+    for n_b, n_p in ((1 << 19, 1 << 22), (1 << 21, 1 << 23)):
+        dt = syn.make_c2_device(ctx, n_b, n_p, rank=rank, world=world)
+        build, probe = dist_bench._relations(dt)
+        xchg = None
+        if p2p:
+            xchg = (dj.PeerExchange(ops.device, n_b, [torch.int64], [True]), dj.PeerExchange(ops.device, n_p, [torch.int64], [True]))
+        single = want = inputs = None
+        modes = [("exchange", lambda: dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS, xchg=xchg))]
+        if p2p:
+            # the join's first scatter pass as the exchange (twice: the receive arrays are reused)
+            modes.append(("fused", lambda: dj.distributed_join_fused(ops, build, probe, dist_bench.OUT_COLS, xchg, total_build_rows=n_b)))
+            modes.append(("fused again", lambda: dj.distributed_join_fused(ops, build, probe, dist_bench.OUT_COLS, xchg)))
+        if n_b == 1 << 19:
+            # the broadcast of the (here: forced) small build side
+            modes.append(("broadcast", lambda: dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS, broadcast_max_rows=n_b)))
+        for mode, run in modes:
+            out = run()
+            assert out is not None, f"{mode}: not eligible?"
+            rows, cols, stats = out
+            if rank == 0:
+                print(f"{mode}:", stats["exchange"], flush=True)
+            np.savez(os.path.join(outdir, f"rank{rank}.npz"), rows=rows, **{f"c{i}": c.to_numpy().reshape(-1) for i, c in enumerate(cols)})
+            dist.barrier()
+            if rank == 0:
+                from oracle import pyoracle as orc
+                parts = [np.load(os.path.join(outdir, f"rank{r}.npz")) for r in range(world)]
+                total = int(sum(p["rows"] for p in parts))
+                types = [0, 1, 2]
+                got = rj.ColumnarTable(num_rows=total, columns=[
+                    rj.Column(t, np.concatenate([p[f"c{i}"].reshape(-1, 8192) for p in parts])) for i, t in enumerate(types)])
+                if single is None:
+                    full = syn.make_c2_device(ctx, n_b, n_p)
+                    inputs = rj.adopt_device(full.plan, full.device_pages, ctx, keep=full.keep)
+                    res = rj.execute_resident(full.plan, inputs, ctx)
+                    single = res.to_columnar()
+                    res.free()
+                    host_plan, _keep = syn.to_host_plan(full, pinned=False)
+                    want = orc.execute(host_plan, impl="port")
+                good = total == n_p == single.num_rows == want.num_rows
+                good = good and orc.result_equal(got, single) and orc.result_equal(single, want)
+                print(f"dist parity ({world} GPUs, {n_b} x {n_p}, {mode}): rows {total}, sent/rank {stats['sent_bytes']} B ->", "OK" if good else "MISMATCH", flush=True)
+                ok = ok and good
+            dist.barrier()
+        if inputs is not None:
+            inputs.free()
+        del xchg, dt
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()

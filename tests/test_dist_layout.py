@@ -1,0 +1,79 @@
+"""The exchange layout of the fused multi-GPU join (radix_join_b200.dist_join.exchange_layout): every rank derives,
+from the all-gathered histograms alone, where its runs start in every owner's receive arrays.  Simulated here for
+G ranks in one process with numpy standing in for the scatter kernel: the runs must tile every owner's arrays
+exactly, digit by digit in ascending order, so that the owner's local plan (prefix sums of `local_hist`) finds
+each pass-1 region where the senders put it."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H  # noqa: F401  (sys.path)
+from radix_join_b200 import dist_join as dj
+
+
+def fmix32(h):
+    h = h.astype(np.uint64)
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(13)
+    h = (h * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(16)
+    return h.astype(np.uint32)
+
+
+@pytest.mark.parametrize("world,bits", [(2, 15), (4, 12), (8, 15), (8, 9), (4, 6), (2, 1)])
+def test_runs_tile_the_owners_arrays(world, bits):
+    rng = np.random.default_rng(world * 100 + bits)
+    g = dj.log2_exact(world)
+    two = bits > dj.MAX_PASS_BITS
+    p1 = (bits + 1) // 2 if two else bits
+    assert p1 >= g
+    keys = [[rng.integers(0, 1 << 20, int(rng.integers(2000, 9000))).astype(np.uint32) for _ in range(2)] for _ in range(world)]
+    part = [[fmix32(k) & np.uint32((1 << bits) - 1) for k in sides] for sides in keys]
+    Hist = torch.zeros(world, 2, 1 << bits, dtype=torch.int64)
+    for s in range(world):
+        for side in range(2):
+            Hist[s, side] = torch.from_numpy(np.bincount(part[s][side], minlength=1 << bits))
+    owned_arrays = [[None, None] for _ in range(world)]
+    layouts = [dj.exchange_layout(Hist, me, g, bits, p1) for me in range(world)]
+    for o in range(world):
+        for side in range(2):
+            owned_arrays[o][side] = np.full(int(layouts[o][2][side]), -1, dtype=np.int64)  # holds the final partition of each tuple
+    # the scatter, emulated: rank s writes its tuples of digit d at cursor[d]...
+    for s in range(world):
+        cursor = layouts[s][0].numpy()
+        for side in range(2):
+            digit = part[s][side] >> np.uint32(bits - p1)
+            for d in range(1 << p1):
+                sel = part[s][side][digit == d]
+                o = d >> (p1 - g)
+                at = int(cursor[side, d])
+                dst = owned_arrays[o][side]
+                assert (dst[at: at + len(sel)] == -1).all(), "runs overlap"
+                dst[at: at + len(sel)] = sel
+    for o in range(world):
+        _cur, local_hist, owned, per_owner, _sent = layouts[o]
+        assert torch.equal(per_owner, torch.stack([lay[2] for lay in layouts]).T)  # everybody agrees on what o receives
+        lo = o * ((1 << bits) >> g)
+        for side in range(2):
+            arr = owned_arrays[o][side]
+            assert (arr >= 0).all(), "holes in the receive array"
+            # grouped by pass-1 digit, ascending: region boundaries = prefix sums of the local histogram
+            lh = local_hist[side].numpy()
+            assert lh.sum() == len(arr) == int(owned[side])
+            digit = arr >> (bits - p1)
+            assert (np.diff(digit) >= 0).all()
+            per_region = lh.reshape(-1, 1 << (bits - p1)).sum(-1)
+            starts = np.concatenate([[0], np.cumsum(per_region)])
+            for j in range(len(per_region)):
+                seg = arr[starts[j]: starts[j + 1]]
+                assert ((seg >> (bits - p1)) == (lo >> (bits - p1)) + j).all()
+            # and the final partitions it owns are exactly its range
+            assert ((arr >= lo) & (arr < lo + ((1 << bits) >> g))).all()
+            assert np.array_equal(np.bincount(arr - lo, minlength=len(lh)), lh)
+
+
+def test_choose_bits_follows_the_engine():
+    assert dj.choose_bits(1 << 26) == 15 and dj.choose_bits((1 << 26) + 1) == 15
+    assert dj.choose_bits(2048) == 0 and dj.choose_bits(2049) == 1
+    assert dj.choose_bits(1 << 19) == 8 and dj.choose_bits((1 << 19) + 256) == 9
