@@ -40,7 +40,7 @@ def run(args, impl="ours"):
     launches0 = ctx.kernel_launches() if ctx else 0
     for name in names:
         t0 = time.perf_counter()
-        plan, _root_cols, scan_rows = job.make_job(name, scale=scale, seed=1)
+        plan, _root_cols, scan_rows = job.make_job(name, scale=scale, seed=1, ctx=ctx)  # ctx: pages written on the device
         t_gen += time.perf_counter() - t0
         entry = {"scan_rows": scan_rows}
         got = None

@@ -339,6 +339,12 @@ typedef struct rj_carry_scatter_t {
     void*           keys_dst_multi[8];
     void*           val_dst_multi[2][8];
     void*           flag_dst_multi[2][8];
+    /* region pass over SCATTERED inputs (the multi-GPU pull): d_src_table[x][0..4] = byte addresses (possibly
+     * peer-mapped) of the keys, value 0, value 1, flag 0, flag 1 of region x, biased so that the element
+     * index is the region's virtual position d_region_start[x] + i; d_region_group[x] = the cursor group
+     * (cursor[group << bits | digit]) region x feeds.  d_keys / val_src / flag_src are then unused. */
+    const uint64_t* d_src_table;
+    const uint32_t* d_region_group;
 } rj_carry_scatter_t;
 int rj_scatter_carry(rj_ctx* ctx, const rj_carry_scatter_t* desc, void* stream);
 
@@ -350,7 +356,15 @@ typedef struct rj_part_side_t {
     uint32_t       n_cols;             /* <= 2 */
     const void*    d_vals[2];
     int32_t        types[2];           /* RJ_INT32 / RJ_INT64 / RJ_FP64 */
-    const uint8_t* d_valid_bytes[2];   /* NULL: the column holds no NULL */
+    const uint8_t* d_valid_bytes[2];   /* NULL: the column holds no NULL (pull: any non-NULL value = has NULLs) */
+    /* pull (local_pass1_bits > 0 only): the pass-1 regions this rank owns are scattered over the ranks' pass-1
+     * arrays; n_sub sub-regions (region-major, sender-minor) described like rj_carry_scatter_t's scattered
+     * inputs.  n_sub == 0: d_keys / d_vals / d_valid_bytes are this rank's own arrays, regions in order. */
+    uint32_t        n_sub;
+    const uint64_t* d_src_table;       /* [n_sub][5] */
+    const uint32_t* d_sub_start;       /* [n_sub + 1] virtual positions */
+    const uint32_t* d_sub_tile;        /* [n_sub + 1] exclusive prefix of ceil(count / 4096) */
+    const uint32_t* d_sub_group;       /* [n_sub] pass-1 region (local numbering) of every sub-region */
 } rj_part_side_t;
 typedef struct rj_part_out_t {
     int32_t side;                      /* 0 = build side, 1 = probe side */
@@ -423,6 +437,16 @@ int rj_filter_table(rj_ctx* ctx, const rj_table_t* table, const rj_pred_t* prog,
  * d_desc, d_valid, NULL, n) + rj_encode_varchar_write then produce the pages (strings longer than 8185 bytes
  * become 0xffff / 0xfffe chains).  Strings are limited to 2^23 - 1 bytes, the buffer to 2^40 bytes. */
 int rj_varchar_descriptors(rj_ctx* ctx, const uint64_t* d_offsets, uint64_t n, uint64_t* d_desc, void* stream);
+
+/* -- result validation on the device (harness side: the sorted-multiset comparison of
+ *    tests/read_sql.cpp:1159-1222) ---------------------------------------------------------------- */
+
+/* Are two ColumnarTables (host pages) the same MULTISET of rows?  Both are decoded on the device, every row
+ * is hashed over all its cells, each table's (hash, row id) pairs are radix-sorted, and the rows at equal
+ * rank are compared in full: validity, value bit patterns (so NaN == NaN and -0.0 != 0.0, like the
+ * reference's variant compare of the bytes it wrote), string bytes.  *equal = 1 iff the column types, row
+ * counts and all pairs agree; *mismatches (may be NULL) = number of cell / hash pairs that differed. */
+int rj_tables_equal(rj_ctx* ctx, const rj_table_t* a, const rj_table_t* b, int32_t* equal, uint64_t* mismatches);
 
 /* ------------------------------------------------------------------------------------------------
  * Profiling: per-kernel-class CUDA-event timings accumulated by the whole-path functions.

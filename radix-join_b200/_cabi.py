@@ -83,12 +83,15 @@ class rj_carry_scatter_t(C.Structure):
                 ("n_val", C.c_uint32), ("val_src", C.c_void_p * 2), ("val_dst", C.c_void_p * 2), ("val_width", C.c_int32 * 2),
                 ("n_flag", C.c_uint32), ("flag_src", C.c_void_p * 2), ("flag_dst", C.c_void_p * 2),
                 ("n_owners", C.c_uint32), ("owner_shift", C.c_int32), ("keys_dst_multi", C.c_void_p * 8),
-                ("val_dst_multi", (C.c_void_p * 8) * 2), ("flag_dst_multi", (C.c_void_p * 8) * 2)]
+                ("val_dst_multi", (C.c_void_p * 8) * 2), ("flag_dst_multi", (C.c_void_p * 8) * 2),
+                ("d_src_table", C.c_void_p), ("d_region_group", C.c_void_p)]
 
 
 class rj_part_side_t(C.Structure):
     _fields_ = [("d_keys", C.c_void_p), ("n", C.c_uint64), ("n_cols", C.c_uint32), ("d_vals", C.c_void_p * 2),
-                ("types", C.c_int32 * 2), ("d_valid_bytes", C.c_void_p * 2)]
+                ("types", C.c_int32 * 2), ("d_valid_bytes", C.c_void_p * 2),
+                ("n_sub", C.c_uint32), ("d_src_table", C.c_void_p), ("d_sub_start", C.c_void_p), ("d_sub_tile", C.c_void_p),
+                ("d_sub_group", C.c_void_p)]
 
 
 class rj_part_out_t(C.Structure):
@@ -174,6 +177,7 @@ PROTOTYPES = {
     "rj_bitmap_logic": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, _vp]),
     "rj_bitmap_select": (C.c_int, [_vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
     "rj_filter_table": (C.c_int, [_vp, C.POINTER(rj_table_t), C.POINTER(rj_pred_t), _u32, _pvp]),
+    "rj_tables_equal": (C.c_int, [_vp, C.POINTER(rj_table_t), C.POINTER(rj_table_t), C.POINTER(_i32), C.POINTER(_u64)]),
     "rj_varchar_descriptors": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "rj_profile_enable": (C.c_int, [_vp, C.c_int]),
     "rj_profile_reset": (C.c_int, [_vp]),

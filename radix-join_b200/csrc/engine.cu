@@ -2333,6 +2333,8 @@ int rj_scatter_carry(rj_ctx* ctx, const rj_carry_scatter_t* d, void* stream) {
             c.flag_src[i] = d->flag_src[i];
             c.flag_dst[i] = static_cast<uint8_t*>(d->flag_dst[i]);
         }
+        c.src_tab = d->d_src_table;
+        c.region_group = d->d_region_group;
         c.n_owners = static_cast<int>(d->n_owners);
         c.owner_shift = d->owner_shift;
         for (int o = 0; o < 8; ++o) {
@@ -2421,11 +2423,20 @@ int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_
                 f.val[c] = sd.d_vals[c];
                 f.ok[c] = sd.d_valid_bytes[c];
             }
-            if (local_pass1_bits == 0) return f; // fully partitioned already
+            if (local_pass1_bits == 0) {
+                if (sd.n_sub > 0) throw EngineError("rj_join_partitioned: sub-regions need a second pass");
+                return f; // fully partitioned already
+            }
             CarryScatter c2;
             c2.keys = f.keys;
             c2.n = sd.n;
             c2.region_start = reg; c2.tile_start = tile; c2.n_regions = 1u << local_pass1_bits;
+            if (sd.n_sub > 0) {
+                // pull: the regions are read where the senders' first pass left them (peer memory)
+                if (!sd.d_src_table || !sd.d_sub_start || !sd.d_sub_tile || !sd.d_sub_group) throw EngineError("rj_join_partitioned: incomplete sub-region description");
+                c2.region_start = sd.d_sub_start; c2.tile_start = sd.d_sub_tile; c2.n_regions = sd.n_sub;
+                c2.src_tab = sd.d_src_table; c2.region_group = sd.d_sub_group;
+            }
             c2.shift = 0; c2.bits = bits2; c2.cursor = cur;
             f.hold[0] = dev_alloc(sd.n * 4 + 64, s);
             c2.keys_out = f.hold[0]->as<uint32_t>();
@@ -2625,6 +2636,72 @@ int rj_filter_table(rj_ctx* ctx, const rj_table_t* table, const rj_pred_t* prog,
 
 int rj_varchar_descriptors(rj_ctx* ctx, const uint64_t* d_offsets, uint64_t n, uint64_t* d_desc, void* stream) {
     return guarded(ctx, [&] { launch_varchar_desc_from_offsets(d_offsets, n, d_desc, ctx->sm_count, pick_stream(ctx, stream)); });
+}
+
+// ---- result validation ------------------------------------------------------------------------------------
+int rj_tables_equal(rj_ctx* ctx, const rj_table_t* a, const rj_table_t* b, int32_t* equal, uint64_t* mismatches) {
+    return guarded(ctx, [&] {
+        if (!a || !b || !equal) throw EngineError("rj_tables_equal: null argument");
+        *equal = 0;
+        if (mismatches) *mismatches = 0;
+        if (a->n_columns != b->n_columns || a->num_rows != b->num_rows) return;
+        for (uint32_t c = 0; c < a->n_columns; ++c)
+            if (a->columns[c].type != b->columns[c].type) return;
+        const uint64_t n = a->num_rows;
+        if (n >= 0xffffffffull) throw EngineError("relation exceeds 2^32-1 rows");
+        if (n == 0 || a->n_columns == 0) {
+            *equal = 1;
+            return;
+        }
+        rj_table_t tabs[2] = {*a, *b};
+        auto in = upload_tables(ctx, tabs, 2, nullptr);
+        rj_plan_t none{};
+        Exec ex(ctx, &none, in.get());
+        cudaStream_t s = ctx->stream;
+        Buf h[2], idx[2];
+        Buf alt_k = dev_alloc(n * 8, s), alt_v = dev_alloc(n * 4, s);
+        Buf counts = dev_alloc(sort_tmp_words(n) * 4, s), base = dev_alloc((sort_tmp_words(n) + 1) * 8, s);
+        Buf scan_tmp = dev_alloc(scan_tmp_bytes(std::max<uint64_t>(sort_tmp_words(n), n)), s);
+        Buf cell = dev_alloc(n * 8, s);
+        for (uint32_t t = 0; t < 2; ++t) {
+            h[t] = dev_alloc_zero(n * 8, s);
+            idx[t] = dev_alloc(n * 4, s);
+            for (uint32_t c = 0; c < a->n_columns; ++c) {
+                const DecodedCol& col = ex.column(t, c);
+                if (col.type == RJ_VARCHAR) {
+                    launch_varchar_hash(col.pages, col.values->as<uint64_t>(), col.valid_ptr(), n, cell->as<uint64_t>(), ctx->sm_count, s);
+                    launch_hash_combine(cell->as<uint64_t>(), col.valid_ptr(), n, h[t]->as<uint64_t>(), ctx->sm_count, s);
+                } else {
+                    launch_hash_fixed_cells(col.values->p, col.valid_ptr(), n, col.type == RJ_INT32 ? 4 : 8, h[t]->as<uint64_t>(), ctx->sm_count, s);
+                }
+            }
+            launch_iota_u32(idx[t]->as<uint32_t>(), n, ctx->sm_count, s);
+            launch_radix_sort_u64(h[t]->as<uint64_t>(), idx[t]->as<uint32_t>(), alt_k->as<uint64_t>(), alt_v->as<uint32_t>(), n,
+                                  counts->as<uint32_t>(), base->as<uint64_t>(), scan_tmp->p, s);
+        }
+        Buf bad = dev_alloc_zero(8, s);
+        auto* d_bad = bad->as<unsigned long long>();
+        launch_keys_differ(h[0]->as<uint64_t>(), h[1]->as<uint64_t>(), n, d_bad, ctx->sm_count, s);
+        Buf keep = dev_alloc(n * 4, s);
+        for (uint32_t c = 0; c < a->n_columns; ++c) {
+            const DecodedCol& ca = ex.column(0, c);
+            const DecodedCol& cb = ex.column(1, c);
+            if (ca.type == RJ_VARCHAR) {
+                launch_varchar_pairs_equal(ca.pages, ca.values->as<uint64_t>(), idx[0]->as<uint32_t>(), cb.pages, cb.values->as<uint64_t>(),
+                                           idx[1]->as<uint32_t>(), n, keep->as<uint32_t>(), ctx->sm_count, s);
+                launch_pairs_equal_varchar_finish(ca.valid_ptr(), idx[0]->as<uint32_t>(), cb.valid_ptr(), idx[1]->as<uint32_t>(), keep->as<uint32_t>(), n,
+                                                  d_bad, ctx->sm_count, s);
+            } else {
+                launch_pairs_equal_fixed(ca.values->p, ca.valid_ptr(), idx[0]->as<uint32_t>(), cb.values->p, cb.valid_ptr(), idx[1]->as<uint32_t>(), n,
+                                         ca.type == RJ_INT32 ? 4 : 8, d_bad, ctx->sm_count, s);
+            }
+        }
+        unsigned long long n_bad = 0;
+        RJ_CUDA(cudaMemcpyAsync(&n_bad, d_bad, 8, cudaMemcpyDeviceToHost, s));
+        RJ_CUDA(cudaStreamSynchronize(s));
+        if (mismatches) *mismatches = n_bad;
+        *equal = n_bad == 0 ? 1 : 0;
+    });
 }
 
 // ---- profiling -------------------------------------------------------------------------------------

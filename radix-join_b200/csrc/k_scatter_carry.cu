@@ -59,6 +59,11 @@ struct CarryArgs {
     // in another GPU's memory, mapped through NVLink -- are listed in `dsts`; cursor[p] indexes the owner's arrays
     const struct MultiCarryDsts* dsts;
     int             owner_shift;
+    // region pass reading SCATTERED inputs (the multi-GPU pull: a region's tuples lie in several peers' pass-1
+    // arrays): src_tab[x][0..4] = byte addresses of (keys, value 0, value 1, flag 0, flag 1) of region x, biased so
+    // that element index = the region's virtual position; region_group[x] = which cursor group x feeds
+    const uint64_t* src_tab;
+    const uint32_t* region_group;
 };
 
 struct MultiCarryDsts {
@@ -90,7 +95,7 @@ struct Layout {
 };
 
 struct Tile {
-    uint32_t lo, cnt, cbase;
+    uint32_t lo, cnt, cbase, reg;
 };
 
 template <bool kRegions, int W0, int W1, bool kMulti = false>
@@ -152,39 +157,51 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
             d.lo = s_region_start[x] + static_cast<uint32_t>(t - s_tile_start[x]) * kTile;
             const uint32_t left = s_region_start[x + 1] - d.lo;
             d.cnt   = left < kTile ? left : kTile;
-            d.cbase = x << a.bits;
+            d.reg   = x;
+            d.cbase = (a.region_group != nullptr ? a.region_group[x] : x) << a.bits;
         } else {
             d.lo = static_cast<uint32_t>(t * kTile);
             const uint64_t left = a.n - t * kTile;
             d.cnt   = left < kTile ? static_cast<uint32_t>(left) : kTile;
             d.cbase = 0;
+            d.reg   = 0;
         }
         return d;
     };
-    // elements between the 16-byte boundary below a region tile's first element and that element
-    auto skew = [&](uint32_t lo, uint32_t width) -> uint32_t { return kRegions ? (lo & (16u / width - 1u)) : 0u; };
+    // Source address of a tile's first element in array `which` (0 keys, 1 / 2 values, 3 / 4 flags) of width w.
+    // A region tile starts at an arbitrary element: its window is loaded from the 16-byte boundary below
+    // (skew = elements skipped) and is up to 16 bytes longer.
+    auto src_addr = [&](const Tile& d, int which, uint32_t w) -> uint64_t {
+        uint64_t base;
+        if (kRegions && a.src_tab != nullptr) base = a.src_tab[static_cast<uint64_t>(d.reg) * 5 + which];
+        else base = reinterpret_cast<uint64_t>(which == 0 ? static_cast<const void*>(a.keys) : (which < 3 ? a.val_src[which - 1] : a.flag_src[which - 3]));
+        return base + static_cast<uint64_t>(d.lo) * w;
+    };
+    auto skew_of = [&](uint64_t addr, uint32_t w) -> uint32_t { return kRegions ? static_cast<uint32_t>(addr & 15u) / w : 0u; };
     auto round16 = [](uint32_t bytes) -> uint32_t { return (bytes + 15u) & ~15u; };
 
     auto issue_keys = [&](const Tile& d, int b) { // one thread
-        const uint32_t off   = skew(d.lo, 4);
+        const uint64_t addr  = src_addr(d, 0, 4);
+        const uint32_t off   = skew_of(addr, 4);
         const uint32_t bytes = round16((d.cnt + off) * 4);
         mbar_arrive_expect_tx(&s_kbar[b], bytes);
-        tma_load_1d(smem + L::oKey + b * L::kKeyWin, a.keys + (d.lo - off), bytes, &s_kbar[b]);
+        tma_load_1d(smem + L::oKey + b * L::kKeyWin, reinterpret_cast<const void*>(addr - off * 4u), bytes, &s_kbar[b]);
     };
     auto issue_wins = [&](const Tile& d) { // one thread
         uint32_t bytes[4] = {0, 0, 0, 0};
-        if (W0) bytes[0] = round16((d.cnt + skew(d.lo, W0)) * W0);
-        if (W1) bytes[1] = round16((d.cnt + skew(d.lo, W1)) * W1);
+        uint64_t addr[4] = {0, 0, 0, 0};
+        if (W0) { addr[0] = src_addr(d, 1, W0 ? W0 : 4); bytes[0] = round16((d.cnt + skew_of(addr[0], W0 ? W0 : 4)) * W0); }
+        if (W1) { addr[1] = src_addr(d, 2, W1 ? W1 : 4); bytes[1] = round16((d.cnt + skew_of(addr[1], W1 ? W1 : 4)) * W1); }
 #pragma unroll
         for (int f = 0; f < 2; ++f)
-            if (kRegions && f < n_flag) bytes[2 + f] = round16(d.cnt + skew(d.lo, 1));
+            if (kRegions && f < n_flag) { addr[2 + f] = src_addr(d, 3 + f, 1); bytes[2 + f] = round16(d.cnt + skew_of(addr[2 + f], 1)); }
         mbar_arrive_expect_tx(&s_vbar, bytes[0] + bytes[1] + bytes[2] + bytes[3]);
-        if (W0) tma_load_1d(smem + L::oV0, static_cast<const char*>(a.val_src[0]) + static_cast<uint64_t>(d.lo - skew(d.lo, W0)) * W0, bytes[0], &s_vbar);
-        if (W1) tma_load_1d(smem + L::oV1, static_cast<const char*>(a.val_src[1]) + static_cast<uint64_t>(d.lo - skew(d.lo, W1)) * W1, bytes[1], &s_vbar);
+        if (W0) tma_load_1d(smem + L::oV0, reinterpret_cast<const void*>(addr[0] & ~15ull), bytes[0], &s_vbar);
+        if (W1) tma_load_1d(smem + L::oV1, reinterpret_cast<const void*>(addr[1] & ~15ull), bytes[1], &s_vbar);
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
             if (kRegions && f < n_flag)
-                tma_load_1d(smem + L::oFlag + f * L::kFlagWin, static_cast<const char*>(a.flag_src[f]) + (d.lo - skew(d.lo, 1)), bytes[2 + f], &s_vbar);
+                tma_load_1d(smem + L::oFlag + f * L::kFlagWin, reinterpret_cast<const void*>(addr[2 + f] & ~15ull), bytes[2 + f], &s_vbar);
         }
     };
 
@@ -205,7 +222,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
             // buffer b^1 held the previous tile's keys: their last read is behind the barrier that ended its copy-out
             if (tid == 0) issue_keys(nxt, b ^ 1);
         }
-        const uint32_t* __restrict__ kw = reinterpret_cast<const uint32_t*>(smem + L::oKey + b * L::kKeyWin) + skew(cur.lo, 4);
+        const uint32_t* __restrict__ kw = reinterpret_cast<const uint32_t*>(smem + L::oKey + b * L::kKeyWin) + skew_of(src_addr(cur, 0, 4), 4);
         const uint32_t cnt = cur.cnt;
         mbar_wait(&s_kbar[b], (it >> 1) & 1);
 
@@ -295,7 +312,10 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
 
         // 3) the permutation: output position inside the tile -> (tile offset | partition << 12 | validity << 30)
         if (kRegions && has_win && n_flag > 0) mbar_wait(&s_vbar, it & 1); // the validity bytes are read here
-        const uint32_t fsk = skew(cur.lo, 1);
+        uint32_t fsk[2] = {0u, 0u};
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+            if (kRegions && f < n_flag) fsk[f] = skew_of(src_addr(cur, 3 + f, 1), 1);
 #pragma unroll
         for (int k = 0; k < kItems; ++k) {
             const uint32_t part = pr[k] >> kOffBits;
@@ -304,7 +324,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
                 if (f < n_flag) {
-                    if (kRegions) fl |= (smem[L::oFlag + f * L::kFlagWin + fsk + k * kT + tid] ? 1u : 0u) << f;
+                    if (kRegions) fl |= (smem[L::oFlag + f * L::kFlagWin + fsk[f] + k * kT + tid] ? 1u : 0u) << f;
                     else fl |= ((__shfl_sync(RJ_FULL_MASK, fword[f], k) >> lane) & 1u) << f;
                 }
             }
@@ -316,8 +336,8 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
         // 4) copy out: consecutive threads write consecutive positions of a partition's run
         const uint32_t total = s_total;
         if (has_win && !(kRegions && n_flag > 0)) mbar_wait(&s_vbar, it & 1);
-        const T0* __restrict__ v0 = reinterpret_cast<const T0*>(smem + L::oV0) + (W0 ? skew(cur.lo, W0 ? W0 : 4) : 0u);
-        const T1* __restrict__ v1 = reinterpret_cast<const T1*>(smem + L::oV1) + (W1 ? skew(cur.lo, W1 ? W1 : 4) : 0u);
+        const T0* __restrict__ v0 = reinterpret_cast<const T0*>(smem + L::oV0) + (W0 ? skew_of(src_addr(cur, 1, W0 ? W0 : 4), W0 ? W0 : 4) : 0u);
+        const T1* __restrict__ v1 = reinterpret_cast<const T1*>(smem + L::oV1) + (W1 ? skew_of(src_addr(cur, 2, W1 ? W1 : 4), W1 ? W1 : 4) : 0u);
         auto copy_out = [&](auto pred_c, uint32_t base) {
             constexpr bool kPred = decltype(pred_c)::value;
             uint32_t off[kDepth], dd[kDepth], fl[kDepth], own[kDepth];
@@ -414,6 +434,8 @@ void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s) {
     a.region_start = c.region_start; a.tile_start = c.tile_start; a.n_regions = c.n_regions;
     a.shift = c.shift; a.bits = c.bits; a.cursor = c.cursor; a.keys_out = c.keys_out;
     a.n_flag = c.n_flag;
+    a.src_tab = c.src_tab;
+    a.region_group = c.region_group;
     for (int f = 0; f < c.n_flag; ++f) {
         a.flag_src[f] = c.flag_src[f];
         a.flag_dst[f] = c.flag_dst[f];
@@ -425,12 +447,13 @@ void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s) {
     for (int i = 0; i < c.n_val; ++i) {
         const int k = order[i];
         if (c.val_width[k] != 4 && c.val_width[k] != 8) throw CudaError("scatter_carry: value columns are 4 or 8 bytes wide");
-        if (reinterpret_cast<uintptr_t>(c.val_src[k]) % 16 != 0) throw CudaError("scatter_carry: value columns must be 16-byte aligned");
+        if (c.src_tab == nullptr && reinterpret_cast<uintptr_t>(c.val_src[k]) % 16 != 0) throw CudaError("scatter_carry: value columns must be 16-byte aligned");
         a.val_src[i] = c.val_src[k];
         a.val_dst[i] = c.val_dst[k];
         w[i] = c.val_width[k];
     }
-    if (reinterpret_cast<uintptr_t>(c.keys) % 16 != 0) throw CudaError("scatter_carry: keys must be 16-byte aligned");
+    if (c.src_tab == nullptr && reinterpret_cast<uintptr_t>(c.keys) % 16 != 0) throw CudaError("scatter_carry: keys must be 16-byte aligned");
+    if (c.src_tab != nullptr && c.region_start == nullptr) throw CudaError("scatter_carry: a source table needs regions");
     const bool regions = c.region_start != nullptr;
     // regions: the exact tile count lives on the device (tile_start[n_regions]); size the grid from its upper bound
     const uint64_t tiles_upper = (c.n + kTile - 1) / kTile + (regions ? c.n_regions : 0);

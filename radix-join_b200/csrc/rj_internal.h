@@ -175,6 +175,10 @@ struct CarryScatter {
     void*           keys_dst_multi[8] = {};
     void*           val_dst_multi[2][8] = {};
     void*           flag_dst_multi[2][8] = {};
+    // region pass over scattered inputs (multi-GPU pull): per-region source addresses (see k_scatter_carry.cu)
+    // and the cursor group of every region; keys / val_src / flag_src are then unused
+    const uint64_t* src_tab = nullptr;      // [n_regions][5] device
+    const uint32_t* region_group = nullptr; // [n_regions] device
 };
 void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s);
 
@@ -189,6 +193,19 @@ void launch_filter_varchar(const void* pages, const uint64_t* desc, const uint32
                            uint32_t rhs_len, uint32_t* out, int sm_count, cudaStream_t s);
 void launch_bitmap_popc(const uint32_t* bits, uint64_t n_words, uint32_t* counts, int sm_count, cudaStream_t s);
 void launch_bitmap_expand(const uint32_t* bits, const uint64_t* start, uint64_t n_words, uint32_t* ids, int sm_count, cudaStream_t s);
+
+// ---- k_sort.cu: result validation (row hashes, LSD radix sort, pairwise comparison) ----------------------
+void launch_hash_fixed_cells(const void* values, const uint32_t* valid, uint64_t n, int width, uint64_t* h, int sm_count, cudaStream_t s);
+void launch_hash_combine(const uint64_t* cell, const uint32_t* valid, uint64_t n, uint64_t* h, int sm_count, cudaStream_t s);
+uint64_t sort_tmp_words(uint64_t n);
+void launch_radix_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t* alt_keys, uint32_t* alt_vals, uint64_t n, uint32_t* counts,
+                           uint64_t* base, void* scan_tmp, cudaStream_t s);
+void launch_iota_u32(uint32_t* out, uint64_t n, int sm_count, cudaStream_t s);
+void launch_pairs_equal_fixed(const void* va, const uint32_t* valid_a, const uint32_t* idx_a, const void* vb, const uint32_t* valid_b,
+                              const uint32_t* idx_b, uint64_t n, int width, unsigned long long* mismatches, int sm_count, cudaStream_t s);
+void launch_pairs_equal_varchar_finish(const uint32_t* valid_a, const uint32_t* idx_a, const uint32_t* valid_b, const uint32_t* idx_b,
+                                       const uint32_t* keep, uint64_t n, unsigned long long* mismatches, int sm_count, cudaStream_t s);
+void launch_keys_differ(const uint64_t* a, const uint64_t* b, uint64_t n, unsigned long long* mismatches, int sm_count, cudaStream_t s);
 
 // ---- k_join.cu ------------------------------------------------------------------------------------
 struct JoinLaunch {

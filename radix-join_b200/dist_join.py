@@ -195,17 +195,44 @@ class CudaOps:
         d.n_val, d.n_flag = nv, nf
         self.ctx.check(self.lib.rj_scatter_carry(self.h, C.byref(d), self.stream))
 
+    def local_scatter(self, keys, valid, payloads, shift, bits, cursor, xchg, me):
+        """scatter pass 1 into THIS rank's arrays of the exchange (symmetric memory: the owners of the regions read
+        them from here in their second pass)"""
+        d = _cabi.rj_carry_scatter_t()
+        d.d_keys, d.d_valid, d.n = self._p(keys), self._p(valid), keys.numel()
+        d.shift, d.bits, d.d_cursor = shift, bits, self._p(cursor)
+        d.d_keys_out = xchg.keys.ptrs[me]
+        nv = nf = 0
+        for i, (values, vbits) in enumerate(payloads):
+            d.val_src[nv], d.val_dst[nv], d.val_width[nv] = self._p(values), xchg.vals[i].ptrs[me], values.element_size()
+            nv += 1
+            if vbits is not None:
+                d.flag_src[nf], d.flag_dst[nf] = self._p(vbits), xchg.valids[i].ptrs[me]
+                nf += 1
+        d.n_val, d.n_flag = nv, nf
+        self.ctx.check(self.lib.rj_scatter_carry(self.h, C.byref(d), self.stream))
+
     def join_partitioned(self, sides, hists, local_bits, local_pass1_bits, hash_bits, out_cols):
         """sides = ((keys, [values], [validity bytes or None], [types]) for build, probe), grouped by their pass-1
         digit (or fully partitioned); hists = per-local-partition tuple counts (int32 tensors).
         -> (n_rows, [ResultPages]) or None when a table met duplicate build keys"""
         from .engine import Result
         cs = []
-        for keys, vals, valids, types in sides:
+        for side in sides:
             sd = _cabi.rj_part_side_t()
-            sd.d_keys, sd.n, sd.n_cols = self._p(keys), keys.numel(), len(vals)
-            for i, (v, vb, t) in enumerate(zip(vals, valids, types)):
-                sd.d_vals[i], sd.types[i], sd.d_valid_bytes[i] = self._p(v), int(t), self._p(vb)
+            if isinstance(side, dict):
+                # pull: the regions are read from the senders' arrays (see pull_layout)
+                sd.d_keys, sd.n, sd.n_cols = None, side["n"], len(side["types"])
+                for i, (t, nullable) in enumerate(zip(side["types"], side["nullable"])):
+                    sd.d_vals[i], sd.types[i], sd.d_valid_bytes[i] = None, int(t), (1 if nullable else None)
+                sd.n_sub = side["table"].shape[0]
+                sd.d_src_table, sd.d_sub_start = self._p(side["table"]), self._p(side["start"])
+                sd.d_sub_tile, sd.d_sub_group = self._p(side["tile"]), self._p(side["group"])
+            else:
+                keys, vals, valids, types = side
+                sd.d_keys, sd.n, sd.n_cols = self._p(keys), keys.numel(), len(vals)
+                for i, (v, vb, t) in enumerate(zip(vals, valids, types)):
+                    sd.d_vals[i], sd.types[i], sd.d_valid_bytes[i] = self._p(v), int(t), self._p(vb)
             cs.append(sd)
         outs = (_cabi.rj_part_out_t * len(out_cols))()
         for i, (side, which, _type) in enumerate(out_cols):
@@ -529,6 +556,35 @@ def exchange_layout(H, me, g, bits, p1):
     return cursor, local_hist, local_hist.sum(-1), tot.sum(-1), sent
 
 
+SCATTER_TILE = 4096  # tuples per scatter tile (csrc/k_scatter_carry.cu)
+
+
+def pull_layout(H, me, g, bits, p1, side, array_ptrs, array_widths):
+    """The pull variant: every rank runs scatter pass 1 into its OWN arrays (grouped by pass-1 digit, cursor = the
+    exclusive prefix of its own digit counts), and the owner of a digit reads that digit's G runs where they lie
+    -- its second pass takes them as sub-regions (region-major, sender-minor).  From H alone:
+        cursor[d]           where this rank's run of digit d starts in its own arrays
+        table[x, a]         byte address of array a (keys, value 0, value 1, flag 0, flag 1) of sub-region x, biased
+                            so that the element index is the sub-region's virtual position
+        start / tile        exclusive prefixes of the sub-regions' tuple and tile counts (n_sub + 1 entries)
+        group[x]            the pass-1 region (local numbering) sub-region x belongs to
+    array_ptrs[a] = int64 tensor [G] of every rank's base address of array a (0 where the array does not exist)."""
+    G, nfin, ndig = H.shape[0], 1 << bits, 1 << p1
+    per = ndig >> g
+    Cnt = H[:, side].view(G, ndig, nfin // ndig).sum(-1)                 # [G, ndig]
+    run_start = torch.cumsum(Cnt, -1) - Cnt                              # sender-local start of every digit run
+    mine = torch.arange(per, device=H.device) + me * per
+    cnt = Cnt[:, mine].T.reshape(-1)                                     # [per * G] region-major, sender-minor
+    zero = torch.zeros(1, dtype=torch.int64, device=H.device)
+    start = torch.cat([zero, torch.cumsum(cnt, 0)])
+    tile = torch.cat([zero, torch.cumsum((cnt + SCATTER_TILE - 1) // SCATTER_TILE, 0)])
+    group = torch.arange(per, device=H.device).repeat_interleave(G)
+    delta = run_start[:, mine].T.reshape(-1) - start[:-1]                # element bias of every sub-region
+    sender = torch.arange(G, device=H.device).repeat(per)
+    table = torch.stack([array_ptrs[a][sender] + delta * array_widths[a] for a in range(5)], dim=1).contiguous()
+    return run_start[me], table, start, tile, group
+
+
 def distributed_join_fused(ops, build, probe, out_cols, xchg, group=None, total_build_rows=None):
     """Key / foreign-key join of two sharded relations where the first scatter pass of the single-GPU algorithm is
     the exchange: every rank histograms its slice over the job's radix digits, the histograms are all-gathered,
@@ -579,31 +635,62 @@ def distributed_join_fused(ops, build, probe, out_cols, xchg, group=None, total_
     if worst[0] > xchg[0].cap or worst[1] > xchg[1].cap:
         raise RuntimeError("peer exchange buffers too small for this key distribution")
     mark()
-    # 3. the exchange = scatter pass 1 into the owners' arrays
-    xchg[0].barrier()                      # every rank is done with the previous contents of its receive arrays
-    for side, (keys, kvalid, pays) in enumerate(rels):
-        ops.exchange_scatter(keys, kvalid, pays, bits - p1, p1, cursor32[side], g, xchg[side])
-    xchg[0].barrier()                      # every rank's stores have landed
-    mark()
-    # 4. local: pass 2 inside every received region, then build + probe + page output
-    sides, sent_bytes = [], 0
-    for side, (rel, x) in enumerate(zip((build, probe), xchg)):
-        n = n_own[side]
-        vals = [x.vals[i].tensor[:n] for i in range(len(rel.payloads))]
-        valids = [x.valids[i].tensor[:n] if rel.payloads[i][3] else None for i in range(len(rel.payloads))]
-        types = [p[2] for p in rel.payloads]
-        sides.append((x.keys.tensor[:n], vals, valids, types))
-        sent_bytes += n_sent[side] * (4 + sum((4 if p[2] == INT32 else 8) + (1 if p[3] else 0) for p in rel.payloads))
+    pull = two and os.environ.get("RJ_DIST_MODE", "pull") == "pull"
+    if pull:
+        # 3. scatter pass 1 stays local (into this rank's symmetric arrays); 4. the owners PULL: their second pass
+        #    reads every region's runs from the senders' memory over NVLink (TMA bulk loads), so the transfer
+        #    overlaps the partitioning and nothing is copied twice.
+        lays, sides = [], []
+        for side, (rel, x) in enumerate(zip((build, probe), xchg)):
+            widths = [4] + [(4 if p[2] == INT32 else 8) for p in rel.payloads] + [0] * (2 - len(rel.payloads)) + [1, 1]
+            ptrs = [x.keys.ptrs]
+            ptrs += [x.vals[i].ptrs for i in range(len(rel.payloads))] + [[0] * world] * (2 - len(rel.payloads))
+            flag_bufs = [x.valids[i] for i in range(len(rel.payloads)) if rel.payloads[i][3]]
+            ptrs += [fb.ptrs for fb in flag_bufs] + [[0] * world] * (2 - len(flag_bufs))
+            tptrs = [torch.tensor(p, dtype=torch.int64, device=hist.device) for p in ptrs]
+            lays.append(pull_layout(H.view(world, 2, 1 << bits).to(torch.int64), me, g, bits, p1, side, tptrs, widths))
+        xchg[0].barrier()                  # every owner is done reading the previous contents of these arrays
+        for side, (keys, kvalid, pays) in enumerate(rels):
+            ops.local_scatter(keys, kvalid, pays, bits - p1, p1, lays[side][0].to(torch.int32).contiguous(), xchg[side], me)
+        xchg[0].barrier()                  # every rank's first pass is complete
+        mark()
+        sent_bytes = 0
+        for side, rel in enumerate((build, probe)):
+            _cur, table, start, tile, group = lays[side]
+            sides.append({"n": n_own[side], "types": [p[2] for p in rel.payloads], "nullable": [bool(p[3]) for p in rel.payloads],
+                          "table": table, "start": start.to(torch.int32).contiguous(), "tile": tile.to(torch.int32).contiguous(),
+                          "group": group.to(torch.int32).contiguous()})
+            sent_bytes += n_sent[side] * (4 + sum((4 if p[2] == INT32 else 8) + (1 if p[3] else 0) for p in rel.payloads))
+        exchange_how = f"scatter pass 1 local, the owners' pass 2 reads its regions from the senders' memory (TMA over NVLink, {p1} of {bits} radix bits)"
+    else:
+        # 3. the exchange = scatter pass 1 into the owners' arrays
+        xchg[0].barrier()                      # every rank is done with the previous contents of its receive arrays
+        for side, (keys, kvalid, pays) in enumerate(rels):
+            ops.exchange_scatter(keys, kvalid, pays, bits - p1, p1, cursor32[side], g, xchg[side])
+        xchg[0].barrier()                      # every rank's stores have landed
+        mark()
+        # 4. local: pass 2 inside every received region, then build + probe + page output
+        sides, sent_bytes = [], 0
+        for side, (rel, x) in enumerate(zip((build, probe), xchg)):
+            n = n_own[side]
+            vals = [x.vals[i].tensor[:n] for i in range(len(rel.payloads))]
+            valids = [x.valids[i].tensor[:n] if rel.payloads[i][3] else None for i in range(len(rel.payloads))]
+            types = [p[2] for p in rel.payloads]
+            sides.append((x.keys.tensor[:n], vals, valids, types))
+            sent_bytes += n_sent[side] * (4 + sum((4 if p[2] == INT32 else 8) + (1 if p[3] else 0) for p in rel.payloads))
+        exchange_how = f"scatter pass 1 of the join written into the owners' memory (peer stores, {p1} of {bits} radix bits)"
     got = ops.join_partitioned(sides, (local_hist32[0], local_hist32[1]), bits - g, (p1 - g) if two else 0, bits, out_cols)
     mark()
     if got is None:
+        if pull:
+            return None  # duplicate build keys: the caller runs the general distributed join
         # duplicate build keys: the general local join on what was received (any order will do)
         ops._types = (tuple(p[2] for p in build.payloads), tuple(p[2] for p in probe.payloads))
         (bk, bvals, bvalids, _), (pk, pvals, pvalids, _) = sides
         got = ops.local_join_encode(bk, bvals, bvalids, pk, pvals, pvalids, out_cols)
     n_rows, cols = got
     stats = {"sent_bytes": sent_bytes, "owned_build": n_own[0], "owned_probe": n_own[1],
-             "exchange": f"scatter pass 1 of the join written into the owners' memory (peer stores, {p1} of {bits} radix bits)"}
+             "exchange": exchange_how}
     if trace:
         names = ["decode+histogram", "layout", "exchange", "pass 2 + join + pages"]
         stats["phase_ms"] = {n: round((b - a) * 1e3, 3) for n, a, b in zip(names, t[:-1], t[1:])}

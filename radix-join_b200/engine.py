@@ -230,3 +230,16 @@ def execute_resident(plan: Plan, inputs: ResidentInputs, ctx: Context) -> Result
     h = C.c_void_p()
     ctx.check(ctx.lib.rj_execute_resident(ctx.handle, flat.pointer(), inputs.handle, C.byref(h)))
     return Result(ctx, h)
+
+
+def tables_equal(a: ColumnarTable, b: ColumnarTable, ctx: Context):
+    """Sorted-multiset comparison of two ColumnarTables on the device (the harness's `compare`,
+    tests/read_sql.cpp:1159-1222): decode, hash every row, radix-sort, compare the rows at equal rank cell by
+    cell.  -> (equal, number of differing cell / hash pairs)"""
+    pa, pb = Plan(), Plan()
+    pa.new_input(a)
+    pb.new_input(b)
+    fa, fb = FlatPlan(pa), FlatPlan(pb)
+    eq, bad = C.c_int32(0), C.c_uint64(0)
+    ctx.check(ctx.lib.rj_tables_equal(ctx.handle, fa.tables, fb.tables, C.byref(eq), C.byref(bad)))
+    return bool(eq.value), int(bad.value)

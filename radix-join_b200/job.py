@@ -25,6 +25,7 @@ import zlib
 
 import numpy as np
 
+from . import pagewriter
 from .plan import Column, ColumnarTable, DataType, Plan
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -293,9 +294,11 @@ def _scaled(rows, scale, min_rows=1):
     return rows if rows <= _SMALL else max(min_rows, int(round(rows * scale)))
 
 
-def make_inputs(query_name, scale=1.0, seed=0, long_strings=False, min_rows=1):
+def make_inputs(query_name, scale=1.0, seed=0, long_strings=False, min_rows=1, ctx=None):
     """alias -> ColumnarTable for every scan of the query.  Only the columns the plan reads carry
-    pages; the others are typed, page-less placeholders (the engine never touches them)."""
+    pages; the others are typed, page-less placeholders (the engine never touches them).
+    With an engine context the pages are written on the device (radix_join_b200.pagewriter) instead of by
+    the numpy loops below: same rows, possibly another (equally legal) page packing."""
     w = workload()
     q = w["queries"][query_name]
     need = needed_columns(query_name)
@@ -327,7 +330,7 @@ def make_inputs(query_name, scale=1.0, seed=0, long_strings=False, min_rows=1):
                     vals = _zipf_ids(rng, n, dom)
                 else:
                     vals = rng.integers(1880, 2020, n).astype(np.int32)
-                cols.append(Column(dt, write_fixed_pages(vals, valid, dt)))
+                cols.append(Column(dt, pagewriter.fixed_pages(ctx, vals, valid, dt) if ctx is not None else write_fixed_pages(vals, valid, dt)))
             else:
                 lens = _string_lengths(rng, n, col)
                 if long_strings and (alias, col) in outputs and n > 0:
@@ -337,13 +340,16 @@ def make_inputs(query_name, scale=1.0, seed=0, long_strings=False, min_rows=1):
                 if valid is not None:
                     lens = np.where(valid, lens, 0)
                 chars = rng.integers(97, 123, int(lens.sum()), dtype=np.uint8)
-                cols.append(Column(dt, write_varchar_pages(lens, chars, valid if valid is not None else np.ones(n, bool))))
+                if ctx is not None:
+                    cols.append(Column(dt, pagewriter.varchar_pages(ctx, lens, chars, valid)))
+                else:
+                    cols.append(Column(dt, write_varchar_pages(lens, chars, valid if valid is not None else np.ones(n, bool))))
         tables[alias] = ColumnarTable(num_rows=n, columns=cols)
     return tables
 
 
-def make_job(query_name, scale=1.0, seed=0, long_strings=False):
+def make_job(query_name, scale=1.0, seed=0, long_strings=False, ctx=None):
     """-> (Plan, root columns, total scan rows) for one JOB query on synthetic inputs"""
-    tables = make_inputs(query_name, scale, seed, long_strings)
+    tables = make_inputs(query_name, scale, seed, long_strings, ctx=ctx)
     plan, root_cols = build_plan(query_name, tables)
     return plan, root_cols, sum(t.num_rows for t in tables.values())

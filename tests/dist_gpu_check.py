@@ -40,6 +40,14 @@ def main():
             # the join's first scatter pass as the exchange (twice: the receive arrays are reused)
             modes.append(("fused", lambda: dj.distributed_join_fused(ops, build, probe, dist_bench.OUT_COLS, xchg, total_build_rows=n_b)))
             modes.append(("fused again", lambda: dj.distributed_join_fused(ops, build, probe, dist_bench.OUT_COLS, xchg)))
+
+            def pushed():
+                os.environ["RJ_DIST_MODE"] = "push"  # peer stores instead of the owners pulling
+                try:
+                    return dj.distributed_join_fused(ops, build, probe, dist_bench.OUT_COLS, xchg, total_build_rows=n_b)
+                finally:
+                    del os.environ["RJ_DIST_MODE"]
+            modes.append(("fused push", pushed))
         if n_b == 1 << 19:
             # the broadcast of the (here: forced) small build side
             modes.append(("broadcast", lambda: dj.distributed_join(ops, build, probe, dist_bench.OUT_COLS, broadcast_max_rows=n_b)))

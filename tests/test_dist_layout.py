@@ -77,3 +77,52 @@ def test_choose_bits_follows_the_engine():
     assert dj.choose_bits(1 << 26) == 15 and dj.choose_bits((1 << 26) + 1) == 15
     assert dj.choose_bits(2048) == 0 and dj.choose_bits(2049) == 1
     assert dj.choose_bits(1 << 19) == 8 and dj.choose_bits((1 << 19) + 256) == 9
+
+
+@pytest.mark.parametrize("world,bits", [(2, 15), (4, 12), (8, 15), (8, 9)])
+def test_pull_layout_addresses_every_tuple_once(world, bits):
+    """pull variant: pass 1 stays local, the owner's second pass reads each region's runs from the senders' arrays
+    through a table of biased addresses -- simulated with address = rank * BIG + element index (widths of 1)"""
+    rng = np.random.default_rng(world * 10 + bits)
+    g = dj.log2_exact(world)
+    p1 = (bits + 1) // 2
+    BIG = 10**9
+    keys = [rng.integers(0, 1 << 20, int(rng.integers(3000, 20000))).astype(np.uint32) for _ in range(world)]
+    part = [fmix32(k) & np.uint32((1 << bits) - 1) for k in keys]
+    Hist = torch.zeros(world, 2, 1 << bits, dtype=torch.int64)
+    for s in range(world):
+        Hist[s, 1] = torch.from_numpy(np.bincount(part[s], minlength=1 << bits))
+    ptrs = [torch.arange(world, dtype=torch.int64) * BIG for _ in range(5)]
+    lays = [dj.pull_layout(Hist, me, g, bits, p1, 1, ptrs, [1] * 5) for me in range(world)]
+    # pass 1, emulated: every rank groups its tuples by digit at its own cursor
+    arrays = []
+    for s in range(world):
+        cur = lays[s][0].numpy().copy()
+        out = np.full(len(keys[s]), -1, dtype=np.int64)
+        digit = part[s] >> np.uint32(bits - p1)
+        for d in range(1 << p1):
+            sel = part[s][digit == d]
+            out[cur[d]: cur[d] + len(sel)] = sel
+        assert (out >= 0).all()
+        arrays.append(out)
+    seen = [np.zeros(len(a), dtype=np.int64) for a in arrays]
+    per = (1 << p1) >> g
+    for me in range(world):
+        _cur, table, start, tile, group = [x.numpy() for x in lays[me]]
+        n_sub = per * world
+        assert table.shape == (n_sub, 5) and len(start) == len(tile) == n_sub + 1 and len(group) == n_sub
+        for x in range(n_sub):
+            cnt = start[x + 1] - start[x]
+            assert tile[x + 1] - tile[x] == (cnt + dj.SCATTER_TILE - 1) // dj.SCATTER_TILE
+            assert group[x] == x // world
+            for i in (range(cnt) if cnt < 50 else [0, cnt // 2, cnt - 1]):
+                addr = table[x, 0] + start[x] + i      # element index = the virtual position
+                q, idx = divmod(int(addr), BIG)
+                assert q == x % world
+                f = arrays[q][idx]
+                assert (f >> (bits - p1)) == me * per + group[x]  # the right pass-1 digit, owned by `me`
+            if cnt:
+                q, idx0 = divmod(int(table[x, 0] + start[x]), BIG)
+                seen[q][idx0: idx0 + cnt] += 1
+    for s in range(world):
+        assert (seen[s] == 1).all(), "every tuple is read by exactly one owner"
