@@ -93,6 +93,15 @@ typedef struct rj_result rj_result; /* result ColumnarTable: pages resident in H
  * Context  -- replaces Contest::build_context / destroy_context (src/execute.cpp:326-330)
  * ---------------------------------------------------------------------------------------------- */
 int         rj_ctx_create(int device, rj_ctx** out);
+/* A device GROUP driven by one process (n_devices a power of two, all with peer access to each other):
+ * the context is a normal context on devices[0]; rj_execute_pages -- what Contest::execute calls -- runs an
+ * eligible plan (one key / foreign-key join of two scans on an INT32 key whose outputs are the key and at
+ * most two fixed-width columns per side, build side > 512 Ki rows) on ALL devices: each takes 1/n of both
+ * tables' rows, scatter pass 1 stays local, the owner of a hash range runs pass 2 out of the other devices'
+ * memory over NVLink, and the devices' result pages are appended in device order.  Everything else runs on
+ * devices[0].  Replaces nothing in the reference (its execute() is a one-socket CPU program); SURVEY 8e. */
+int         rj_ctx_create_multi(const int* devices, uint32_t n_devices, rj_ctx** out);
+int         rj_ctx_group_size(const rj_ctx* ctx);
 void        rj_ctx_destroy(rj_ctx* ctx);
 const char* rj_last_error(const rj_ctx* ctx); /* ctx may be NULL: error of the last failed rj_ctx_create */
 int         rj_ctx_device(const rj_ctx* ctx);

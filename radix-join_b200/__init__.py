@@ -12,14 +12,14 @@ sm_100 device and fails loudly otherwise.
 """
 from ._cabi import PAGE_SIZE, EngineMissing, load_library
 from .engine import (Context, EngineError, ResidentInputs, Result, adopt_device, build_context,
-                     destroy_context, execute, execute_resident, execute_streamed,
+                     destroy_context, execute, execute_pages, execute_resident, execute_streamed,
                      execute_streamed_columnar, execute_to_device, tables_equal, upload)
 from .statement import Comparison, LogicalOperation, Statement, filter_table, filter_table_to_device
 from .plan import (Column, ColumnarTable, DataType, FlatPlan, JoinNode, Plan, PlanNode, ScanNode)
 
 __all__ = [
     "PAGE_SIZE", "EngineMissing", "load_library", "Context", "EngineError", "ResidentInputs", "Result",
-    "adopt_device", "build_context", "destroy_context", "execute", "execute_resident",
+    "adopt_device", "build_context", "destroy_context", "execute", "execute_pages", "execute_resident",
     "execute_streamed", "execute_streamed_columnar", "execute_to_device", "upload", "Column", "ColumnarTable", "DataType", "FlatPlan", "JoinNode",
     "Plan", "PlanNode", "ScanNode", "Comparison", "LogicalOperation", "Statement", "filter_table", "filter_table_to_device", "tables_equal",
 ]

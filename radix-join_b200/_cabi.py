@@ -129,6 +129,8 @@ class rj_page_alloc_t(C.Structure):
 
 PROTOTYPES = {
     "rj_ctx_create": (C.c_int, [C.c_int, _pvp]),
+    "rj_ctx_create_multi": (C.c_int, [C.POINTER(C.c_int), _u32, _pvp]),
+    "rj_ctx_group_size": (C.c_int, [_vp]),
     "rj_ctx_destroy": (None, [_vp]),
     "rj_last_error": (C.c_char_p, [_vp]),
     "rj_ctx_device": (C.c_int, [_vp]),

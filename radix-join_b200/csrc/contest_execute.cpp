@@ -13,6 +13,7 @@
 //     (src/execute.cpp:280; the harness catches std::exception, tests/read_sql.cpp:1329-1332).
 #include <malloc.h>
 
+#include <cstdlib>
 #include <limits>
 #include <stdexcept>
 #include <string>
@@ -32,6 +33,18 @@ void* build_context() {
     mallopt(M_TOP_PAD, 256 << 20);
     mallopt(M_MMAP_THRESHOLD, 1 << 30);
     rj_ctx* ctx = nullptr;
+    // RJ_GPUS=N (a power of two): one context over devices 0..N-1; large key / foreign-key joins of two scans
+    // then run on all of them (rj_ctx_create_multi), everything else on device 0
+    int n_gpus = 1;
+    if (const char* env = std::getenv("RJ_GPUS")) n_gpus = std::atoi(env);
+    if (n_gpus > 1) {
+        std::vector<int> devices(n_gpus);
+        for (int i = 0; i < n_gpus; ++i) devices[i] = i;
+        if (rj_ctx_create_multi(devices.data(), static_cast<uint32_t>(n_gpus), &ctx) != 0) {
+            throw std::runtime_error(std::string("rj_ctx_create_multi: ") + rj_last_error(nullptr));
+        }
+        return ctx;
+    }
     if (rj_ctx_create(0, &ctx) != 0) {
         throw std::runtime_error(std::string("rj_ctx_create: ") + rj_last_error(nullptr));
     }

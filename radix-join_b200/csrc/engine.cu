@@ -60,6 +60,8 @@ struct rj_ctx {
     // rj_execute_streamed: uploads and downloads run beside the kernels on their own streams
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t  up_ev[2] = {nullptr, nullptr};
+    // rj_ctx_create_multi: the contexts of the other devices of the group (this one is device 0 of it)
+    std::vector<rj_ctx*> subs;
 };
 
 static thread_local std::string g_create_error;
@@ -1574,6 +1576,8 @@ int rj_ctx_create(int device, rj_ctx** out) {
 
 void rj_ctx_destroy(rj_ctx* ctx) {
     if (!ctx) return;
+    for (rj_ctx* sub: ctx->subs) rj_ctx_destroy(sub);
+    ctx->subs.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     profile_collect(ctx);
@@ -2047,6 +2051,430 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
 
 } // namespace
 
+// ================================================================================================
+// multi-device execution of ONE plan from ONE process (rj_ctx_create_multi)
+// ================================================================================================
+// The reference's execute() is a single call from a single thread (tests/read_sql.cpp:1308-1317); to let it
+// use several GPUs the same algorithm the torchrun driver runs with one process per GPU
+// (radix_join_b200/dist_join.py: distributed_join_fused, pull variant) is run here by one host thread per
+// device: each device takes a 1/G slice of the rows of both tables, decodes it, histograms the keys over
+// the job's radix digits; from all devices' histograms every device derives where the runs of each pass-1
+// digit lie; scatter pass 1 stays LOCAL; the owner of a digit range then runs scatter pass 2 directly out of
+// the other devices' pass-1 arrays (peer access, TMA bulk loads over NVLink) and the fused build / probe /
+// page-output kernel on the partitions it owns.  The devices' result page lists are appended in device
+// order for every column, which keeps the columns row-aligned (include/plan.h:102-105).
+// Eligible: the plan is one key / foreign-key join of two scans on an INT32 key, the outputs are the key and
+// at most two fixed-width columns per side, and the build side needs two scatter passes (> 512 Ki rows);
+// anything else runs on the group's first device as before.
+namespace {
+
+std::unique_ptr<rj_result> join_partitioned_impl(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_side_t* probe,
+                                                 const uint32_t* d_hist_build, const uint32_t* d_hist_probe, int32_t local_bits,
+                                                 int32_t local_pass1_bits, int32_t hash_bits, const rj_part_out_t* outs, uint32_t n_out);
+
+struct FusedShape {
+    uint32_t table[2] = {0, 0};     // [0] build side (the smaller table), [1] probe side
+    uint32_t key_col[2] = {0, 0};
+    std::vector<uint32_t> cols[2];  // carried columns per side
+    std::vector<int32_t>  types[2];
+    rj_part_out_t outs[kEmitMaxOut];
+    uint32_t n_out = 0;
+};
+
+bool analyze_fused_root(const rj_plan_t* plan, FusedShape* fs) {
+    if (!plan || plan->root >= plan->n_nodes) return false;
+    const rj_node_t& nd = plan->nodes[plan->root];
+    if (!nd.is_join || nd.left >= plan->n_nodes || nd.right >= plan->n_nodes) return false;
+    const rj_node_t &ln = plan->nodes[nd.left], &rn = plan->nodes[nd.right];
+    if (ln.is_join || rn.is_join || nd.left == nd.right) return false;
+    if (nd.n_output_attrs < 1 || nd.n_output_attrs > static_cast<uint32_t>(kEmitMaxOut)) return false;
+    if (nd.left_attr >= ln.n_output_attrs || nd.right_attr >= rn.n_output_attrs) return false;
+    if (ln.base_table_id >= plan->n_inputs || rn.base_table_id >= plan->n_inputs || ln.base_table_id == rn.base_table_id) return false;
+    const rj_table_t &tl = plan->inputs[ln.base_table_id], &tr = plan->inputs[rn.base_table_id];
+    const uint64_t lkey = ln.output_attrs[nd.left_attr].index, rkey = rn.output_attrs[nd.right_attr].index;
+    if (lkey >= tl.n_columns || rkey >= tr.n_columns) return false;
+    // the key type comes from the build side's declaration (src/execute.cpp:271-273); both physical columns must be INT32
+    const rj_node_t& bnode = nd.build_left ? ln : rn;
+    if (bnode.output_attrs[nd.build_left ? nd.left_attr : nd.right_attr].type != RJ_INT32) return false;
+    if (tl.columns[lkey].type != RJ_INT32 || tr.columns[rkey].type != RJ_INT32) return false;
+    if (tl.num_rows == 0 || tr.num_rows == 0 || tl.num_rows >= 0xffffffffull || tr.num_rows >= 0xffffffffull) return false;
+    const bool table_left = tl.num_rows <= tr.num_rows;
+    fs->table[0] = static_cast<uint32_t>(table_left ? ln.base_table_id : rn.base_table_id);
+    fs->table[1] = static_cast<uint32_t>(table_left ? rn.base_table_id : ln.base_table_id);
+    fs->key_col[0] = static_cast<uint32_t>(table_left ? lkey : rkey);
+    fs->key_col[1] = static_cast<uint32_t>(table_left ? rkey : lkey);
+    fs->n_out = nd.n_output_attrs;
+    for (uint32_t a = 0; a < nd.n_output_attrs; ++a) {
+        const uint64_t src = nd.output_attrs[a].index;
+        if (src >= uint64_t(ln.n_output_attrs) + rn.n_output_attrs) return false;
+        const bool     from_left = src < ln.n_output_attrs;
+        const rj_node_t& sn = from_left ? ln : rn;
+        const uint64_t col = sn.output_attrs[from_left ? src : src - ln.n_output_attrs].index;
+        const rj_table_t& tb = from_left ? tl : tr;
+        if (col >= tb.n_columns) return false;
+        const int32_t t = tb.columns[col].type;
+        if (t == RJ_VARCHAR || t != nd.output_attrs[a].type) return false;
+        const int side = (from_left == table_left) ? 0 : 1;
+        if (col == fs->key_col[side]) {
+            fs->outs[a] = rj_part_out_t{side, -1};
+            continue;
+        }
+        auto& list = fs->cols[side];
+        size_t i = 0;
+        while (i < list.size() && list[i] != col) ++i;
+        if (i == list.size()) {
+            if (list.size() == static_cast<size_t>(kEmitMaxPay)) return false;
+            list.push_back(static_cast<uint32_t>(col));
+            fs->types[side].push_back(t);
+        }
+        fs->outs[a] = rj_part_out_t{side, static_cast<int32_t>(i)};
+    }
+    return true;
+}
+
+// a reusable barrier of the device threads; a thread that failed keeps arriving so that nobody waits for ever
+class HostBarrier {
+public:
+    explicit HostBarrier(int n): n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        const uint64_t gen = gen_;
+        if (++count_ == n_) {
+            count_ = 0;
+            ++gen_;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return gen_ != gen; });
+        }
+    }
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int n_, count_ = 0;
+    uint64_t gen_ = 0;
+};
+
+rj_ctx* group_ctx(rj_ctx* ctx, int d) { return d == 0 ? ctx : ctx->subs[d - 1]; }
+
+struct MultiJob {
+    int G = 0, g = 0, bits = 0, p1 = 0;
+    const rj_plan_t* plan = nullptr;
+    FusedShape fs;
+    std::vector<StreamCol> cols[2];         // per side: key column first, then the carried columns (row prefixes)
+    uint64_t rows_per_dev[2] = {0, 0};
+    std::vector<uint32_t> H;                // [G][2][2^bits]
+    struct Arrays { uint64_t a[5] = {0, 0, 0, 0, 0}; }; // keys, value 0, value 1, flag 0, flag 1 (device addresses)
+    std::vector<Arrays> staging;            // [G * 2]
+    std::vector<std::unique_ptr<rj_result>> results;
+    std::vector<uint8_t> failed_dup;
+    std::mutex mu;
+    std::exception_ptr err;
+    std::atomic<bool> failed{false};
+    void fail(std::exception_ptr e) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!err) err = e;
+        failed.store(true);
+    }
+};
+
+// pages of column `sc` that hold rows [r0, r1)
+void page_range_of(const StreamCol& sc, uint64_t r0, uint64_t r1, uint64_t* p0, uint64_t* p1) {
+    const auto& pre = sc.row_prefix;
+    const uint64_t np = pre.size() - 1;
+    *p0 = std::upper_bound(pre.begin(), pre.end(), r0) - pre.begin();
+    *p0 = *p0 ? *p0 - 1 : 0;
+    if (*p0 > np) *p0 = np;
+    *p1 = std::lower_bound(pre.begin(), pre.end(), r1) - pre.begin();
+    if (*p1 > np) *p1 = np;
+    if (*p1 < *p0) *p1 = *p0;
+}
+
+void multi_device_thread(rj_ctx* ctx, MultiJob* job, HostBarrier* bar, int me, OutputSink* sink) {
+    cudaSetDevice(ctx->device);
+    t_home_stream = ctx->stream;
+    t_cache = ctx->cache;
+    cudaStream_t s = ctx->stream;
+    const int G = job->G, bits = job->bits, p1 = job->p1, g = job->g;
+    const uint32_t nfin = 1u << bits, ndig = 1u << p1, per = ndig >> g, fin_per_dig = nfin / ndig;
+    auto guard = [&](auto fn) {
+        if (job->failed.load()) return;
+        try {
+            fn();
+        } catch (...) {
+            job->fail(std::current_exception());
+        }
+    };
+    rj_inputs in;
+    std::unique_ptr<Exec> ex;
+    const DecodedCol* key[2] = {nullptr, nullptr};
+    std::vector<const DecodedCol*> carried[2];
+    uint64_t n_local[2] = {0, 0};
+    Buf stage_buf[2][5], cursor_buf[2];
+    // ---- phase 1: upload this device's row windows, decode, histogram ---------------------------------------
+    guard([&] {
+        in.tables.resize(job->plan->n_inputs);
+        TaskGroup up;
+        up.open();
+        std::vector<Buf> slots;
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t    T = job->fs.table[side];
+            const rj_table_t& ht = job->plan->inputs[T];
+            const uint64_t r0 = std::min<uint64_t>(ht.num_rows, uint64_t(me) * job->rows_per_dev[side]);
+            const uint64_t r1 = std::min<uint64_t>(ht.num_rows, r0 + job->rows_per_dev[side]);
+            n_local[side] = r1 - r0;
+            TableDev& td = in.tables[T];
+            td.num_rows = r1 - r0;
+            td.cols.resize(ht.n_columns);
+            for (uint32_t c = 0; c < ht.n_columns; ++c) td.cols[c].type = ht.columns[c].type;
+            for (auto& sc: job->cols[side]) {
+                uint64_t pa, pb;
+                page_range_of(sc, r0, r1, &pa, &pb);
+                ColumnDev& cd = td.cols[sc.col];
+                cd.n_pages = r1 > r0 ? pb - pa : 0;
+                cd.owned = dev_alloc(std::max<uint64_t>(1, cd.n_pages) * RJ_PAGE_SIZE, s);
+                cd.pages = cd.owned->as<uint8_t>();
+                cd.page_rows = cd.n_pages ? sc.row_prefix[pb] - sc.row_prefix[pa] : 0;
+                cd.windowed = true;
+                cd.skip_rows = cd.n_pages ? std::min(r0, sc.row_prefix[pb]) - sc.row_prefix[pa] : 0;
+                cd.window_nulls = sc.has_null;
+                if (cd.n_pages) upload_pages_async(ctx, ht.columns[sc.col], pa, cd.n_pages, cd.owned->as<uint8_t>(), s, &up, nullptr);
+            }
+        }
+        up.seal();
+        up.wait(); // every copy is on the stream
+        ex = std::make_unique<Exec>(ctx, job->plan, &in);
+        Buf hist = dev_alloc_zero(size_t(2) * nfin * 4, s);
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t T = job->fs.table[side];
+            key[side] = &ex->column(T, job->fs.key_col[side]);
+            for (uint32_t c: job->fs.cols[side]) carried[side].push_back(&ex->column(T, c));
+            launch_radix_histogram(key[side]->values->p, key[side]->valid_ptr(), n_local[side], 4, 0, bits, hist->as<uint32_t>() + side * nfin, ctx->sm_count, s);
+        }
+        RJ_CUDA(cudaMemcpyAsync(job->H.data() + size_t(me) * 2 * nfin, hist->p, size_t(2) * nfin * 4, cudaMemcpyDeviceToHost, s));
+        // the arrays pass 1 writes and the digits' owners read
+        for (int side = 0; side < 2; ++side) {
+            const uint64_t n = n_local[side];
+            MultiJob::Arrays& ar = job->staging[size_t(me) * 2 + side];
+            stage_buf[side][0] = dev_alloc(n * 4 + 64, s);
+            ar.a[0] = reinterpret_cast<uint64_t>(stage_buf[side][0]->p);
+            int nf = 0;
+            for (size_t c = 0; c < carried[side].size(); ++c) {
+                const int w = job->fs.types[side][c] == RJ_INT32 ? 4 : 8;
+                stage_buf[side][1 + c] = dev_alloc(n * w + 64, s);
+                ar.a[1 + c] = reinterpret_cast<uint64_t>(stage_buf[side][1 + c]->p);
+                if (job->cols[side][1 + c].has_null) {
+                    stage_buf[side][3 + nf] = dev_alloc(n + 64, s);
+                    ar.a[3 + nf] = reinterpret_cast<uint64_t>(stage_buf[side][3 + nf]->p);
+                    ++nf;
+                }
+            }
+        }
+        RJ_CUDA(cudaStreamSynchronize(s));
+    });
+    bar->wait(); // A: every device's histogram and array addresses are known
+    // ---- phase 2 + 3: layout from the histograms, scatter pass 1 into this device's own arrays ------------------
+    std::vector<uint64_t> cnt(size_t(G) * 2 * ndig, 0); // [q][side][digit]
+    guard([&] {
+        for (int q = 0; q < G; ++q)
+            for (int side = 0; side < 2; ++side) {
+                const uint32_t* h = job->H.data() + (size_t(q) * 2 + side) * nfin;
+                uint64_t* c = cnt.data() + (size_t(q) * 2 + side) * ndig;
+                for (uint32_t d = 0; d < ndig; ++d) {
+                    uint64_t sum = 0;
+                    for (uint32_t f = 0; f < fin_per_dig; ++f) sum += h[d * fin_per_dig + f];
+                    c[d] = sum;
+                }
+            }
+        for (int side = 0; side < 2; ++side) {
+            std::vector<uint32_t> cur(ndig);
+            uint64_t run = 0;
+            const uint64_t* c = cnt.data() + (size_t(me) * 2 + side) * ndig;
+            for (uint32_t d = 0; d < ndig; ++d) {
+                cur[d] = static_cast<uint32_t>(run);
+                run += c[d];
+            }
+            cursor_buf[side] = dev_alloc(ndig * 4, s);
+            RJ_CUDA(cudaMemcpyAsync(cursor_buf[side]->p, cur.data(), ndig * 4, cudaMemcpyHostToDevice, s));
+            RJ_CUDA(cudaStreamSynchronize(s)); // `cur` dies with this scope
+            CarryScatter c1;
+            c1.keys = key[side]->values->as<uint32_t>();
+            c1.valid = key[side]->valid_ptr();
+            c1.n = n_local[side];
+            c1.shift = bits - p1; c1.bits = p1; c1.cursor = cursor_buf[side]->as<uint32_t>();
+            c1.keys_out = stage_buf[side][0]->as<uint32_t>();
+            for (size_t k = 0; k < carried[side].size(); ++k) {
+                c1.val_src[c1.n_val] = carried[side][k]->values->p;
+                c1.val_dst[c1.n_val] = stage_buf[side][1 + k]->p;
+                c1.val_width[c1.n_val++] = job->fs.types[side][k] == RJ_INT32 ? 4 : 8;
+                if (job->cols[side][1 + k].has_null) {
+                    if (!carried[side][k]->valid) throw EngineError("internal: a nullable column decoded without a validity bitmap");
+                    c1.flag_src[c1.n_flag] = carried[side][k]->valid_ptr();
+                    c1.flag_dst[c1.n_flag] = stage_buf[side][3 + c1.n_flag]->as<uint8_t>();
+                    ++c1.n_flag;
+                }
+            }
+            StageScope sc(ctx, RJ_ST_SCATTER, s, 1, n_local[side] * 8);
+            launch_scatter_carry(c1, ctx->sm_count, s);
+        }
+        RJ_CUDA(cudaStreamSynchronize(s));
+    });
+    bar->wait(); // B: every device's first pass is complete
+    // ---- phase 4: second pass out of the senders' arrays, join, pages ------------------------------------------
+    guard([&] {
+        rj_part_side_t sides[2];
+        Buf tabs[2][4], lhist[2];
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t n_sub = per * G;
+            std::vector<uint64_t> table(size_t(n_sub) * 5, 0);
+            std::vector<uint32_t> start(n_sub + 1, 0), tile(n_sub + 1, 0), group(n_sub, 0);
+            const int widths[5] = {4, carried[side].size() > 0 ? (job->fs.types[side][0] == RJ_INT32 ? 4 : 8) : 0,
+                                   carried[side].size() > 1 ? (job->fs.types[side][1] == RJ_INT32 ? 4 : 8) : 0, 1, 1};
+            // sender-local start of every digit run
+            std::vector<uint64_t> run_start(size_t(G) * ndig);
+            for (int q = 0; q < G; ++q) {
+                uint64_t run = 0;
+                for (uint32_t d = 0; d < ndig; ++d) {
+                    run_start[size_t(q) * ndig + d] = run;
+                    run += cnt[(size_t(q) * 2 + side) * ndig + d];
+                }
+            }
+            uint64_t pos = 0, tiles = 0;
+            for (uint32_t j = 0; j < per; ++j) {
+                const uint32_t d = static_cast<uint32_t>(me) * per + j;
+                for (int q = 0; q < G; ++q) {
+                    const uint32_t x = j * G + q;
+                    const uint64_t c = cnt[(size_t(q) * 2 + side) * ndig + d];
+                    start[x] = static_cast<uint32_t>(pos);
+                    tile[x] = static_cast<uint32_t>(tiles);
+                    group[x] = j;
+                    const int64_t delta = static_cast<int64_t>(run_start[size_t(q) * ndig + d]) - static_cast<int64_t>(pos);
+                    const MultiJob::Arrays& ar = job->staging[size_t(q) * 2 + side];
+                    for (int a = 0; a < 5; ++a) table[size_t(x) * 5 + a] = ar.a[a] + static_cast<uint64_t>(delta * widths[a]);
+                    pos += c;
+                    tiles += (c + scatter_tile(4) - 1) / scatter_tile(4);
+                }
+            }
+            start[n_sub] = static_cast<uint32_t>(pos);
+            tile[n_sub] = static_cast<uint32_t>(tiles);
+            // tuples per final partition of the range this device owns
+            std::vector<uint32_t> lh(nfin >> g, 0);
+            for (int q = 0; q < G; ++q) {
+                const uint32_t* h = job->H.data() + (size_t(q) * 2 + side) * nfin + size_t(me) * (nfin >> g);
+                for (uint32_t f = 0; f < (nfin >> g); ++f) lh[f] += h[f];
+            }
+            tabs[side][0] = dev_alloc(table.size() * 8, s);
+            tabs[side][1] = dev_alloc(start.size() * 4, s);
+            tabs[side][2] = dev_alloc(tile.size() * 4, s);
+            tabs[side][3] = dev_alloc(group.size() * 4, s);
+            lhist[side] = dev_alloc(lh.size() * 4, s);
+            RJ_CUDA(cudaMemcpyAsync(tabs[side][0]->p, table.data(), table.size() * 8, cudaMemcpyHostToDevice, s));
+            RJ_CUDA(cudaMemcpyAsync(tabs[side][1]->p, start.data(), start.size() * 4, cudaMemcpyHostToDevice, s));
+            RJ_CUDA(cudaMemcpyAsync(tabs[side][2]->p, tile.data(), tile.size() * 4, cudaMemcpyHostToDevice, s));
+            RJ_CUDA(cudaMemcpyAsync(tabs[side][3]->p, group.data(), group.size() * 4, cudaMemcpyHostToDevice, s));
+            RJ_CUDA(cudaMemcpyAsync(lhist[side]->p, lh.data(), lh.size() * 4, cudaMemcpyHostToDevice, s));
+            RJ_CUDA(cudaStreamSynchronize(s)); // the host vectors die with this scope
+            rj_part_side_t& sd = sides[side];
+            sd = rj_part_side_t{};
+            sd.n = pos;
+            sd.n_cols = static_cast<uint32_t>(carried[side].size());
+            for (size_t k = 0; k < carried[side].size(); ++k) {
+                sd.types[k] = job->fs.types[side][k];
+                sd.d_valid_bytes[k] = job->cols[side][1 + k].has_null ? reinterpret_cast<const uint8_t*>(1) : nullptr; // "has NULLs": the bytes come through the table
+            }
+            sd.n_sub = n_sub;
+            sd.d_src_table = tabs[side][0]->as<uint64_t>();
+            sd.d_sub_start = tabs[side][1]->as<uint32_t>();
+            sd.d_sub_tile = tabs[side][2]->as<uint32_t>();
+            sd.d_sub_group = tabs[side][3]->as<uint32_t>();
+        }
+        auto res = join_partitioned_impl(ctx, &sides[0], &sides[1], lhist[0]->as<uint32_t>(), lhist[1]->as<uint32_t>(), bits - g, p1 - g, bits,
+                                         job->fs.outs, job->fs.n_out);
+        if (!res) job->failed_dup[me] = 1;
+        job->results[me] = std::move(res);
+    });
+    bar->wait(); // C: nobody reads anybody's arrays any more; the verdict on duplicate keys is in
+    bool dup = false;
+    for (int q = 0; q < G; ++q) dup = dup || job->failed_dup[q];
+    if (!dup) {
+        guard([&] {
+            // the root's declared column types (they equal the physical ones: analyze_fused_root checked)
+            ensure_copy_streams(ctx);
+            sink->deliver(ctx, job->results[me].get(), ctx->d2h_stream);
+            RJ_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+        });
+    }
+    ex.reset();
+    t_cache.reset();
+}
+
+// -> true when the plan ran on the whole group (rows in *total); false: not eligible, run it on one device
+bool execute_multi(rj_ctx* ctx, const rj_plan_t* plan, const std::vector<OutputSink*>& sinks, uint64_t* total) {
+    const int G = static_cast<int>(ctx->subs.size()) + 1;
+    if (G < 2 || (G & (G - 1)) != 0 || getenv("RJ_NO_MULTI") != nullptr) return false;
+    MultiJob job;
+    if (!analyze_fused_root(plan, &job.fs)) return false;
+    int g = 0;
+    while ((1 << g) < G) ++g;
+    const uint64_t nb = plan->inputs[job.fs.table[0]].num_rows;
+    int bits = 0;
+    while ((nb >> bits) > kJoinTargetFill && bits < kMaxTotalBits) ++bits;
+    if (bits <= kMaxPassBits) return false; // one scatter pass: a small join, one device is enough
+    const int p1 = pass1_bits_of(bits);
+    if (p1 <= g) return false; // the owners need a second pass of their own
+    job.G = G; job.g = g; job.bits = bits; job.p1 = p1; job.plan = plan;
+    // page headers of the columns in play: rows before every page
+    for (int side = 0; side < 2; ++side) {
+        const rj_table_t& ht = plan->inputs[job.fs.table[side]];
+        std::vector<uint32_t> want = {job.fs.key_col[side]};
+        for (uint32_t c: job.fs.cols[side]) want.push_back(c);
+        for (uint32_t c: want) {
+            const rj_column_t& hc = ht.columns[c];
+            if (hc.n_pages && !hc.pages && !hc.contiguous) throw EngineError("column has pages but no page pointers");
+            StreamCol sc;
+            sc.col = c;
+            sc.row_prefix.assign(hc.n_pages + 1, 0);
+            std::atomic<uint64_t> non_null{0};
+            pool_for(ctx, hc.n_pages, 4096, [&](uint64_t b, uint64_t e) {
+                uint64_t nn = 0;
+                for (uint64_t i = b; i < e; ++i) {
+                    uint64_t r = 0;
+                    page_counts(host_page(hc, i), hc.type, &r, &nn);
+                    sc.row_prefix[i + 1] = r;
+                }
+                non_null.fetch_add(nn, std::memory_order_relaxed);
+            });
+            for (uint64_t i = 0; i < hc.n_pages; ++i) sc.row_prefix[i + 1] += sc.row_prefix[i];
+            if (sc.row_prefix[hc.n_pages] > ht.num_rows) throw EngineError("row_idx");
+            sc.has_null = non_null.load() != ht.num_rows;
+            job.cols[side].push_back(std::move(sc));
+        }
+        const uint64_t per_dev = (ht.num_rows + G - 1) / G;
+        job.rows_per_dev[side] = (per_dev + 4095) & ~uint64_t(4095);
+    }
+    job.H.assign(size_t(G) * 2 * (size_t(1) << bits), 0);
+    job.staging.resize(size_t(G) * 2);
+    job.results.resize(G);
+    job.failed_dup.assign(G, 0);
+    HostBarrier bar(G);
+    std::vector<std::thread> threads;
+    for (int d = 1; d < G; ++d) threads.emplace_back(multi_device_thread, group_ctx(ctx, d), &job, &bar, d, sinks[d]);
+    multi_device_thread(ctx, &job, &bar, 0, sinks[0]);
+    for (auto& t: threads) t.join();
+    // this thread's bindings were reset by its own device pass: restore them for the caller
+    cudaSetDevice(ctx->device);
+    t_home_stream = ctx->stream;
+    t_cache = ctx->cache;
+    if (job.err) std::rethrow_exception(job.err);
+    for (int q = 0; q < G; ++q)
+        if (job.failed_dup[q]) return false; // duplicate build keys: nothing was delivered, the general path runs on one device
+    uint64_t rows = 0;
+    for (auto& r: job.results) rows += r ? r->num_rows : 0;
+    *total = rows;
+    return true;
+}
+
+} // namespace
+
 int rj_execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, rj_page_sink_t sink, void* user,
                         uint64_t* num_rows) {
     return guarded(ctx, [&] {
@@ -2062,6 +2490,32 @@ int rj_execute_pages(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, c
     return guarded(ctx, [&] {
         if (!plan) throw EngineError("null plan");
         if (!alloc || !alloc->new_pages || !alloc->append) throw EngineError("rj_execute_pages: no page allocator");
+        if (!ctx->subs.empty()) {
+            // a device group: one sink per device, handed over in device order (each device's share of the result
+            // holds the same rows in every column)
+            const int G = static_cast<int>(ctx->subs.size()) + 1;
+            std::vector<std::unique_ptr<PageSink>> sinks;
+            std::vector<OutputSink*> raw;
+            for (int d = 0; d < G; ++d) {
+                sinks.push_back(std::make_unique<PageSink>(alloc, ensure_pipe(group_ctx(ctx, d))));
+                raw.push_back(sinks.back().get());
+            }
+            uint64_t n = 0;
+            bool done = false;
+            try {
+                done = execute_multi(ctx, plan, raw, &n);
+                if (done)
+                    for (auto& sk: sinks) sk->finish();
+            } catch (...) {
+                for (auto& sk: sinks) sk->abort();
+                throw;
+            }
+            if (done) {
+                if (num_rows) *num_rows = n;
+                return;
+            }
+            for (auto& sk: sinks) sk->abort(); // nothing was delivered
+        }
         PageSink out(alloc, ensure_pipe(ctx));
         uint64_t n = 0;
         try {
@@ -2073,6 +2527,50 @@ int rj_execute_pages(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, c
         if (num_rows) *num_rows = n;
     });
 }
+
+int rj_ctx_create_multi(const int* devices, uint32_t n_devices, rj_ctx** out) {
+    if (!devices || n_devices == 0 || !out) {
+        g_create_error = "rj_ctx_create_multi: no devices";
+        return 1;
+    }
+    rj_ctx* first = nullptr;
+    if (rj_ctx_create(devices[0], &first) != 0) return 1;
+    try {
+        for (uint32_t i = 1; i < n_devices; ++i) {
+            rj_ctx* sub = nullptr;
+            if (rj_ctx_create(devices[i], &sub) != 0) throw EngineError(g_create_error);
+            first->subs.push_back(sub);
+        }
+        // every device of the group reads every other one's memory (scatter pass 2 pulls its regions over NVLink)
+        for (uint32_t i = 0; i < n_devices; ++i) {
+            RJ_CUDA(cudaSetDevice(devices[i]));
+            for (uint32_t j = 0; j < n_devices; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                RJ_CUDA(cudaDeviceCanAccessPeer(&can, devices[i], devices[j]));
+                if (!can) throw EngineError("rj_ctx_create_multi: the devices cannot access each other's memory");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) RJ_CUDA(e);
+                cudaGetLastError();
+            }
+        }
+        // the host cores are shared by the devices' worker pools
+        const int per = std::max(2, first->host_threads / static_cast<int>(n_devices));
+        first->host_threads = per;
+        for (rj_ctx* sub: first->subs) sub->host_threads = per;
+        RJ_CUDA(cudaSetDevice(devices[0]));
+        *out = first;
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        for (rj_ctx* sub: first->subs) rj_ctx_destroy(sub);
+        first->subs.clear();
+        rj_ctx_destroy(first);
+        return 1;
+    }
+}
+
+int rj_ctx_group_size(const rj_ctx* ctx) { return ctx ? static_cast<int>(ctx->subs.size()) + 1 : 0; }
 
 uint64_t rj_result_num_rows(const rj_result* r) { return r->num_rows; }
 uint32_t rj_result_num_columns(const rj_result* r) { return static_cast<uint32_t>(r->cols.size()); }
@@ -2348,12 +2846,13 @@ int rj_scatter_carry(rj_ctx* ctx, const rj_carry_scatter_t* d, void* stream) {
     });
 }
 
-int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_side_t* probe, const uint32_t* d_hist_build,
-                        const uint32_t* d_hist_probe, int32_t local_bits, int32_t local_pass1_bits, int32_t hash_bits,
-                        const rj_part_out_t* outs, uint32_t n_out, rj_result** out) {
-    return guarded(ctx, [&] {
-        if (!build || !probe || !outs || !out) throw EngineError("rj_join_partitioned: null argument");
-        *out = nullptr;
+namespace {
+// second scatter pass + fused join on partitioned inputs; nullptr when a table met a duplicate build key.
+// Runs on ctx->stream of the CURRENT device (the caller has bound device, home stream and block cache).
+std::unique_ptr<rj_result> join_partitioned_impl(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_side_t* probe,
+                                                 const uint32_t* d_hist_build, const uint32_t* d_hist_probe, int32_t local_bits,
+                                                 int32_t local_pass1_bits, int32_t hash_bits, const rj_part_out_t* outs, uint32_t n_out) {
+    {
         if (local_bits < 0 || local_bits > kMaxTotalBits || local_pass1_bits < 0 || local_pass1_bits > kMaxPassBits ||
             local_bits - local_pass1_bits > kMaxPassBits || (local_pass1_bits && local_bits <= local_pass1_bits))
             throw EngineError("rj_join_partitioned: radix bits out of range");
@@ -2399,10 +2898,7 @@ int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_
             }
         }
         if (!join_emit_fits(L)) throw EngineError("rj_join_partitioned: the columns do not fit shared memory");
-        if (nb == 0 || np == 0) { // src/execute.cpp:50: an empty side gives typed, page-less columns
-            *out = res.release();
-            return;
-        }
+        if (nb == 0 || np == 0) return res; // src/execute.cpp:50: an empty side gives typed, page-less columns
         const uint32_t nparts = 1u << local_bits;
         const int      bits2 = local_bits - local_pass1_bits;
         Buf plan_mem = dev_alloc(partition_plan_words(local_bits, local_pass1_bits) * 4, s);
@@ -2496,7 +2992,7 @@ int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_
         uint32_t h[4] = {0, 0, 0, 0};
         RJ_CUDA(cudaMemcpyAsync(h, counters->p, 16, cudaMemcpyDeviceToHost, s));
         RJ_CUDA(cudaStreamSynchronize(s));
-        if (h[1] != 0) return; // duplicate build keys: *out stays NULL
+        if (h[1] != 0) return nullptr; // duplicate build keys
         const uint64_t chunks = h[0];
         if (chunks > max_chunks) throw EngineError("internal: the fused join produced more chunks than planned");
         res->num_rows = static_cast<uint64_t>(h[2]) | (static_cast<uint64_t>(h[3]) << 32);
@@ -2508,9 +3004,22 @@ int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_
             if (rc.n_pages == 0) rc.pages.reset();
         }
         if (ctx->profiling) ctx->stats[RJ_ST_JOIN_EMIT].bytes += out_page_bytes;
-        *out = res.release();
+        return res;
+    }
+}
+} // namespace
+
+int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_side_t* probe, const uint32_t* d_hist_build,
+                        const uint32_t* d_hist_probe, int32_t local_bits, int32_t local_pass1_bits, int32_t hash_bits,
+                        const rj_part_out_t* outs, uint32_t n_out, rj_result** out) {
+    return guarded(ctx, [&] {
+        if (!build || !probe || !outs || !out) throw EngineError("rj_join_partitioned: null argument");
+        *out = nullptr;
+        auto res = join_partitioned_impl(ctx, build, probe, d_hist_build, d_hist_probe, local_bits, local_pass1_bits, hash_bits, outs, n_out);
+        *out = res.release(); // NULL: duplicate build keys
     });
 }
+
 
 // ---- pre-filters ----------------------------------------------------------------------------------------
 int rj_filter_compare(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n, int32_t type, int32_t op,

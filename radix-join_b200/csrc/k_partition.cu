@@ -42,6 +42,35 @@ __global__ void __launch_bounds__(1024)
     __syncthreads();
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (sizeof(K) == 4 && (reinterpret_cast<uintptr_t>(keys) & 15u) == 0) {
+        // 4-byte keys: 16-byte loads, four of them in flight per thread (64 KB per SM in flight: one CTA of 1024
+        // threads per SM has to cover the whole bandwidth-delay product); four consecutive keys share one
+        // validity word
+        const uint4*   keys4 = reinterpret_cast<const uint4*>(keys);
+        const uint64_t n4 = n / 4;
+        auto count4 = [&](const uint4& k, uint64_t j) {
+            uint32_t vb = 0xfu;
+            if (valid) vb = (valid[(j * 4) >> 5] >> ((j * 4) & 31u)) & 0xfu;
+            if (vb & 1u) atomicAdd(&s_hist[(hash_key(k.x) >> shift) & mask], 1u);
+            if (vb & 2u) atomicAdd(&s_hist[(hash_key(k.y) >> shift) & mask], 1u);
+            if (vb & 4u) atomicAdd(&s_hist[(hash_key(k.z) >> shift) & mask], 1u);
+            if (vb & 8u) atomicAdd(&s_hist[(hash_key(k.w) >> shift) & mask], 1u);
+        };
+        uint64_t j = i;
+        for (; j + 3 * stride < n4; j += 4 * stride) {
+            const uint4 a = ld_stream_u128(keys4 + j), b = ld_stream_u128(keys4 + j + stride), c = ld_stream_u128(keys4 + j + 2 * stride),
+                        d = ld_stream_u128(keys4 + j + 3 * stride);
+            count4(a, j);
+            count4(b, j + stride);
+            count4(c, j + 2 * stride);
+            count4(d, j + 3 * stride);
+        }
+        for (; j < n4; j += stride) count4(ld_stream_u128(keys4 + j), j);
+        // the last n % 4 keys
+        for (uint64_t t = n4 * 4 + i; t < n; t += stride)
+            if (!valid || test_bit(valid, t)) atomicAdd(&s_hist[(hash_key(keys[t]) >> shift) & mask], 1u);
+        i = n; // nothing left for the scalar loops below
+    }
     // 4 independent loads in flight per thread
     for (; i + 3 * stride < n; i += 4 * stride) {
         K k0 = keys[i], k1 = keys[i + stride], k2 = keys[i + 2 * stride], k3 = keys[i + 3 * stride];

@@ -64,6 +64,7 @@ struct CarryArgs {
     // that element index = the region's virtual position; region_group[x] = which cursor group x feeds
     const uint64_t* src_tab;
     const uint32_t* region_group;
+    int             val_tab[2]; // table column (0 / 1) of the kernel's value 0 / 1 (the launcher puts the wider one first)
 };
 
 struct MultiCarryDsts {
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
     // (skew = elements skipped) and is up to 16 bytes longer.
     auto src_addr = [&](const Tile& d, int which, uint32_t w) -> uint64_t {
         uint64_t base;
-        if (kRegions && a.src_tab != nullptr) base = a.src_tab[static_cast<uint64_t>(d.reg) * 5 + which];
+        if (kRegions && a.src_tab != nullptr) base = a.src_tab[static_cast<uint64_t>(d.reg) * 5 + ((which == 1 || which == 2) ? 1 + a.val_tab[which - 1] : which)];
         else base = reinterpret_cast<uint64_t>(which == 0 ? static_cast<const void*>(a.keys) : (which < 3 ? a.val_src[which - 1] : a.flag_src[which - 3]));
         return base + static_cast<uint64_t>(d.lo) * w;
     };
@@ -450,6 +451,7 @@ void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s) {
         if (c.src_tab == nullptr && reinterpret_cast<uintptr_t>(c.val_src[k]) % 16 != 0) throw CudaError("scatter_carry: value columns must be 16-byte aligned");
         a.val_src[i] = c.val_src[k];
         a.val_dst[i] = c.val_dst[k];
+        a.val_tab[i] = k;
         w[i] = c.val_width[k];
     }
     if (c.src_tab == nullptr && reinterpret_cast<uintptr_t>(c.keys) % 16 != 0) throw CudaError("scatter_carry: keys must be 16-byte aligned");

@@ -571,7 +571,7 @@ def pull_layout(H, me, g, bits, p1, side, array_ptrs, array_widths):
     array_ptrs[a] = int64 tensor [G] of every rank's base address of array a (0 where the array does not exist)."""
     G, nfin, ndig = H.shape[0], 1 << bits, 1 << p1
     per = ndig >> g
-    Cnt = H[:, side].view(G, ndig, nfin // ndig).sum(-1)                 # [G, ndig]
+    Cnt = H[:, side].reshape(G, ndig, nfin // ndig).sum(-1)              # [G, ndig]
     run_start = torch.cumsum(Cnt, -1) - Cnt                              # sender-local start of every digit run
     mine = torch.arange(per, device=H.device) + me * per
     cnt = Cnt[:, mine].T.reshape(-1)                                     # [per * G] region-major, sender-minor
@@ -606,7 +606,7 @@ def distributed_join_fused(ops, build, probe, out_cols, xchg, group=None, total_
     bits = choose_bits(total_build_rows)
     two = bits > MAX_PASS_BITS
     p1 = (bits + 1) // 2 if two else bits
-    if p1 < g or bits - g < 0 or g == 0:
+    if p1 < g or bits - g < 0 or g == 0 or (two and p1 == g):
         return None
     trace = os.environ.get("RJ_DIST_TRACE") and hasattr(ops, "sync")
     t = [time.perf_counter()]
@@ -628,7 +628,8 @@ def distributed_join_fused(ops, build, probe, out_cols, xchg, group=None, total_
     # 2. all ranks' histograms -> layout (device math), one small read-back
     H = torch.empty(world * (2 << bits), dtype=torch.int32, device=hist.device)
     dist.all_gather_into_tensor(H, hist, group=group)
-    cursor, local_hist, owned, per_owner, sent = exchange_layout(H.view(world, 2, 1 << bits).to(torch.int64), me, g, bits, p1)
+    H64 = H.view(world, 2, 1 << bits).to(torch.int64)
+    cursor, local_hist, owned, per_owner, sent = exchange_layout(H64, me, g, bits, p1)
     cursor32, local_hist32 = cursor.to(torch.int32).contiguous(), local_hist.to(torch.int32).contiguous()
     info = torch.cat([owned, per_owner.max(-1).values, sent]).cpu()
     n_own, worst, n_sent = [int(x) for x in info[:2]], [int(x) for x in info[2:4]], [int(x) for x in info[4:6]]
@@ -648,7 +649,7 @@ def distributed_join_fused(ops, build, probe, out_cols, xchg, group=None, total_
             flag_bufs = [x.valids[i] for i in range(len(rel.payloads)) if rel.payloads[i][3]]
             ptrs += [fb.ptrs for fb in flag_bufs] + [[0] * world] * (2 - len(flag_bufs))
             tptrs = [torch.tensor(p, dtype=torch.int64, device=hist.device) for p in ptrs]
-            lays.append(pull_layout(H.view(world, 2, 1 << bits).to(torch.int64), me, g, bits, p1, side, tptrs, widths))
+            lays.append(pull_layout(H64, me, g, bits, p1, side, tptrs, widths))
         xchg[0].barrier()                  # every owner is done reading the previous contents of these arrays
         for side, (keys, kvalid, pays) in enumerate(rels):
             ops.local_scatter(keys, kvalid, pays, bits - p1, p1, lays[side][0].to(torch.int32).contiguous(), xchg[side], me)

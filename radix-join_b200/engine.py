@@ -22,9 +22,14 @@ class Context:
     """The opaque `void* context` of Contest::build_context()."""
 
     def __init__(self, device=0):
+        """device: one index, or a list of indices = a device group driven by this process (rj_ctx_create_multi)"""
         self.lib = _cabi.load_library()
         h = C.c_void_p()
-        rc = self.lib.rj_ctx_create(int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self.lib.rj_ctx_create_multi(arr, len(device), C.byref(h))
+        else:
+            rc = self.lib.rj_ctx_create(int(device), C.byref(h))
         if rc != 0:
             msg = self.lib.rj_last_error(None)
             raise EngineError(msg.decode() if msg else f"rj_ctx_create failed ({rc})")
@@ -39,6 +44,10 @@ class Context:
         if self.handle:
             self.lib.rj_ctx_destroy(self.handle)
             self.handle = None
+
+    @property
+    def group_size(self):
+        return int(self.lib.rj_ctx_group_size(self.handle))
 
     @property
     def sm_count(self):
@@ -243,3 +252,50 @@ def tables_equal(a: ColumnarTable, b: ColumnarTable, ctx: Context):
     eq, bad = C.c_int32(0), C.c_uint64(0)
     ctx.check(ctx.lib.rj_tables_equal(ctx.handle, fa.tables, fb.tables, C.byref(eq), C.byref(bad)))
     return bool(eq.value), int(bad.value)
+
+
+def execute_pages(plan: Plan, ctx: Context) -> ColumnarTable:
+    """Contest::execute's own data path (rj_execute_pages): every result page is allocated individually by a
+    callback, the transfers are pipelined, and a device-group context runs eligible plans on all its GPUs."""
+    flat = FlatPlan(plan)
+    root = plan.nodes[plan.root]
+    cols = [[] for _ in root.output_attrs]
+    keep, failure = [], []
+    import threading
+    lock = threading.Lock()
+
+    def new_pages(_user, n, out):
+        try:
+            bufs = [np.empty(PAGE_SIZE, dtype=np.uint8) for _ in range(n)]
+            with lock:
+                keep.extend(bufs)
+            for i, b in enumerate(bufs):
+                out[i] = b.ctypes.data
+            return 0
+        except Exception as e:  # noqa: BLE001
+            failure.append(e)
+            return 1
+
+    def append(_user, column, _type, pages, n):
+        cols[column].extend(int(pages[i]) for i in range(n))
+        return 0
+
+    def free_pages(_user, _n, _pages):
+        return None
+
+    alloc = _cabi.rj_page_alloc_t()
+    f_new = _cabi.rj_page_alloc_t._fields_[1][1](new_pages)
+    f_app = _cabi.rj_page_alloc_t._fields_[2][1](append)
+    f_free = _cabi.rj_page_alloc_t._fields_[3][1](free_pages)
+    alloc.user, alloc.new_pages, alloc.append, alloc.free_pages = None, f_new, f_app, f_free
+    n = C.c_uint64(0)
+    rc = ctx.lib.rj_execute_pages(ctx.handle, flat.pointer(), 0, C.byref(alloc), C.byref(n))
+    if failure:
+        raise failure[0]
+    ctx.check(rc)
+    by_addr = {b.ctypes.data: b for b in keep}
+    t = ColumnarTable(num_rows=int(n.value))
+    for c, (_, dtype) in enumerate(root.output_attrs):
+        pages = np.stack([by_addr[a] for a in cols[c]]) if cols[c] else None
+        t.columns.append(Column(dtype, pages))
+    return t

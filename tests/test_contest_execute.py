@@ -64,3 +64,15 @@ def test_config2_sample_matches_the_reference():
 def test_config2_sample_windowed():
     res = run_harness("parity", "c2", "--div", "128", env={"RJ_WINDOW_BYTES": str(8 << 20), "RJ_PIPE_BUFS": "3"})
     assert res["rows"] == res["ref_rows"] == (1 << 29) // 128
+
+
+@needs_harness
+def test_config2_sample_on_a_device_group_matches_the_reference():
+    """RJ_GPUS=2: Contest::build_context opens a device group (rj_ctx_create_multi) and the join runs on both
+    GPUs -- row slices per device, scatter pass 1 local, pass 2 pulling its regions over NVLink, result page
+    lists appended in device order -- against the unmodified reference on the same Plan (1/16 scale: 4 Mi x 32 Mi,
+    a two-pass join)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = run_harness("parity", "c2", "--div", "16", env={"RJ_GPUS": "2"})
+    assert res["rows"] == res["ref_rows"] == (1 << 29) // 16

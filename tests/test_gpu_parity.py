@@ -674,3 +674,181 @@ def test_config2_full_size_multiset_checksum(ctx):
     types = [t for _, t in host_plan.nodes[host_plan.root].output_attrs]
     assert max(len(v) for v in chunks.values()) >= 2
     assert syn.host_chunks_checksum(ctx, types, chunks) == dt.expected_checksum
+
+
+def _carry_desc(keys, valid_words, n, shift, bits, cursor, vals, flags):
+    from radix_join_b200 import _cabi
+    d = _cabi.rj_carry_scatter_t()
+    d.d_keys, d.d_valid, d.n = keys.data_ptr(), (valid_words.data_ptr() if valid_words is not None else None), n
+    d.shift, d.bits, d.d_cursor = shift, bits, cursor.data_ptr()
+    d.n_val, d.n_flag = len(vals), len(flags)
+    return d
+
+
+@pytest.mark.parametrize("widths", [(8,), (4, 8), (8, 4), (4, 4), ()])
+def test_stage_scatter_carry_two_passes_and_scattered_sources(ctx, widths):
+    """rj_scatter_carry: flat pass (bitmaps in, bytes out, NULL keys dropped), region pass over its output, and the
+    same region pass reading its regions through a table of per-region source addresses (the multi-GPU pull) --
+    every tuple must arrive in its final partition with its values and validity bytes; 4- and 8-byte columns in
+    both orders (the kernel takes the wider one first)"""
+    from radix_join_b200 import _cabi
+    rng = np.random.default_rng(sum(widths) + len(widths))
+    n, b1, b2 = 500_003, 5, 4
+    keys = rng.integers(0, 1 << 30, n).astype(np.uint32)
+    kvalid = rng.random(n) > 0.05
+    vals = [rng.integers(0, 2**31 if w == 4 else 2**62, n).astype(np.uint32 if w == 4 else np.uint64) for w in widths]
+    vvalid = [rng.random(n) > 0.3 for _ in widths]
+
+    def words(mask):
+        by = np.packbits(mask, bitorder="little")
+        return dev(np.concatenate([by, np.zeros((-len(by)) % 4 + 8, np.uint8)]).view(np.int32))
+    h = H.hash_keys(keys)
+    full = h & np.uint32((1 << (b1 + b2)) - 1)
+    d1 = full >> np.uint32(b2)
+    n_valid = int(kvalid.sum())
+    lib, hd = ctx.lib, ctx.handle
+    d_keys, d_kvalid = dev(keys), words(kvalid)
+    d_vals, d_vbits = [dev(v) for v in vals], [words(m) for m in vvalid]
+    # ---- flat pass by the top b1 of the b1 + b2 bits
+    cnt1 = np.bincount(d1[kvalid], minlength=1 << b1)
+    start1 = np.concatenate([[0], np.cumsum(cnt1)]).astype(np.uint32)
+    cur1 = dev(start1[:-1].view(np.int32).copy())
+    k1 = torch.zeros(n + 16, dtype=torch.int32, device="cuda")
+    v1 = [torch.zeros((n + 16) * (w // 4), dtype=torch.int32, device="cuda") for w in widths]
+    f1 = [torch.zeros(n + 16, dtype=torch.uint8, device="cuda") for _ in widths]
+    d = _carry_desc(d_keys, d_kvalid, n, b2, b1, cur1, vals, vvalid)
+    d.d_keys_out = k1.data_ptr()
+    for i, w in enumerate(widths):
+        d.val_src[i], d.val_dst[i], d.val_width[i] = d_vals[i].data_ptr(), v1[i].data_ptr(), w
+        d.flag_src[i], d.flag_dst[i] = d_vbits[i].data_ptr(), f1[i].data_ptr()
+    ctx.check(lib.rj_scatter_carry(hd, C.byref(d), None))
+    torch.cuda.synchronize()
+    ko = k1.cpu().numpy().view(np.uint32)[:n_valid]
+    assert np.all(np.diff(((H.hash_keys(ko) & np.uint32((1 << (b1 + b2)) - 1)) >> np.uint32(b2)).astype(np.int64)) >= 0)
+
+    def check_final(kf, vf, ff):
+        """kf / vf / ff: final arrays; compare the multiset of (key, values, flags) tuples with the input's"""
+        got = [kf.astype(np.uint64)] + [v.astype(np.uint64) for v in vf] + [f.astype(np.uint64) for f in ff]
+        want = [keys[kvalid].astype(np.uint64)] + [v[kvalid].astype(np.uint64) for v in vals] + [m[kvalid].astype(np.uint64) for m in vvalid]
+        go = np.lexsort(got[::-1])
+        wo = np.lexsort(want[::-1])
+        for a, b in zip(got, want):
+            assert np.array_equal(a[go], b[wo])
+        assert np.all(np.diff((H.hash_keys(kf) & np.uint32((1 << (b1 + b2)) - 1)).astype(np.int64)) >= 0)  # final partition order
+
+    # ---- region pass (second pass) over the flat pass's output
+    cnt_full = np.bincount(full[kvalid], minlength=1 << (b1 + b2))
+    off = np.concatenate([[0], np.cumsum(cnt_full)]).astype(np.uint32)
+    tiles = (cnt1 + 4095) // 4096
+    tile_start = np.concatenate([[0], np.cumsum(tiles)]).astype(np.uint32)
+
+    def region_pass(extra):
+        cur2 = dev(off[:-1].view(np.int32).copy())
+        k2 = torch.zeros(n + 16, dtype=torch.int32, device="cuda")
+        v2 = [torch.zeros((n + 16) * (w // 4), dtype=torch.int32, device="cuda") for w in widths]
+        f2 = [torch.zeros(n + 16, dtype=torch.uint8, device="cuda") for _ in widths]
+        d = _carry_desc(k1, None, n_valid, 0, b2, cur2, vals, vvalid)
+        d.d_keys_out = k2.data_ptr()
+        for i, w in enumerate(widths):
+            d.val_src[i], d.val_dst[i], d.val_width[i] = v1[i].data_ptr(), v2[i].data_ptr(), w
+            d.flag_src[i], d.flag_dst[i] = f1[i].data_ptr(), f2[i].data_ptr()
+        keep = extra(d)
+        ctx.check(lib.rj_scatter_carry(hd, C.byref(d), None))
+        torch.cuda.synchronize()
+        del keep
+        kf = k2.cpu().numpy().view(np.uint32)[:n_valid]
+        vf = [v.cpu().numpy().view(np.uint32 if w == 4 else np.uint64)[:n_valid] for v, w in zip(v2, widths)]
+        ff = [f.cpu().numpy()[:n_valid] for f in f2]
+        check_final(kf, vf, ff)
+
+    def plain(d):
+        rs, ts = dev(start1.view(np.int32).copy()), dev(tile_start.view(np.int32).copy())
+        d.d_region_start, d.d_tile_start, d.n_regions = rs.data_ptr(), ts.data_ptr(), 1 << b1
+        return rs, ts
+    region_pass(plain)
+
+    def scattered(d):
+        # every region split in two sub-regions read through the address table, in swapped order inside the table's
+        # address space: sub-region x = (region r, half q) with biased base addresses
+        n_sub = 2 << b1
+        sub_cnt = np.zeros(n_sub, dtype=np.int64)
+        src_start = np.zeros(n_sub, dtype=np.int64)
+        for r in range(1 << b1):
+            a = int(cnt1[r]) // 3
+            sub_cnt[2 * r], sub_cnt[2 * r + 1] = int(cnt1[r]) - a, a            # the second part of the run first
+            src_start[2 * r], src_start[2 * r + 1] = int(start1[r]) + a, int(start1[r])
+        vstart = np.concatenate([[0], np.cumsum(sub_cnt)])
+        vtile = np.concatenate([[0], np.cumsum((sub_cnt + 4095) // 4096)])
+        table = np.zeros((n_sub, 5), dtype=np.int64)
+        bases = [k1.data_ptr()] + [v.data_ptr() for v in v1] + [0] * (2 - len(widths)) + [f.data_ptr() for f in f1] + [0] * (2 - len(widths))
+        ws = [4] + list(widths) + [0] * (2 - len(widths)) + [1, 1]
+        for a in range(5):
+            table[:, a] = bases[a] + (src_start - vstart[:-1]) * ws[a]
+        t_tab, t_start, t_tile = dev(table), dev(vstart.astype(np.int32)), dev(vtile.astype(np.int32))
+        t_group = dev(np.repeat(np.arange(1 << b1, dtype=np.int32), 2))
+        d.d_keys = None
+        d.d_src_table, d.d_region_group = t_tab.data_ptr(), t_group.data_ptr()
+        d.d_region_start, d.d_tile_start, d.n_regions = t_start.data_ptr(), t_tile.data_ptr(), n_sub
+        for i in range(len(widths)):
+            d.val_src[i] = None
+            d.flag_src[i] = None
+        return t_tab, t_start, t_tile, t_group
+    region_pass(scattered)
+
+
+def test_stage_join_partitioned_single_pass(ctx):
+    """rj_join_partitioned on inputs that a flat rj_scatter_carry pass partitioned completely (local_pass1_bits = 0)"""
+    from radix_join_b200 import _cabi
+    rng = np.random.default_rng(12)
+    nb, np_, bits = 100_000, 700_000, 6
+    bk = rng.permutation(nb).astype(np.uint32)
+    ba = rng.integers(0, 2**62, nb).astype(np.uint64)
+    pk = rng.integers(0, int(nb * 1.1), np_).astype(np.uint32)
+    pb = rng.integers(0, 2**31, np_).astype(np.uint32)
+    pvalid = rng.random(np_) > 0.2
+    lib, hd = ctx.lib, ctx.handle
+
+    def part(keys, vals, width, vmask):
+        n = len(keys)
+        dig = H.hash_keys(keys) & np.uint32((1 << bits) - 1)
+        cnt = np.bincount(dig, minlength=1 << bits)
+        cur = dev(np.concatenate([[0], np.cumsum(cnt)])[:-1].astype(np.int32))
+        ko = torch.zeros(n + 16, dtype=torch.int32, device="cuda")
+        vo = torch.zeros((n + 16) * (width // 4), dtype=torch.int32, device="cuda")
+        fo = torch.zeros(n + 16, dtype=torch.uint8, device="cuda") if vmask is not None else None
+        d_k, d_v = dev(keys), dev(vals)
+        d = _cabi.rj_carry_scatter_t()
+        d.d_keys, d.n, d.shift, d.bits, d.d_cursor, d.d_keys_out = d_k.data_ptr(), n, 0, bits, cur.data_ptr(), ko.data_ptr()
+        d.n_val, d.val_src[0], d.val_dst[0], d.val_width[0] = 1, d_v.data_ptr(), vo.data_ptr(), width
+        if vmask is not None:
+            by = np.packbits(vmask, bitorder="little")
+            d_w = dev(np.concatenate([by, np.zeros((-len(by)) % 4 + 8, np.uint8)]).view(np.int32))
+            d.n_flag, d.flag_src[0], d.flag_dst[0] = 1, d_w.data_ptr(), fo.data_ptr()
+        ctx.check(lib.rj_scatter_carry(hd, C.byref(d), None))
+        torch.cuda.synchronize()
+        return ko, vo, fo, dev(cnt.astype(np.int32))
+    bko, bvo, _, bh = part(bk, ba, 8, None)
+    pko, pvo, pfo, ph = part(pk, pb, 4, pvalid)
+    sides = []
+    for ko, vo, fo, n, t in ((bko, bvo, None, nb, INT64), (pko, pvo, pfo, np_, INT32)):
+        sd = _cabi.rj_part_side_t()
+        sd.d_keys, sd.n, sd.n_cols = ko.data_ptr(), n, 1
+        sd.d_vals[0], sd.types[0], sd.d_valid_bytes[0] = vo.data_ptr(), int(t), (fo.data_ptr() if fo is not None else None)
+        sides.append(sd)
+    outs = (_cabi.rj_part_out_t * 3)()
+    outs[0].side, outs[0].col = 1, -1
+    outs[1].side, outs[1].col = 0, 0
+    outs[2].side, outs[2].col = 1, 0
+    hres = C.c_void_p()
+    ctx.check(lib.rj_join_partitioned(hd, C.byref(sides[0]), C.byref(sides[1]), bh.data_ptr(), ph.data_ptr(), bits, 0, bits, outs, 3, C.byref(hres)))
+    assert hres.value
+    from radix_join_b200.engine import Result
+    res = Result(ctx, hres)
+    got = res.to_columnar()
+    res.free()
+    hit = pk < nb
+    assert got.num_rows == int(hit.sum())
+    inv = np.empty(nb, dtype=np.int64)
+    inv[bk] = np.arange(nb)
+    want_rows = H.sort_rows([(int(k), int(ba[inv[k]]), (int(v) if ok else None)) for k, v, ok in zip(pk[hit], pb[hit], pvalid[hit])])
+    assert H.rows_of(got) == want_rows
