@@ -389,6 +389,19 @@ int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_
                         int32_t local_pass1_bits, int32_t hash_bits, const rj_part_out_t* outs, uint32_t n_out,
                         rj_result** out);
 
+/* Layout of the multi-GPU pull exchange, computed on the device from the all-gathered histograms:
+ * d_hist [G][2][2^bits] (rank, side, final partition).  With ndig = 2^pass1_bits, for each side (0 build, 1 probe):
+ *   d_cursor [2][ndig]        where this rank's run of every pass-1 digit starts in its OWN pass-1 arrays
+ *   d_table  [2][ndig][5]     biased source addresses of the sub-regions this rank owns (rj_part_side_t.d_src_table)
+ *   d_start / d_tile [2][ndig+1], d_group [2][ndig]   the sub-regions' tuple / tile prefixes and pass-1 regions
+ *   d_local_hist [2][2^bits / G]   tuples per final partition of the owned range
+ *   d_scalars [2][2]          tuples this rank owns / stores into other ranks' ranges
+ * d_ptrs [2][5][8]: every rank's base address of (keys, value 0, value 1, flag 0, flag 1) per side (0 = absent),
+ * d_widths [2][5] their element widths.  G = 2^g <= 8. */
+int rj_dist_layout(rj_ctx* ctx, const uint32_t* d_hist, int32_t me, int32_t g, int32_t bits, int32_t pass1_bits,
+                   const uint64_t* d_ptrs, const int32_t* d_widths, uint32_t* d_cursor, uint64_t* d_table, uint32_t* d_start,
+                   uint32_t* d_tile, uint32_t* d_group, uint32_t* d_local_hist, uint64_t* d_scalars, void* stream);
+
 /* -- pre-filter evaluation (harness side: Statement::eval on InnerColumns, src/statement.cpp:46-133,
  *    186-200; include/inner_column.h:170-325,386-562) and filter + emit (src/build_table.cpp:94-119,
  *    247-303) ------------------------------------------------------------------------------------- */

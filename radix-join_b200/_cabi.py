@@ -170,6 +170,7 @@ PROTOTYPES = {
     "rj_encode_varchar_write": (C.c_int, [_vp, _vp, _vp, _vp]),
     "rj_encode_varchar_free": (None, [_vp, _vp]),
     "rj_gen_fixed_pages": (C.c_int, [_vp, _vp, _vp, _u64, _i32, _vp, C.POINTER(_u64), _vp]),
+    "rj_dist_layout": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rj_scatter_carry": (C.c_int, [_vp, C.POINTER(rj_carry_scatter_t), _vp]),
     "rj_join_partitioned": (C.c_int, [_vp, C.POINTER(rj_part_side_t), C.POINTER(rj_part_side_t), _vp, _vp, _i32, _i32, _i32,
                                       C.POINTER(rj_part_out_t), _u32, _pvp]),

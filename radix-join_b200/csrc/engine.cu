@@ -349,7 +349,16 @@ void upload_pages_async(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t
     if (!c.pages && !c.contiguous) throw EngineError("column has pages but no page pointers");
     HostPipe* hp = ensure_pipe(ctx);
     const int type = c.type;
-    if (!c.pages) {
+    // a contiguous buffer in PAGEABLE host memory (a numpy array, a std::vector) would be staged by the driver on
+    // one thread at 6-10 GB/s; above a few MB it takes the same road as individually allocated pages -- worker
+    // threads copy it into the pinned ring, the DMA engine reads from there (~25 GB/s and overlapped)
+    bool pageable_contiguous = false;
+    if (!c.pages && cnt * size_t(RJ_PAGE_SIZE) >= (size_t(4) << 20)) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, c.contiguous) != cudaSuccess) cudaGetLastError();
+        pageable_contiguous = attr.type == cudaMemoryTypeUnregistered;
+    }
+    if (!c.pages && !pageable_contiguous) {
         const uint8_t* src = static_cast<const uint8_t*>(c.contiguous) + p0 * RJ_PAGE_SIZE;
         RJ_CUDA(cudaMemcpyAsync(dst, src, cnt * size_t(RJ_PAGE_SIZE), cudaMemcpyHostToDevice, stream));
         if (counters) {
@@ -368,7 +377,8 @@ void upload_pages_async(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t
         }
         return;
     }
-    const void* const* pages = c.pages + p0;
+    const void* const* pages = c.pages ? c.pages + p0 : nullptr;
+    const uint8_t*     flat = c.pages ? nullptr : static_cast<const uint8_t*>(c.contiguous) + p0 * RJ_PAGE_SIZE;
     const uint64_t per = HostPipe::kBufBytes / RJ_PAGE_SIZE;
     for (uint64_t q = 0; q < cnt; q += per) {
         const uint64_t m = std::min<uint64_t>(per, cnt - q);
@@ -378,7 +388,7 @@ void upload_pages_async(rj_ctx* ctx, const rj_column_t& c, uint64_t p0, uint64_t
                 PinnedBuf* buf = hp->up.acquire();
                 uint64_t r = 0, v = 0;
                 for (uint64_t i = 0; i < m; ++i) {
-                    const uint8_t* pg = static_cast<const uint8_t*>(pages[q + i]);
+                    const uint8_t* pg = pages ? static_cast<const uint8_t*>(pages[q + i]) : flat + (q + i) * RJ_PAGE_SIZE;
                     copy_page(buf->p + i * RJ_PAGE_SIZE, pg);
                     if (counters) page_counts(pg, type, &r, &v);
                 }
@@ -2470,6 +2480,13 @@ bool execute_multi(rj_ctx* ctx, const rj_plan_t* plan, const std::vector<OutputS
     uint64_t rows = 0;
     for (auto& r: job.results) rows += r ? r->num_rows : 0;
     *total = rows;
+    if (getenv("RJ_TRACE") != nullptr) {
+        fprintf(stderr, "[rj multi] %d devices: %d radix bits (%d in pass 1), build %llu + probe %llu rows in slices of %llu / %llu, %llu result rows:",
+                G, bits, p1, (unsigned long long)plan->inputs[job.fs.table[0]].num_rows, (unsigned long long)plan->inputs[job.fs.table[1]].num_rows,
+                (unsigned long long)job.rows_per_dev[0], (unsigned long long)job.rows_per_dev[1], (unsigned long long)rows);
+        for (auto& r: job.results) fprintf(stderr, " %llu", (unsigned long long)(r ? r->num_rows : 0));
+        fprintf(stderr, "\n");
+    }
     return true;
 }
 
@@ -2587,12 +2604,20 @@ int rj_result_fetch(rj_ctx* ctx, const rj_result* r, uint32_t col, void* const* 
         if (rc.n_pages == 0) return;
         if (!dst_pages && !dst_contiguous) throw EngineError("no destination pages");
         StageScope scope(ctx, RJ_ST_D2H, ctx->stream, 1, rc.n_pages * uint64_t(RJ_PAGE_SIZE));
-        if (!dst_pages) {
+        bool pageable_contiguous = false;
+        if (!dst_pages && rc.n_pages * size_t(RJ_PAGE_SIZE) >= (size_t(4) << 20)) {
+            // a large pageable destination (numpy): through the pinned ring like individually allocated pages
+            cudaPointerAttributes attr{};
+            if (cudaPointerGetAttributes(&attr, dst_contiguous) != cudaSuccess) cudaGetLastError();
+            pageable_contiguous = attr.type == cudaMemoryTypeUnregistered;
+        }
+        if (!dst_pages && !pageable_contiguous) {
             // contiguous destination: one DMA into the caller's buffer
             RJ_CUDA(cudaMemcpyAsync(dst_contiguous, rc.pages->p, rc.n_pages * size_t(RJ_PAGE_SIZE), cudaMemcpyDeviceToHost, ctx->stream));
             RJ_CUDA(cudaStreamSynchronize(ctx->stream));
             return;
         }
+        uint8_t* const flat = dst_pages ? nullptr : static_cast<uint8_t*>(dst_contiguous);
         // individually allocated destination pages: D2H into pinned ring buffers, scattered by the pool
         HostPipe*      hp = ensure_pipe(ctx);
         TaskGroup      group;
@@ -2612,7 +2637,8 @@ int rj_result_fetch(rj_ctx* ctx, const rj_result* r, uint32_t col, void* const* 
                 group.add();
                 TaskGroup* g = &group;
                 hp->waiter.after(buf->ev, [=] {
-                    for (uint64_t i = 0; i < m; ++i) std::memcpy(dst_pages[q + i], buf->p + i * RJ_PAGE_SIZE, RJ_PAGE_SIZE);
+                    for (uint64_t i = 0; i < m; ++i) copy_page(flat ? flat + (q + i) * RJ_PAGE_SIZE : dst_pages[q + i], buf->p + i * RJ_PAGE_SIZE);
+                    copy_fence();
                     hp->down.release(buf);
                     g->done();
                 });
@@ -3020,6 +3046,15 @@ int rj_join_partitioned(rj_ctx* ctx, const rj_part_side_t* build, const rj_part_
     });
 }
 
+
+int rj_dist_layout(rj_ctx* ctx, const uint32_t* d_hist, int32_t me, int32_t g, int32_t bits, int32_t pass1_bits, const uint64_t* d_ptrs,
+                   const int32_t* d_widths, uint32_t* d_cursor, uint64_t* d_table, uint32_t* d_start, uint32_t* d_tile, uint32_t* d_group,
+                   uint32_t* d_local_hist, uint64_t* d_scalars, void* stream) {
+    return guarded(ctx, [&] {
+        launch_dist_layout(d_hist, me, g, bits, pass1_bits, d_ptrs, d_widths, d_cursor, d_table, d_start, d_tile, d_group, d_local_hist,
+                           reinterpret_cast<unsigned long long*>(d_scalars), pick_stream(ctx, stream));
+    });
+}
 
 // ---- pre-filters ----------------------------------------------------------------------------------------
 int rj_filter_compare(rj_ctx* ctx, const void* d_values, const uint32_t* d_valid, uint64_t n, int32_t type, int32_t op,

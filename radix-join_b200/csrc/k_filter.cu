@@ -296,3 +296,101 @@ void launch_bitmap_expand(const uint32_t* bits, const uint64_t* start, uint64_t 
 }
 
 } // namespace rj
+
+// ---- layout of the multi-GPU pull exchange, from the all-gathered histograms (one small kernel instead of ~60
+//      tensor operations; see radix_join_b200/dist_join.py: pull_layout, which this mirrors) ------------------
+namespace rj {
+namespace {
+
+constexpr int kLayoutThreads = 1024;
+
+// one block per side (blockIdx.x: 0 build, 1 probe).  H[q][side][f]: tuples of rank q in final partition f.
+__global__ void __launch_bounds__(kLayoutThreads)
+    dist_layout_kernel(const uint32_t* __restrict__ H, int me, int g, int bits, int p1, const uint64_t* __restrict__ ptrs /* [2][5][8] */,
+                       const int* __restrict__ widths /* [2][5] */, uint32_t* __restrict__ cursor /* [2][ndig] */,
+                       uint64_t* __restrict__ table /* [2][ndig][5] */, uint32_t* __restrict__ start /* [2][ndig+1] */,
+                       uint32_t* __restrict__ tile /* [2][ndig+1] */, uint32_t* __restrict__ group /* [2][ndig] */,
+                       uint32_t* __restrict__ local_hist /* [2][nfin >> g] */, unsigned long long* __restrict__ scalars /* [2][2]: owned, sent */) {
+    __shared__ uint32_t s_cnt[8 * 256];   // [q][digit]
+    __shared__ uint32_t s_run[8 * 256];   // sender-local start of every digit run
+    __shared__ uint32_t s_sub_start[257], s_sub_tile[257];
+    __shared__ unsigned long long s_owned;
+    const int side = blockIdx.x, G = 1 << g, tid = threadIdx.x;
+    const uint32_t nfin = 1u << bits, ndig = 1u << p1, per = ndig >> g, fpd = nfin / ndig;
+    if (tid == 0) s_owned = 0;
+    // 1. tuples per (sender, pass-1 digit)
+    for (uint32_t i = tid; i < static_cast<uint32_t>(G) * ndig; i += kLayoutThreads) {
+        const uint32_t q = i / ndig, d = i % ndig;
+        const uint32_t* h = H + (static_cast<size_t>(q) * 2 + side) * nfin + static_cast<size_t>(d) * fpd;
+        uint32_t sum = 0;
+        for (uint32_t f = 0; f < fpd; ++f) sum += h[f];
+        s_cnt[q * 256 + d] = sum;
+    }
+    __syncthreads();
+    // 2. every sender's run starts (exclusive prefix over its digits); 3. the sub-regions this rank owns
+    if (tid < G) {
+        uint32_t run = 0;
+        for (uint32_t d = 0; d < ndig; ++d) {
+            s_run[tid * 256 + d] = run;
+            run += s_cnt[tid * 256 + d];
+        }
+    }
+    if (tid == 32) { // another warp: sub-region x = j * G + q
+        uint32_t pos = 0, tiles = 0;
+        for (uint32_t x = 0; x < per * G; ++x) {
+            const uint32_t c = s_cnt[(x % G) * 256 + me * per + x / G];
+            s_sub_start[x] = pos;
+            s_sub_tile[x] = tiles;
+            pos += c;
+            tiles += (c + 4095u) / 4096u;
+        }
+        s_sub_start[per * G] = pos;
+        s_sub_tile[per * G] = tiles;
+    }
+    __syncthreads();
+    for (uint32_t d = tid; d < ndig; d += kLayoutThreads) cursor[side * ndig + d] = s_run[me * 256 + d];
+    const uint32_t n_sub = per * G;
+    for (uint32_t x = tid; x <= n_sub; x += kLayoutThreads) {
+        start[side * (ndig + 1) + x] = s_sub_start[x];
+        tile[side * (ndig + 1) + x] = s_sub_tile[x];
+        if (x < n_sub) {
+            const uint32_t q = x % G, d = me * per + x / G;
+            group[side * ndig + x] = x / G;
+            const long long delta = static_cast<long long>(s_run[q * 256 + d]) - static_cast<long long>(s_sub_start[x]);
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+                table[(static_cast<size_t>(side) * ndig + x) * 5 + a] =
+                    ptrs[(side * 5 + a) * 8 + q] + static_cast<uint64_t>(delta * widths[side * 5 + a]);
+        }
+    }
+    // 4. tuples per final partition of the range this rank owns; what it owns / sends in total
+    const uint32_t nloc = nfin >> g;
+    unsigned long long mine = 0;
+    for (uint32_t f = tid; f < nloc; f += kLayoutThreads) {
+        uint32_t sum = 0;
+        for (int q = 0; q < G; ++q) sum += H[(static_cast<size_t>(q) * 2 + side) * nfin + static_cast<size_t>(me) * nloc + f];
+        local_hist[side * nloc + f] = sum;
+        mine += sum;
+    }
+    atomicAdd(&s_owned, mine);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long sent = 0;
+        for (uint32_t d = 0; d < ndig; ++d)
+            if (d / per != static_cast<uint32_t>(me)) sent += s_cnt[me * 256 + d];
+        scalars[side * 2 + 0] = s_owned;
+        scalars[side * 2 + 1] = sent;
+    }
+}
+
+} // namespace
+
+void launch_dist_layout(const uint32_t* H, int me, int g, int bits, int p1, const uint64_t* ptrs, const int* widths, uint32_t* cursor,
+                        uint64_t* table, uint32_t* start, uint32_t* tile, uint32_t* group, uint32_t* local_hist,
+                        unsigned long long* scalars, cudaStream_t s) {
+    if (g < 1 || g > 3 || p1 > 8 || p1 <= g || bits < p1 || bits > 15) throw CudaError("dist_layout: unsupported geometry");
+    dist_layout_kernel<<<2, kLayoutThreads, 0, s>>>(H, me, g, bits, p1, ptrs, widths, cursor, table, start, tile, group, local_hist, scalars);
+    RJ_LAUNCH_CHECK();
+}
+
+} // namespace rj

@@ -182,6 +182,9 @@ struct CarryScatter {
 };
 void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s);
 
+void launch_dist_layout(const uint32_t* H, int me, int g, int bits, int p1, const uint64_t* ptrs, const int* widths, uint32_t* cursor,
+                        uint64_t* table, uint32_t* start, uint32_t* tile, uint32_t* group, uint32_t* local_hist,
+                        unsigned long long* scalars, cudaStream_t s); // k_filter.cu
 void launch_varchar_desc_from_offsets(const uint64_t* off, uint64_t n, uint64_t* desc, int sm_count, cudaStream_t s); // k_varchar.cu
 
 // ---- k_filter.cu: predicates on decoded columns, bitmap algebra, bitmap -> row ids -------------------------

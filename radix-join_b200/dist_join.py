@@ -195,6 +195,19 @@ class CudaOps:
         d.n_val, d.n_flag = nv, nf
         self.ctx.check(self.lib.rj_scatter_carry(self.h, C.byref(d), self.stream))
 
+    def dist_layout(self, H, me, g, bits, p1, ptrs, widths):
+        """pull_layout for both sides in ONE kernel (rj_dist_layout).  H: int32 [G * 2 * 2**bits]; ptrs: int64 [2, 5, 8];
+        widths: int32 [2, 5].  -> dict of device tensors (see include/rj_b200.h)"""
+        ndig, nloc = 1 << p1, (1 << bits) >> g
+        out = {"cursor": self.empty(2 * ndig, torch.int32), "table": self.empty(2 * ndig * 5, torch.int64),
+               "start": self.empty(2 * (ndig + 1), torch.int32), "tile": self.empty(2 * (ndig + 1), torch.int32),
+               "group": self.empty(2 * ndig, torch.int32), "local_hist": self.empty(2 * nloc, torch.int32),
+               "scalars": self.empty(4, torch.int64)}
+        self.ctx.check(self.lib.rj_dist_layout(self.h, self._p(H), me, g, bits, p1, self._p(ptrs), self._p(widths), self._p(out["cursor"]),
+                                               self._p(out["table"]), self._p(out["start"]), self._p(out["tile"]), self._p(out["group"]),
+                                               self._p(out["local_hist"]), self._p(out["scalars"]), self.stream))
+        return out
+
     def local_scatter(self, keys, valid, payloads, shift, bits, cursor, xchg, me):
         """scatter pass 1 into THIS rank's arrays of the exchange (symmetric memory: the owners of the regions read
         them from here in their second pass)"""
@@ -628,42 +641,70 @@ def distributed_join_fused(ops, build, probe, out_cols, xchg, group=None, total_
     # 2. all ranks' histograms -> layout (device math), one small read-back
     H = torch.empty(world * (2 << bits), dtype=torch.int32, device=hist.device)
     dist.all_gather_into_tensor(H, hist, group=group)
-    H64 = H.view(world, 2, 1 << bits).to(torch.int64)
-    cursor, local_hist, owned, per_owner, sent = exchange_layout(H64, me, g, bits, p1)
-    cursor32, local_hist32 = cursor.to(torch.int32).contiguous(), local_hist.to(torch.int32).contiguous()
-    info = torch.cat([owned, per_owner.max(-1).values, sent]).cpu()
-    n_own, worst, n_sent = [int(x) for x in info[:2]], [int(x) for x in info[2:4]], [int(x) for x in info[4:6]]
-    if worst[0] > xchg[0].cap or worst[1] > xchg[1].cap:
-        raise RuntimeError("peer exchange buffers too small for this key distribution")
-    mark()
     pull = two and os.environ.get("RJ_DIST_MODE", "pull") == "pull"
+    payload_bytes = [sum((4 if p[2] == INT32 else 8) + (1 if p[3] else 0) for p in rel.payloads) for rel in (build, probe)]
     if pull:
         # 3. scatter pass 1 stays local (into this rank's symmetric arrays); 4. the owners PULL: their second pass
         #    reads every region's runs from the senders' memory over NVLink (TMA bulk loads), so the transfer
         #    overlaps the partitioning and nothing is copied twice.
-        lays, sides = [], []
-        for side, (rel, x) in enumerate(zip((build, probe), xchg)):
+        all_ptrs, all_widths = [], []
+        for rel, x in zip((build, probe), xchg):
+            if rel.n_rows > x.cap:
+                raise RuntimeError("peer exchange buffers too small for this rank's slice")
             widths = [4] + [(4 if p[2] == INT32 else 8) for p in rel.payloads] + [0] * (2 - len(rel.payloads)) + [1, 1]
             ptrs = [x.keys.ptrs]
             ptrs += [x.vals[i].ptrs for i in range(len(rel.payloads))] + [[0] * world] * (2 - len(rel.payloads))
             flag_bufs = [x.valids[i] for i in range(len(rel.payloads)) if rel.payloads[i][3]]
             ptrs += [fb.ptrs for fb in flag_bufs] + [[0] * world] * (2 - len(flag_bufs))
-            tptrs = [torch.tensor(p, dtype=torch.int64, device=hist.device) for p in ptrs]
-            lays.append(pull_layout(H64, me, g, bits, p1, side, tptrs, widths))
+            all_ptrs.append([list(p) + [0] * (8 - world) for p in ptrs])
+            all_widths.append(widths)
+        if hasattr(ops, "dist_layout"):
+            key = (id(xchg[0]), id(xchg[1]), tuple(map(tuple, all_widths)))
+            cache = getattr(ops, "_layout_consts", None)
+            if cache is None or cache[0] != key:
+                cache = (key, torch.tensor(all_ptrs, dtype=torch.int64, device=hist.device), torch.tensor(all_widths, dtype=torch.int32, device=hist.device))
+                ops._layout_consts = cache
+            lay = ops.dist_layout(H, me, g, bits, p1, cache[1], cache[2])
+            ndig, nloc = 1 << p1, (1 << bits) >> g
+            info = lay["scalars"].cpu()            # the one host round trip: what this rank owns
+            n_own, n_sent = [int(info[0]), int(info[2])], [int(info[1]), int(info[3])]
+            cursors = [lay["cursor"][s * ndig: (s + 1) * ndig] for s in range(2)]
+            local_hist32 = [lay["local_hist"][s * nloc: (s + 1) * nloc] for s in range(2)]
+            subs = [{"table": lay["table"][s * ndig * 5: (s + 1) * ndig * 5].view(ndig, 5), "start": lay["start"][s * (ndig + 1): (s + 1) * (ndig + 1)],
+                     "tile": lay["tile"][s * (ndig + 1): (s + 1) * (ndig + 1)], "group": lay["group"][s * ndig: (s + 1) * ndig]} for s in range(2)]
+        else:
+            H64 = H.view(world, 2, 1 << bits).to(torch.int64)
+            _cur, local_hist, owned, _per_owner, sent = exchange_layout(H64, me, g, bits, p1)
+            local_hist32 = local_hist.to(torch.int32).contiguous()
+            info = torch.cat([owned, sent]).cpu()
+            n_own, n_sent = [int(x) for x in info[:2]], [int(x) for x in info[2:4]]
+            cursors, subs = [], []
+            for side in range(2):
+                tptrs = [torch.tensor(p[:world], dtype=torch.int64, device=hist.device) for p in all_ptrs[side]]
+                cur, table, start, tile, grp = pull_layout(H64, me, g, bits, p1, side, tptrs, all_widths[side])
+                cursors.append(cur.to(torch.int32).contiguous())
+                subs.append({"table": table, "start": start.to(torch.int32).contiguous(), "tile": tile.to(torch.int32).contiguous(),
+                             "group": grp.to(torch.int32).contiguous()})
+        mark()
         xchg[0].barrier()                  # every owner is done reading the previous contents of these arrays
         for side, (keys, kvalid, pays) in enumerate(rels):
-            ops.local_scatter(keys, kvalid, pays, bits - p1, p1, lays[side][0].to(torch.int32).contiguous(), xchg[side], me)
+            ops.local_scatter(keys, kvalid, pays, bits - p1, p1, cursors[side], xchg[side], me)
         xchg[0].barrier()                  # every rank's first pass is complete
         mark()
-        sent_bytes = 0
+        sides, sent_bytes = [], 0
         for side, rel in enumerate((build, probe)):
-            _cur, table, start, tile, group = lays[side]
-            sides.append({"n": n_own[side], "types": [p[2] for p in rel.payloads], "nullable": [bool(p[3]) for p in rel.payloads],
-                          "table": table, "start": start.to(torch.int32).contiguous(), "tile": tile.to(torch.int32).contiguous(),
-                          "group": group.to(torch.int32).contiguous()})
-            sent_bytes += n_sent[side] * (4 + sum((4 if p[2] == INT32 else 8) + (1 if p[3] else 0) for p in rel.payloads))
+            sides.append(dict(subs[side], n=n_own[side], types=[p[2] for p in rel.payloads], nullable=[bool(p[3]) for p in rel.payloads]))
+            sent_bytes += n_sent[side] * (4 + payload_bytes[side])
         exchange_how = f"scatter pass 1 local, the owners' pass 2 reads its regions from the senders' memory (TMA over NVLink, {p1} of {bits} radix bits)"
     else:
+        H64 = H.view(world, 2, 1 << bits).to(torch.int64)
+        cursor, local_hist, owned, per_owner, sent = exchange_layout(H64, me, g, bits, p1)
+        cursor32, local_hist32 = cursor.to(torch.int32).contiguous(), local_hist.to(torch.int32).contiguous()
+        info = torch.cat([owned, per_owner.max(-1).values, sent]).cpu()
+        n_own, worst, n_sent = [int(x) for x in info[:2]], [int(x) for x in info[2:4]], [int(x) for x in info[4:6]]
+        if worst[0] > xchg[0].cap or worst[1] > xchg[1].cap:
+            raise RuntimeError("peer exchange buffers too small for this key distribution")
+        mark()
         # 3. the exchange = scatter pass 1 into the owners' arrays
         xchg[0].barrier()                      # every rank is done with the previous contents of its receive arrays
         for side, (keys, kvalid, pays) in enumerate(rels):

@@ -23,7 +23,7 @@ HARNESS = os.path.join(H.ROOT, "oracle", "_ref", "contest_harness")
 needs_harness = pytest.mark.skipif(not os.path.exists(HARNESS), reason="oracle/_ref/contest_harness not built")
 
 
-def run_harness(*args, env=None, timeout=1500):
+def run_harness(*args, env=None, timeout=1500, want_stderr=False):
     e = dict(os.environ)
     e.update(env or {})
     out = subprocess.run([HARNESS, *args], capture_output=True, text=True, timeout=timeout, env=e)
@@ -31,7 +31,7 @@ def run_harness(*args, env=None, timeout=1500):
     assert lines, (out.returncode, out.stdout[-2000:], out.stderr[-4000:])
     res = json.loads(lines[-1])
     assert out.returncode == 0 and res["ok"], (res, out.stderr[-2000:])
-    return res
+    return (res, out.stderr) if want_stderr else res
 
 
 @needs_harness
@@ -74,5 +74,6 @@ def test_config2_sample_on_a_device_group_matches_the_reference():
     a two-pass join)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    res = run_harness("parity", "c2", "--div", "16", env={"RJ_GPUS": "2"})
+    res, err = run_harness("parity", "c2", "--div", "16", env={"RJ_GPUS": "2", "RJ_TRACE": "1"}, want_stderr=True)
     assert res["rows"] == res["ref_rows"] == (1 << 29) // 16
+    assert "[rj multi] 2 devices" in err, err[-2000:]  # the join did run on the group, not on device 0 alone

@@ -126,3 +126,40 @@ def test_pull_layout_addresses_every_tuple_once(world, bits):
                 seen[q][idx0: idx0 + cnt] += 1
     for s in range(world):
         assert (seen[s] == 1).all(), "every tuple is read by exactly one owner"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,bits", [(2, 15), (8, 15), (4, 10)])
+def test_layout_kernel_matches_the_tensor_version(world, bits):
+    """rj_dist_layout (one kernel) against pull_layout / exchange_layout (tensor operations) on random histograms"""
+    import radix_join_b200 as rj
+    ctx = rj.build_context(0)
+    try:
+        ops = dj.CudaOps(ctx)
+        g = dj.log2_exact(world)
+        p1 = (bits + 1) // 2
+        rng = np.random.default_rng(bits)
+        Hn = rng.integers(0, 3000, (world, 2, 1 << bits)).astype(np.int32)
+        Hn[:, :, rng.integers(0, 1 << bits, 500)] = 0
+        H = torch.from_numpy(Hn).cuda()
+        widths = [[4, 8, 0, 1, 1], [4, 8, 4, 1, 1]]
+        ptrs = rng.integers(1 << 30, 1 << 40, (2, 5, 8)).astype(np.int64) // 16 * 16
+        for me in range(world):
+            lay = ops.dist_layout(H.reshape(-1), me, g, bits, p1, torch.from_numpy(ptrs).cuda(), torch.tensor(widths, dtype=torch.int32, device="cuda"))
+            torch.cuda.synchronize()
+            ndig, nloc = 1 << p1, (1 << bits) >> g
+            H64 = H.to(torch.int64)
+            _c, local_hist, owned, _po, sent = dj.exchange_layout(H64, me, g, bits, p1)
+            assert torch.equal(lay["local_hist"].view(2, nloc).to(torch.int64), local_hist)
+            assert lay["scalars"].tolist() == [int(owned[0]), int(sent[0]), int(owned[1]), int(sent[1])]
+            for side in range(2):
+                tp = [torch.from_numpy(ptrs[side, a, :world].copy()).cuda() for a in range(5)]
+                cur, table, start, tile, group = dj.pull_layout(H64, me, g, bits, p1, side, tp, widths[side])
+                assert torch.equal(lay["cursor"].view(2, ndig)[side].to(torch.int64), cur)
+                assert torch.equal(lay["start"].view(2, ndig + 1)[side].to(torch.int64), start)
+                assert torch.equal(lay["tile"].view(2, ndig + 1)[side].to(torch.int64), tile)
+                assert torch.equal(lay["group"].view(2, ndig)[side].to(torch.int64), group)
+                assert torch.equal(lay["table"].view(2, ndig, 5)[side], table)
+        ops.close()
+    finally:
+        rj.destroy_context(ctx)
