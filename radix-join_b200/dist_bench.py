@@ -20,14 +20,32 @@ def _relations(dt):
 
 
 OUT_COLS = [("b", "key", dj.INT32), ("b", 0, dj.INT64), ("p", 0, dj.FP64)]  # (R.k, R.a, S.b)
+NVLINK_PEAK_GBS = 770.0  # peer copy bandwidth measured on this pool in round 1 (900 GB/s nominal per direction)
+
+
+def _nvlink_roofline(stats, xchg_gb, scatter_ms, join_ms, hbm_peak, hbm_src):
+    """the exchange kernel against the NVLink roofline: in the pull variant the owners' scatter pass 2 reads the
+    regions out of the senders' memory, so its CUDA-event time (engine stage `scatter`, max over ranks) moves the
+    bytes one rank exchanges per step"""
+    pulled = "pass 2 reads" in stats["exchange"] or "pass 2 reads its regions" in stats["exchange"]
+    achieved = xchg_gb / (scatter_ms / 1e3) if (pulled and scatter_ms > 0) else None
+    return {"bound": "nvlink", "kernel": "scatter_carry_kernel (regions): scatter pass 2 pulling its regions from the peers" if pulled else "partition + exchange",
+            "achieved": round(achieved, 1) if achieved else None, "peak": NVLINK_PEAK_GBS, "unit": "GB/s",
+            "frac": round(achieved / NVLINK_PEAK_GBS, 4) if achieved else None, "traffic": None,
+            "stage_ms_max_over_ranks": {"scatter_pass2": round(scatter_ms, 3), "join_emit": round(join_ms, 3)},
+            "note": f"bytes one rank exchanges per step: {xchg_gb:.3f} GB (>= {xchg_gb / NVLINK_PEAK_GBS * 1e3:.2f} ms at {NVLINK_PEAK_GBS:.0f} GB/s); the same kernel "
+                    f"also partitions what it reads, so it is bound by the slower of NVLink and its own shared-memory work; "
+                    f"single-GPU kernel rooflines are in the --gpus 1 line; HBM peak {hbm_peak} GB/s ({hbm_src})"}
 
 
 def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    # rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION in this image) out of it
-    os.environ["NCCL_DEBUG"] = os.environ.get("RJ_NCCL_DEBUG", "NONE")  # WARN and above print the banner
+    # rank 0 prints exactly one line on stdout (NCCL_DEBUG=VERSION in this image would put a banner there)
+    # NCCL's log (version banner, rank / channel set-up) goes to a file per rank next to stderr, not to stdout
+    os.environ["NCCL_DEBUG"] = os.environ.get("RJ_NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = build_context(local)
     ops = dj.CudaOps(ctx)
@@ -79,6 +97,8 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     assert parity["multiset_checksum"], (sum_got, sum_exp)
 
     launches0 = ctx.kernel_launches()
+    ctx.profile_enable(True)   # CUDA events around the engine's stages (here: scatter pass 2 = the NVLink pull, join + pages)
+    ctx.profile_reset()
     dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
@@ -92,6 +112,10 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # the job is as slow as its slowest rank
     launches = ctx.kernel_launches() - launches0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    stage_ms = torch.tensor([prof["scatter"]["ms"] / args.steps, prof["join_emit"]["ms"] / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(stage_ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = float(ms) / args.steps
     value = (n_build + n_probe) / 1e6 / (ms_per_step / 1e3)
@@ -130,9 +154,35 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
         sec = sum(times) / len(times)
         tot_in = torch.tensor([in_bytes, out_bytes], dtype=torch.int64, device="cuda")
         dist.all_reduce(tot_in)
+        # the floor of this number: what the box moves between pinned host memory and ALL the GPUs at once, both
+        # directions busy (the ranks share PCIe switches and the host's memory system)
+        probe_bytes = 256 << 20
+        hp_in = torch.empty(probe_bytes, dtype=torch.uint8, pin_memory=True)
+        hp_out = torch.empty(probe_bytes, dtype=torch.uint8, pin_memory=True)
+        dp_in = torch.empty(probe_bytes, dtype=torch.uint8, device="cuda")
+        dp_out = torch.empty(probe_bytes, dtype=torch.uint8, device="cuda")
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        best = None
+        for _ in range(3):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _rep in range(4):
+                with torch.cuda.stream(s_up):
+                    dp_in.copy_(hp_in, non_blocking=True)
+                with torch.cuda.stream(s_down):
+                    hp_out.copy_(dp_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt_p = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(dt_p, op=dist.ReduceOp.MAX)
+            best = float(dt_p) if best is None else min(best, float(dt_p))
+        agg_gbs_each_way = 4 * probe_bytes * world / 1e9 / best
         e2e = {"value": round((n_build + n_probe) / 1e6 / sec, 2), "unit": unit, "h2d_bytes_per_step": int(tot_in[0]),
                "d2h_bytes_per_step": int(tot_in[1]), "ms_per_step": round(sec * 1e3, 2), "steps": len(times),
-               "host_buffers": "pinned, contiguous per column and rank; host clock, max over ranks"}
+               "host_buffers": "pinned, contiguous per column and rank; host clock, max over ranks",
+               "pcie_probe": {"aggregate_gbs_each_way": round(agg_gbs_each_way, 1),
+                              "what": f"all {world} ranks copy 1 GiB host->device and 1 GiB device->host at the same time (pinned memory)",
+                              "floor_ms": round(max(int(tot_in[0]), int(tot_in[1])) / 1e9 / agg_gbs_each_way * 1e3, 1)}}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -147,10 +197,7 @@ def run(args, n_build, n_probe, metric, unit, ClockSampler, measured_peak):
                        "cache": "per-rank inputs and intermediates are far larger than the 126 MB L2; no flush needed",
                        "tuples": "build rows + probe rows (SURVEY 8d)"},
             "clocks": clocks, "gpu_launches": launches,
-            "roofline": {"bound": "nvlink", "kernel": "partition + exchange", "achieved": None, "peak": 770.0, "unit": "GB/s",
-                         "frac": None, "traffic": None,
-                         "note": f"max bytes one rank sends per step: {xchg_gbs:.3f} GB (>= {xchg_gbs / 770.0 * 1e3:.2f} ms at the measured 770 GB/s peer bandwidth); "
-                                 f"single-GPU kernel rooflines are in the --gpus 1 line; HBM peak {peak} GB/s ({peak_src})"},
+            "roofline": _nvlink_roofline(stats, xchg_gbs, float(stage_ms[0]), float(stage_ms[1]), peak, peak_src),
             "e2e": e2e, "cpu_baseline": None, "parity": parity,
         }
         print(json.dumps(line), flush=True)
