@@ -99,9 +99,13 @@ struct Tile {
     uint32_t lo, cnt, cbase, reg;
 };
 
-template <bool kRegions, int W0, int W1, bool kMulti = false>
-__global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kernel(const CarryArgs a) {
+// T = threads per CTA: 512 for the flat pass (32 warps per SM hide the latency of the ranking atomics), 256 for the
+// region pass (measured: 3.02 vs 3.25 ms on config 2's probe side -- its windows arrive later, fewer threads per
+// barrier help more than more warps)
+template <bool kRegions, int W0, int W1, bool kMulti = false, int T = 512>
+__global__ void __launch_bounds__(T, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kernel(const CarryArgs a) {
     static_assert(!(kRegions && kMulti), "the exchange is a flat pass");
+    constexpr int kT = T, kItems = static_cast<int>(kTile) / T, kWarps = T / 32, kDepth = T == 256 ? 8 : 4;
     using L  = Layout<kRegions, W0, W1>;
     using T0 = typename ValT<W0>::type;
     using T1 = typename ValT<W1>::type;
@@ -397,7 +401,8 @@ __global__ void __launch_bounds__(kT, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kern
 
 template <bool kRegions, int W0, int W1, bool kMulti = false>
 void launch_one(const CarryArgs& a, uint64_t tiles_upper, int sm_count, cudaStream_t s) {
-    auto         kern = scatter_carry_kernel<kRegions, W0, W1, kMulti>;
+    constexpr int kT = kRegions ? 256 : 512;
+    auto         kern = scatter_carry_kernel<kRegions, W0, W1, kMulti, kT>;
     const size_t smem = Layout<kRegions, W0, W1>::kBytes;
     static SmemConfigured cfg;
     cfg.ensure(kern, smem);
