@@ -1436,7 +1436,7 @@ std::unique_ptr<rj_result> Exec::root_fused(uint64_t n) {
         for (int c = 0; c < L.n_bpay; ++c) in_bytes += nb * (L.bwidth[c] + (L.bvalid[c] ? 1 : 0));
         for (int c = 0; c < L.n_ppay; ++c) in_bytes += np * (L.pwidth[c] + (L.pvalid[c] ? 1 : 0));
         StageScope sc(ctx, RJ_ST_JOIN_EMIT, s, 1, in_bytes);
-        launch_join_emit(L, ctx->sm_count, s);
+        launch_join_emit(L, np, ctx->sm_count, s);
     }
     RJ_CUDA(cudaMemcpyAsync(h, counters->p, 16, cudaMemcpyDeviceToHost, s));
     RJ_CUDA(cudaStreamSynchronize(s));
@@ -3013,7 +3013,7 @@ std::unique_ptr<rj_result> join_partitioned_impl(rj_ctx* ctx, const rj_part_side
         for (int c = 0; c < L.n_ppay; ++c) in_bytes += np * (L.pwidth[c] + (L.pvalid[c] ? 1 : 0));
         {
             StageScope sc(ctx, RJ_ST_JOIN_EMIT, s, 1, in_bytes);
-            launch_join_emit(L, ctx->sm_count, s);
+            launch_join_emit(L, np, ctx->sm_count, s);
         }
         uint32_t h[4] = {0, 0, 0, 0};
         RJ_CUDA(cudaMemcpyAsync(h, counters->p, 16, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,613 @@
+// Root join fused with page output: build + probe in shared memory, result PAGES written straight from
+// the join kernel.  (The kernel template; k_join_emit.cu / k_join_emit_b1.cu / k_join_emit_b2.cu instantiate
+// it for 0 / 1 / 2 carried build columns so that the instantiations compile in parallel.)
+//
+// Replaces, for the root of the plan, hash_join_omp's per-bucket build / probe / row emission
+// (reference src/execute.cpp:196-261) together with Table::to_columnar of the result
+// (src/build_table.cpp:456-594).  The general path (k_join.cu + k_gather_encode.cu) emits (build, probe)
+// position pairs and gathers every output column through them: on config 2 that is 1.6 G gathers of 4-8
+// bytes, each its own 128-byte L1 wavefront, and the LSU -- not DRAM -- bounds the encode.  Here both
+// sides arrive FULLY partitioned with their output columns travelling beside the keys
+// (k_scatter_carry.cu), so a work unit reads its probe tuples and their columns sequentially, looks the
+// build columns up in shared memory, and stores finished rows into the result pages.  No pair list, no
+// gather, no separate encode pass.
+//
+// Memory pipeline.  A unit's probe tuples are consumed in batches of 2048; the keys, carried values and
+// validity bytes of a batch arrive by 1-D TMA bulk copies into one of two shared-memory buffers.  A buffer
+// is handed back by its 16 consumer warps through an mbarrier (one arrival per warp), so warps never wait
+// for one another inside a unit: only the thread that requests the next batch waits for the slowest
+// reader of the buffer it is about to overwrite.  The build side's carried columns arrive by TMA while the
+// hash table is being filled.
+//
+// Result pages.  Row alignment across columns (include/plan.h:102-105: columns are row-aligned by
+// cumulative row index, page boundaries are free) is kept by emitting CHUNKS of 1984 rows: one page of
+// every 4-byte column (1984 rows, the engine's fixed fill) and two pages of 992 rows of every 8-byte
+// column.  Chunk c owns pages c / 2c, 2c+1 of every column, so the columns' page lists enumerate the same
+// rows in the same order.  (8-byte pages hold 992 instead of 1007 rows: 1.5 % more pages, the price of
+// page-aligned chunks.)
+//
+// EVERY WARP OWNS ITS OPEN CHUNK (round-2 rewrite; the earlier version shared two open chunks per CTA and
+// spent two thirds of its 1320 warp instructions per 128 tuples on the packed shared-memory atomic, the
+// REDUX counts, the page-boundary hand-over between warps and three CTA barriers per batch).  A page stores
+// only its non-NULL values, packed (src/build_table.cpp:484-501), so a row's value slot depends on every
+// earlier row of its page; with a chunk per warp all of that is warp-local register state: rows so far,
+// non-NULL values so far per nullable column (and at the 992-row page boundary), and the chunk's validity
+// bitmaps -- 62 words per nullable column, two per lane.  A batch item (32 tuples) is placed with one
+// ballot per nullable column; values go straight from registers to their final place in global memory,
+// consecutive rows of the warp to consecutive addresses.  A chunk is reserved with one global atomic,
+// issued a few items before the open one fills up so that its latency is never waited for.
+// Cost: every warp ends the launch with a partly filled chunk; the launcher sizes the grid so that a warp
+// fills at least kEmitMinChunksPerWarp chunks (<= ~3 % more pages).
+//
+// Build keys must be unique inside every table (every key / foreign-key join): the 64-bit CAS insert sees
+// an equal key for free, raises a global flag and the whole launch is abandoned -- the engine then runs
+// the general path, which handles duplicates with chains.
+#pragma once
+#include "rj_common.cuh"
+#include "rj_internal.h"
+
+#include <type_traits>
+
+namespace rj {
+namespace emit {
+
+constexpr int      kThreads    = 512;
+constexpr int      kWarps      = kThreads / 32;
+constexpr uint32_t kSlots      = kEmitSlots;       // 4096 x 64-bit (key | local build index << 32)
+constexpr uint32_t kSlotMask   = kSlots - 1;
+constexpr uint32_t kCap        = kEmitBuildCap;    // 3072 build tuples per table (75 % fill)
+constexpr int      kBuildItems = kCap / kThreads;  // 6
+constexpr int      kItems      = 4;                // probe tuples per thread and batch
+constexpr uint32_t kBatch      = kItems * kThreads;
+constexpr uint32_t kChunkRows  = kEmitChunkRows;   // 1984 = 62 bitmap words
+constexpr uint32_t kHalfRows   = kChunkRows / 2;   // 992 rows per 8-byte page = 31 bitmap words
+constexpr uint32_t kHalfWords  = kHalfRows / 32;
+constexpr uint32_t kNone       = 0xffffffffu;
+constexpr uint32_t kReserveAt  = kChunkRows - 6 * 32; // the next chunk is reserved ~6 items before it is needed
+constexpr int      kSources    = 1 + 2 * kEmitMaxPay; // the key, the build columns, the probe columns
+
+__device__ __forceinline__ uint32_t probe_step(uint32_t k) { return ((k * 0x9E3779B1u) >> 20) | 1u; }
+
+struct EmitArgs {
+    const uint32_t* bkeys;
+    const uint32_t* pkeys;
+    const uint32_t* off_b;
+    const uint32_t* off_p;
+    const uint32_t* unit_start;
+    uint32_t*       unit_cursor;
+    uint32_t        nparts;
+    int             part_bits;
+    uint32_t        probe_chunk; // probe tuples per work unit
+    // carried columns, in final partition order beside the keys
+    const void*    bpay[kEmitMaxPay];
+    const uint8_t* bvalid[kEmitMaxPay]; // one byte per tuple, NULL = the column holds no NULL
+    int            bwidth[kEmitMaxPay];
+    const void*    ppay[kEmitMaxPay];
+    const uint8_t* pvalid[kEmitMaxPay];
+    int            pwidth[kEmitMaxPay];
+    // output columns by SOURCE (0 = the join key, 1 + c = build column c, 1 + kEmitMaxPay + c = probe column c):
+    // src_pages = the pages of the first output column that shows the source (NULL: none does), src_rest = bit j
+    // for every further output column j that shows it (SELECT a, a ...: rare)
+    uint8_t* src_pages[kSources];
+    uint32_t src_rest[kSources];
+    uint8_t* out_pages[kEmitMaxOut];
+    // shared-memory layout (byte offsets into the dynamic segment, computed by the launcher); the second probe
+    // buffer lies sm_pstride bytes behind the first
+    uint32_t sm_bpay[kEmitMaxPay], sm_bvalid[kEmitMaxPay];
+    uint32_t sm_pkeys, sm_ppay[kEmitMaxPay], sm_pvalid[kEmitMaxPay], sm_pstride;
+    // results
+    uint32_t*           chunk_counter;
+    unsigned long long* row_counter;
+    uint32_t*           abort_flag; // set when a table meets a duplicate build key
+};
+
+__device__ __forceinline__ uint32_t round16(uint32_t b) { return (b + 15u) & ~15u; }
+
+constexpr int popc_c(int x) { return x == 0 ? 0 : (x & 1) + popc_c(x >> 1); }
+
+// NB / NP: carried build / probe columns; NM: which of them hold NULLs (bit c = build column c, bit
+// kEmitMaxPay + c = probe column c; the nullable columns are numbered in bit order); WM: which of them are 8
+// bytes wide (same bits), or -1 = the widths are read from the arguments at run time.
+template <int NB, int NP, int NM, int WM>
+__global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_constant__ EmitArgs a) {
+    constexpr int NN  = popc_c(NM);
+    constexpr int NNX = NN > 0 ? NN : 1;
+    // compile-time loops over the carried columns: f(column index constant, nullable index constant (-1: no NULLs))
+    auto for_build = [](auto&& f) {
+        if constexpr (NB > 0) f(std::integral_constant<int, 0>{}, std::integral_constant<int, (NM & 1) ? 0 : -1>{});
+        if constexpr (NB > 1) f(std::integral_constant<int, 1>{}, std::integral_constant<int, (NM & 2) ? popc_c(NM & 1) : -1>{});
+    };
+    auto for_probe = [](auto&& f) {
+        if constexpr (NP > 0) f(std::integral_constant<int, 0>{}, std::integral_constant<int, (NM & 4) ? popc_c(NM & 3) : -1>{});
+        if constexpr (NP > 1) f(std::integral_constant<int, 1>{}, std::integral_constant<int, (NM & 8) ? popc_c(NM & 7) : -1>{});
+    };
+    auto bwide = [&](int c) -> bool { return WM >= 0 ? ((WM >> c) & 1) != 0 : a.bwidth[c] == 8; };
+    auto pwide = [&](int c) -> bool { return WM >= 0 ? ((WM >> (kEmitMaxPay + c)) & 1) != 0 : a.pwidth[c] == 8; };
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_unit, s_part;
+    __shared__ __align__(8) uint64_t s_bbar, s_full[2], s_empty[2];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt = lanemask_lt();
+    const uint32_t n_units = a.unit_start[a.nparts];
+    const int      part_bits = a.part_bits;
+    if (tid == 0) {
+        mbar_init(&s_bbar, 1);
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], kWarps);
+        mbar_init(&s_empty[1], kWarps);
+        fence_mbar_init();
+    }
+    uint32_t unit_no = 0, batch_no = 0; // mbarrier phases
+
+    // ---- the warp's open chunk: warp-uniform register state (c_next: lane 0) ---------------------------------
+    uint32_t c_open = kNone;     // chunk being filled
+    uint32_t c_next = kNone;     // lane 0: chunk reserved ahead (valid when have_next)
+    bool     have_next = false;
+    uint32_t rows = 0;           // rows placed in the open chunk
+    uint32_t closed = 0;         // full chunks this warp has written
+    uint32_t nv[NNX], nvh[NNX];  // non-NULL values of nullable column nn among all rows / among rows [0, 992)
+    uint32_t pend[NNX];          // validity bits of the chunk's last, incomplete bitmap word (complete words are in place)
+#pragma unroll
+    for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = 0u;
+
+    // every output column that shows source S: f(pages of the column)
+    auto for_outputs = [&](int S, auto&& f) {
+        uint8_t* const first = a.src_pages[S];
+        if (first != nullptr) f(first);
+        for (uint32_t m = a.src_rest[S]; m; m &= m - 1) f(a.out_pages[__ffs(m) - 1]);
+    };
+    // where word w of chunk c's validity bitmap lies in a column's FULL pages (4-byte column: one page of 62
+    // words; 8-byte column: two pages of 31 words)
+    auto bitmap_word = [&](uint8_t* pages, bool wide, uint32_t c, uint32_t w) -> uint32_t* {
+        if (wide) {
+            const uint32_t h = w >= kHalfWords ? 1u : 0u;
+            return reinterpret_cast<uint32_t*>(pages + (2ull * c + h) * RJ_PAGE + (RJ_PAGE - kHalfRows / 8)) + (w - h * kHalfWords);
+        }
+        return reinterpret_cast<uint32_t*>(pages + static_cast<uint64_t>(c) * RJ_PAGE + (RJ_PAGE - kChunkRows / 8)) + w;
+    };
+
+    // one batch of probe tuples [base, base + cnt) into its buffer (one thread).  q = the batch's number: the
+    // buffer was last used by batch q - 2, whose readers hand it back through s_empty
+    auto issue_probe = [&](uint32_t q, uint32_t base, uint32_t cnt) {
+        const int s = q & 1;
+        uint8_t* const buf = smem + (s ? a.sm_pstride : 0u);
+        if (q >= 2) mbar_wait(&s_empty[s], ((q >> 1) - 1) & 1);
+        uint32_t bytes = round16((cnt + (base & 3u)) * 4u);
+        uint32_t pb[kEmitMaxPay] = {}, vb[kEmitMaxPay] = {};
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+            const uint32_t w = pwide(c) ? 8u : 4u;
+            pb[c] = round16((cnt + (base & (16u / w - 1u))) * w);
+            vb[c] = (NM >> (kEmitMaxPay + c)) & 1 ? round16(cnt + (base & 15u)) : 0u;
+            bytes += pb[c] + vb[c];
+        }
+        mbar_arrive_expect_tx(&s_full[s], bytes);
+        tma_load_1d(buf + a.sm_pkeys, a.pkeys + (base - (base & 3u)), round16((cnt + (base & 3u)) * 4u), &s_full[s]);
+#pragma unroll
+        for (int c = 0; c < NP; ++c) {
+            const uint32_t w = pwide(c) ? 8u : 4u;
+            const uint32_t sk = base & (16u / w - 1u);
+            tma_load_1d(buf + a.sm_ppay[c], static_cast<const char*>(a.ppay[c]) + static_cast<uint64_t>(base - sk) * w, pb[c], &s_full[s]);
+            if (vb[c]) tma_load_1d(buf + a.sm_pvalid[c], a.pvalid[c] + (base - (base & 15u)), vb[c], &s_full[s]);
+        }
+    };
+
+    // Pages of chunk c, which holds n rows, in every output column of source S: headers, and the validity
+    // bitmaps that are not in place yet.  (x0, x1) = the chunk's bitmap in lane layout (lane l: words l and
+    // 32 + l); in_place: the bitmaps of FULL pages have been written word by word already (nullable sources);
+    // v_all / v_half = non-NULL values among all rows / among rows [0, 992).
+    auto write_meta_source = [&](int S, bool wide, uint32_t c, uint32_t n, uint32_t x0, uint32_t x1, bool in_place, uint32_t v_all, uint32_t v_half) {
+        for_outputs(S, [&](uint8_t* col_pages) {
+            const int pages = wide ? 2 : 1;
+            for (int h = 0; h < pages; ++h) {
+                uint8_t* pg = col_pages + (static_cast<uint64_t>(pages) * c + h) * RJ_PAGE;
+                const uint32_t rows_pg = !wide ? n : (h == 0 ? (n < kHalfRows ? n : kHalfRows) : (n > kHalfRows ? n - kHalfRows : 0u));
+                const uint32_t fw = h * kHalfWords; // first chunk word of the page's bitmap
+                const uint32_t bytes = (rows_pg + 7) >> 3;
+                uint8_t* dst = pg + RJ_PAGE - bytes;
+                if (in_place && rows_pg == (wide ? kHalfRows : kChunkRows)) {
+                    // nothing to do
+                } else if ((rows_pg & 31u) == 0) { // word-aligned
+                    const uint32_t words = rows_pg >> 5;
+                    if (lane >= fw && lane - fw < words) reinterpret_cast<uint32_t*>(dst)[lane - fw] = x0;
+                    if (lane + 32 - fw < words) reinterpret_cast<uint32_t*>(dst)[lane + 32 - fw] = x1;
+                } else {
+                    for (uint32_t b0 = 0; b0 < bytes; b0 += 32) {
+                        const uint32_t b = b0 + lane;
+                        const uint32_t cw = fw + (b >> 2);
+                        const uint32_t w0 = __shfl_sync(RJ_FULL_MASK, x0, cw & 31u), w1 = __shfl_sync(RJ_FULL_MASK, x1, cw & 31u);
+                        if (b < bytes) dst[b] = static_cast<uint8_t>((cw < 32 ? w0 : w1) >> (8 * (b & 3u)));
+                    }
+                }
+                if (lane == 0) *reinterpret_cast<uint32_t*>(pg) = rows_pg | ((!wide ? v_all : (h == 0 ? v_half : v_all - v_half)) << 16);
+            }
+        });
+    };
+    auto write_meta = [&](uint32_t c, uint32_t n) {
+        // a column without NULLs: ones below row n
+        const uint32_t fullw = n >> 5, tail = (1u << (n & 31u)) - 1u;
+        const uint32_t o0 = lane < fullw ? 0xffffffffu : (lane == fullw ? tail : 0u);
+        const uint32_t o1 = lane + 32 < fullw ? 0xffffffffu : (lane + 32 == fullw ? tail : 0u);
+        const uint32_t nh = n < kHalfRows ? n : kHalfRows;
+        // a nullable column of a partly filled chunk: its complete words come back from where they were stored
+        // (the positions of a full page), the incomplete one from `pend`
+        auto nullable_meta = [&](int S, bool wide, auto n_c) {
+            constexpr int N = decltype(n_c)::value;
+            uint32_t x0 = 0u, x1 = 0u;
+            if (n != kChunkRows && a.src_pages[S] != nullptr) {
+                __syncwarp(); // lane 0 stored the words
+                if (lane < fullw) x0 = __ldcg(bitmap_word(a.src_pages[S], wide, c, lane));
+                else if (lane == fullw) x0 = pend[N];
+                if (lane + 32 < fullw) x1 = __ldcg(bitmap_word(a.src_pages[S], wide, c, lane + 32));
+                else if (lane + 32 == fullw) x1 = pend[N];
+                __syncwarp();
+            }
+            write_meta_source(S, wide, c, n, x0, x1, true, nv[N], n >= kHalfRows ? nvh[N] : nv[N]);
+        };
+        write_meta_source(0, false, c, n, o0, o1, false, n, nh); // the key: INT32, never NULL in a match
+        for_build([&](auto c_c, auto n_c) {
+            constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
+            if constexpr (N >= 0) nullable_meta(1 + C, bwide(C), n_c);
+            else write_meta_source(1 + C, bwide(C), c, n, o0, o1, false, n, nh);
+        });
+        for_probe([&](auto c_c, auto n_c) {
+            constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
+            if constexpr (N >= 0) nullable_meta(1 + kEmitMaxPay + C, pwide(C), n_c);
+            else write_meta_source(1 + kEmitMaxPay + C, pwide(C), c, n, o0, o1, false, n, nh);
+        });
+    };
+
+    uint32_t u_next = 0;
+    if (tid == 0) u_next = atomicAdd(a.unit_cursor, 1u);
+    for (;;) {
+        // ---- next work unit, in global order (see k_join.cu); the cursor was advanced one unit ahead --------
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t u = __shfl_sync(RJ_FULL_MASK, u_next, 0);
+            if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(a.abort_flag)) u = 0xffffffffu; // somebody met a duplicate key
+            u = __shfl_sync(RJ_FULL_MASK, u, 0);
+            uint32_t lo = 0, hi = a.nparts;
+            if (u < n_units) {
+                while (hi - lo > 1) {
+                    const uint32_t span = hi - lo;
+                    const uint32_t step = (span + 31) / 32;
+                    const uint32_t probe = lo + (lane + 1) * step;
+                    const bool     le = probe < hi && a.unit_start[probe] <= u;
+                    const uint32_t k = __popc(__ballot_sync(RJ_FULL_MASK, le));
+                    const uint32_t nlo = lo + k * step;
+                    const uint32_t nhi = (k < 32 && lo + (k + 1) * step < hi) ? lo + (k + 1) * step : hi;
+                    lo = nlo;
+                    hi = nhi;
+                }
+                if (lane == 0) u_next = atomicAdd(a.unit_cursor, 1u); // returns while this unit is being processed
+            }
+            if (lane == 0) {
+                s_unit = u;
+                s_part = lo;
+            }
+        }
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= n_units) break;
+        const uint32_t part = s_part;
+        const uint32_t local = u - a.unit_start[part];
+        const uint32_t b_lo = a.off_b[part], b_hi = a.off_b[part + 1];
+        const uint32_t p_lo = a.off_p[part], p_hi = a.off_p[part + 1];
+        const uint32_t n_pchunks = (p_hi - p_lo + a.probe_chunk - 1) / a.probe_chunk;
+        const uint32_t bc = local / n_pchunks, pc = local - bc * n_pchunks;
+        const uint32_t bs = b_lo + bc * kCap;
+        const uint32_t nb = (b_hi - bs > kCap) ? kCap : b_hi - bs;
+        const uint32_t ps = p_lo + pc * a.probe_chunk;
+        const uint32_t pe = (p_hi - ps > a.probe_chunk) ? ps + a.probe_chunk : p_hi;
+
+        // ---- build: the carried columns and the first probe batch are requested, then the table is filled -----
+        if (tid == 0) {
+            // (the barrier at the top of the loop ended every read of the previous unit's table and columns)
+            uint32_t bytes = 0, pb[kEmitMaxPay] = {}, vb[kEmitMaxPay] = {};
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                const uint32_t w = bwide(c) ? 8u : 4u;
+                pb[c] = round16((nb + (bs & (16u / w - 1u))) * w);
+                vb[c] = (NM >> c) & 1 ? round16(nb + (bs & 15u)) : 0u;
+                bytes += pb[c] + vb[c];
+            }
+            if (NB > 0) {
+                mbar_arrive_expect_tx(&s_bbar, bytes);
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    const uint32_t w = bwide(c) ? 8u : 4u;
+                    const uint32_t sk = bs & (16u / w - 1u);
+                    tma_load_1d(smem + a.sm_bpay[c], static_cast<const char*>(a.bpay[c]) + static_cast<uint64_t>(bs - sk) * w, pb[c], &s_bbar);
+                    if (vb[c]) tma_load_1d(smem + a.sm_bvalid[c], a.bvalid[c] + (bs - (bs & 15u)), vb[c], &s_bbar);
+                }
+            }
+            if (ps < pe) issue_probe(batch_no, ps, pe - ps < kBatch ? pe - ps : kBatch);
+        }
+        uint32_t bkey[kBuildItems];
+#pragma unroll
+        for (int k = 0; k < kBuildItems; ++k) {
+            const uint32_t i = k * kThreads + tid;
+            bkey[k] = i < nb ? a.bkeys[bs + i] : 0u;
+        }
+        unsigned long long* const slots = reinterpret_cast<unsigned long long*>(smem); // table first: 32 KB
+        for (uint32_t s = tid; s < kSlots; s += kThreads) slots[s] = ~0ull;
+        __syncthreads();
+        bool dup = false;
+#pragma unroll
+        for (int k = 0; k < kBuildItems; ++k) {
+            const uint32_t i = k * kThreads + tid;
+            if (i < nb) {
+                const uint32_t           key  = bkey[k];
+                const unsigned long long mine = static_cast<unsigned long long>(key) | (static_cast<unsigned long long>(i) << 32);
+                uint32_t       sl   = (hash_key(key) >> part_bits) & kSlotMask;
+                const uint32_t step = probe_step(key);
+                for (;;) {
+                    unsigned long long cur = slots[sl];
+                    if (cur == ~0ull) cur = atomicCAS(&slots[sl], ~0ull, mine);
+                    if (cur == ~0ull) break;
+                    if (static_cast<uint32_t>(cur) == key) {
+                        dup = true;
+                        break;
+                    }
+                    sl = (sl + step) & kSlotMask;
+                }
+            }
+            __syncwarp();
+        }
+        if (__syncthreads_or(dup ? 1 : 0)) {
+            // not a key / foreign-key join: leave it to the general path (outstanding bulk copies land in this
+            // CTA's shared memory before it retires)
+            if (tid == 0) atomicExch(a.abort_flag, 1u);
+            if (NB > 0) mbar_wait(&s_bbar, unit_no & 1);
+            if (ps < pe) mbar_wait(&s_full[batch_no & 1], (batch_no >> 1) & 1);
+            return;
+        }
+        if (NB > 0) mbar_wait(&s_bbar, unit_no & 1);
+        ++unit_no;
+
+        // ---- probe ------------------------------------------------------------------------------------------
+        for (uint32_t base = ps; base < pe; base += kBatch, ++batch_no) {
+            const int      sb = batch_no & 1;
+            const uint32_t cnt = pe - base < kBatch ? pe - base : kBatch;
+            if (tid == 0 && base + kBatch < pe) {
+                const uint32_t nbase = base + kBatch;
+                issue_probe(batch_no + 1, nbase, pe - nbase < kBatch ? pe - nbase : kBatch);
+            }
+            __syncwarp();
+            mbar_wait(&s_full[sb], (batch_no >> 1) & 1);
+            const uint8_t* const  buf = smem + (sb ? a.sm_pstride : 0u);
+            const uint32_t* const pk = reinterpret_cast<const uint32_t*>(buf + a.sm_pkeys) + (base & 3u);
+
+#pragma unroll
+            for (int k = 0; k < kItems; ++k) {
+                const uint32_t i = k * kThreads + tid;
+                const uint32_t key = pk[i]; // past cnt: stale bytes, never used
+                uint32_t lidx = kNone;
+                if (i < cnt) {
+                    // at most one match: the table holds distinct keys.  A slot is (key, build index); an empty
+                    // one has index 0xffffffff
+                    uint32_t       off   = ((hash_key(key) >> part_bits) & kSlotMask) * 8u;
+                    const uint32_t step8 = probe_step(key) * 8u;
+                    for (;;) {
+                        const uint2 e = *reinterpret_cast<const uint2*>(smem + off);
+                        if (e.y == kNone) break;
+                        if (e.x == key) {
+                            lidx = e.y;
+                            break;
+                        }
+                        off = (off + step8) & (kSlotMask * 8u);
+                    }
+                }
+                __syncwarp();
+                bool           act = lidx != kNone;
+                const uint32_t bal = __ballot_sync(RJ_FULL_MASK, act);
+                if (bal == 0) continue;
+
+                // the row's validity in the nullable columns, and its values
+                bool ok[NNX];
+                uint64_t bval[NB > 0 ? NB : 1], pval[NP > 0 ? NP : 1];
+                for_build([&](auto c_c, auto n_c) {
+                    constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
+                    const uint32_t at = act ? lidx : 0u;
+                    if constexpr (N >= 0) ok[N] = act && (smem + a.sm_bvalid[C] + (bs & 15u))[at] != 0;
+                    const uint8_t* col = smem + a.sm_bpay[C];
+                    if (bwide(C)) bval[C] = (reinterpret_cast<const uint64_t*>(col) + (bs & 1u))[at];
+                    else bval[C] = (reinterpret_cast<const uint32_t*>(col) + (bs & 3u))[at];
+                });
+                for_probe([&](auto c_c, auto n_c) {
+                    constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
+                    if constexpr (N >= 0) ok[N] = act && (buf + a.sm_pvalid[C] + (base & 15u))[i] != 0;
+                    const uint8_t* col = buf + a.sm_ppay[C];
+                    if (pwide(C)) pval[C] = (reinterpret_cast<const uint64_t*>(col) + (base & 1u))[i];
+                    else pval[C] = (reinterpret_cast<const uint32_t*>(col) + (base & 3u))[i];
+                });
+
+                // place the matched rows: row index in the open chunk; rows past its end go to the next one
+                uint32_t r = rows + __popc(bal & lt);
+                uint32_t left = __popc(bal);
+                for (;;) {
+                    if (c_open == kNone) {
+                        if (!have_next && lane == 0) c_next = atomicAdd(a.chunk_counter, 1u);
+                        c_open = __shfl_sync(RJ_FULL_MASK, c_next, 0);
+                        have_next = false;
+                    }
+                    const bool     now = act && r < kChunkRows;
+                    const uint32_t nowb = __ballot_sync(RJ_FULL_MASK, now);
+                    const uint32_t n_now = __popc(nowb);
+                    uint32_t okb[NNX], v[NNX];
+#pragma unroll
+                    for (int nn = 0; nn < NN; ++nn) {
+                        okb[nn] = __ballot_sync(RJ_FULL_MASK, now && ok[nn]);
+                        v[nn]   = nv[nn] + __popc(okb[nn] & lt);
+                    }
+                    if (NN > 0 && rows < kHalfRows && rows + n_now >= kHalfRows) {
+                        // the rows of this round reach the second page of the 8-byte columns
+                        const uint32_t lowb = __ballot_sync(RJ_FULL_MASK, now && r < kHalfRows);
+#pragma unroll
+                        for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn] + __popc(okb[nn] & lowb);
+                    }
+                    const uint32_t w0 = rows >> 5, sh = rows & 31u; // the bitmap word the round's first row falls into
+                    // One source's value into every output column that shows it, and -- for a nullable source -- the
+                    // validity bits of the rows placed now (rows [rows, rows + n_now) of the chunk: two bitmap words at
+                    // most; a word goes to its place in the page as soon as it is complete).  N = index among the
+                    // nullable columns, -1: the source holds no NULL.
+                    auto emit = [&](auto n_c, int S, bool wide, uint64_t val) {
+                        constexpr int N = decltype(n_c)::value;
+                        bool st = now;
+                        if constexpr (N >= 0) st = now && ok[N];
+                        uint32_t at; // value slot, in units of the value width, from the chunk's first data byte
+                        if (wide) {
+                            const bool h = r >= kHalfRows;
+                            if constexpr (N >= 0) at = v[N] - (h ? nvh[N] : 0u); else at = r - (h ? kHalfRows : 0u);
+                            at += h ? RJ_PAGE / 8 : 0u;
+                        } else {
+                            if constexpr (N >= 0) at = v[N]; else at = r;
+                        }
+                        uint32_t word = 0u, carry = 0u;
+                        bool     complete = false;
+                        if constexpr (N >= 0) {
+                            uint32_t lo, hi;
+                            if (nowb == RJ_FULL_MASK) { // rows are the lanes in order
+                                lo = okb[N] << sh;
+                                hi = sh ? okb[N] >> (32u - sh) : 0u;
+                            } else {
+                                const uint32_t bit = st ? (1u << (r & 31u)) : 0u;
+                                const bool     first = (r >> 5) == w0;
+                                lo = __reduce_or_sync(RJ_FULL_MASK, first ? bit : 0u);
+                                hi = __reduce_or_sync(RJ_FULL_MASK, first ? 0u : bit);
+                            }
+                            word = pend[N] | lo;
+                            carry = hi;
+                            complete = sh + n_now >= 32u;
+                            pend[N] = complete ? carry : word;
+                        }
+                        for_outputs(S, [&](uint8_t* pages) {
+                            if (wide) {
+                                uint64_t* p = reinterpret_cast<uint64_t*>(pages + 2ull * c_open * RJ_PAGE + 8) + at;
+                                if (st) *p = val;
+                            } else {
+                                uint32_t* p = reinterpret_cast<uint32_t*>(pages + static_cast<uint64_t>(c_open) * RJ_PAGE + 4) + at;
+                                if (st) *p = static_cast<uint32_t>(val);
+                            }
+                            if constexpr (N >= 0) {
+                                if (complete && lane == 0) *bitmap_word(pages, wide, c_open, w0) = word;
+                            }
+                        });
+                    };
+                    emit(std::integral_constant<int, -1>{}, 0, false, key);
+                    for_build([&](auto c_c, auto n_c) { emit(n_c, 1 + decltype(c_c)::value, bwide(decltype(c_c)::value), bval[decltype(c_c)::value]); });
+                    for_probe([&](auto c_c, auto n_c) { emit(n_c, 1 + kEmitMaxPay + decltype(c_c)::value, pwide(decltype(c_c)::value), pval[decltype(c_c)::value]); });
+                    rows += n_now;
+                    left -= n_now;
+#pragma unroll
+                    for (int nn = 0; nn < NN; ++nn) nv[nn] += __popc(okb[nn]);
+                    if (rows == kChunkRows) {
+                        write_meta(c_open, kChunkRows);
+                        ++closed;
+                        c_open = kNone;
+                        rows = 0;
+#pragma unroll
+                        for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = 0u;
+                    } else if (!have_next && rows >= kReserveAt) {
+                        if (lane == 0) c_next = atomicAdd(a.chunk_counter, 1u); // consumed when the open chunk closes
+                        have_next = true;
+                    }
+                    if (left == 0) break;
+                    act = act && !now;
+                    r -= kChunkRows;
+                }
+            }
+            // this warp is done with the batch's buffer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[sb]);
+        }
+    }
+    // the partly filled chunk of this warp, and the chunk it may hold in reserve (an empty one)
+    if (c_open != kNone) write_meta(c_open, rows);
+    if (have_next) {
+        const uint32_t c = __shfl_sync(RJ_FULL_MASK, c_next, 0);
+#pragma unroll
+        for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = 0u;
+        write_meta(c, 0u);
+    }
+    if (lane == 0) {
+        const unsigned long long total = static_cast<unsigned long long>(closed) * kChunkRows + (c_open != kNone ? rows : 0u);
+        if (total) atomicAdd(a.row_counter, total);
+    }
+}
+
+// one instantiation's launch: its attributes (dynamic shared-memory limit, carve-out) are set once per device.
+// (The statics must be per INSTANTIATION: every join_emit_kernel<...> has the same function-pointer type, so a
+// generic lambda taking the pointer would share one set of statics among all of them.)
+template <int NB, int NP, int NM, int WM>
+static void launch_emit_instance(const EmitArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
+    auto kern = join_emit_kernel<NB, NP, NM, WM>;
+    static SmemConfigured cfg;
+    static bool carved[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!carved[dev & 63]) {
+        // two CTAs of ~112 KB per SM need the whole shared-memory carve-out
+        RJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        carved[dev & 63] = true;
+    }
+    cfg.ensure(kern, smem);
+    kern<<<grid, kThreads, smem, s>>>(a);
+}
+
+// Every (probe columns, nullable columns) combination of one build-column count; false: no instantiation
+// matches.  With at most one carried column per side (configs 1 and 2, every key / foreign-key join with one
+// payload per table) the column widths are compile-time constants as well; wider shapes read them at run time.
+template <int NB>
+static bool launch_emit_nb(const EmitArgs& a, int n_ppay, int null_mask, int width_mask, size_t smem, unsigned grid, cudaStream_t s) {
+    bool launched = false;
+    auto try_launch = [&](auto np_c, auto nm_c) {
+        constexpr int P = decltype(np_c)::value, M = decltype(nm_c)::value;
+        constexpr int allowed = ((1 << NB) - 1) | (((1 << P) - 1) << kEmitMaxPay);
+        if constexpr ((M & ~allowed) == 0) {
+            if (!launched && n_ppay == P && null_mask == M) {
+                if constexpr (NB <= 1 && P <= 1) {
+                    switch (width_mask) {
+                    case 0: launch_emit_instance<NB, P, M, 0>(a, smem, grid, s); break;
+                    case 1: if constexpr (NB == 1) launch_emit_instance<NB, P, M, 1>(a, smem, grid, s); break;
+                    case 4: if constexpr (P == 1) launch_emit_instance<NB, P, M, 4>(a, smem, grid, s); break;
+                    case 5: if constexpr (NB == 1 && P == 1) launch_emit_instance<NB, P, M, 5>(a, smem, grid, s); break;
+                    default: return;
+                    }
+                } else {
+                    launch_emit_instance<NB, P, M, -1>(a, smem, grid, s);
+                }
+                launched = true;
+            }
+        }
+    };
+    auto for_nm = [&](auto np_c) {
+#ifdef RJ_EMIT_DEV_ONLY  // development builds: only config 2's shape (see Makefile)
+        try_launch(np_c, std::integral_constant<int, 5>{});
+#else
+        try_launch(np_c, std::integral_constant<int, 0>{});  try_launch(np_c, std::integral_constant<int, 1>{});
+        try_launch(np_c, std::integral_constant<int, 2>{});  try_launch(np_c, std::integral_constant<int, 3>{});
+        try_launch(np_c, std::integral_constant<int, 4>{});  try_launch(np_c, std::integral_constant<int, 5>{});
+        try_launch(np_c, std::integral_constant<int, 6>{});  try_launch(np_c, std::integral_constant<int, 7>{});
+        try_launch(np_c, std::integral_constant<int, 8>{});  try_launch(np_c, std::integral_constant<int, 9>{});
+        try_launch(np_c, std::integral_constant<int, 10>{}); try_launch(np_c, std::integral_constant<int, 11>{});
+        try_launch(np_c, std::integral_constant<int, 12>{}); try_launch(np_c, std::integral_constant<int, 13>{});
+        try_launch(np_c, std::integral_constant<int, 14>{}); try_launch(np_c, std::integral_constant<int, 15>{});
+#endif
+    };
+    for_nm(std::integral_constant<int, 0>{});
+    for_nm(std::integral_constant<int, 1>{});
+    for_nm(std::integral_constant<int, 2>{});
+    return launched;
+}
+
+} // namespace emit
+
+// defined in k_join_emit.cu / k_join_emit_b1.cu / k_join_emit_b2.cu
+bool launch_join_emit_b0(const emit::EmitArgs& a, int n_ppay, int null_mask, int width_mask, size_t smem, unsigned grid, cudaStream_t s);
+bool launch_join_emit_b1(const emit::EmitArgs& a, int n_ppay, int null_mask, int width_mask, size_t smem, unsigned grid, cudaStream_t s);
+bool launch_join_emit_b2(const emit::EmitArgs& a, int n_ppay, int null_mask, int width_mask, size_t smem, unsigned grid, cudaStream_t s);
+
+} // namespace rj

@@ -269,12 +269,23 @@ struct JoinEmitLaunch {
     unsigned long long* row_counter = nullptr;
     uint32_t*           abort_flag = nullptr;
 };
-inline unsigned join_emit_grid(int sm_count) { return static_cast<unsigned>(sm_count) * 2; }
-// chunks a launch can produce: every probe tuple matches at most once; every CTA ends with a partial chunk
-// and the two (empty) chunks it held in reserve
-inline uint64_t join_emit_max_chunks(uint64_t n_probe, int sm_count) { return n_probe / kEmitChunkRows + 3 * join_emit_grid(sm_count) + 1; }
+constexpr uint32_t kEmitWarps = 16;            // warps per CTA of join_emit_kernel: every warp owns an open chunk
+constexpr uint32_t kEmitMinChunksPerWarp = 16; // grid sizing: a warp should fill this many chunks before it leaves one partly filled
+// Two CTAs per SM when the probe side is large; fewer CTAs for small probe sides so that the partly filled chunk
+// every warp ends with stays a small fraction (<= ~3 %) of the result's pages.
+inline unsigned join_emit_grid(uint64_t n_probe, int sm_count) {
+    const uint64_t per_cta = uint64_t(kEmitChunkRows) * kEmitMinChunksPerWarp * kEmitWarps;
+    const uint64_t want = (n_probe + per_cta - 1) / per_cta;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * 2;
+    return static_cast<unsigned>(want < 1 ? 1 : (want > cap ? cap : want));
+}
+// chunks a launch can produce: every probe tuple matches at most once; every warp ends with at most one partly
+// filled chunk and one (empty) chunk held in reserve
+inline uint64_t join_emit_max_chunks(uint64_t n_probe, int sm_count) {
+    return n_probe / kEmitChunkRows + 2ull * kEmitWarps * join_emit_grid(n_probe, sm_count) + 1;
+}
 bool join_emit_fits(const JoinEmitLaunch& L);
-void launch_join_emit(const JoinEmitLaunch& L, int sm_count, cudaStream_t s);
+void launch_join_emit(const JoinEmitLaunch& L, uint64_t n_probe, int sm_count, cudaStream_t s);
 
 // ---- k_gather_encode.cu ---------------------------------------------------------------------------
 void launch_gather(const void* src, const uint32_t* src_valid, const uint32_t* idx, uint64_t n,
