@@ -62,6 +62,13 @@ void launch_join_emit(const JoinEmitLaunch& L, uint64_t n_probe, int sm_count, c
         if (a.src_pages[src] == nullptr) a.src_pages[src] = L.out_pages[j];
         else a.src_rest[src] |= 1u << j;
     }
+    // the rank-structure table needs the hash to be a bijection with at most 17 bits left (see the kernel)
+    a.direct = L.part_bits >= 15 && L.part_bits <= 27 ? 1 : 0;
+    a.all_once = 1;
+    for (int src = 0; src < emit::kSources; ++src) {
+        const bool used = src == 0 || (src <= kEmitMaxPay ? src - 1 < L.n_bpay : src - 1 - kEmitMaxPay < L.n_ppay);
+        if (used && (a.src_pages[src] == nullptr || a.src_rest[src] != 0)) a.all_once = 0;
+    }
     a.chunk_counter = L.chunk_counter; a.row_counter = L.row_counter; a.abort_flag = L.abort_flag;
     const size_t smem = join_emit_layout(L, &a);
     if (smem > 226 * 1024) throw CudaError("join_emit: the columns do not fit shared memory");

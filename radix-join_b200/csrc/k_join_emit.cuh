@@ -99,6 +99,8 @@ struct EmitArgs {
     uint32_t*           chunk_counter;
     unsigned long long* row_counter;
     uint32_t*           abort_flag; // set when a table meets a duplicate build key
+    int direct;   // the table is the rank structure over the hash bits left by the partitioning (see the kernel)
+    int all_once; // the key and every carried column are shown by exactly one output column (no SELECT a, a; key shown)
 };
 
 __device__ __forceinline__ uint32_t round16(uint32_t b) { return (b + 15u) & ~15u; }
@@ -148,24 +150,32 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     uint32_t rows = 0;           // rows placed in the open chunk
     uint32_t closed = 0;         // full chunks this warp has written
     uint32_t nv[NNX], nvh[NNX];  // non-NULL values of nullable column nn among all rows / among rows [0, 992)
-    uint32_t pend[NNX];          // validity bits of the chunk's last, incomplete bitmap word (complete words are in place)
+    uint32_t pend[NNX];          // validity bits of the chunk's last, incomplete bitmap word
+    uint32_t held[NNX];          // PER LANE: the latest complete bitmap word w with (w & 31) == lane, until it is flushed
 #pragma unroll
-    for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = 0u;
+    for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = held[nn] = 0u;
+    // first page of the open chunk in the (first) output column of the key / of every carried column
+    uint8_t* cb_key = nullptr;
+    uint8_t* cb_b[NB > 0 ? NB : 1] = {};
+    uint8_t* cb_p[NP > 0 ? NP : 1] = {};
+    const bool direct = a.direct != 0;
+    const bool all_once = a.all_once != 0;
 
-    // every output column that shows source S: f(pages of the column)
-    auto for_outputs = [&](int S, auto&& f) {
+    // every output column that shows source S: f(first page of chunk c in that column)
+    auto for_outputs = [&](int S, bool wide, uint32_t c, auto&& f) {
+        const uint64_t chunk_bytes = wide ? 2ull * RJ_PAGE : 1ull * RJ_PAGE;
         uint8_t* const first = a.src_pages[S];
-        if (first != nullptr) f(first);
-        for (uint32_t m = a.src_rest[S]; m; m &= m - 1) f(a.out_pages[__ffs(m) - 1]);
+        if (first != nullptr) f(first + chunk_bytes * c);
+        for (uint32_t m = a.src_rest[S]; m; m &= m - 1) f(a.out_pages[__ffs(m) - 1] + chunk_bytes * c);
     };
-    // where word w of chunk c's validity bitmap lies in a column's FULL pages (4-byte column: one page of 62
-    // words; 8-byte column: two pages of 31 words)
-    auto bitmap_word = [&](uint8_t* pages, bool wide, uint32_t c, uint32_t w) -> uint32_t* {
+    // where word w of a chunk's validity bitmap lies in a column's FULL pages (4-byte column: one page of 62
+    // words; 8-byte column: two pages of 31 words); cb = the chunk's first page in the column
+    auto bitmap_word = [&](uint8_t* cb, bool wide, uint32_t w) -> uint32_t* {
         if (wide) {
             const uint32_t h = w >= kHalfWords ? 1u : 0u;
-            return reinterpret_cast<uint32_t*>(pages + (2ull * c + h) * RJ_PAGE + (RJ_PAGE - kHalfRows / 8)) + (w - h * kHalfWords);
+            return reinterpret_cast<uint32_t*>(cb + h * RJ_PAGE + (RJ_PAGE - kHalfRows / 8)) + (w - h * kHalfWords);
         }
-        return reinterpret_cast<uint32_t*>(pages + static_cast<uint64_t>(c) * RJ_PAGE + (RJ_PAGE - kChunkRows / 8)) + w;
+        return reinterpret_cast<uint32_t*>(cb + (RJ_PAGE - kChunkRows / 8)) + w;
     };
 
     // one batch of probe tuples [base, base + cnt) into its buffer (one thread).  q = the batch's number: the
@@ -199,16 +209,16 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     // 32 + l); in_place: the bitmaps of FULL pages have been written word by word already (nullable sources);
     // v_all / v_half = non-NULL values among all rows / among rows [0, 992).
     auto write_meta_source = [&](int S, bool wide, uint32_t c, uint32_t n, uint32_t x0, uint32_t x1, bool in_place, uint32_t v_all, uint32_t v_half) {
-        for_outputs(S, [&](uint8_t* col_pages) {
+        for_outputs(S, wide, c, [&](uint8_t* cb) {
             const int pages = wide ? 2 : 1;
             for (int h = 0; h < pages; ++h) {
-                uint8_t* pg = col_pages + (static_cast<uint64_t>(pages) * c + h) * RJ_PAGE;
+                uint8_t* pg = cb + h * RJ_PAGE;
                 const uint32_t rows_pg = !wide ? n : (h == 0 ? (n < kHalfRows ? n : kHalfRows) : (n > kHalfRows ? n - kHalfRows : 0u));
                 const uint32_t fw = h * kHalfWords; // first chunk word of the page's bitmap
                 const uint32_t bytes = (rows_pg + 7) >> 3;
                 uint8_t* dst = pg + RJ_PAGE - bytes;
-                if (in_place && rows_pg == (wide ? kHalfRows : kChunkRows)) {
-                    // nothing to do
+                if (in_place && n == kChunkRows) {
+                    // a full chunk of a nullable source: every word has been flushed to its place
                 } else if ((rows_pg & 31u) == 0) { // word-aligned
                     const uint32_t words = rows_pg >> 5;
                     if (lane >= fw && lane - fw < words) reinterpret_cast<uint32_t*>(dst)[lane - fw] = x0;
@@ -231,16 +241,20 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
         const uint32_t o0 = lane < fullw ? 0xffffffffu : (lane == fullw ? tail : 0u);
         const uint32_t o1 = lane + 32 < fullw ? 0xffffffffu : (lane + 32 == fullw ? tail : 0u);
         const uint32_t nh = n < kHalfRows ? n : kHalfRows;
-        // a nullable column of a partly filled chunk: its complete words come back from where they were stored
-        // (the positions of a full page), the incomplete one from `pend`
+        // a nullable column of a partly filled chunk: the complete words that were flushed come back from where
+        // they were stored (the positions of a full page), the others from `held`, the incomplete one from `pend`
         auto nullable_meta = [&](int S, bool wide, auto n_c) {
             constexpr int N = decltype(n_c)::value;
             uint32_t x0 = 0u, x1 = 0u;
-            if (n != kChunkRows && a.src_pages[S] != nullptr) {
-                __syncwarp(); // lane 0 stored the words
-                if (lane < fullw) x0 = __ldcg(bitmap_word(a.src_pages[S], wide, c, lane));
+            if (n != kChunkRows && (a.src_pages[S] != nullptr || a.src_rest[S] != 0u)) {
+                uint8_t* const pages = a.src_pages[S] != nullptr ? a.src_pages[S] : a.out_pages[__ffs(a.src_rest[S]) - 1];
+                uint8_t* const cb = pages + (wide ? 2ull * RJ_PAGE : 1ull * RJ_PAGE) * c;
+                const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;         // words [0, first_flush] are flushed together
+                const bool     flushed = fullw > first_flush;
+                __syncwarp();
+                if (lane < fullw) x0 = (flushed && lane <= first_flush) ? __ldcg(bitmap_word(cb, wide, lane)) : held[N];
                 else if (lane == fullw) x0 = pend[N];
-                if (lane + 32 < fullw) x1 = __ldcg(bitmap_word(a.src_pages[S], wide, c, lane + 32));
+                if (lane + 32 < fullw) x1 = held[N];
                 else if (lane + 32 == fullw) x1 = pend[N];
                 __syncwarp();
             }
@@ -302,18 +316,30 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
         const uint32_t ps = p_lo + pc * a.probe_chunk;
         const uint32_t pe = (p_hi - ps > a.probe_chunk) ? ps + a.probe_chunk : p_hi;
 
-        // ---- build: the carried columns and the first probe batch are requested, then the table is filled -----
+        // ---- build: the first probe batch is requested, then the table is filled ------------------------------
+        // Two kinds of table.
+        // HASH (any partition count): 4096 slots of (key, build index), double hashing; the carried build columns
+        //   arrive by TMA in partition order and are indexed with the build index.
+        // DIRECT (the partitioning consumed so many hash bits that at most 17 are left, i.e. >= 2^15 partitions):
+        //   fmix32 is a bijection on 32-bit keys, so inside a partition the remaining hash bits x IDENTIFY the
+        //   key.  The table is a bitmap over x with a running count per 32-bit word, (bits, rank of the word's first
+        //   bit) in one 64-bit entry: a probe is ONE shared-memory load, a bit test and a popcount -- no key
+        //   comparison, no probe sequence, no divergence between the lanes of a warp (the hash table's probe loop
+        //   ran as long as the unluckiest of 32 lanes: ~4 rounds at 50 % fill).  The carried build columns are
+        //   stored by rank.  A duplicate build key shows up as a bit that is already set.
+        const int      rem_words_log = 32 - part_bits - 5;             // direct: 2^(32 - part_bits) bits
+        const uint32_t bskew8 = direct ? 0u : (bs & 1u), bskew4 = direct ? 0u : (bs & 3u), bskew1 = direct ? 0u : (bs & 15u);
         if (tid == 0) {
             // (the barrier at the top of the loop ended every read of the previous unit's table and columns)
-            uint32_t bytes = 0, pb[kEmitMaxPay] = {}, vb[kEmitMaxPay] = {};
+            if (NB > 0 && !direct) {
+                uint32_t bytes = 0, pb[kEmitMaxPay] = {}, vb[kEmitMaxPay] = {};
 #pragma unroll
-            for (int c = 0; c < NB; ++c) {
-                const uint32_t w = bwide(c) ? 8u : 4u;
-                pb[c] = round16((nb + (bs & (16u / w - 1u))) * w);
-                vb[c] = (NM >> c) & 1 ? round16(nb + (bs & 15u)) : 0u;
-                bytes += pb[c] + vb[c];
-            }
-            if (NB > 0) {
+                for (int c = 0; c < NB; ++c) {
+                    const uint32_t w = bwide(c) ? 8u : 4u;
+                    pb[c] = round16((nb + (bs & (16u / w - 1u))) * w);
+                    vb[c] = (NM >> c) & 1 ? round16(nb + (bs & 15u)) : 0u;
+                    bytes += pb[c] + vb[c];
+                }
                 mbar_arrive_expect_tx(&s_bbar, bytes);
 #pragma unroll
                 for (int c = 0; c < NB; ++c) {
@@ -332,40 +358,101 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
             bkey[k] = i < nb ? a.bkeys[bs + i] : 0u;
         }
         unsigned long long* const slots = reinterpret_cast<unsigned long long*>(smem); // table first: 32 KB
-        for (uint32_t s = tid; s < kSlots; s += kThreads) slots[s] = ~0ull;
-        __syncthreads();
         bool dup = false;
+        if (direct) {
+            uint2* const   ent = reinterpret_cast<uint2*>(smem);
+            const uint32_t n_words = 1u << rem_words_log;
+            for (uint32_t s = tid; s < n_words; s += kThreads) ent[s] = make_uint2(0u, 0u);
+            __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kBuildItems; ++k) {
-            const uint32_t i = k * kThreads + tid;
-            if (i < nb) {
-                const uint32_t           key  = bkey[k];
-                const unsigned long long mine = static_cast<unsigned long long>(key) | (static_cast<unsigned long long>(i) << 32);
-                uint32_t       sl   = (hash_key(key) >> part_bits) & kSlotMask;
-                const uint32_t step = probe_step(key);
-                for (;;) {
-                    unsigned long long cur = slots[sl];
-                    if (cur == ~0ull) cur = atomicCAS(&slots[sl], ~0ull, mine);
-                    if (cur == ~0ull) break;
-                    if (static_cast<uint32_t>(cur) == key) {
-                        dup = true;
-                        break;
-                    }
-                    sl = (sl + step) & kSlotMask;
+            for (int k = 0; k < kBuildItems; ++k) {
+                if (k * kThreads + tid < nb) {
+                    const uint32_t x = hash_key(bkey[k]) >> part_bits;
+                    const uint32_t bit = 1u << (x & 31u);
+                    if (atomicOr(&ent[x >> 5].x, bit) & bit) dup = true;
                 }
             }
-            __syncwarp();
+            __syncthreads();
+            // rank of every word's first bit: thread t scans words [t * per, (t + 1) * per)
+            {
+                __shared__ uint32_t s_wsum[kWarps];
+                const uint32_t per = n_words > kThreads ? n_words / kThreads : 1u; // 8 at 17 bits
+                uint32_t mine = 0;
+                if (tid * per < n_words)
+                    for (uint32_t j = 0; j < per; ++j) mine += __popc(ent[tid * per + j].x);
+                uint32_t inc = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
+                    if (lane >= static_cast<uint32_t>(d)) inc += o;
+                }
+                if (lane == 31) s_wsum[tid >> 5] = inc;
+                __syncthreads();
+                uint32_t run = inc - mine;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) run += w < static_cast<int>(tid >> 5) ? s_wsum[w] : 0u;
+                if (tid * per < n_words)
+                    for (uint32_t j = 0; j < per; ++j) {
+                        ent[tid * per + j].y = run;
+                        run += __popc(ent[tid * per + j].x);
+                    }
+            }
+            __syncthreads();
+            // the carried build columns, by rank
+            if (NB > 0) {
+#pragma unroll
+                for (int k = 0; k < kBuildItems; ++k) {
+                    const uint32_t i = k * kThreads + tid;
+                    if (i < nb) {
+                        const uint32_t x = hash_key(bkey[k]) >> part_bits;
+                        const uint2    e = ent[x >> 5];
+                        const uint32_t pos = e.y + __popc(e.x & ((1u << (x & 31u)) - 1u));
+                        for_build([&](auto c_c, auto n_c) {
+                            constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
+                            if (bwide(C)) reinterpret_cast<uint64_t*>(smem + a.sm_bpay[C])[pos] = static_cast<const uint64_t*>(a.bpay[C])[bs + i];
+                            else reinterpret_cast<uint32_t*>(smem + a.sm_bpay[C])[pos] = static_cast<const uint32_t*>(a.bpay[C])[bs + i];
+                            if constexpr (N >= 0) (smem + a.sm_bvalid[C])[pos] = a.bvalid[C][bs + i];
+                        });
+                    }
+                }
+            }
+        } else {
+            for (uint32_t s = tid; s < kSlots; s += kThreads) slots[s] = ~0ull;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kBuildItems; ++k) {
+                const uint32_t i = k * kThreads + tid;
+                if (i < nb) {
+                    const uint32_t           key  = bkey[k];
+                    const unsigned long long mine = static_cast<unsigned long long>(key) | (static_cast<unsigned long long>(i) << 32);
+                    uint32_t       sl   = (hash_key(key) >> part_bits) & kSlotMask;
+                    const uint32_t step = probe_step(key);
+                    for (;;) {
+                        unsigned long long cur = slots[sl];
+                        if (cur == ~0ull) cur = atomicCAS(&slots[sl], ~0ull, mine);
+                        if (cur == ~0ull) break;
+                        if (static_cast<uint32_t>(cur) == key) {
+                            dup = true;
+                            break;
+                        }
+                        sl = (sl + step) & kSlotMask;
+                    }
+                }
+                __syncwarp();
+            }
         }
         if (__syncthreads_or(dup ? 1 : 0)) {
             // not a key / foreign-key join: leave it to the general path (outstanding bulk copies land in this
             // CTA's shared memory before it retires)
             if (tid == 0) atomicExch(a.abort_flag, 1u);
-            if (NB > 0) mbar_wait(&s_bbar, unit_no & 1);
+            if (NB > 0 && !direct) mbar_wait(&s_bbar, unit_no & 1);
             if (ps < pe) mbar_wait(&s_full[batch_no & 1], (batch_no >> 1) & 1);
             return;
         }
-        if (NB > 0) mbar_wait(&s_bbar, unit_no & 1);
-        ++unit_no;
+        if (NB > 0 && !direct) {
+            mbar_wait(&s_bbar, unit_no & 1);
+            ++unit_no;
+        }
 
         // ---- probe ------------------------------------------------------------------------------------------
         for (uint32_t base = ps; base < pe; base += kBatch, ++batch_no) {
@@ -385,16 +472,23 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                 const uint32_t i = k * kThreads + tid;
                 const uint32_t key = pk[i]; // past cnt: stale bytes, never used
                 uint32_t lidx = kNone;
-                if (i < cnt) {
+                if (direct) {
+                    // the remaining hash bits identify the key: one load, a bit test, a popcount
+                    const uint32_t x = hash_key(key) >> part_bits;
+                    const uint2    e = reinterpret_cast<const uint2*>(smem)[x >> 5];
+                    const uint32_t below = e.x & ((1u << (x & 31u)) - 1u);
+                    if (i < cnt && ((e.x >> (x & 31u)) & 1u)) lidx = e.y + __popc(below);
+                } else if (i < cnt) {
                     // at most one match: the table holds distinct keys.  A slot is (key, build index); an empty
                     // one has index 0xffffffff
                     uint32_t       off   = ((hash_key(key) >> part_bits) & kSlotMask) * 8u;
                     const uint32_t step8 = probe_step(key) * 8u;
                     for (;;) {
-                        const uint2 e = *reinterpret_cast<const uint2*>(smem + off);
-                        if (e.y == kNone) break;
-                        if (e.x == key) {
-                            lidx = e.y;
+                        uint32_t ex, ey;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(smem_u32(smem) + off));
+                        if (ey == kNone) break;
+                        if (ex == key) {
+                            lidx = ey;
                             break;
                         }
                         off = (off + step8) & (kSlotMask * 8u);
@@ -411,10 +505,10 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                 for_build([&](auto c_c, auto n_c) {
                     constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
                     const uint32_t at = act ? lidx : 0u;
-                    if constexpr (N >= 0) ok[N] = act && (smem + a.sm_bvalid[C] + (bs & 15u))[at] != 0;
+                    if constexpr (N >= 0) ok[N] = act && (smem + a.sm_bvalid[C] + bskew1)[at] != 0;
                     const uint8_t* col = smem + a.sm_bpay[C];
-                    if (bwide(C)) bval[C] = (reinterpret_cast<const uint64_t*>(col) + (bs & 1u))[at];
-                    else bval[C] = (reinterpret_cast<const uint32_t*>(col) + (bs & 3u))[at];
+                    if (bwide(C)) bval[C] = (reinterpret_cast<const uint64_t*>(col) + bskew8)[at];
+                    else bval[C] = (reinterpret_cast<const uint32_t*>(col) + bskew4)[at];
                 });
                 for_probe([&](auto c_c, auto n_c) {
                     constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
@@ -432,6 +526,9 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                         if (!have_next && lane == 0) c_next = atomicAdd(a.chunk_counter, 1u);
                         c_open = __shfl_sync(RJ_FULL_MASK, c_next, 0);
                         have_next = false;
+                        cb_key = a.src_pages[0] + static_cast<uint64_t>(c_open) * RJ_PAGE;
+                        for_build([&](auto c_c, auto) { cb_b[decltype(c_c)::value] = a.src_pages[1 + decltype(c_c)::value] + static_cast<uint64_t>(c_open) * (bwide(decltype(c_c)::value) ? 2 * RJ_PAGE : RJ_PAGE); });
+                        for_probe([&](auto c_c, auto) { cb_p[decltype(c_c)::value] = a.src_pages[1 + kEmitMaxPay + decltype(c_c)::value] + static_cast<uint64_t>(c_open) * (pwide(decltype(c_c)::value) ? 2 * RJ_PAGE : RJ_PAGE); });
                     }
                     const bool     now = act && r < kChunkRows;
                     const uint32_t nowb = __ballot_sync(RJ_FULL_MASK, now);
@@ -451,10 +548,12 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                     const uint32_t w0 = rows >> 5, sh = rows & 31u; // the bitmap word the round's first row falls into
                     // One source's value into every output column that shows it, and -- for a nullable source -- the
                     // validity bits of the rows placed now (rows [rows, rows + n_now) of the chunk: two bitmap words at
-                    // most; a word goes to its place in the page as soon as it is complete).  N = index among the
-                    // nullable columns, -1: the source holds no NULL.
-                    auto emit = [&](auto n_c, int S, bool wide, uint64_t val) {
-                        constexpr int N = decltype(n_c)::value;
+                    // most).  A complete word stays with lane (w & 31) until 31 / 32 of them (one page's worth, or the
+                    // chunk's second half) go out in one store.  N = index among the nullable columns, -1: the source
+                    // holds no NULL.  kOnce: every source is shown by exactly one output column, whose chunk base is cb.
+                    auto emit = [&](auto once_c, auto n_c, int S, bool wide, uint64_t val, uint8_t* cb) {
+                        constexpr int  N = decltype(n_c)::value;
+                        constexpr bool kOnce = decltype(once_c)::value;
                         bool st = now;
                         if constexpr (N >= 0) st = now && ok[N];
                         uint32_t at; // value slot, in units of the value width, from the chunk's first data byte
@@ -465,8 +564,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                         } else {
                             if constexpr (N >= 0) at = v[N]; else at = r;
                         }
-                        uint32_t word = 0u, carry = 0u;
-                        bool     complete = false;
+                        bool flush = false;
                         if constexpr (N >= 0) {
                             uint32_t lo, hi;
                             if (nowb == RJ_FULL_MASK) { // rows are the lanes in order
@@ -478,27 +576,38 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                                 lo = __reduce_or_sync(RJ_FULL_MASK, first ? bit : 0u);
                                 hi = __reduce_or_sync(RJ_FULL_MASK, first ? 0u : bit);
                             }
-                            word = pend[N] | lo;
-                            carry = hi;
-                            complete = sh + n_now >= 32u;
-                            pend[N] = complete ? carry : word;
+                            const uint32_t word = pend[N] | lo;
+                            const bool     complete = sh + n_now >= 32u;
+                            pend[N] = complete ? hi : word;
+                            if (complete && lane == (w0 & 31u)) held[N] = word;
+                            flush = complete && (w0 == (wide ? kHalfWords - 1 : 31u) || w0 == kChunkRows / 32 - 1);
                         }
-                        for_outputs(S, [&](uint8_t* pages) {
+                        auto store = [&](uint8_t* base) {
                             if (wide) {
-                                uint64_t* p = reinterpret_cast<uint64_t*>(pages + 2ull * c_open * RJ_PAGE + 8) + at;
-                                if (st) *p = val;
+                                if (st) (reinterpret_cast<uint64_t*>(base + 8))[at] = val;
                             } else {
-                                uint32_t* p = reinterpret_cast<uint32_t*>(pages + static_cast<uint64_t>(c_open) * RJ_PAGE + 4) + at;
-                                if (st) *p = static_cast<uint32_t>(val);
+                                if (st) (reinterpret_cast<uint32_t*>(base + 4))[at] = static_cast<uint32_t>(val);
                             }
                             if constexpr (N >= 0) {
-                                if (complete && lane == 0) *bitmap_word(pages, wide, c_open, w0) = word;
+                                if (flush) {
+                                    // lane l holds word wl = the largest w <= w0 with (w & 31) == l; the words up to the
+                                    // first flush point went out then
+                                    const uint32_t wl = w0 - ((w0 - lane) & 31u);
+                                    const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
+                                    const bool     mine = wl <= w0 && (w0 == first_flush || wl > first_flush); // (wl wraps above w0 when no such word exists)
+                                    if (mine) *bitmap_word(base, wide, wl) = held[N];
+                                }
                             }
-                        });
+                        };
+                        if constexpr (kOnce) store(cb);
+                        else for_outputs(S, wide, c_open, store);
                     };
-                    emit(std::integral_constant<int, -1>{}, 0, false, key);
-                    for_build([&](auto c_c, auto n_c) { emit(n_c, 1 + decltype(c_c)::value, bwide(decltype(c_c)::value), bval[decltype(c_c)::value]); });
-                    for_probe([&](auto c_c, auto n_c) { emit(n_c, 1 + kEmitMaxPay + decltype(c_c)::value, pwide(decltype(c_c)::value), pval[decltype(c_c)::value]); });
+                    auto emit_all = [&](auto once_c) {
+                        emit(once_c, std::integral_constant<int, -1>{}, 0, false, key, cb_key);
+                        for_build([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + decltype(c_c)::value, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
+                        for_probe([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + kEmitMaxPay + decltype(c_c)::value, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
+                    };
+                    if (all_once) emit_all(std::true_type{}); else emit_all(std::false_type{});
                     rows += n_now;
                     left -= n_now;
 #pragma unroll
@@ -509,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                         c_open = kNone;
                         rows = 0;
 #pragma unroll
-                        for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = 0u;
+                        for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = held[nn] = 0u;
                     } else if (!have_next && rows >= kReserveAt) {
                         if (lane == 0) c_next = atomicAdd(a.chunk_counter, 1u); // consumed when the open chunk closes
                         have_next = true;
@@ -529,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     if (have_next) {
         const uint32_t c = __shfl_sync(RJ_FULL_MASK, c_next, 0);
 #pragma unroll
-        for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = 0u;
+        for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = held[nn] = 0u;
         write_meta(c, 0u);
     }
     if (lane == 0) {

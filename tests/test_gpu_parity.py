@@ -796,29 +796,36 @@ def test_stage_scatter_carry_two_passes_and_scattered_sources(ctx, widths):
     region_pass(scattered)
 
 
-def test_stage_join_partitioned_single_pass(ctx):
-    """rj_join_partitioned on inputs that a flat rj_scatter_carry pass partitioned completely (local_pass1_bits = 0)"""
+@pytest.mark.parametrize("bits,p1,build_nulls", [(6, 0, False), (15, 7, True), (15, 7, False)])
+def test_stage_join_partitioned(ctx, bits, p1, build_nulls):
+    """rj_join_partitioned on inputs that a flat rj_scatter_carry pass partitioned completely (local_pass1_bits = 0:
+    the hash-table kernel), and on pass-1 partitioned inputs with 15 radix bits in all: the engine runs the second
+    pass itself and the join kernel uses its rank-structure table (the 17 hash bits the partitioning leaves identify
+    a 32-bit key: k_join_emit.cuh, DIRECT)"""
     from radix_join_b200 import _cabi
     rng = np.random.default_rng(12)
-    nb, np_, bits = 100_000, 700_000, 6
-    bk = rng.permutation(nb).astype(np.uint32)
+    nb, np_ = 100_000, 700_000
+    bk = (rng.permutation(4 * nb)[:nb] * 977 + 12345).astype(np.uint32)
     ba = rng.integers(0, 2**62, nb).astype(np.uint64)
-    pk = rng.integers(0, int(nb * 1.1), np_).astype(np.uint32)
+    bvalid = (rng.random(nb) > 0.3) if build_nulls else None
+    pk = np.where(rng.random(np_) < 0.9, bk[rng.integers(0, nb, np_)], rng.integers(0, 2**32, np_).astype(np.uint32)).astype(np.uint32)
     pb = rng.integers(0, 2**31, np_).astype(np.uint32)
     pvalid = rng.random(np_) > 0.2
     lib, hd = ctx.lib, ctx.handle
 
     def part(keys, vals, width, vmask):
         n = len(keys)
-        dig = H.hash_keys(keys) & np.uint32((1 << bits) - 1)
-        cnt = np.bincount(dig, minlength=1 << bits)
-        cur = dev(np.concatenate([[0], np.cumsum(cnt)])[:-1].astype(np.int32))
+        part_id = H.hash_keys(keys) & np.uint32((1 << bits) - 1)
+        cnt = np.bincount(part_id, minlength=1 << bits)
+        pass_bits, shift = (p1, bits - p1) if p1 else (bits, 0)
+        dig_cnt = np.bincount(part_id >> shift, minlength=1 << pass_bits)
+        cur = dev(np.concatenate([[0], np.cumsum(dig_cnt)])[:-1].astype(np.int32))
         ko = torch.zeros(n + 16, dtype=torch.int32, device="cuda")
         vo = torch.zeros((n + 16) * (width // 4), dtype=torch.int32, device="cuda")
         fo = torch.zeros(n + 16, dtype=torch.uint8, device="cuda") if vmask is not None else None
         d_k, d_v = dev(keys), dev(vals)
         d = _cabi.rj_carry_scatter_t()
-        d.d_keys, d.n, d.shift, d.bits, d.d_cursor, d.d_keys_out = d_k.data_ptr(), n, 0, bits, cur.data_ptr(), ko.data_ptr()
+        d.d_keys, d.n, d.shift, d.bits, d.d_cursor, d.d_keys_out = d_k.data_ptr(), n, shift, pass_bits, cur.data_ptr(), ko.data_ptr()
         d.n_val, d.val_src[0], d.val_dst[0], d.val_width[0] = 1, d_v.data_ptr(), vo.data_ptr(), width
         if vmask is not None:
             by = np.packbits(vmask, bitorder="little")
@@ -827,10 +834,10 @@ def test_stage_join_partitioned_single_pass(ctx):
         ctx.check(lib.rj_scatter_carry(hd, C.byref(d), None))
         torch.cuda.synchronize()
         return ko, vo, fo, dev(cnt.astype(np.int32))
-    bko, bvo, _, bh = part(bk, ba, 8, None)
+    bko, bvo, bfo, bh = part(bk, ba, 8, bvalid)
     pko, pvo, pfo, ph = part(pk, pb, 4, pvalid)
     sides = []
-    for ko, vo, fo, n, t in ((bko, bvo, None, nb, INT64), (pko, pvo, pfo, np_, INT32)):
+    for ko, vo, fo, n, t in ((bko, bvo, bfo, nb, INT64), (pko, pvo, pfo, np_, INT32)):
         sd = _cabi.rj_part_side_t()
         sd.d_keys, sd.n, sd.n_cols = ko.data_ptr(), n, 1
         sd.d_vals[0], sd.types[0], sd.d_valid_bytes[0] = vo.data_ptr(), int(t), (fo.data_ptr() if fo is not None else None)
@@ -840,15 +847,17 @@ def test_stage_join_partitioned_single_pass(ctx):
     outs[1].side, outs[1].col = 0, 0
     outs[2].side, outs[2].col = 1, 0
     hres = C.c_void_p()
-    ctx.check(lib.rj_join_partitioned(hd, C.byref(sides[0]), C.byref(sides[1]), bh.data_ptr(), ph.data_ptr(), bits, 0, bits, outs, 3, C.byref(hres)))
+    ctx.check(lib.rj_join_partitioned(hd, C.byref(sides[0]), C.byref(sides[1]), bh.data_ptr(), ph.data_ptr(), bits, p1, bits, outs, 3, C.byref(hres)))
     assert hres.value
     from radix_join_b200.engine import Result
     res = Result(ctx, hres)
     got = res.to_columnar()
     res.free()
-    hit = pk < nb
+    inv = {int(k): i for i, k in enumerate(bk)}
+    hit = np.array([int(k) in inv for k in pk])
     assert got.num_rows == int(hit.sum())
-    inv = np.empty(nb, dtype=np.int64)
-    inv[bk] = np.arange(nb)
-    want_rows = H.sort_rows([(int(k), int(ba[inv[k]]), (int(v) if ok else None)) for k, v, ok in zip(pk[hit], pb[hit], pvalid[hit])])
+    def build_val(k):
+        i = inv[int(k)]
+        return int(ba[i]) if bvalid is None or bvalid[i] else None
+    want_rows = H.sort_rows([(int(k), build_val(k), (int(v) if ok else None)) for k, v, ok in zip(pk[hit], pb[hit], pvalid[hit])])
     assert H.rows_of(got) == want_rows
