@@ -1408,7 +1408,7 @@ std::unique_ptr<rj_result> Exec::root_fused(uint64_t n) {
     Buf counters = dev_alloc_zero(32, s); // chunk counter @0, abort flag @4, rows @8
     L.bkeys = B.keys->as<uint32_t>();
     L.pkeys = P.keys->as<uint32_t>();
-    L.off_b = pl.off_b; L.off_p = pl.off_p; L.unit_start = pl.unit_start; L.unit_cursor = pl.unit_cursor;
+    L.off_b = pl.off_b; L.off_p = pl.off_p; L.unit_start = pl.unit_start; L.unit_cursor = pl.unit_cursor; L.unit_part = pl.unit_part;
     L.nparts = nparts; L.part_bits = bits;
     for (int c = 0; c < L.n_bpay; ++c) {
         L.bpay[c] = B.val[c]->p;
@@ -2994,7 +2994,7 @@ std::unique_ptr<rj_result> join_partitioned_impl(rj_ctx* ctx, const rj_part_side
         Buf counters = dev_alloc_zero(32, s); // chunk counter @0, abort flag @4, rows @8
         L.bkeys = B.keys;
         L.pkeys = P.keys;
-        L.off_b = pl.off_b; L.off_p = pl.off_p; L.unit_start = pl.unit_start; L.unit_cursor = pl.unit_cursor;
+        L.off_b = pl.off_b; L.off_p = pl.off_p; L.unit_start = pl.unit_start; L.unit_cursor = pl.unit_cursor; L.unit_part = pl.unit_part; L.unit_part = pl.unit_part;
         L.nparts = nparts;
         L.part_bits = hash_bits;
         for (int c = 0; c < L.n_bpay; ++c) { L.bpay[c] = B.val[c]; L.bvalid[c] = B.ok[c]; }

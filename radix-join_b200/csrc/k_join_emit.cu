@@ -24,13 +24,13 @@ static size_t join_emit_layout(const JoinEmitLaunch& L, EmitArgs* a) {
     EmitArgs& r = a ? *a : tmp;
     for (int c = 0; c < L.n_bpay; ++c) r.sm_bpay[c] = take(size_t(kEmitBuildCap) * L.bwidth[c] + 16);
     for (int c = 0; c < L.n_bpay; ++c) r.sm_bvalid[c] = L.bvalid[c] ? take(kEmitBuildCap + 16) : 0;
-    // two probe buffers of identical layout
+    // kStages probe buffers of identical layout
     r.sm_pkeys = take(size_t(kBatch) * 4 + 16);
     for (int c = 0; c < L.n_ppay; ++c) r.sm_ppay[c] = take(size_t(kBatch) * L.pwidth[c] + 16);
     for (int c = 0; c < L.n_ppay; ++c) r.sm_pvalid[c] = L.pvalid[c] ? take(kBatch + 16) : 0;
     off = (off + 15) / 16 * 16;
     r.sm_pstride = static_cast<uint32_t>(off - r.sm_pkeys);
-    return off + r.sm_pstride;
+    return off + size_t(emit::kStages - 1) * r.sm_pstride;
 }
 
 bool join_emit_fits(const JoinEmitLaunch& L) {
@@ -42,6 +42,7 @@ void launch_join_emit(const JoinEmitLaunch& L, uint64_t n_probe, int sm_count, c
     EmitArgs a{};
     a.bkeys = L.bkeys; a.pkeys = L.pkeys; a.off_b = L.off_b; a.off_p = L.off_p;
     a.unit_start = L.unit_start; a.unit_cursor = L.unit_cursor; a.nparts = L.nparts; a.part_bits = L.part_bits;
+    a.unit_part = L.unit_part; a.unit_part_cap = L.unit_part ? 2 * L.nparts : 0;
     a.probe_chunk = kEmitProbeChunk;
     int null_mask = 0, width_mask = 0;
     for (int c = 0; c < kEmitMaxPay; ++c) {

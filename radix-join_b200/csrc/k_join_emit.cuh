@@ -12,12 +12,13 @@
 // build columns up in shared memory, and stores finished rows into the result pages.  No pair list, no
 // gather, no separate encode pass.
 //
-// Memory pipeline.  A unit's probe tuples are consumed in batches of 2048; the keys, carried values and
-// validity bytes of a batch arrive by 1-D TMA bulk copies into one of two shared-memory buffers.  A buffer
-// is handed back by its 16 consumer warps through an mbarrier (one arrival per warp), so warps never wait
-// for one another inside a unit: only the thread that requests the next batch waits for the slowest
-// reader of the buffer it is about to overwrite.  The build side's carried columns arrive by TMA while the
-// hash table is being filled.
+// Memory pipeline.  A unit's probe tuples are consumed in batches of 512 (one ITEM of 32 tuples per warp); the
+// keys, carried values and validity bytes of a batch arrive by 1-D TMA bulk copies into one of eight
+// shared-memory buffers.  A buffer is handed back by its 16 consumer warps through an mbarrier (one arrival per
+// warp), so warps never wait for one another inside a unit; the thread that requests batches does so as far
+// ahead as buffers are free and never waits for a reader unless the batch it needs itself is missing.  (With
+// two buffers of 2048 tuples that thread waited for the slowest reader at every batch, became the slowest
+// itself, and the whole CTA marched in its step: ~10 polls of the barrier per item.)
 //
 // Result pages.  Row alignment across columns (include/plan.h:102-105: columns are row-aligned by
 // cumulative row index, page boundaries are free) is kept by emitting CHUNKS of 1984 rows: one page of
@@ -57,8 +58,10 @@ constexpr uint32_t kSlots      = kEmitSlots;       // 4096 x 64-bit (key | local
 constexpr uint32_t kSlotMask   = kSlots - 1;
 constexpr uint32_t kCap        = kEmitBuildCap;    // 3072 build tuples per table (75 % fill)
 constexpr int      kBuildItems = kCap / kThreads;  // 6
-constexpr int      kItems      = 4;                // probe tuples per thread and batch
-constexpr uint32_t kBatch      = kItems * kThreads;
+constexpr int      kConsumers  = kWarps - 1;       // warps that probe; the last warp requests the data and looks the next unit up
+constexpr uint32_t kBatch      = kConsumers * 32;  // probe tuples per batch: one ITEM of 32 per consumer warp
+constexpr uint32_t kStages     = 8;                // probe batches in flight per CTA (power of two)
+constexpr uint32_t kUpFront    = 4;                // batches requested before the table is built (the others: while it is probed)
 constexpr uint32_t kChunkRows  = kEmitChunkRows;   // 1984 = 62 bitmap words
 constexpr uint32_t kHalfRows   = kChunkRows / 2;   // 992 rows per 8-byte page = 31 bitmap words
 constexpr uint32_t kHalfWords  = kHalfRows / 32;
@@ -75,6 +78,8 @@ struct EmitArgs {
     const uint32_t* off_p;
     const uint32_t* unit_start;
     uint32_t*       unit_cursor;
+    const uint32_t* unit_part;     // partition of unit u for u < unit_part_cap
+    uint32_t        unit_part_cap;
     uint32_t        nparts;
     int             part_bits;
     uint32_t        probe_chunk; // probe tuples per work unit
@@ -126,8 +131,8 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     auto bwide = [&](int c) -> bool { return WM >= 0 ? ((WM >> c) & 1) != 0 : a.bwidth[c] == 8; };
     auto pwide = [&](int c) -> bool { return WM >= 0 ? ((WM >> (kEmitMaxPay + c)) & 1) != 0 : a.pwidth[c] == 8; };
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t s_unit, s_part;
-    __shared__ __align__(8) uint64_t s_bbar, s_full[2], s_empty[2];
+    __shared__ uint32_t s_desc[2][6]; // [round & 1]: the round's unit -- its number, then unit_start / off_b / off_b+1 / off_p / off_p+1 of its partition
+    __shared__ __align__(8) uint64_t s_bbar, s_full[kStages], s_empty[kStages];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt = lanemask_lt();
@@ -135,10 +140,10 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     const int      part_bits = a.part_bits;
     if (tid == 0) {
         mbar_init(&s_bbar, 1);
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        mbar_init(&s_empty[0], kWarps);
-        mbar_init(&s_empty[1], kWarps);
+        for (uint32_t st = 0; st < kStages; ++st) {
+            mbar_init(&s_full[st], 1);
+            mbar_init(&s_empty[st], kConsumers);
+        }
         fence_mbar_init();
     }
     uint32_t unit_no = 0, batch_no = 0; // mbarrier phases
@@ -179,11 +184,11 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     };
 
     // one batch of probe tuples [base, base + cnt) into its buffer (one thread).  q = the batch's number: the
-    // buffer was last used by batch q - 2, whose readers hand it back through s_empty
+    // buffer was last used by batch q - kStages, whose readers hand it back through s_empty
     auto issue_probe = [&](uint32_t q, uint32_t base, uint32_t cnt) {
-        const int s = q & 1;
-        uint8_t* const buf = smem + (s ? a.sm_pstride : 0u);
-        if (q >= 2) mbar_wait(&s_empty[s], ((q >> 1) - 1) & 1);
+        const uint32_t s = q & (kStages - 1);
+        uint8_t* const buf = smem + s * a.sm_pstride;
+        if (q >= kStages) mbar_wait(&s_empty[s], ((q / kStages) - 1) & 1);
         uint32_t bytes = round16((cnt + (base & 3u)) * 4u);
         uint32_t pb[kEmitMaxPay] = {}, vb[kEmitMaxPay] = {};
 #pragma unroll
@@ -273,48 +278,83 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
         });
     };
 
-    uint32_t u_next = 0;
-    if (tid == 0) u_next = atomicAdd(a.unit_cursor, 1u);
-    for (;;) {
-        // ---- next work unit, in global order (see k_join.cu); the cursor was advanced one unit ahead --------
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t u = __shfl_sync(RJ_FULL_MASK, u_next, 0);
-            if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(a.abort_flag)) u = 0xffffffffu; // somebody met a duplicate key
-            u = __shfl_sync(RJ_FULL_MASK, u, 0);
-            uint32_t lo = 0, hi = a.nparts;
-            if (u < n_units) {
-                while (hi - lo > 1) {
-                    const uint32_t span = hi - lo;
-                    const uint32_t step = (span + 31) / 32;
-                    const uint32_t probe = lo + (lane + 1) * step;
-                    const bool     le = probe < hi && a.unit_start[probe] <= u;
-                    const uint32_t k = __popc(__ballot_sync(RJ_FULL_MASK, le));
-                    const uint32_t nlo = lo + k * step;
-                    const uint32_t nhi = (k < 32 && lo + (k + 1) * step < hi) ? lo + (k + 1) * step : hi;
-                    lo = nlo;
-                    hi = nhi;
-                }
-                if (lane == 0) u_next = atomicAdd(a.unit_cursor, 1u); // returns while this unit is being processed
-            }
-            if (lane == 0) {
-                s_unit = u;
-                s_part = lo;
-            }
+    // a chunk for the rows that are about to be placed
+    auto ensure_open = [&]() {
+        if (c_open == kNone) {
+            if (!have_next && lane == 0) c_next = atomicAdd(a.chunk_counter, 1u);
+            c_open = __shfl_sync(RJ_FULL_MASK, c_next, 0);
+            have_next = false;
+            cb_key = a.src_pages[0] + static_cast<uint64_t>(c_open) * RJ_PAGE;
+            for_build([&](auto c_c, auto) { cb_b[decltype(c_c)::value] = a.src_pages[1 + decltype(c_c)::value] + static_cast<uint64_t>(c_open) * (bwide(decltype(c_c)::value) ? 2 * RJ_PAGE : RJ_PAGE); });
+            for_probe([&](auto c_c, auto) { cb_p[decltype(c_c)::value] = a.src_pages[1 + kEmitMaxPay + decltype(c_c)::value] + static_cast<uint64_t>(c_open) * (pwide(decltype(c_c)::value) ? 2 * RJ_PAGE : RJ_PAGE); });
         }
-        __syncthreads();
-        const uint32_t u = s_unit;
+    };
+    // rows have been placed: close the chunk when it is full, reserve the next one shortly before
+    auto after_place = [&]() {
+        if (rows == kChunkRows) {
+            write_meta(c_open, kChunkRows);
+            ++closed;
+            c_open = kNone;
+            rows = 0;
+#pragma unroll
+            for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = held[nn] = 0u;
+        } else if (!have_next && rows >= kReserveAt) {
+            if (lane == 0) c_next = atomicAdd(a.chunk_counter, 1u); // consumed when the open chunk closes
+            have_next = true;
+        }
+    };
+
+    // Work units are handed out in global order (see k_join.cu) by an atomic cursor.  The producer warp's first
+    // lane looks the NEXT unit up while the consumers probe the current one, so none of its dependent global loads
+    // (cursor -> the unit's partition -> the partition's offsets) is ever waited for by the CTA; it leaves the
+    // descriptor in s_desc[next round & 1] and pulls the unit's build tuples towards L2.
+    auto lookup_unit = [&](uint32_t* d) { // one thread
+        uint32_t u = atomicAdd(a.unit_cursor, 1u);
+        if (*reinterpret_cast<volatile uint32_t*>(a.abort_flag)) u = 0xffffffffu; // somebody met a duplicate key
+        d[0] = u;
+        if (u >= n_units) return;
+        uint32_t part;
+        if (u < a.unit_part_cap) {
+            part = a.unit_part[u];
+        } else { // beyond the table (heavily skewed partitions): unit_start[lo] <= u < unit_start[hi]
+            uint32_t lo = 0, hi = a.nparts;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (a.unit_start[mid] <= u) lo = mid; else hi = mid;
+            }
+            part = lo;
+        }
+        const uint32_t us = a.unit_start[part], blo = a.off_b[part], bhi = a.off_b[part + 1], plo = a.off_p[part], phi = a.off_p[part + 1];
+        d[1] = us; d[2] = blo; d[3] = bhi; d[4] = plo; d[5] = phi;
+        // the unit's build tuples towards L2 (its probe tuples are requested by TMA while the table is built)
+        const uint32_t n_pc = (phi - plo + a.probe_chunk - 1) / a.probe_chunk;
+        const uint32_t bs_n = blo + ((u - us) / n_pc) * kCap;
+        const uint32_t nb_n = bhi - bs_n > kCap ? kCap : bhi - bs_n;
+        prefetch_l2_bulk(a.bkeys + (bs_n & ~3u), round16((nb_n + 3u) * 4u));
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            const uint32_t w = bwide(c) ? 8u : 4u;
+            prefetch_l2_bulk(static_cast<const char*>(a.bpay[c]) + static_cast<uint64_t>(bs_n & ~3u) * w, round16((nb_n + 3u) * w));
+            if ((NM >> c) & 1) prefetch_l2_bulk(a.bvalid[c] + (bs_n & ~15u), round16(nb_n + 15u));
+        }
+    };
+    const bool producer = (tid >> 5) == static_cast<uint32_t>(kConsumers);
+    if (producer && lane == 0) lookup_unit(s_desc[0]);
+    for (uint32_t round = 0;; ++round) {
+        __syncthreads(); // every warp is done with the previous unit's table and columns; this round's descriptor is in place
+        const uint32_t* const dsc = s_desc[round & 1];
+        const uint32_t u = dsc[0];
         if (u >= n_units) break;
-        const uint32_t part = s_part;
-        const uint32_t local = u - a.unit_start[part];
-        const uint32_t b_lo = a.off_b[part], b_hi = a.off_b[part + 1];
-        const uint32_t p_lo = a.off_p[part], p_hi = a.off_p[part + 1];
+        const uint32_t local = u - dsc[1];
+        const uint32_t b_lo = dsc[2], b_hi = dsc[3];
+        const uint32_t p_lo = dsc[4], p_hi = dsc[5];
         const uint32_t n_pchunks = (p_hi - p_lo + a.probe_chunk - 1) / a.probe_chunk;
         const uint32_t bc = local / n_pchunks, pc = local - bc * n_pchunks;
         const uint32_t bs = b_lo + bc * kCap;
         const uint32_t nb = (b_hi - bs > kCap) ? kCap : b_hi - bs;
         const uint32_t ps = p_lo + pc * a.probe_chunk;
         const uint32_t pe = (p_hi - ps > a.probe_chunk) ? ps + a.probe_chunk : p_hi;
+        const uint32_t n_batches = (pe - ps + kBatch - 1) / kBatch;
 
         // ---- build: the first probe batch is requested, then the table is filled ------------------------------
         // Two kinds of table.
@@ -328,8 +368,8 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
         //   ran as long as the unluckiest of 32 lanes: ~4 rounds at 50 % fill).  The carried build columns are
         //   stored by rank.  A duplicate build key shows up as a bit that is already set.
         const int      rem_words_log = 32 - part_bits - 5;             // direct: 2^(32 - part_bits) bits
-        const uint32_t bskew8 = direct ? 0u : (bs & 1u), bskew4 = direct ? 0u : (bs & 3u), bskew1 = direct ? 0u : (bs & 15u);
-        if (tid == 0) {
+        const uint32_t bskew1 = direct ? 0u : (bs & 15u); // TMA windows start on a 16-byte boundary: elements to skip
+        if (producer && lane == 0) {
             // (the barrier at the top of the loop ended every read of the previous unit's table and columns)
             if (NB > 0 && !direct) {
                 uint32_t bytes = 0, pb[kEmitMaxPay] = {}, vb[kEmitMaxPay] = {};
@@ -349,7 +389,10 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                     if (vb[c]) tma_load_1d(smem + a.sm_bvalid[c], a.bvalid[c] + (bs - (bs & 15u)), vb[c], &s_bbar);
                 }
             }
-            if (ps < pe) issue_probe(batch_no, ps, pe - ps < kBatch ? pe - ps : kBatch);
+            for (uint32_t j = 0; j < kUpFront && j < n_batches; ++j) {
+                const uint32_t base = ps + j * kBatch;
+                issue_probe(batch_no + j, base, pe - base < kBatch ? pe - base : kBatch);
+            }
         }
         uint32_t bkey[kBuildItems];
 #pragma unroll
@@ -446,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
             // CTA's shared memory before it retires)
             if (tid == 0) atomicExch(a.abort_flag, 1u);
             if (NB > 0 && !direct) mbar_wait(&s_bbar, unit_no & 1);
-            if (ps < pe) mbar_wait(&s_full[batch_no & 1], (batch_no >> 1) & 1);
+            for (uint32_t j = 0; j < kUpFront && j < n_batches; ++j) mbar_wait(&s_full[(batch_no + j) & (kStages - 1)], ((batch_no + j) / kStages) & 1);
             return;
         }
         if (NB > 0 && !direct) {
@@ -455,50 +498,54 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
         }
 
         // ---- probe ------------------------------------------------------------------------------------------
-        for (uint32_t base = ps; base < pe; base += kBatch, ++batch_no) {
-            const int      sb = batch_no & 1;
-            const uint32_t cnt = pe - base < kBatch ? pe - base : kBatch;
-            if (tid == 0 && base + kBatch < pe) {
-                const uint32_t nbase = base + kBatch;
-                issue_probe(batch_no + 1, nbase, pe - nbase < kBatch ? pe - nbase : kBatch);
+        if (producer) {
+            // the data: every further batch as soon as its buffer is free; then the next unit
+            if (lane == 0) {
+                for (uint32_t j = kUpFront; j < n_batches; ++j) {
+                    const uint32_t base = ps + j * kBatch;
+                    issue_probe(batch_no + j, base, pe - base < kBatch ? pe - base : kBatch);
+                }
+                lookup_unit(s_desc[(round + 1) & 1]);
             }
             __syncwarp();
-            mbar_wait(&s_full[sb], (batch_no >> 1) & 1);
-            const uint8_t* const  buf = smem + (sb ? a.sm_pstride : 0u);
-            const uint32_t* const pk = reinterpret_cast<const uint32_t*>(buf + a.sm_pkeys) + (base & 3u);
-
-#pragma unroll
-            for (int k = 0; k < kItems; ++k) {
-                const uint32_t i = k * kThreads + tid;
-                const uint32_t key = pk[i]; // past cnt: stale bytes, never used
-                uint32_t lidx = kNone;
-                if (direct) {
-                    // the remaining hash bits identify the key: one load, a bit test, a popcount
-                    const uint32_t x = hash_key(key) >> part_bits;
-                    const uint2    e = reinterpret_cast<const uint2*>(smem)[x >> 5];
-                    const uint32_t below = e.x & ((1u << (x & 31u)) - 1u);
-                    if (i < cnt && ((e.x >> (x & 31u)) & 1u)) lidx = e.y + __popc(below);
-                } else if (i < cnt) {
-                    // at most one match: the table holds distinct keys.  A slot is (key, build index); an empty
-                    // one has index 0xffffffff
-                    uint32_t       off   = ((hash_key(key) >> part_bits) & kSlotMask) * 8u;
-                    const uint32_t step8 = probe_step(key) * 8u;
-                    for (;;) {
-                        uint32_t ex, ey;
-                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(smem_u32(smem) + off));
-                        if (ey == kNone) break;
-                        if (ex == key) {
-                            lidx = ey;
-                            break;
-                        }
-                        off = (off + step8) & (kSlotMask * 8u);
+            batch_no += n_batches;
+            continue;
+        }
+        for (uint32_t j = 0; j < n_batches; ++j, ++batch_no) {
+            const uint32_t base = ps + j * kBatch;
+            const uint32_t cnt = pe - base < kBatch ? pe - base : kBatch;
+            const uint32_t stage = batch_no & (kStages - 1);
+            mbar_wait(&s_full[stage], (batch_no / kStages) & 1);
+            const uint8_t* const  buf = smem + stage * a.sm_pstride;
+            const uint32_t        i = tid; // one tuple per thread and batch: an ITEM = the 32 tuples of a warp
+            const uint32_t        key = (reinterpret_cast<const uint32_t*>(buf + a.sm_pkeys) + (base & 3u))[i]; // past cnt: stale bytes, never used
+            uint32_t lidx = kNone;
+            if (direct) {
+                // the remaining hash bits identify the key: one load, a bit test, a popcount
+                const uint32_t x = hash_key(key) >> part_bits;
+                const uint2    e = reinterpret_cast<const uint2*>(smem)[x >> 5];
+                const uint32_t below = e.x & ((1u << (x & 31u)) - 1u);
+                if (i < cnt && ((e.x >> (x & 31u)) & 1u)) lidx = e.y + __popc(below);
+            } else if (i < cnt) {
+                // at most one match: the table holds distinct keys.  A slot is (key, build index); an empty
+                // one has index 0xffffffff
+                uint32_t       off   = ((hash_key(key) >> part_bits) & kSlotMask) * 8u;
+                const uint32_t step8 = probe_step(key) * 8u;
+                for (;;) {
+                    uint32_t ex, ey;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(smem_u32(smem) + off));
+                    if (ey == kNone) break;
+                    if (ex == key) {
+                        lidx = ey;
+                        break;
                     }
+                    off = (off + step8) & (kSlotMask * 8u);
                 }
-                __syncwarp();
-                bool           act = lidx != kNone;
-                const uint32_t bal = __ballot_sync(RJ_FULL_MASK, act);
-                if (bal == 0) continue;
-
+            }
+            __syncwarp();
+            bool           act = lidx != kNone;
+            const uint32_t bal = __ballot_sync(RJ_FULL_MASK, act);
+            if (bal != 0) {
                 // the row's validity in the nullable columns, and its values
                 bool ok[NNX];
                 uint64_t bval[NB > 0 ? NB : 1], pval[NP > 0 ? NP : 1];
@@ -507,8 +554,8 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                     const uint32_t at = act ? lidx : 0u;
                     if constexpr (N >= 0) ok[N] = act && (smem + a.sm_bvalid[C] + bskew1)[at] != 0;
                     const uint8_t* col = smem + a.sm_bpay[C];
-                    if (bwide(C)) bval[C] = (reinterpret_cast<const uint64_t*>(col) + bskew8)[at];
-                    else bval[C] = (reinterpret_cast<const uint32_t*>(col) + bskew4)[at];
+                    if (bwide(C)) bval[C] = (reinterpret_cast<const uint64_t*>(col) + (bskew1 & 1u))[at];
+                    else bval[C] = (reinterpret_cast<const uint32_t*>(col) + (bskew1 & 3u))[at];
                 });
                 for_probe([&](auto c_c, auto n_c) {
                     constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
@@ -518,119 +565,149 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                     else pval[C] = (reinterpret_cast<const uint32_t*>(col) + (base & 3u))[i];
                 });
 
-                // place the matched rows: row index in the open chunk; rows past its end go to the next one
+                // place the matched rows: row index in the open chunk; rows past its end go to the next one (a second
+                // round)
                 uint32_t r = rows + __popc(bal & lt);
                 uint32_t left = __popc(bal);
                 for (;;) {
-                    if (c_open == kNone) {
-                        if (!have_next && lane == 0) c_next = atomicAdd(a.chunk_counter, 1u);
-                        c_open = __shfl_sync(RJ_FULL_MASK, c_next, 0);
-                        have_next = false;
-                        cb_key = a.src_pages[0] + static_cast<uint64_t>(c_open) * RJ_PAGE;
-                        for_build([&](auto c_c, auto) { cb_b[decltype(c_c)::value] = a.src_pages[1 + decltype(c_c)::value] + static_cast<uint64_t>(c_open) * (bwide(decltype(c_c)::value) ? 2 * RJ_PAGE : RJ_PAGE); });
-                        for_probe([&](auto c_c, auto) { cb_p[decltype(c_c)::value] = a.src_pages[1 + kEmitMaxPay + decltype(c_c)::value] + static_cast<uint64_t>(c_open) * (pwide(decltype(c_c)::value) ? 2 * RJ_PAGE : RJ_PAGE); });
-                    }
-                    const bool     now = act && r < kChunkRows;
-                    const uint32_t nowb = __ballot_sync(RJ_FULL_MASK, now);
-                    const uint32_t n_now = __popc(nowb);
-                    uint32_t okb[NNX], v[NNX];
-#pragma unroll
-                    for (int nn = 0; nn < NN; ++nn) {
-                        okb[nn] = __ballot_sync(RJ_FULL_MASK, now && ok[nn]);
-                        v[nn]   = nv[nn] + __popc(okb[nn] & lt);
-                    }
-                    if (NN > 0 && rows < kHalfRows && rows + n_now >= kHalfRows) {
-                        // the rows of this round reach the second page of the 8-byte columns
-                        const uint32_t lowb = __ballot_sync(RJ_FULL_MASK, now && r < kHalfRows);
-#pragma unroll
-                        for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn] + __popc(okb[nn] & lowb);
-                    }
-                    const uint32_t w0 = rows >> 5, sh = rows & 31u; // the bitmap word the round's first row falls into
-                    // One source's value into every output column that shows it, and -- for a nullable source -- the
-                    // validity bits of the rows placed now (rows [rows, rows + n_now) of the chunk: two bitmap words at
-                    // most).  A complete word stays with lane (w & 31) until 31 / 32 of them (one page's worth, or the
-                    // chunk's second half) go out in one store.  N = index among the nullable columns, -1: the source
-                    // holds no NULL.  kOnce: every source is shown by exactly one output column, whose chunk base is cb.
-                    auto emit = [&](auto once_c, auto n_c, int S, bool wide, uint64_t val, uint8_t* cb) {
-                        constexpr int  N = decltype(n_c)::value;
-                        constexpr bool kOnce = decltype(once_c)::value;
-                        bool st = now;
-                        if constexpr (N >= 0) st = now && ok[N];
-                        uint32_t at; // value slot, in units of the value width, from the chunk's first data byte
-                        if (wide) {
-                            const bool h = r >= kHalfRows;
-                            if constexpr (N >= 0) at = v[N] - (h ? nvh[N] : 0u); else at = r - (h ? kHalfRows : 0u);
-                            at += h ? RJ_PAGE / 8 : 0u;
-                        } else {
-                            if constexpr (N >= 0) at = v[N]; else at = r;
-                        }
-                        bool flush = false;
-                        if constexpr (N >= 0) {
-                            uint32_t lo, hi;
-                            if (nowb == RJ_FULL_MASK) { // rows are the lanes in order
-                                lo = okb[N] << sh;
-                                hi = sh ? okb[N] >> (32u - sh) : 0u;
-                            } else {
-                                const uint32_t bit = st ? (1u << (r & 31u)) : 0u;
-                                const bool     first = (r >> 5) == w0;
-                                lo = __reduce_or_sync(RJ_FULL_MASK, first ? bit : 0u);
-                                hi = __reduce_or_sync(RJ_FULL_MASK, first ? 0u : bit);
-                            }
-                            const uint32_t word = pend[N] | lo;
-                            const bool     complete = sh + n_now >= 32u;
-                            pend[N] = complete ? hi : word;
-                            if (complete && lane == (w0 & 31u)) held[N] = word;
-                            flush = complete && (w0 == (wide ? kHalfWords - 1 : 31u) || w0 == kChunkRows / 32 - 1);
-                        }
-                        auto store = [&](uint8_t* base) {
-                            if (wide) {
-                                if (st) (reinterpret_cast<uint64_t*>(base + 8))[at] = val;
-                            } else {
-                                if (st) (reinterpret_cast<uint32_t*>(base + 4))[at] = static_cast<uint32_t>(val);
-                            }
+                    ensure_open();
+                    if (all_once && left == 32u && rows + 32u <= (rows < kHalfRows ? kHalfRows : kChunkRows)) {
+                        // DENSE item (every lane matched -- the rule in a key / foreign-key join) that lies inside one page
+                        // of every column: rows are the lanes in order and complete exactly one bitmap word.  Everything
+                        // but the value slots is warp-uniform.  (The two items of a chunk that straddle row 992 or 1984,
+                        // and items with unmatched lanes, take the general round below.)
+                        const bool     h = rows >= kHalfRows;
+                        const uint32_t w0 = rows >> 5, sh = rows & 31u;
+                        auto dense = [&](auto n_c, bool wide, uint64_t val, uint8_t* cb) {
+                            constexpr int N = decltype(n_c)::value;
+                            uint32_t at;
+                            bool     st = true;
                             if constexpr (N >= 0) {
-                                if (flush) {
-                                    // lane l holds word wl = the largest w <= w0 with (w & 31) == l; the words up to the
-                                    // first flush point went out then
+                                const uint32_t okb = __ballot_sync(RJ_FULL_MASK, ok[N]);
+                                st = ok[N];
+                                at = nv[N] + __popc(okb & lt);
+                                if (wide && h) at += RJ_PAGE / 8 - nvh[N];
+                                nv[N] += __popc(okb);
+                                if (lane == (w0 & 31u)) held[N] = pend[N] | (okb << sh);
+                                pend[N] = sh ? okb >> (32u - sh) : 0u;
+                                const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
+                                if (w0 == first_flush || w0 == kChunkRows / 32 - 1) {
                                     const uint32_t wl = w0 - ((w0 - lane) & 31u);
-                                    const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
-                                    const bool     mine = wl <= w0 && (w0 == first_flush || wl > first_flush); // (wl wraps above w0 when no such word exists)
-                                    if (mine) *bitmap_word(base, wide, wl) = held[N];
+                                    if (wl <= w0 && (w0 == first_flush || wl > first_flush)) *bitmap_word(cb, wide, wl) = held[N];
                                 }
+                            } else {
+                                at = rows + lane;
+                                if (wide && h) at += RJ_PAGE / 8 - kHalfRows;
+                            }
+                            if (wide) {
+                                if (st) (reinterpret_cast<uint64_t*>(cb + 8))[at] = val;
+                            } else {
+                                if (st) (reinterpret_cast<uint32_t*>(cb + 4))[at] = static_cast<uint32_t>(val);
                             }
                         };
-                        if constexpr (kOnce) store(cb);
-                        else for_outputs(S, wide, c_open, store);
-                    };
-                    auto emit_all = [&](auto once_c) {
-                        emit(once_c, std::integral_constant<int, -1>{}, 0, false, key, cb_key);
-                        for_build([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + decltype(c_c)::value, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
-                        for_probe([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + kEmitMaxPay + decltype(c_c)::value, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
-                    };
-                    if (all_once) emit_all(std::true_type{}); else emit_all(std::false_type{});
-                    rows += n_now;
-                    left -= n_now;
+                        dense(std::integral_constant<int, -1>{}, false, key, cb_key);
+                        for_build([&](auto c_c, auto n_c) { dense(n_c, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
+                        for_probe([&](auto c_c, auto n_c) { dense(n_c, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
+                        rows += 32u;
+                        left = 0;
+                        if (NN > 0 && rows == kHalfRows) { // the 8-byte columns' first page is complete
 #pragma unroll
-                    for (int nn = 0; nn < NN; ++nn) nv[nn] += __popc(okb[nn]);
-                    if (rows == kChunkRows) {
-                        write_meta(c_open, kChunkRows);
-                        ++closed;
-                        c_open = kNone;
-                        rows = 0;
+                            for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn];
+                        }
+                    } else {
+                        const bool     now = act && r < kChunkRows;
+                        const uint32_t nowb = __ballot_sync(RJ_FULL_MASK, now);
+                        const uint32_t n_now = __popc(nowb);
+                        uint32_t okb[NNX], v[NNX];
 #pragma unroll
-                        for (int nn = 0; nn < NNX; ++nn) nv[nn] = nvh[nn] = pend[nn] = held[nn] = 0u;
-                    } else if (!have_next && rows >= kReserveAt) {
-                        if (lane == 0) c_next = atomicAdd(a.chunk_counter, 1u); // consumed when the open chunk closes
-                        have_next = true;
+                        for (int nn = 0; nn < NN; ++nn) {
+                            okb[nn] = __ballot_sync(RJ_FULL_MASK, now && ok[nn]);
+                            v[nn]   = nv[nn] + __popc(okb[nn] & lt);
+                        }
+                        if (NN > 0 && rows < kHalfRows && rows + n_now >= kHalfRows) {
+                            // the rows of this round reach the second page of the 8-byte columns
+                            const uint32_t lowb = __ballot_sync(RJ_FULL_MASK, now && r < kHalfRows);
+#pragma unroll
+                            for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn] + __popc(okb[nn] & lowb);
+                        }
+                        const uint32_t w0 = rows >> 5, sh = rows & 31u; // the bitmap word the round's first row falls into
+                        // One source's value into every output column that shows it, and -- for a nullable source -- the
+                        // validity bits of the rows placed now (rows [rows, rows + n_now) of the chunk: two bitmap words
+                        // at most).  A complete word stays with lane (w & 31) until 31 / 32 of them (one page's worth, or
+                        // the chunk's second half) go out in one store.  N = index among the nullable columns, -1: the
+                        // source holds no NULL.  kOnce: every source is shown by exactly one output column, whose chunk
+                        // base is cb.
+                        auto emit = [&](auto once_c, auto n_c, int S, bool wide, uint64_t val, uint8_t* cb) {
+                            constexpr int  N = decltype(n_c)::value;
+                            constexpr bool kOnce = decltype(once_c)::value;
+                            bool st = now;
+                            if constexpr (N >= 0) st = now && ok[N];
+                            uint32_t at; // value slot, in units of the value width, from the chunk's first data byte
+                            if (wide) {
+                                const bool h = r >= kHalfRows;
+                                if constexpr (N >= 0) at = v[N] - (h ? nvh[N] : 0u); else at = r - (h ? kHalfRows : 0u);
+                                at += h ? RJ_PAGE / 8 : 0u;
+                            } else {
+                                if constexpr (N >= 0) at = v[N]; else at = r;
+                            }
+                            bool flush = false;
+                            if constexpr (N >= 0) {
+                                uint32_t lo, hi;
+                                if (nowb == RJ_FULL_MASK) { // rows are the lanes in order
+                                    lo = okb[N] << sh;
+                                    hi = sh ? okb[N] >> (32u - sh) : 0u;
+                                } else {
+                                    const uint32_t bit = st ? (1u << (r & 31u)) : 0u;
+                                    const bool     first = (r >> 5) == w0;
+                                    lo = __reduce_or_sync(RJ_FULL_MASK, first ? bit : 0u);
+                                    hi = __reduce_or_sync(RJ_FULL_MASK, first ? 0u : bit);
+                                }
+                                const uint32_t word = pend[N] | lo;
+                                const bool     complete = sh + n_now >= 32u;
+                                pend[N] = complete ? hi : word;
+                                if (complete && lane == (w0 & 31u)) held[N] = word;
+                                flush = complete && (w0 == (wide ? kHalfWords - 1 : 31u) || w0 == kChunkRows / 32 - 1);
+                            }
+                            auto store = [&](uint8_t* base_page) {
+                                if (wide) {
+                                    if (st) (reinterpret_cast<uint64_t*>(base_page + 8))[at] = val;
+                                } else {
+                                    if (st) (reinterpret_cast<uint32_t*>(base_page + 4))[at] = static_cast<uint32_t>(val);
+                                }
+                                if constexpr (N >= 0) {
+                                    if (flush) {
+                                        // lane l holds word wl = the largest w <= w0 with (w & 31) == l; the words up to
+                                        // the first flush point went out then
+                                        const uint32_t wl = w0 - ((w0 - lane) & 31u);
+                                        const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
+                                        const bool     mine = wl <= w0 && (w0 == first_flush || wl > first_flush); // (wl wraps above w0 when no such word exists)
+                                        if (mine) *bitmap_word(base_page, wide, wl) = held[N];
+                                    }
+                                }
+                            };
+                            if constexpr (kOnce) store(cb);
+                            else for_outputs(S, wide, c_open, store);
+                        };
+                        auto emit_all = [&](auto once_c) {
+                            emit(once_c, std::integral_constant<int, -1>{}, 0, false, key, cb_key);
+                            for_build([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + decltype(c_c)::value, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
+                            for_probe([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + kEmitMaxPay + decltype(c_c)::value, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
+                        };
+                        if (all_once) emit_all(std::true_type{}); else emit_all(std::false_type{});
+                        rows += n_now;
+                        left -= n_now;
+#pragma unroll
+                        for (int nn = 0; nn < NN; ++nn) nv[nn] += __popc(okb[nn]);
+                        act = act && !now;
+                        r -= kChunkRows; // (meaningful for the rows of a second round only)
                     }
+                    after_place();
                     if (left == 0) break;
-                    act = act && !now;
-                    r -= kChunkRows;
                 }
             }
             // this warp is done with the batch's buffer
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[sb]);
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
         }
     }
     // the partly filled chunk of this warp, and the chunk it may hold in reserve (an empty one)

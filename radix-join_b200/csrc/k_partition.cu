@@ -181,6 +181,12 @@ __global__ void __launch_bounds__(kPlanThreads)
         if (nb == 0 || np == 0) return 0u;
         return ((nb + build_cap - 1) / build_cap) * ((np + probe_chunk - 1) / probe_chunk);
     });
+    // unit -> partition for the first 2 * nparts units: the join kernels look a unit up with one load instead of a
+    // search over unit_start
+    for (uint32_t i = threadIdx.x; i < nparts; i += kPlanThreads) {
+        const uint32_t hi = plan.unit_start[i + 1] < 2 * nparts ? plan.unit_start[i + 1] : 2 * nparts;
+        for (uint32_t u = plan.unit_start[i]; u < hi; ++u) plan.unit_part[u] = i;
+    }
 }
 
 // ---- scatter: flat pass, segmented pass 2, multi-GPU exchange ---------------------------------------
@@ -552,7 +558,7 @@ unsigned resident_grid(Kern kern, size_t smem, uint64_t n_tiles, int sm_count) {
 size_t partition_plan_words(int total_bits, int pass1_bits) {
     const size_t nparts = size_t(1) << total_bits;
     const size_t nreg   = pass1_bits > 0 ? (size_t(1) << pass1_bits) : 0;
-    return 2 * (nparts + 1) + 2 * nparts + (nparts + 1) + (nreg ? 2 * (nreg + 1) + 2 * nreg + 2 * (nreg + 1) : 0) + 16;
+    return 2 * (nparts + 1) + 2 * nparts + (nparts + 1) + 2 * nparts + (nreg ? 2 * (nreg + 1) + 2 * nreg + 2 * (nreg + 1) : 0) + 16;
 }
 
 void partition_plan_carve(uint32_t* base, int total_bits, int pass1_bits, PartitionPlanDev* plan) {
@@ -565,6 +571,7 @@ void partition_plan_carve(uint32_t* base, int total_bits, int pass1_bits, Partit
     plan->cur_p = p; p += nparts;
     plan->unit_start = p; p += nparts + 1;
     plan->unit_cursor = p; p += 1;
+    plan->unit_part = p; p += 2 * nparts;
     if (nreg) {
         plan->reg_b = p; p += nreg + 1;
         plan->reg_p = p; p += nreg + 1;

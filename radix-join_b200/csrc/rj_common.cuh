@@ -57,6 +57,11 @@ __device__ __forceinline__ bool test_bit(const uint32_t* __restrict__ bitmap, ui
 // pull one 128-byte line towards L2 without waiting for it
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// pull [p, p + bytes) towards L2 with ONE instruction (the TMA unit does it); p and bytes are multiples of 16
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

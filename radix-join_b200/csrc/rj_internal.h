@@ -79,6 +79,7 @@ struct PartitionPlanDev {
     uint32_t* tile_p;       // [nreg+1]
     uint32_t* unit_start;   // [nparts+1] exclusive prefix of join work units per partition
     uint32_t* unit_cursor;  // [1]        dynamic work distribution of the join kernel
+    uint32_t* unit_part;    // [2 * nparts] partition of work unit u, for the first 2 * nparts units (the others: search unit_start)
 };
 
 size_t partition_plan_words(int total_bits, int pass1_bits);
@@ -250,6 +251,7 @@ struct JoinEmitLaunch {
     const uint32_t* off_p = nullptr;
     const uint32_t* unit_start = nullptr; // [nparts+1], units of (kEmitBuildCap build) x (kEmitProbeChunk probe) tuples
     uint32_t*       unit_cursor = nullptr;
+    const uint32_t* unit_part = nullptr;  // [2 * nparts] (PartitionPlanDev::unit_part), may be NULL
     uint32_t        nparts = 1;
     int             part_bits = 0;
     int             n_bpay = 0, n_ppay = 0;
