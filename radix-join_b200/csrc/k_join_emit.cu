@@ -13,7 +13,7 @@ bool launch_join_emit_b0(const EmitArgs& a, int n_ppay, int null_mask, int width
 }
 
 static size_t join_emit_layout(const JoinEmitLaunch& L, EmitArgs* a) {
-    size_t off = sizeof(uint64_t) * kEmitSlots;
+    size_t off = sizeof(uint64_t) * kEmitSlots; // offsets are relative to the table (emit::kBarBytes of mbarriers lie in front)
     auto   take = [&](size_t bytes) {
         off = (off + 15) / 16 * 16;
         const size_t at = off;
@@ -30,7 +30,7 @@ static size_t join_emit_layout(const JoinEmitLaunch& L, EmitArgs* a) {
     for (int c = 0; c < L.n_ppay; ++c) r.sm_pvalid[c] = L.pvalid[c] ? take(kBatch + 16) : 0;
     off = (off + 15) / 16 * 16;
     r.sm_pstride = static_cast<uint32_t>(off - r.sm_pkeys);
-    return off + size_t(emit::kStages - 1) * r.sm_pstride;
+    return off + size_t(emit::kStages - 1) * r.sm_pstride + emit::kBarBytes;
 }
 
 bool join_emit_fits(const JoinEmitLaunch& L) {

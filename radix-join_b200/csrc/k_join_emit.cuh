@@ -61,6 +61,7 @@ constexpr int      kBuildItems = kCap / kThreads;  // 6
 constexpr int      kConsumers  = kWarps - 1;       // warps that probe; the last warp requests the data and looks the next unit up
 constexpr uint32_t kBatch      = kConsumers * 32;  // probe tuples per batch: one ITEM of 32 per consumer warp
 constexpr uint32_t kStages     = 8;                // probe batches in flight per CTA (power of two)
+constexpr uint32_t kBarBytes   = 256;              // mbarriers in front of the table
 constexpr uint32_t kUpFront    = 4;                // batches requested before the table is built (the others: while it is probed)
 constexpr uint32_t kChunkRows  = kEmitChunkRows;   // 1984 = 62 bitmap words
 constexpr uint32_t kHalfRows   = kChunkRows / 2;   // 992 rows per 8-byte page = 31 bitmap words
@@ -130,9 +131,16 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     };
     auto bwide = [&](int c) -> bool { return WM >= 0 ? ((WM >> c) & 1) != 0 : a.bwidth[c] == 8; };
     auto pwide = [&](int c) -> bool { return WM >= 0 ? ((WM >> (kEmitMaxPay + c)) & 1) != 0 : a.pwidth[c] == 8; };
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_all[];
+    // the mbarriers live at the start of the dynamic segment so that every shared-memory address the probe loop
+    // needs is ONE register (sbase) plus a constant or an argument
+    uint64_t* const s_bars  = reinterpret_cast<uint64_t*>(smem_all);
+    uint64_t&       s_bbar  = s_bars[0];
+    uint64_t* const s_full  = s_bars + 1;
+    uint64_t* const s_empty = s_bars + 1 + kStages;
+    uint8_t* const  smem    = smem_all + kBarBytes; // the table, then the columns (offsets: EmitArgs::sm_*)
+    const uint32_t  sbase   = smem_u32(smem);
     __shared__ uint32_t s_desc[2][6]; // [round & 1]: the round's unit -- its number, then unit_start / off_b / off_b+1 / off_p / off_p+1 of its partition
-    __shared__ __align__(8) uint64_t s_bbar, s_full[kStages], s_empty[kStages];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt = lanemask_lt();
@@ -515,15 +523,15 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
             const uint32_t base = ps + j * kBatch;
             const uint32_t cnt = pe - base < kBatch ? pe - base : kBatch;
             const uint32_t stage = batch_no & (kStages - 1);
-            mbar_wait(&s_full[stage], (batch_no / kStages) & 1);
-            const uint8_t* const  buf = smem + stage * a.sm_pstride;
+            mbar_wait_addr(sbase - kBarBytes + 8u + stage * 8u, (batch_no / kStages) & 1);
+            const uint32_t        buf = sbase + stage * a.sm_pstride; // shared-memory address of the batch's buffer
             const uint32_t        i = tid; // one tuple per thread and batch: an ITEM = the 32 tuples of a warp
-            const uint32_t        key = (reinterpret_cast<const uint32_t*>(buf + a.sm_pkeys) + (base & 3u))[i]; // past cnt: stale bytes, never used
+            const uint32_t        key = lds_u32(buf + a.sm_pkeys + ((base & 3u) + i) * 4u); // past cnt: stale bytes, never used
             uint32_t lidx = kNone;
             if (direct) {
                 // the remaining hash bits identify the key: one load, a bit test, a popcount
                 const uint32_t x = hash_key(key) >> part_bits;
-                const uint2    e = reinterpret_cast<const uint2*>(smem)[x >> 5];
+                const uint2    e = lds_v2(sbase + (x >> 5) * 8u);
                 const uint32_t below = e.x & ((1u << (x & 31u)) - 1u);
                 if (i < cnt && ((e.x >> (x & 31u)) & 1u)) lidx = e.y + __popc(below);
             } else if (i < cnt) {
@@ -552,17 +560,15 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                 for_build([&](auto c_c, auto n_c) {
                     constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
                     const uint32_t at = act ? lidx : 0u;
-                    if constexpr (N >= 0) ok[N] = act && (smem + a.sm_bvalid[C] + bskew1)[at] != 0;
-                    const uint8_t* col = smem + a.sm_bpay[C];
-                    if (bwide(C)) bval[C] = (reinterpret_cast<const uint64_t*>(col) + (bskew1 & 1u))[at];
-                    else bval[C] = (reinterpret_cast<const uint32_t*>(col) + (bskew1 & 3u))[at];
+                    if constexpr (N >= 0) ok[N] = act && lds_u8(sbase + a.sm_bvalid[C] + bskew1 + at) != 0;
+                    if (bwide(C)) bval[C] = lds_u64(sbase + a.sm_bpay[C] + ((bskew1 & 1u) + at) * 8u);
+                    else bval[C] = lds_u32(sbase + a.sm_bpay[C] + ((bskew1 & 3u) + at) * 4u);
                 });
                 for_probe([&](auto c_c, auto n_c) {
                     constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
-                    if constexpr (N >= 0) ok[N] = act && (buf + a.sm_pvalid[C] + (base & 15u))[i] != 0;
-                    const uint8_t* col = buf + a.sm_ppay[C];
-                    if (pwide(C)) pval[C] = (reinterpret_cast<const uint64_t*>(col) + (base & 1u))[i];
-                    else pval[C] = (reinterpret_cast<const uint32_t*>(col) + (base & 3u))[i];
+                    if constexpr (N >= 0) ok[N] = act && lds_u8(buf + a.sm_pvalid[C] + (base & 15u) + i) != 0;
+                    if (pwide(C)) pval[C] = lds_u64(buf + a.sm_ppay[C] + ((base & 1u) + i) * 8u);
+                    else pval[C] = lds_u32(buf + a.sm_ppay[C] + ((base & 3u) + i) * 4u);
                 });
 
                 // place the matched rows: row index in the open chunk; rows past its end go to the next one (a second
@@ -707,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
             }
             // this warp is done with the batch's buffer
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            if (lane == 0) mbar_arrive_addr(sbase - kBarBytes + 8u + (kStages + stage) * 8u);
         }
     }
     // the partly filled chunk of this warp, and the chunk it may hold in reserve (an empty one)
