@@ -1,28 +1,33 @@
 // Per-partition build + probe in shared memory -- the GPU replacement of the reference's per-bucket
 // open-addressing join (src/execute.cpp:196-249: table of cap = pow2 >= 2*cnt slots, linear probing,
-// duplicates listed per slot, one output row per (probe row, matching build row)).
+// duplicates listed per slot, one output row per (probe row, matching build row)).  This is the GENERAL join:
+// any key type (4-byte keys, or 8-byte keys / VARCHAR hashes), duplicates on both sides, output = (build
+// position, probe position) pairs that the caller gathers through.  Root joins of two scans on an INT32 key
+// take the fused kernel instead (k_join_emit.cuh).
 //
-// One CTA = one work unit = (partition, build chunk, probe chunk):
-//   build : <= 6144 build tuples (2048 on average: 25 % fill) go into an 8192-slot linear-probing table
-//           in shared memory.  For 4-byte keys a slot is ONE 64-bit word (key | row id << 32) claimed
-//           with a 64-bit CAS, so a probe step is a single LDS.64 and a failed CAS tells the inserter
-//           whether it collided with an EQUAL key: the CTA learns for free whether the build side of
-//           this table has duplicate keys.  Duplicates take separate slots; with duplicates the probe
-//           walks the whole cluster and emits every equal key (the reference's "one row per duplicate",
-//           tests/unit_tests.cpp:125-161), without duplicates (every key/foreign-key join) it stops
-//           at the first match.
-//   probe : the probe chunk is streamed in super-batches of 8 tuples per thread (4096 per CTA) whose 16
-//           global loads are in flight one super-batch ahead.  The warp walks its 32 clusters in
-//           lockstep ROUNDS: every lane walks to its next match (or the end of its cluster), then the
-//           warp emits all matches of the round with one ballot + one shared-memory atomic.  (The first
-//           version emitted inside the divergent walk: ncu showed 3-8 active threads per instruction.)
-//           Pairs are staged in shared memory and flushed once per super-batch with ONE global atomic
-//           and coalesced stores.  A lane that finds the staging buffer full remembers item + slot and
-//           resumes after the flush, so any number of duplicates per probe tuple is handled.
-// Partitions whose build side exceeds one table are processed as several build chunks against the
-// same probe tuples (the union of the chunk joins is the join) -- the overflow path.
-// The slot hash uses the hash bits ABOVE the ones consumed by partitioning, so tuples of one
-// partition (which share the low bits) still spread over the table.
+// One CTA = one work unit = (partition, build chunk, probe chunk), handed out IN ORDER by a global atomic
+// cursor (see below why):
+//   build : <= 6144 build tuples (2048 on average: 25 % fill) go into an 8192-slot open-addressing table in
+//           shared memory with DOUBLE hashing (the stride of a key's probe sequence is a second hash of the
+//           key).  For 4-byte keys a slot is ONE 64-bit word (key | row id << 32) claimed with a 64-bit CAS,
+//           so a probe step is a single LDS.64 and a failed CAS tells the inserter whether it collided with
+//           an EQUAL key.  The table holds every distinct key once; further tuples of that key hang off the
+//           slot as a chain (dup_head / dup_next, private to the CTA) -- the counterpart of the reference's
+//           slot_idxs vectors (src/execute.cpp:203-223): a key with d duplicates costs O(d) to build and only
+//           probes of that very key walk them.  8-byte keys keep duplicates as separate entries along the
+//           key's own sequence.  (Details at `struct Table`.)
+//   probe : the probe chunk (a.probe_chunk tuples: 16384, fewer when the probe side is too small to give
+//           every SM a unit) is streamed in super-batches of 4-8 tuples per thread whose global loads are in
+//           flight one super-batch ahead.  The warp walks in lockstep ROUNDS: every lane walks to its next
+//           match (or the end of its sequence / chain), then the warp emits all matches of the round with one
+//           ballot + one shared-memory atomic (the first version emitted inside the divergent walk: ncu
+//           showed 3-8 active threads per instruction).  Pairs are staged in shared memory and flushed with
+//           ONE global atomic and coalesced stores.  A lane that finds the staging buffer full remembers item
+//           + position and resumes after the flush, so any number of duplicates per probe tuple is handled.
+// Partitions whose build side exceeds one table are processed as several build chunks against the same
+// probe tuples (the union of the chunk joins is the join) -- the overflow path.
+// The slot hash uses the hash bits ABOVE the ones consumed by partitioning, so tuples of one partition
+// (which share the low bits) still spread over the table.
 #include "rj_common.cuh"
 #include "rj_internal.h"
 
@@ -52,6 +57,7 @@ struct JoinArgs {
     const uint32_t* off_b;
     const uint32_t* off_p;
     const uint32_t* unit_start;
+    uint32_t        probe_chunk; // probe tuples per work unit
     uint32_t*       unit_cursor;
     uint32_t        nparts;
     int             part_bits;
@@ -218,12 +224,12 @@ __global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
             const uint32_t local = u - a.unit_start[part];
             const uint32_t b_lo = a.off_b[part], b_hi = a.off_b[part + 1];
             const uint32_t p_lo = a.off_p[part], p_hi = a.off_p[part + 1];
-            const uint32_t n_pchunks = (p_hi - p_lo + kJoinProbeChunk - 1) / kJoinProbeChunk;
+            const uint32_t n_pchunks = (p_hi - p_lo + a.probe_chunk - 1) / a.probe_chunk;
             const uint32_t bc = local / n_pchunks, pc = local - bc * n_pchunks;
             const uint32_t bs = b_lo + bc * kJoinBuildCap;
             const uint32_t be = (b_hi - bs > kJoinBuildCap) ? bs + kJoinBuildCap : b_hi;
-            const uint32_t ps = p_lo + pc * kJoinProbeChunk;
-            const uint32_t pe = (p_hi - ps > kJoinProbeChunk) ? ps + kJoinProbeChunk : p_hi;
+            const uint32_t ps = p_lo + pc * a.probe_chunk;
+            const uint32_t pe = (p_hi - ps > a.probe_chunk) ? ps + a.probe_chunk : p_hi;
 
             // first probe super-batch: issue its loads before anything else so they overlap the build
             K        nkey[kItems];
@@ -505,6 +511,7 @@ void run_join(const JoinLaunch& L, int sm_count, cudaStream_t s) {
     a.bkeys = L.bkeys; a.bidx = L.bidx; a.bvalid = L.bvalid;
     a.pkeys = L.pkeys; a.pidx = L.pidx; a.pvalid = L.pvalid;
     a.off_b = L.off_b; a.off_p = L.off_p; a.unit_start = L.unit_start; a.unit_cursor = L.unit_cursor;
+    a.probe_chunk = L.probe_chunk ? L.probe_chunk : kJoinProbeChunk;
     a.nparts = L.nparts; a.part_bits = L.part_bits;
     a.out_b = L.out_b; a.out_p = L.out_p; a.capacity = L.capacity; a.out_count = L.out_count;
     a.dup_next = L.dup_next; a.dup_head = L.dup_head;

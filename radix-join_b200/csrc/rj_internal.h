@@ -222,6 +222,7 @@ struct JoinLaunch {
     const uint32_t* off_b;  // [nparts+1]
     const uint32_t* off_p;
     const uint32_t* unit_start; // [nparts+1]
+    uint32_t        probe_chunk; // probe tuples per work unit (0: kJoinProbeChunk); must match the partition plan's
     uint32_t*       unit_cursor; // device word, zeroed before every launch: next unit to hand out
     uint32_t        nparts;
     int             part_bits;  // hash bits consumed by the partitioning
