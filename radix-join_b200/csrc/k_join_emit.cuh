@@ -106,6 +106,7 @@ struct EmitArgs {
     unsigned long long* row_counter;
     uint32_t*           abort_flag; // set when a table meets a duplicate build key
     int direct;   // the table is the rank structure over the hash bits left by the partitioning (see the kernel)
+    uint32_t n_active; // consumer warps that probe (1 .. kConsumers): the others idle, see the launcher
     int all_once; // the key and every carried column are shown by exactly one output column (no SELECT a, a; key shown)
 };
 
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
         mbar_init(&s_bbar, 1);
         for (uint32_t st = 0; st < kStages; ++st) {
             mbar_init(&s_full[st], 1);
-            mbar_init(&s_empty[st], kConsumers);
+            mbar_init(&s_empty[st], a.n_active);
         }
         fence_mbar_init();
     }
@@ -519,13 +520,18 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
             batch_no += n_batches;
             continue;
         }
+        if ((tid >> 5) >= a.n_active) { // a probe side too small to give every warp a few chunks of rows: this warp idles
+            batch_no += n_batches;
+            continue;
+        }
         for (uint32_t j = 0; j < n_batches; ++j, ++batch_no) {
             const uint32_t base = ps + j * kBatch;
             const uint32_t cnt = pe - base < kBatch ? pe - base : kBatch;
             const uint32_t stage = batch_no & (kStages - 1);
             mbar_wait_addr(sbase - kBarBytes + 8u + stage * 8u, (batch_no / kStages) & 1);
             const uint32_t        buf = sbase + stage * a.sm_pstride; // shared-memory address of the batch's buffer
-            const uint32_t        i = tid; // one tuple per thread and batch: an ITEM = the 32 tuples of a warp
+            // an ITEM = 32 consecutive tuples of the batch; the active warps share the batch's kConsumers items
+            for (uint32_t i = tid; i < kBatch; i += a.n_active * 32u) {
             const uint32_t        key = lds_u32(buf + a.sm_pkeys + ((base & 3u) + i) * 4u); // past cnt: stale bytes, never used
             uint32_t lidx = kNone;
             if (direct) {
@@ -710,6 +716,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                     after_place();
                     if (left == 0) break;
                 }
+            }
             }
             // this warp is done with the batch's buffer
             __syncwarp();

@@ -1,6 +1,7 @@
 // Host-side internal interface of the engine: the context, the launch wrappers of every kernel
 // file, and small RAII helpers.  Nothing here is exported; the C-ABI lives in engine.cu.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -276,16 +277,36 @@ constexpr uint32_t kEmitWarps = 16;            // warps per CTA of join_emit_ker
 constexpr uint32_t kEmitMinChunksPerWarp = 16; // grid sizing: a warp should fill this many chunks before it leaves one partly filled
 // Two CTAs per SM when the probe side is large; fewer CTAs for small probe sides so that the partly filled chunk
 // every warp ends with stays a small fraction (<= ~3 %) of the result's pages.
-inline unsigned join_emit_grid(uint64_t n_probe, int sm_count) {
-    const uint64_t per_cta = uint64_t(kEmitChunkRows) * kEmitMinChunksPerWarp * kEmitWarps;
-    const uint64_t want = (n_probe + per_cta - 1) / per_cta;
+inline uint64_t join_emit_env(const char* name, uint64_t dflt) { // tuning knobs (profiling)
+    const char* e = getenv(name);
+    return e && atoll(e) > 0 ? static_cast<uint64_t>(atoll(e)) : dflt;
+}
+// n_parts: partitions of the join (>= 1 work unit each): a CTA should not have to build more than
+// kEmitUnitsPerCta tables however few probe tuples there are (the windows of a streamed execute() probe ~600
+// tuples per partition against all 2^15 tables)
+constexpr uint32_t kEmitUnitsPerCta = 64;
+inline unsigned join_emit_grid(uint64_t n_probe, uint64_t n_parts, int sm_count) {
+    static const uint64_t min_chunks = join_emit_env("RJ_EMIT_MIN_CHUNKS", kEmitMinChunksPerWarp);
+    static const uint64_t units_per_cta = join_emit_env("RJ_EMIT_UNITS_PER_CTA", kEmitUnitsPerCta);
+    const uint64_t per_cta = uint64_t(kEmitChunkRows) * min_chunks * kEmitWarps;
+    uint64_t want = (n_probe + per_cta - 1) / per_cta;
+    want = want > n_parts / units_per_cta ? want : n_parts / units_per_cta;
     const uint64_t cap = static_cast<uint64_t>(sm_count) * 2;
     return static_cast<unsigned>(want < 1 ? 1 : (want > cap ? cap : want));
 }
+// Warps per CTA that probe and emit (the others idle): as many as get kEmitMinChunksPerWarp chunks' worth of probe
+// tuples each.  When the grid is sized by the number of tables rather than by the probe side, this keeps the partly
+// filled chunks few; the probe work of such a launch is small next to its table builds anyway.
+inline uint32_t join_emit_active_warps(uint64_t n_probe, unsigned grid) {
+    static const uint64_t min_chunks = join_emit_env("RJ_EMIT_MIN_CHUNKS", kEmitMinChunksPerWarp);
+    const uint64_t per_warp = uint64_t(kEmitChunkRows) * min_chunks * grid;
+    const uint64_t w = (n_probe + per_warp - 1) / per_warp;
+    return static_cast<uint32_t>(w < 1 ? 1 : (w > kEmitWarps - 1 ? kEmitWarps - 1 : w));
+}
 // chunks a launch can produce: every probe tuple matches at most once; every warp ends with at most one partly
 // filled chunk and one (empty) chunk held in reserve
-inline uint64_t join_emit_max_chunks(uint64_t n_probe, int sm_count) {
-    return n_probe / kEmitChunkRows + 2ull * kEmitWarps * join_emit_grid(n_probe, sm_count) + 1;
+inline uint64_t join_emit_max_chunks(uint64_t n_probe, uint64_t n_parts, int sm_count) {
+    return n_probe / kEmitChunkRows + 2ull * kEmitWarps * join_emit_grid(n_probe, n_parts, sm_count) + 1;
 }
 bool join_emit_fits(const JoinEmitLaunch& L);
 void launch_join_emit(const JoinEmitLaunch& L, uint64_t n_probe, int sm_count, cudaStream_t s);
