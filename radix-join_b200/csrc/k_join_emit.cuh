@@ -37,8 +37,8 @@
 // ballot per nullable column; values go straight from registers to their final place in global memory,
 // consecutive rows of the warp to consecutive addresses.  A chunk is reserved with one global atomic,
 // issued a few items before the open one fills up so that its latency is never waited for.
-// Cost: every warp ends the launch with a partly filled chunk; the launcher sizes the grid so that a warp
-// fills at least kEmitMinChunksPerWarp chunks (<= ~3 % more pages).
+// Cost: every emitting warp ends the launch with a partly filled chunk; the launcher lets only as many warps per
+// CTA emit as get kEmitMinChunksPerWarp chunks' worth of probe tuples each (<= ~3 % more pages), the others idle.
 //
 // Build keys must be unique inside every table (every key / foreign-key join): the 64-bit CAS insert sees
 // an equal key for free, raises a global flag and the whole launch is abandoned -- the engine then runs
@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
     uint8_t* cb_p[NP > 0 ? NP : 1] = {};
     const bool direct = a.direct != 0;
     const bool all_once = a.all_once != 0;
+    const bool all_active = a.n_active == static_cast<uint32_t>(kConsumers); // every consumer warp probes: one item per warp and batch
 
     // every output column that shows source S: f(first page of chunk c in that column)
     auto for_outputs = [&](int S, bool wide, uint32_t c, auto&& f) {
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
             mbar_wait_addr(sbase - kBarBytes + 8u + stage * 8u, (batch_no / kStages) & 1);
             const uint32_t        buf = sbase + stage * a.sm_pstride; // shared-memory address of the batch's buffer
             // an ITEM = 32 consecutive tuples of the batch; the active warps share the batch's kConsumers items
-            for (uint32_t i = tid; i < kBatch; i += a.n_active * 32u) {
+            auto process_item = [&](const uint32_t i) {
             const uint32_t        key = lds_u32(buf + a.sm_pkeys + ((base & 3u) + i) * 4u); // past cnt: stale bytes, never used
             uint32_t lidx = kNone;
             if (direct) {
@@ -717,7 +718,9 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
                     if (left == 0) break;
                 }
             }
-            }
+            };
+            if (all_active) process_item(tid);
+            else for (uint32_t i = tid; i < kBatch; i += a.n_active * 32u) process_item(i);
             // this warp is done with the batch's buffer
             __syncwarp();
             if (lane == 0) mbar_arrive_addr(sbase - kBarBytes + 8u + (kStages + stage) * 8u);
