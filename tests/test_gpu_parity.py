@@ -282,7 +282,11 @@ def test_one_heavy_build_key_uses_the_overflow_path(ctx):
 
 
 @pytest.mark.parametrize("n_build,n_probe", [(200_000, 1_000_000),     # one scatter pass (6 bits)
-                                             (3_000_000, 4_000_000)])  # two passes (10 bits)
+                                             (3_000_000, 4_000_000),   # two passes (10 bits)
+                                             # 4 partitions of ~500 K probe tuples each = 8 work units per partition:
+                                             # more units than the planner's unit -> partition table holds
+                                             # (2 x partitions), so the fused join looks the others up by search
+                                             (6_000, 2_000_000)])
 def test_partitioned_join_with_payloads(ctx, n_build, n_probe):
     rng = np.random.default_rng(n_build)
     bk = rng.permutation(n_build).astype(np.int32)
