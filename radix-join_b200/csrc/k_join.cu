@@ -164,7 +164,9 @@ struct Table<uint64_t> {
 };
 
 template <typename K>
-__global__ void __launch_bounds__(kJoinThreads, 2) join_kernel(JoinArgs a) {
+// 4-byte keys: two CTAs of 96 KB per SM; 8-byte keys need 128 KB of table + staging: one CTA per SM, and no reason to
+// cap it at 64 registers
+__global__ void __launch_bounds__(kJoinThreads, sizeof(K) == 4 ? 2 : 1) join_kernel(JoinArgs a) {
     constexpr int      kItems = Table<K>::kProbeItems;
     constexpr uint32_t kBatch = kItems * kJoinThreads;
     constexpr bool     kChains = sizeof(K) == 4; // duplicates of a key hang off its slot (see Table)
@@ -517,7 +519,8 @@ void run_join(const JoinLaunch& L, int sm_count, cudaStream_t s) {
     a.dup_next = L.dup_next; a.dup_head = L.dup_head;
     if (sizeof(K) == 4 && (!a.dup_next || !a.dup_head)) throw std::runtime_error("join: duplicate-chain scratch missing");
     // persistent grid: 2 CTAs per SM pull batches of work units in a strided order
-    join_kernel<K><<<join_grid(sm_count), kJoinThreads, smem, s>>>(a);
+    const unsigned grid = sizeof(K) == 4 ? join_grid(sm_count) : static_cast<unsigned>(sm_count); // resident CTAs only
+    join_kernel<K><<<grid, kJoinThreads, smem, s>>>(a);
     RJ_LAUNCH_CHECK();
 }
 
