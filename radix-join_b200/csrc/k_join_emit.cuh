@@ -340,12 +340,15 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
         const uint32_t n_pc = (phi - plo + a.probe_chunk - 1) / a.probe_chunk;
         const uint32_t bs_n = blo + ((u - us) / n_pc) * kCap;
         const uint32_t nb_n = bhi - bs_n > kCap ? kCap : bhi - bs_n;
-        prefetch_l2_bulk(a.bkeys + (bs_n & ~3u), round16((nb_n + 3u) * 4u));
+        // (whole 16-byte pieces strictly inside the unit's tuples: a prefetch never leaves the arrays)
+        const uint32_t f4 = (bs_n + 3u) & ~3u, l4 = (bs_n + nb_n) & ~3u;     // 4-element (>= 16-byte) boundaries
+        const uint32_t f16 = (bs_n + 15u) & ~15u, l16 = (bs_n + nb_n) & ~15u;
+        if (l4 > f4) prefetch_l2_bulk(a.bkeys + f4, (l4 - f4) * 4u);
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
             const uint32_t w = bwide(c) ? 8u : 4u;
-            prefetch_l2_bulk(static_cast<const char*>(a.bpay[c]) + static_cast<uint64_t>(bs_n & ~3u) * w, round16((nb_n + 3u) * w));
-            if ((NM >> c) & 1) prefetch_l2_bulk(a.bvalid[c] + (bs_n & ~15u), round16(nb_n + 15u));
+            if (l4 > f4) prefetch_l2_bulk(static_cast<const char*>(a.bpay[c]) + static_cast<uint64_t>(f4) * w, (l4 - f4) * w);
+            if (((NM >> c) & 1) && l16 > f16) prefetch_l2_bulk(a.bvalid[c] + f16, l16 - f16);
         }
     };
     const bool producer = (tid >> 5) == static_cast<uint32_t>(kConsumers);
