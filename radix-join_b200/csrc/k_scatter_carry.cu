@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(T, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kerne
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_region_start[kRegions ? 258 : 1];
     __shared__ uint32_t s_tile_start[kRegions ? 258 : 1];
+    __shared__ Tile s_next_tile[2]; // regions: the next tile's description, by parity of the iteration
     __shared__ __align__(8) uint64_t s_kbar[2];
     __shared__ __align__(8) uint64_t s_vbar;
     __shared__ void* s_dst[kMulti ? MultiCarryDsts::kArrays : 1][8];
@@ -223,7 +224,10 @@ __global__ void __launch_bounds__(T, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kerne
         const bool     has_next = tn < n_tiles;
         Tile           nxt = cur;
         if (has_next) {
-            nxt = describe(tn);
+            // regions: finding a tile's region is a search over up to 256 region starts -- done by the one thread
+            // that needs the answer now (to request the keys); the others pick it up behind the tile's last barrier
+            if (!kRegions || tid == 0) nxt = describe(tn);
+            if (kRegions && tid == 0) s_next_tile[b] = nxt;
             // buffer b^1 held the previous tile's keys: their last read is behind the barrier that ended its copy-out
             if (tid == 0) issue_keys(nxt, b ^ 1);
         }
@@ -286,31 +290,37 @@ __global__ void __launch_bounds__(T, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kerne
         }
         __syncthreads();
 
-        // 2) exclusive scan of the counts; the global runs are reserved now and their bases used after staging
+        // 2) exclusive scan of the counts; the global runs are reserved now and their bases used after staging.  Only
+        //    the warps that hold a bin take part (4 of 16 at 7 bits); the others go straight to the barriers
         uint32_t g = 0, start = 0;
         {
-            const uint32_t c = tid < nb ? s_count[tid] : 0u;
-            uint32_t inc = c;
+            const uint32_t scan_warps = (nb + 31u) >> 5;
+            uint32_t c = 0, inc = 0;
+            if (warp < scan_warps) {
+                c = tid < nb ? s_count[tid] : 0u;
+                inc = c;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
-                if (lane >= d) inc += o;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(RJ_FULL_MASK, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                if (lane == 31) s_warp_sums[warp] = inc;
+                if (tid < nb && c) g = atomicAdd(&a.cursor[cur.cbase + tid], c);
             }
-            if (lane == 31) s_warp_sums[warp] = inc;
-            if (tid < nb && c) g = atomicAdd(&a.cursor[cur.cbase + tid], c);
             __syncthreads();
-            uint32_t prefix = 0;
-#pragma unroll
-            for (uint32_t w = 0; w < kWarps; ++w) prefix += w < warp ? s_warp_sums[w] : 0u;
-            start = prefix + inc - c;
-            if (tid < nb) {
-                s_start[tid] = start;
-                s_count[tid] = 0; // ready for the next tile
-            }
-            if (tid == kT - 1) {
-                s_total     = prefix + inc;
-                s_start[nb] = prefix + inc; // dropped tuples: behind everything that is copied out
-                s_count[nb] = 0;
+            if (warp < scan_warps) {
+                uint32_t prefix = 0;
+                for (uint32_t w = 0; w < warp; ++w) prefix += s_warp_sums[w];
+                start = prefix + inc - c;
+                if (tid < nb) {
+                    s_start[tid] = start;
+                    s_count[tid] = 0; // ready for the next tile
+                }
+                if (tid == nb - 1) {
+                    s_total     = prefix + inc;
+                    s_start[nb] = prefix + inc; // dropped tuples: behind everything that is copied out
+                    s_count[nb] = 0;
+                }
             }
         }
         __syncthreads();
@@ -386,7 +396,11 @@ __global__ void __launch_bounds__(T, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kerne
                 if (f < n_flag) {
 #pragma unroll
                     for (int j = 0; j < kDepth; ++j)
-                        if (in[j]) (kMulti ? static_cast<uint8_t*>(s_dst[MultiCarryDsts::kFlag0 + f][own[j]]) : a.flag_dst[f])[dd[j]] = static_cast<uint8_t>((fl[j] >> f) & 1u);
+                        // single GPU: the launcher has filled the validity bytes with 1, only the NULLs are stored (a
+                        // byte store costs the LSU as much as a key store: 12 % of this kernel's stall samples when every
+                        // tuple stored its byte)
+                        if (in[j] && (kMulti || !((fl[j] >> f) & 1u)))
+                            (kMulti ? static_cast<uint8_t*>(s_dst[MultiCarryDsts::kFlag0 + f][own[j]]) : a.flag_dst[f])[dd[j]] = static_cast<uint8_t>((fl[j] >> f) & 1u);
                 }
             }
         };
@@ -394,6 +408,7 @@ __global__ void __launch_bounds__(T, (W0 + W1 > 12) ? 1 : 2) scatter_carry_kerne
         for (; base + kDepth * kT <= total; base += kDepth * kT) copy_out(std::false_type{}, base);
         if (base < total) copy_out(std::true_type{}, base);
         __syncthreads(); // every read of the windows and of perm is done
+        if (kRegions && has_next) nxt = s_next_tile[b];
         if (has_next && has_win && tid == 0) issue_wins(nxt);
         cur = nxt;
     }
@@ -488,6 +503,8 @@ void launch_scatter_carry(const CarryScatter& c, int sm_count, cudaStream_t s) {
         dispatch<false, true>(a, w[0], w[1], tiles_upper, sm_count, s);
         return;
     }
+    // validity bytes: all ones, the kernel stores the NULLs (see copy_out)
+    for (int f = 0; f < c.n_flag; ++f) RJ_CUDA(cudaMemsetAsync(c.flag_dst[f], 1, c.n, s));
     if (regions) dispatch<true>(a, w[0], w[1], tiles_upper, sm_count, s);
     else dispatch<false>(a, w[0], w[1], tiles_upper, sm_count, s);
 }
