@@ -15,7 +15,8 @@
  *     reference's error contract (src/execute.cpp:280, tests/read_sql.cpp:1329-1332).
  *   - no torch / C++ types in any signature; device pointers are `void*` / `uint64_t` addresses in the
  *     CUDA primary context of the device the context was created on; streams are `void*`
- *     (a `cudaStream_t`; NULL = the context's own stream).
+ *     (a `cudaStream_t`; NULL = the context's own non-blocking stream, which a stage call first orders behind the
+ *     work already queued on the legacy default stream -- where a caller without streams prepared its buffers).
  *   - there is NO CPU fallback: if no sm_100 device is present every entry point fails.
  */
 #ifndef RJ_B200_H

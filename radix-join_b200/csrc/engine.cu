@@ -1562,7 +1562,20 @@ int guarded(rj_ctx* ctx, F f) {
     }
 }
 
-cudaStream_t pick_stream(rj_ctx* ctx, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : ctx->stream; }
+// Stage entry points: a caller that passes no stream gets the context's (non-blocking) stream.  Such a caller
+// prepares its buffers on the default stream (torch does: a zero-fill may still be queued there), so the context's
+// stream is first ordered behind everything the legacy default stream has been given.
+cudaStream_t pick_stream(rj_ctx* ctx, void* stream) {
+    if (stream) return static_cast<cudaStream_t>(stream);
+    static thread_local cudaEvent_t ev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaEvent_t& e = ev[dev & 63];
+    if (!e) RJ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    RJ_CUDA(cudaEventRecord(e, cudaStreamLegacy));
+    RJ_CUDA(cudaStreamWaitEvent(ctx->stream, e, 0));
+    return ctx->stream;
+}
 
 } // namespace
 
