@@ -1887,13 +1887,11 @@ struct PendingDownload {
 };
 
 uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_bytes, OutputSink& out) {
-    bool auto_window = false;
     if (chunk_bytes == 0) {
         // RJ_WINDOW_BYTES: window size of callers that cannot pass one (Contest::execute); tests use it to
         // cut small inputs into many windows
         const char* env = getenv("RJ_WINDOW_BYTES");
-        auto_window = !(env && atoll(env) > 0);
-        chunk_bytes = auto_window ? uint64_t(256) << 20 : static_cast<uint64_t>(atoll(env));
+        chunk_bytes = env && atoll(env) > 0 ? static_cast<uint64_t>(atoll(env)) : uint64_t(256) << 20;
     }
     ensure_copy_streams(ctx);
     ensure_pipe(ctx);
@@ -1935,8 +1933,6 @@ uint64_t execute_streamed(rj_ctx* ctx, const rj_plan_t* plan, uint64_t chunk_byt
     // (Every window joins against ALL tables of the other side -- 2^15 of them at config 2 -- so the fused join sizes
     // its grid by the tables and lets only as many warps emit as the window's probe tuples can feed: measured on
     // config 2, Contest::execute, 256 MiB windows 355 ms, 512 MiB 368 ms.)
-    (void)auto_window;
-
     // page headers of the streamed table: rows before every page, per column
     std::vector<StreamCol> cols;
     for (uint32_t c = 0; c < ht.n_columns; ++c) {

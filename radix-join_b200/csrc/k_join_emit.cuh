@@ -536,191 +536,191 @@ __global__ void __launch_bounds__(kThreads, 2) join_emit_kernel(const __grid_con
             const uint32_t        buf = sbase + stage * a.sm_pstride; // shared-memory address of the batch's buffer
             // an ITEM = 32 consecutive tuples of the batch; the active warps share the batch's kConsumers items
             auto process_item = [&](const uint32_t i) {
-            const uint32_t        key = lds_u32(buf + a.sm_pkeys + ((base & 3u) + i) * 4u); // past cnt: stale bytes, never used
-            uint32_t lidx = kNone;
-            if (direct) {
-                // the remaining hash bits identify the key: one load, a bit test, a popcount
-                const uint32_t x = hash_key(key) >> part_bits;
-                const uint2    e = lds_v2(sbase + (x >> 5) * 8u);
-                const uint32_t below = e.x & ((1u << (x & 31u)) - 1u);
-                if (i < cnt && ((e.x >> (x & 31u)) & 1u)) lidx = e.y + __popc(below);
-            } else if (i < cnt) {
-                // at most one match: the table holds distinct keys.  A slot is (key, build index); an empty
-                // one has index 0xffffffff
-                uint32_t       off   = ((hash_key(key) >> part_bits) & kSlotMask) * 8u;
-                const uint32_t step8 = probe_step(key) * 8u;
-                for (;;) {
-                    uint32_t ex, ey;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(smem_u32(smem) + off));
-                    if (ey == kNone) break;
-                    if (ex == key) {
-                        lidx = ey;
-                        break;
+                const uint32_t        key = lds_u32(buf + a.sm_pkeys + ((base & 3u) + i) * 4u); // past cnt: stale bytes, never used
+                uint32_t lidx = kNone;
+                if (direct) {
+                    // the remaining hash bits identify the key: one load, a bit test, a popcount
+                    const uint32_t x = hash_key(key) >> part_bits;
+                    const uint2    e = lds_v2(sbase + (x >> 5) * 8u);
+                    const uint32_t below = e.x & ((1u << (x & 31u)) - 1u);
+                    if (i < cnt && ((e.x >> (x & 31u)) & 1u)) lidx = e.y + __popc(below);
+                } else if (i < cnt) {
+                    // at most one match: the table holds distinct keys.  A slot is (key, build index); an empty
+                    // one has index 0xffffffff
+                    uint32_t       off   = ((hash_key(key) >> part_bits) & kSlotMask) * 8u;
+                    const uint32_t step8 = probe_step(key) * 8u;
+                    for (;;) {
+                        uint32_t ex, ey;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(smem_u32(smem) + off));
+                        if (ey == kNone) break;
+                        if (ex == key) {
+                            lidx = ey;
+                            break;
+                        }
+                        off = (off + step8) & (kSlotMask * 8u);
                     }
-                    off = (off + step8) & (kSlotMask * 8u);
                 }
-            }
-            __syncwarp();
-            bool           act = lidx != kNone;
-            const uint32_t bal = __ballot_sync(RJ_FULL_MASK, act);
-            if (bal != 0) {
-                // the row's validity in the nullable columns, and its values
-                bool ok[NNX];
-                uint64_t bval[NB > 0 ? NB : 1], pval[NP > 0 ? NP : 1];
-                for_build([&](auto c_c, auto n_c) {
-                    constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
-                    const uint32_t at = act ? lidx : 0u;
-                    if constexpr (N >= 0) ok[N] = act && lds_u8(sbase + a.sm_bvalid[C] + bskew1 + at) != 0;
-                    if (bwide(C)) bval[C] = lds_u64(sbase + a.sm_bpay[C] + ((bskew1 & 1u) + at) * 8u);
-                    else bval[C] = lds_u32(sbase + a.sm_bpay[C] + ((bskew1 & 3u) + at) * 4u);
-                });
-                for_probe([&](auto c_c, auto n_c) {
-                    constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
-                    if constexpr (N >= 0) ok[N] = act && lds_u8(buf + a.sm_pvalid[C] + (base & 15u) + i) != 0;
-                    if (pwide(C)) pval[C] = lds_u64(buf + a.sm_ppay[C] + ((base & 1u) + i) * 8u);
-                    else pval[C] = lds_u32(buf + a.sm_ppay[C] + ((base & 3u) + i) * 4u);
-                });
+                __syncwarp();
+                bool           act = lidx != kNone;
+                const uint32_t bal = __ballot_sync(RJ_FULL_MASK, act);
+                if (bal != 0) {
+                    // the row's validity in the nullable columns, and its values
+                    bool ok[NNX];
+                    uint64_t bval[NB > 0 ? NB : 1], pval[NP > 0 ? NP : 1];
+                    for_build([&](auto c_c, auto n_c) {
+                        constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
+                        const uint32_t at = act ? lidx : 0u;
+                        if constexpr (N >= 0) ok[N] = act && lds_u8(sbase + a.sm_bvalid[C] + bskew1 + at) != 0;
+                        if (bwide(C)) bval[C] = lds_u64(sbase + a.sm_bpay[C] + ((bskew1 & 1u) + at) * 8u);
+                        else bval[C] = lds_u32(sbase + a.sm_bpay[C] + ((bskew1 & 3u) + at) * 4u);
+                    });
+                    for_probe([&](auto c_c, auto n_c) {
+                        constexpr int C = decltype(c_c)::value, N = decltype(n_c)::value;
+                        if constexpr (N >= 0) ok[N] = act && lds_u8(buf + a.sm_pvalid[C] + (base & 15u) + i) != 0;
+                        if (pwide(C)) pval[C] = lds_u64(buf + a.sm_ppay[C] + ((base & 1u) + i) * 8u);
+                        else pval[C] = lds_u32(buf + a.sm_ppay[C] + ((base & 3u) + i) * 4u);
+                    });
 
-                // place the matched rows: row index in the open chunk; rows past its end go to the next one (a second
-                // round)
-                uint32_t r = rows + __popc(bal & lt);
-                uint32_t left = __popc(bal);
-                for (;;) {
-                    ensure_open();
-                    if (all_once && left == 32u && rows + 32u <= (rows < kHalfRows ? kHalfRows : kChunkRows)) {
-                        // DENSE item (every lane matched -- the rule in a key / foreign-key join) that lies inside one page
-                        // of every column: rows are the lanes in order and complete exactly one bitmap word.  Everything
-                        // but the value slots is warp-uniform.  (The two items of a chunk that straddle row 992 or 1984,
-                        // and items with unmatched lanes, take the general round below.)
-                        const bool     h = rows >= kHalfRows;
-                        const uint32_t w0 = rows >> 5, sh = rows & 31u;
-                        auto dense = [&](auto n_c, bool wide, uint64_t val, uint8_t* cb) {
-                            constexpr int N = decltype(n_c)::value;
-                            uint32_t at;
-                            bool     st = true;
-                            if constexpr (N >= 0) {
-                                const uint32_t okb = __ballot_sync(RJ_FULL_MASK, ok[N]);
-                                st = ok[N];
-                                at = nv[N] + __popc(okb & lt);
-                                if (wide && h) at += RJ_PAGE / 8 - nvh[N];
-                                nv[N] += __popc(okb);
-                                if (lane == (w0 & 31u)) held[N] = pend[N] | (okb << sh);
-                                pend[N] = sh ? okb >> (32u - sh) : 0u;
-                                const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
-                                if (w0 == first_flush || w0 == kChunkRows / 32 - 1) {
-                                    const uint32_t wl = w0 - ((w0 - lane) & 31u);
-                                    if (wl <= w0 && (w0 == first_flush || wl > first_flush)) *bitmap_word(cb, wide, wl) = held[N];
-                                }
-                            } else {
-                                at = rows + lane;
-                                if (wide && h) at += RJ_PAGE / 8 - kHalfRows;
-                            }
-                            if (wide) {
-                                if (st) (reinterpret_cast<uint64_t*>(cb + 8))[at] = val;
-                            } else {
-                                if (st) (reinterpret_cast<uint32_t*>(cb + 4))[at] = static_cast<uint32_t>(val);
-                            }
-                        };
-                        dense(std::integral_constant<int, -1>{}, false, key, cb_key);
-                        for_build([&](auto c_c, auto n_c) { dense(n_c, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
-                        for_probe([&](auto c_c, auto n_c) { dense(n_c, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
-                        rows += 32u;
-                        left = 0;
-                        if (NN > 0 && rows == kHalfRows) { // the 8-byte columns' first page is complete
-#pragma unroll
-                            for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn];
-                        }
-                    } else {
-                        const bool     now = act && r < kChunkRows;
-                        const uint32_t nowb = __ballot_sync(RJ_FULL_MASK, now);
-                        const uint32_t n_now = __popc(nowb);
-                        uint32_t okb[NNX], v[NNX];
-#pragma unroll
-                        for (int nn = 0; nn < NN; ++nn) {
-                            okb[nn] = __ballot_sync(RJ_FULL_MASK, now && ok[nn]);
-                            v[nn]   = nv[nn] + __popc(okb[nn] & lt);
-                        }
-                        if (NN > 0 && rows < kHalfRows && rows + n_now >= kHalfRows) {
-                            // the rows of this round reach the second page of the 8-byte columns
-                            const uint32_t lowb = __ballot_sync(RJ_FULL_MASK, now && r < kHalfRows);
-#pragma unroll
-                            for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn] + __popc(okb[nn] & lowb);
-                        }
-                        const uint32_t w0 = rows >> 5, sh = rows & 31u; // the bitmap word the round's first row falls into
-                        // One source's value into every output column that shows it, and -- for a nullable source -- the
-                        // validity bits of the rows placed now (rows [rows, rows + n_now) of the chunk: two bitmap words
-                        // at most).  A complete word stays with lane (w & 31) until 31 / 32 of them (one page's worth, or
-                        // the chunk's second half) go out in one store.  N = index among the nullable columns, -1: the
-                        // source holds no NULL.  kOnce: every source is shown by exactly one output column, whose chunk
-                        // base is cb.
-                        auto emit = [&](auto once_c, auto n_c, int S, bool wide, uint64_t val, uint8_t* cb) {
-                            constexpr int  N = decltype(n_c)::value;
-                            constexpr bool kOnce = decltype(once_c)::value;
-                            bool st = now;
-                            if constexpr (N >= 0) st = now && ok[N];
-                            uint32_t at; // value slot, in units of the value width, from the chunk's first data byte
-                            if (wide) {
-                                const bool h = r >= kHalfRows;
-                                if constexpr (N >= 0) at = v[N] - (h ? nvh[N] : 0u); else at = r - (h ? kHalfRows : 0u);
-                                at += h ? RJ_PAGE / 8 : 0u;
-                            } else {
-                                if constexpr (N >= 0) at = v[N]; else at = r;
-                            }
-                            bool flush = false;
-                            if constexpr (N >= 0) {
-                                uint32_t lo, hi;
-                                if (nowb == RJ_FULL_MASK) { // rows are the lanes in order
-                                    lo = okb[N] << sh;
-                                    hi = sh ? okb[N] >> (32u - sh) : 0u;
-                                } else {
-                                    const uint32_t bit = st ? (1u << (r & 31u)) : 0u;
-                                    const bool     first = (r >> 5) == w0;
-                                    lo = __reduce_or_sync(RJ_FULL_MASK, first ? bit : 0u);
-                                    hi = __reduce_or_sync(RJ_FULL_MASK, first ? 0u : bit);
-                                }
-                                const uint32_t word = pend[N] | lo;
-                                const bool     complete = sh + n_now >= 32u;
-                                pend[N] = complete ? hi : word;
-                                if (complete && lane == (w0 & 31u)) held[N] = word;
-                                flush = complete && (w0 == (wide ? kHalfWords - 1 : 31u) || w0 == kChunkRows / 32 - 1);
-                            }
-                            auto store = [&](uint8_t* base_page) {
-                                if (wide) {
-                                    if (st) (reinterpret_cast<uint64_t*>(base_page + 8))[at] = val;
-                                } else {
-                                    if (st) (reinterpret_cast<uint32_t*>(base_page + 4))[at] = static_cast<uint32_t>(val);
-                                }
+                    // place the matched rows: row index in the open chunk; rows past its end go to the next one (a second
+                    // round)
+                    uint32_t r = rows + __popc(bal & lt);
+                    uint32_t left = __popc(bal);
+                    for (;;) {
+                        ensure_open();
+                        if (all_once && left == 32u && rows + 32u <= (rows < kHalfRows ? kHalfRows : kChunkRows)) {
+                            // DENSE item (every lane matched -- the rule in a key / foreign-key join) that lies inside one page
+                            // of every column: rows are the lanes in order and complete exactly one bitmap word.  Everything
+                            // but the value slots is warp-uniform.  (The two items of a chunk that straddle row 992 or 1984,
+                            // and items with unmatched lanes, take the general round below.)
+                            const bool     h = rows >= kHalfRows;
+                            const uint32_t w0 = rows >> 5, sh = rows & 31u;
+                            auto dense = [&](auto n_c, bool wide, uint64_t val, uint8_t* cb) {
+                                constexpr int N = decltype(n_c)::value;
+                                uint32_t at;
+                                bool     st = true;
                                 if constexpr (N >= 0) {
-                                    if (flush) {
-                                        // lane l holds word wl = the largest w <= w0 with (w & 31) == l; the words up to
-                                        // the first flush point went out then
+                                    const uint32_t okb = __ballot_sync(RJ_FULL_MASK, ok[N]);
+                                    st = ok[N];
+                                    at = nv[N] + __popc(okb & lt);
+                                    if (wide && h) at += RJ_PAGE / 8 - nvh[N];
+                                    nv[N] += __popc(okb);
+                                    if (lane == (w0 & 31u)) held[N] = pend[N] | (okb << sh);
+                                    pend[N] = sh ? okb >> (32u - sh) : 0u;
+                                    const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
+                                    if (w0 == first_flush || w0 == kChunkRows / 32 - 1) {
                                         const uint32_t wl = w0 - ((w0 - lane) & 31u);
-                                        const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
-                                        const bool     mine = wl <= w0 && (w0 == first_flush || wl > first_flush); // (wl wraps above w0 when no such word exists)
-                                        if (mine) *bitmap_word(base_page, wide, wl) = held[N];
+                                        if (wl <= w0 && (w0 == first_flush || wl > first_flush)) *bitmap_word(cb, wide, wl) = held[N];
                                     }
+                                } else {
+                                    at = rows + lane;
+                                    if (wide && h) at += RJ_PAGE / 8 - kHalfRows;
+                                }
+                                if (wide) {
+                                    if (st) (reinterpret_cast<uint64_t*>(cb + 8))[at] = val;
+                                } else {
+                                    if (st) (reinterpret_cast<uint32_t*>(cb + 4))[at] = static_cast<uint32_t>(val);
                                 }
                             };
-                            if constexpr (kOnce) store(cb);
-                            else for_outputs(S, wide, c_open, store);
-                        };
-                        auto emit_all = [&](auto once_c) {
-                            emit(once_c, std::integral_constant<int, -1>{}, 0, false, key, cb_key);
-                            for_build([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + decltype(c_c)::value, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
-                            for_probe([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + kEmitMaxPay + decltype(c_c)::value, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
-                        };
-                        if (all_once) emit_all(std::true_type{}); else emit_all(std::false_type{});
-                        rows += n_now;
-                        left -= n_now;
+                            dense(std::integral_constant<int, -1>{}, false, key, cb_key);
+                            for_build([&](auto c_c, auto n_c) { dense(n_c, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
+                            for_probe([&](auto c_c, auto n_c) { dense(n_c, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
+                            rows += 32u;
+                            left = 0;
+                            if (NN > 0 && rows == kHalfRows) { // the 8-byte columns' first page is complete
 #pragma unroll
-                        for (int nn = 0; nn < NN; ++nn) nv[nn] += __popc(okb[nn]);
-                        act = act && !now;
-                        r -= kChunkRows; // (meaningful for the rows of a second round only)
+                                for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn];
+                            }
+                        } else {
+                            const bool     now = act && r < kChunkRows;
+                            const uint32_t nowb = __ballot_sync(RJ_FULL_MASK, now);
+                            const uint32_t n_now = __popc(nowb);
+                            uint32_t okb[NNX], v[NNX];
+#pragma unroll
+                            for (int nn = 0; nn < NN; ++nn) {
+                                okb[nn] = __ballot_sync(RJ_FULL_MASK, now && ok[nn]);
+                                v[nn]   = nv[nn] + __popc(okb[nn] & lt);
+                            }
+                            if (NN > 0 && rows < kHalfRows && rows + n_now >= kHalfRows) {
+                                // the rows of this round reach the second page of the 8-byte columns
+                                const uint32_t lowb = __ballot_sync(RJ_FULL_MASK, now && r < kHalfRows);
+#pragma unroll
+                                for (int nn = 0; nn < NN; ++nn) nvh[nn] = nv[nn] + __popc(okb[nn] & lowb);
+                            }
+                            const uint32_t w0 = rows >> 5, sh = rows & 31u; // the bitmap word the round's first row falls into
+                            // One source's value into every output column that shows it, and -- for a nullable source -- the
+                            // validity bits of the rows placed now (rows [rows, rows + n_now) of the chunk: two bitmap words
+                            // at most).  A complete word stays with lane (w & 31) until 31 / 32 of them (one page's worth, or
+                            // the chunk's second half) go out in one store.  N = index among the nullable columns, -1: the
+                            // source holds no NULL.  kOnce: every source is shown by exactly one output column, whose chunk
+                            // base is cb.
+                            auto emit = [&](auto once_c, auto n_c, int S, bool wide, uint64_t val, uint8_t* cb) {
+                                constexpr int  N = decltype(n_c)::value;
+                                constexpr bool kOnce = decltype(once_c)::value;
+                                bool st = now;
+                                if constexpr (N >= 0) st = now && ok[N];
+                                uint32_t at; // value slot, in units of the value width, from the chunk's first data byte
+                                if (wide) {
+                                    const bool h = r >= kHalfRows;
+                                    if constexpr (N >= 0) at = v[N] - (h ? nvh[N] : 0u); else at = r - (h ? kHalfRows : 0u);
+                                    at += h ? RJ_PAGE / 8 : 0u;
+                                } else {
+                                    if constexpr (N >= 0) at = v[N]; else at = r;
+                                }
+                                bool flush = false;
+                                if constexpr (N >= 0) {
+                                    uint32_t lo, hi;
+                                    if (nowb == RJ_FULL_MASK) { // rows are the lanes in order
+                                        lo = okb[N] << sh;
+                                        hi = sh ? okb[N] >> (32u - sh) : 0u;
+                                    } else {
+                                        const uint32_t bit = st ? (1u << (r & 31u)) : 0u;
+                                        const bool     first = (r >> 5) == w0;
+                                        lo = __reduce_or_sync(RJ_FULL_MASK, first ? bit : 0u);
+                                        hi = __reduce_or_sync(RJ_FULL_MASK, first ? 0u : bit);
+                                    }
+                                    const uint32_t word = pend[N] | lo;
+                                    const bool     complete = sh + n_now >= 32u;
+                                    pend[N] = complete ? hi : word;
+                                    if (complete && lane == (w0 & 31u)) held[N] = word;
+                                    flush = complete && (w0 == (wide ? kHalfWords - 1 : 31u) || w0 == kChunkRows / 32 - 1);
+                                }
+                                auto store = [&](uint8_t* base_page) {
+                                    if (wide) {
+                                        if (st) (reinterpret_cast<uint64_t*>(base_page + 8))[at] = val;
+                                    } else {
+                                        if (st) (reinterpret_cast<uint32_t*>(base_page + 4))[at] = static_cast<uint32_t>(val);
+                                    }
+                                    if constexpr (N >= 0) {
+                                        if (flush) {
+                                            // lane l holds word wl = the largest w <= w0 with (w & 31) == l; the words up to
+                                            // the first flush point went out then
+                                            const uint32_t wl = w0 - ((w0 - lane) & 31u);
+                                            const uint32_t first_flush = wide ? kHalfWords - 1 : 31u;
+                                            const bool     mine = wl <= w0 && (w0 == first_flush || wl > first_flush); // (wl wraps above w0 when no such word exists)
+                                            if (mine) *bitmap_word(base_page, wide, wl) = held[N];
+                                        }
+                                    }
+                                };
+                                if constexpr (kOnce) store(cb);
+                                else for_outputs(S, wide, c_open, store);
+                            };
+                            auto emit_all = [&](auto once_c) {
+                                emit(once_c, std::integral_constant<int, -1>{}, 0, false, key, cb_key);
+                                for_build([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + decltype(c_c)::value, bwide(decltype(c_c)::value), bval[decltype(c_c)::value], cb_b[decltype(c_c)::value]); });
+                                for_probe([&](auto c_c, auto n_c) { emit(once_c, n_c, 1 + kEmitMaxPay + decltype(c_c)::value, pwide(decltype(c_c)::value), pval[decltype(c_c)::value], cb_p[decltype(c_c)::value]); });
+                            };
+                            if (all_once) emit_all(std::true_type{}); else emit_all(std::false_type{});
+                            rows += n_now;
+                            left -= n_now;
+#pragma unroll
+                            for (int nn = 0; nn < NN; ++nn) nv[nn] += __popc(okb[nn]);
+                            act = act && !now;
+                            r -= kChunkRows; // (meaningful for the rows of a second round only)
+                        }
+                        after_place();
+                        if (left == 0) break;
                     }
-                    after_place();
-                    if (left == 0) break;
                 }
-            }
             };
             if (all_active) process_item(tid);
             else for (uint32_t i = tid; i < kBatch; i += a.n_active * 32u) process_item(i);
