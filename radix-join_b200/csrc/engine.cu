@@ -1450,6 +1450,8 @@ std::unique_ptr<rj_result> Exec::root_fused(uint64_t n) {
     L.chunk_counter = counters->as<uint32_t>();
     L.abort_flag = counters->as<uint32_t>() + 1;
     L.row_counter = reinterpret_cast<unsigned long long*>(counters->as<uint8_t>() + 8);
+    // a window of a streamed execute() ships its pages over PCIe right away: fewer partly filled ones
+    L.min_chunks_per_warp = streamed_table != 0xffffffffu ? kEmitMinChunksPerWarp : kEmitMinChunksResident;
     RJ_CUDA(cudaMemsetAsync(pl.unit_cursor, 0, 4, s));
     uint32_t h[4] = {0, 0, 0, 0};
     {
@@ -3040,6 +3042,7 @@ std::unique_ptr<rj_result> join_partitioned_impl(rj_ctx* ctx, const rj_part_side
             rc.pages = dev_alloc(max_chunks * (L.out_width[a] == 4 ? 1 : 2) * size_t(RJ_PAGE_SIZE), s);
             L.out_pages[a] = rc.pages->as<uint8_t>();
         }
+        L.min_chunks_per_warp = kEmitMinChunksResident;
         L.chunk_counter = counters->as<uint32_t>();
         L.abort_flag = counters->as<uint32_t>() + 1;
         L.row_counter = reinterpret_cast<unsigned long long*>(counters->as<uint8_t>() + 8);

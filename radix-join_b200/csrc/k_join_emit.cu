@@ -74,7 +74,7 @@ void launch_join_emit(const JoinEmitLaunch& L, uint64_t n_probe, int sm_count, c
     const size_t smem = join_emit_layout(L, &a);
     if (smem > 226 * 1024) throw CudaError("join_emit: the columns do not fit shared memory");
     const unsigned grid = join_emit_grid(n_probe, L.nparts, sm_count);
-    a.n_active = join_emit_active_warps(n_probe, grid);
+    a.n_active = join_emit_active_warps(n_probe, grid, L.min_chunks_per_warp);
     bool launched = false;
     switch (L.n_bpay) {
     case 0: launched = launch_join_emit_b0(a, L.n_ppay, null_mask, width_mask, smem, grid, s); break;

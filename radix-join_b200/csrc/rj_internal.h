@@ -246,6 +246,13 @@ constexpr uint32_t kEmitProbeChunk = 65536; // probe tuples per work unit (a tab
 constexpr uint32_t kEmitChunkRows = 1984;  // rows per output chunk: 1 page per 4-byte column, 2 x 992 rows per 8-byte column
 constexpr int      kEmitMaxPay    = 2;     // carried columns per side
 constexpr int      kEmitMaxOut    = 4;     // output columns
+constexpr uint32_t kEmitWarps = 16;            // warps per CTA of join_emit_kernel: every warp owns an open chunk
+constexpr uint32_t kEmitMinChunksPerWarp = 16; // an emitting warp should fill this many chunks before it leaves one partly filled (<= 3 % more pages): results that travel over PCIe
+constexpr uint32_t kEmitMinChunksResident = 8; // ... when the result pages stay in HBM (<= 6 %): more warps emit (N = 8: 14 instead of 7 per CTA)
+inline uint64_t join_emit_env(const char* name, uint64_t dflt) { // tuning knobs (profiling)
+    const char* e = getenv(name);
+    return e && atoll(e) > 0 ? static_cast<uint64_t>(atoll(e)) : dflt;
+}
 struct JoinEmitLaunch {
     const uint32_t* bkeys = nullptr; // both sides fully partitioned, 4-byte keys, NULL keys already dropped
     const uint32_t* pkeys = nullptr;
@@ -272,15 +279,8 @@ struct JoinEmitLaunch {
     uint32_t*           chunk_counter = nullptr;    // zeroed by the caller
     unsigned long long* row_counter = nullptr;
     uint32_t*           abort_flag = nullptr;
+    uint32_t            min_chunks_per_warp = kEmitMinChunksPerWarp; // see join_emit_active_warps
 };
-constexpr uint32_t kEmitWarps = 16;            // warps per CTA of join_emit_kernel: every warp owns an open chunk
-constexpr uint32_t kEmitMinChunksPerWarp = 16; // grid sizing: a warp should fill this many chunks before it leaves one partly filled
-// Two CTAs per SM when the probe side is large; fewer CTAs for small probe sides so that the partly filled chunk
-// every warp ends with stays a small fraction (<= ~3 %) of the result's pages.
-inline uint64_t join_emit_env(const char* name, uint64_t dflt) { // tuning knobs (profiling)
-    const char* e = getenv(name);
-    return e && atoll(e) > 0 ? static_cast<uint64_t>(atoll(e)) : dflt;
-}
 // Two CTAs per SM, or one per partition when there are fewer partitions than that (a partition is at least one
 // work unit; CTAs without a unit retire at once).  How many chunks are left partly filled is governed by the
 // number of warps that emit, not by the grid: see join_emit_active_warps.
@@ -293,8 +293,9 @@ inline unsigned join_emit_grid(uint64_t n_probe, uint64_t n_parts, int sm_count)
 // tuples each, so that the partly filled chunk every emitting warp ends with stays a small fraction (<= ~3 %) of
 // the result's pages.  A small probe side is better served by a few warps on EVERY SM than by all warps of a few
 // CTAs (config 1, 10 M probe tuples: 0.39 ms per execute with the former, 1.2 ms with the latter).
-inline uint32_t join_emit_active_warps(uint64_t n_probe, unsigned grid) {
-    static const uint64_t min_chunks = join_emit_env("RJ_EMIT_MIN_CHUNKS", kEmitMinChunksPerWarp);
+inline uint32_t join_emit_active_warps(uint64_t n_probe, unsigned grid, uint32_t min_chunks_per_warp = kEmitMinChunksPerWarp) {
+    static const uint64_t forced = join_emit_env("RJ_EMIT_MIN_CHUNKS", 0);
+    const uint64_t min_chunks = forced ? forced : (min_chunks_per_warp ? min_chunks_per_warp : kEmitMinChunksPerWarp);
     const uint64_t per_warp = uint64_t(kEmitChunkRows) * min_chunks * grid;
     const uint64_t w = (n_probe + per_warp - 1) / per_warp;
     return static_cast<uint32_t>(w < 1 ? 1 : (w > kEmitWarps - 1 ? kEmitWarps - 1 : w));

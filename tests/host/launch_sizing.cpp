@@ -13,9 +13,10 @@ int main() {
     const uint64_t parts[] = {1, 2, 4, 128, 512, 4096, 32768};
     for (int sm: sms)
         for (uint64_t np: probes)
-            for (uint64_t p: parts) {
+            for (uint64_t p: parts)
+            for (uint32_t mc: {kEmitMinChunksPerWarp, kEmitMinChunksResident}) {
                 const unsigned grid = join_emit_grid(np, p, sm);
-                const uint32_t act  = join_emit_active_warps(np, grid);
+                const uint32_t act  = join_emit_active_warps(np, grid, mc);
                 const uint64_t cap  = join_emit_max_chunks(np, p, sm);
                 // every emitting warp may leave one partly filled chunk and one reserved (empty) chunk behind
                 const uint64_t need = np / kEmitChunkRows + 2ull * act * grid;
@@ -25,7 +26,7 @@ int main() {
                     ++bad;
                 }
                 // the partly filled chunks stay a small fraction of the result once the probe side is large
-                if (np >= 100000000ull && 2ull * act * grid * 16 > np / kEmitChunkRows * 2) {
+                if (np >= 100000000ull && 2ull * act * grid * mc > np / kEmitChunkRows * 2) {
                     std::printf("waste: sm %d np %llu parts %llu -> grid %u active %u\n", sm, (unsigned long long)np, (unsigned long long)p, grid, act);
                     ++bad;
                 }
