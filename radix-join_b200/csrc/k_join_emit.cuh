@@ -38,7 +38,8 @@
 // consecutive rows of the warp to consecutive addresses.  A chunk is reserved with one global atomic,
 // issued a few items before the open one fills up so that its latency is never waited for.
 // Cost: every emitting warp ends the launch with a partly filled chunk; the launcher lets only as many warps per
-// CTA emit as get kEmitMinChunksPerWarp chunks' worth of probe tuples each (<= ~3 % more pages), the others idle.
+// CTA emit as get kEmitMinChunksPerWarp (results shipped over PCIe) / kEmitMinChunksResident chunks' worth of probe
+// tuples each (<= ~3 % / 6 % more pages), the others idle.
 //
 // Build keys must be unique inside every table (every key / foreign-key join): the 64-bit CAS insert sees
 // an equal key for free, raises a global flag and the whole launch is abandoned -- the engine then runs
